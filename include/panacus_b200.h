@@ -1,0 +1,147 @@
+/*
+ * panacus_b200.h -- C ABI of libpanacus_b200.so: the B200 (sm_100a) implementation of panacus's
+ * counting hot path (coverage histogram, ordered / permuted growth, all-pairs group intersections).
+ *
+ * The reference (marschall-lab/panacus @ 395ba41, v0.4.1) has no FFI; the seam this library serves
+ * is the set of in-process Rust call sites listed next to each entry point below.  A Rust
+ * `extern "C"` block binding exactly these symbols is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns PGX_OK (0) or a negative pgx_status; nothing throws or unwinds;
+ *     pgx_last_error() returns a thread-local description of the last failure.
+ *   - all pointers are plain host pointers unless the parameter name starts with `d_`
+ *     (device pointer on the handle's device).  The caller owns every buffer it passes.
+ *   - one handle is driven by one host thread at a time; handles on different devices are
+ *     independent.
+ *   - item ids are 1..=n_items; row 0 of every per-item array is the reference's dummy item
+ *     (src/graph_broker/graph.rs:323-324, abacus.rs:551,1000-1002) and is never counted.
+ *
+ * Data layout ("abacus bitmap", node-major): (n_items + 1) rows of `row_words` u64, row i = item i,
+ * bit (g % 64) of word (g / 64) set iff group g contains item i (after the reference's de-duplication
+ * and exclude rules, abacus.rs:719-744 / 859-899).  row_words = pgx_row_words(n_groups): ceil(G/64)
+ * rounded up to an even number when > 1, so rows are 16-byte aligned for 128-bit loads / TMA bulk copies.
+ * Bits >= n_groups and the padding word are ignored.  weight[i] = node length in bp (u32,
+ * graph.rs:341-350) minus the item's uncovered bps (abacus.rs:1016-1023) when counting bp.
+ */
+#ifndef PANACUS_B200_H
+#define PANACUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PGX_OK = 0,
+    PGX_ERR_INVALID = -1,     /* bad argument */
+    PGX_ERR_CUDA = -2,        /* CUDA runtime error (message in pgx_last_error) */
+    PGX_ERR_NOMEM = -3,       /* host or device allocation failed */
+    PGX_ERR_UNSUPPORTED = -4, /* shape outside what the kernels support */
+    PGX_ERR_STATE = -5        /* call order violated (e.g. no bitmap uploaded yet) */
+} pgx_status;
+
+typedef struct pgx_abacus pgx_abacus;
+
+/* library / device ------------------------------------------------------------------------------ */
+const char *pgx_version(void);
+const char *pgx_last_error(void);
+int pgx_device_count(int *n);
+/* u64 words per bitmap row for n_groups groups (see layout above). */
+uint32_t pgx_row_words(uint32_t n_groups);
+
+/* handle ---------------------------------------------------------------------------------------- */
+/* Allocates a zeroed device bitmap of (n_items+1) x pgx_row_words(n_groups) u64 and a weight vector
+ * (all ones).  Replaces the host-side AbacusByGroup{r,c,v} / AbacusByTotal{countable}
+ * (src/graph_broker/abacus.rs:486-503, 790-800). */
+int pgx_abacus_create(pgx_abacus **out, int device, uint64_t n_items, uint32_t n_groups);
+void pgx_abacus_destroy(pgx_abacus *a);
+/* Work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the handle's own stream). */
+int pgx_abacus_set_stream(pgx_abacus *a, void *cuda_stream);
+int pgx_abacus_shape(const pgx_abacus *a, uint64_t *n_items, uint32_t *n_groups, uint32_t *row_words);
+
+/* Host -> device copy of a packed bitmap ((n_items+1) x host_row_words u64, host_row_words >=
+ * ceil(G/64)) and of the weights (n_items+1 u32, or NULL = keep).  bitmap may be NULL (= keep). */
+int pgx_abacus_upload(pgx_abacus *a, const uint64_t *bitmap, uint32_t host_row_words, const uint32_t *weight);
+/* Use caller-owned device buffers in place (no copy); d_weight may be NULL (= unit weights).
+ * The bitmap must use pgx_row_words(n_groups) words per row. */
+int pgx_abacus_adopt_device(pgx_abacus *a, uint64_t *d_bitmap, uint32_t *d_weight);
+/* Device-side build from ItemTable slices (src/util.rs:80-93): ORs bit `group_id` into the row of
+ * every item in items[0..n_steps) that is not flagged in `exclude` (n_items+1 bytes, or NULL).
+ * Same result as AbacusByTotal::coverage / compute_row_storage_space's de-duplicated incidence
+ * (abacus.rs:719-744, 859-899).  Ids are the reference's u64 ItemIdSize. */
+int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, uint32_t group_id,
+                       const uint8_t *exclude);
+int pgx_abacus_clear(pgx_abacus *a);
+/* Device -> host copy of the bitmap in the packed host layout (host_row_words per row). */
+int pgx_abacus_download(pgx_abacus *a, uint64_t *bitmap, uint32_t host_row_words);
+
+/* hot path -------------------------------------------------------------------------------------- */
+/* Coverage histogram.  Replaces AbacusByTotal::coverage + construct_hist / construct_hist_bps
+ * (abacus.rs:719-787) as called from Hist::from_abacus (src/graph_broker/hist.rs:39-49,
+ * src/graph_broker.rs:353-362), before the sparse uncovered_bps patch (abacus.rs:779-785), which
+ * stays on the host.
+ *   hist_count[c]  = #items (1..=N) contained in exactly c groups        (G+1 entries, or NULL)
+ *   hist_weight[c] = sum of weight[i] over those items                    (G+1 entries, or NULL)
+ *   countable[i]   = number of groups containing item i; countable[0] = UINT32_MAX
+ *                    (N+1 entries, or NULL) */
+int pgx_hist(pgx_abacus *a, uint64_t *hist_count, uint64_t *hist_weight, uint32_t *countable);
+
+/* Ordered growth.  Replaces AbacusByGroup::calc_growth (abacus.rs:989-1032) as called from
+ * analyses/ordered_histgrowth.rs:184-186 and io.rs:575, for n_thresholds (coverage, quorum) pairs
+ * in one pass over the bitmap.
+ *   cov_abs[t]        = max(1, t_coverage.to_absolute(G))                          (abacus.rs:997)
+ *   quorum_thr[t*G+g] = ceil((g as f64 + 1.0) * max(0, q_t)) as usize, computed by the host in f64
+ *                       (abacus.rs:998,1010); NULL = all zero (q = 0 for every pair)
+ *   col_order         = NULL: growth in group-index order 0..G-1.  Otherwise a permutation of
+ *                       0..G-1: position j of the curve adds group col_order[j] (the reference gets
+ *                       the same by re-building the abacus under `--order`, abacus.rs:324-326); when
+ *                       given, quorum_thr is indexed by position j.
+ *   weighted          = 0: count items (node / edge); 1: sum weight[i] (bp)
+ *   curve[t*G+j]      = exact integer value of res[j]; the reference's f64 is `curve as f64`. */
+int pgx_ordered_growth(pgx_abacus *a, uint32_t n_thresholds, const uint32_t *cov_abs,
+                       const uint32_t *quorum_thr, const uint32_t *col_order, int weighted,
+                       uint64_t *curve);
+
+/* hist + ordered growth in a single pass over the bitmap (what `histgrowth`-style runs need);
+ * any of hist_count / hist_weight may be NULL. */
+int pgx_hist_ordered_growth(pgx_abacus *a, uint64_t *hist_count, uint64_t *hist_weight,
+                            uint32_t n_thresholds, const uint32_t *cov_abs, const uint32_t *quorum_thr,
+                            int weighted, uint64_t *curve);
+
+/* Ordered growth under n_orders different group orders (the permutation-sampled growth estimator
+ * of BASELINE.json config 3; each order is one `--order` run of the reference).
+ *   orders[p*G + j]  = group added at position j of order p (each row a permutation of 0..G-1)
+ *   curves[(p*T + t)*G + j] */
+int pgx_permuted_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t n_thresholds,
+                        const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted, uint64_t *curves);
+
+/* Integer part of Similarity::set_table (src/analyses/similarity.rs:125-150) for group rows
+ * [row_begin, row_end):
+ *   inter[(x-row_begin)*G + y] = sum over items of w * [x in item] * [y in item]
+ *   len[x]                     = sum over items of w * [x in item]          (all G groups)
+ * with w = 1 (weighted = 0) or weight[i] (weighted = 1).  The f32 Jaccard division
+ * (similarity.rs:153-163) and the clustering stay on the host. */
+int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint64_t *inter,
+                   uint64_t *len);
+
+/* asynchronous / device-resident variants (used for kernel-only timing and multi-GPU reduction) -- */
+/* Enqueues the fused pass on the handle's stream and leaves the raw accumulators in device memory:
+ *   d_out[0 .. G]                 hist_count
+ *   d_out[G+1 .. 2G+1]            hist_weight
+ *   d_out[2G+2 + t*G + j]         first-difference of curve t at column j (curve = prefix sum)
+ * d_out must hold pgx_fused_out_words(G, T) u64.  No synchronisation is performed. */
+size_t pgx_fused_out_words(uint32_t n_groups, uint32_t n_thresholds);
+int pgx_fused_pass_async(pgx_abacus *a, int want_hist_count, int want_hist_weight, uint32_t n_thresholds,
+                         const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted,
+                         uint64_t *d_out);
+/* Number of kernel launches issued through this handle so far (for bench accounting). */
+uint64_t pgx_launch_count(const pgx_abacus *a);
+/* Name and launch geometry of the last hot-path kernel (for logs). */
+int pgx_last_launch_info(const pgx_abacus *a, char *buf, size_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANACUS_B200_H */

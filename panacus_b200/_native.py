@@ -1,0 +1,99 @@
+"""Loader for libpanacus_b200.so (the C ABI declared in include/panacus_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded, every hot-path
+entry point raises.  Build it with ``python -c 'import __graft_entry__ as g; g.build()'`` or
+``make -C panacus_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpanacus_b200.so")
+
+# every symbol include/panacus_b200.h declares (tests check that the .so exports all of them)
+EXPORTS = [
+    "pgx_version", "pgx_last_error", "pgx_device_count", "pgx_row_words",
+    "pgx_abacus_create", "pgx_abacus_destroy", "pgx_abacus_set_stream", "pgx_abacus_shape",
+    "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_clear",
+    "pgx_abacus_download", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
+    "pgx_permuted_growth", "pgx_similarity", "pgx_fused_out_words", "pgx_fused_pass_async",
+    "pgx_launch_count", "pgx_last_launch_info",
+]
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: the CUDA extension is not built (run __graft_entry__.build()); "
+            "panacus_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    u64p, u32p, u8p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    vp = C.c_void_p
+    L.pgx_version.restype = C.c_char_p
+    L.pgx_version.argtypes = []
+    L.pgx_last_error.restype = C.c_char_p
+    L.pgx_last_error.argtypes = []
+    L.pgx_device_count.restype = C.c_int
+    L.pgx_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.pgx_row_words.restype = C.c_uint32
+    L.pgx_row_words.argtypes = [C.c_uint32]
+    L.pgx_abacus_create.restype = C.c_int
+    L.pgx_abacus_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint64, C.c_uint32]
+    L.pgx_abacus_destroy.restype = None
+    L.pgx_abacus_destroy.argtypes = [vp]
+    L.pgx_abacus_set_stream.restype = C.c_int
+    L.pgx_abacus_set_stream.argtypes = [vp, vp]
+    L.pgx_abacus_shape.restype = C.c_int
+    L.pgx_abacus_shape.argtypes = [vp, u64p, u32p, u32p]
+    L.pgx_abacus_upload.restype = C.c_int
+    L.pgx_abacus_upload.argtypes = [vp, vp, C.c_uint32, vp]
+    L.pgx_abacus_adopt_device.restype = C.c_int
+    L.pgx_abacus_adopt_device.argtypes = [vp, vp, vp]
+    L.pgx_abacus_scatter.restype = C.c_int
+    L.pgx_abacus_scatter.argtypes = [vp, vp, C.c_uint64, C.c_uint32, vp]
+    L.pgx_abacus_clear.restype = C.c_int
+    L.pgx_abacus_clear.argtypes = [vp]
+    L.pgx_abacus_download.restype = C.c_int
+    L.pgx_abacus_download.argtypes = [vp, vp, C.c_uint32]
+    L.pgx_hist.restype = C.c_int
+    L.pgx_hist.argtypes = [vp, vp, vp, vp]
+    L.pgx_ordered_growth.restype = C.c_int
+    L.pgx_ordered_growth.argtypes = [vp, C.c_uint32, vp, vp, vp, C.c_int, vp]
+    L.pgx_hist_ordered_growth.restype = C.c_int
+    L.pgx_hist_ordered_growth.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_int, vp]
+    L.pgx_permuted_growth.restype = C.c_int
+    L.pgx_permuted_growth.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_int, vp]
+    L.pgx_similarity.restype = C.c_int
+    L.pgx_similarity.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp]
+    L.pgx_fused_out_words.restype = C.c_size_t
+    L.pgx_fused_out_words.argtypes = [C.c_uint32, C.c_uint32]
+    L.pgx_fused_pass_async.restype = C.c_int
+    L.pgx_fused_pass_async.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, vp, vp, C.c_int, vp]
+    L.pgx_launch_count.restype = C.c_uint64
+    L.pgx_launch_count.argtypes = [vp]
+    L.pgx_last_launch_info.restype = C.c_int
+    L.pgx_last_launch_info.argtypes = [vp, C.c_char_p, C.c_size_t]
+    _lib = L
+    return L
+
+
+class PgxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pgx error {code}: {msg}")
+        self.code = code
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise PgxError(rc, lib().pgx_last_error().decode(errors="replace"))

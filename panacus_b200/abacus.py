@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference interface for the counting hot path, on top of the C ABI.
+
+Names follow the reference (marschall-lab/panacus @ 395ba41):
+
+  * ``Threshold``            src/util.rs:327-364
+  * ``DeviceAbacus``         stands in for AbacusByTotal + AbacusByGroup (src/graph_broker/abacus.rs:486-503,
+                             790-800): the item x group incidence lives on the GPU as a bitmap
+  * ``DeviceAbacus.hist``    Hist::from_abacus -> construct_hist / construct_hist_bps (abacus.rs:746-787)
+  * ``DeviceAbacus.calc_growth``  AbacusByGroup::calc_growth (abacus.rs:989-1032), f64 result like the reference
+  * ``quorum_thresholds``    the per-column integer cutoff ``ceil((c[k] + 1) * q)`` of abacus.rs:1010
+
+This module only marshals arrays; all counting runs in libpanacus_b200.so.  It never imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native
+
+
+@dataclass(frozen=True)
+class Threshold:
+    """src/util.rs:327-364.  kind: 'relative' (f64 in [0,1]) or 'absolute' (usize)."""
+    kind: str
+    value: float
+
+    @staticmethod
+    def relative(v: float) -> "Threshold":
+        return Threshold("relative", float(v))
+
+    @staticmethod
+    def absolute(v: int) -> "Threshold":
+        return Threshold("absolute", int(v))
+
+    def to_absolute(self, n: int) -> int:
+        """src/util.rs:351-356: Absolute(c) -> c, Relative(c) -> ceil(n * c) as usize"""
+        if self.kind == "absolute":
+            return int(self.value)
+        v = math.ceil(float(n) * self.value)
+        return max(0, int(v))
+
+    def to_relative(self, n: int) -> float:
+        """src/util.rs:358-363"""
+        if self.kind == "relative":
+            return self.value
+        return float(int(self.value)) / float(n)
+
+    def get_string(self) -> str:
+        """src/util.rs:344-349 (Rust `{}` formatting of usize / f64)"""
+        if self.kind == "absolute":
+            return str(int(self.value))
+        v = self.value
+        if v == math.floor(v) and abs(v) < 1e16:
+            return str(int(v))
+        return repr(v)
+
+
+def row_words(n_groups: int) -> int:
+    """u64 words per device bitmap row (include/panacus_b200.h: pgx_row_words)."""
+    w = (n_groups + 63) // 64
+    return 1 if w <= 1 else (w + 1) // 2 * 2
+
+
+def quorum_thresholds(n_groups: int, q: float) -> np.ndarray:
+    """thr[g] = ceil((g as f64 + 1.0) * q) as usize, evaluated in f64 exactly like abacus.rs:1010."""
+    q = max(0.0, float(q))
+    return np.array([max(0, int(math.ceil((float(g) + 1.0) * q))) for g in range(n_groups)], dtype=np.uint32)
+
+
+def growth_cutoffs(n_groups: int, t_coverage: Threshold, t_quorum: Threshold):
+    """(cov_abs, quorum_thr[G]) handed to the GPU for one (coverage, quorum) pair (abacus.rs:997-998)."""
+    c = max(1, t_coverage.to_absolute(n_groups))
+    q = max(0.0, t_quorum.to_relative(n_groups))
+    return c, quorum_thresholds(n_groups, q)
+
+
+def pack_bits(bits: np.ndarray) -> np.ndarray:
+    """bool/uint8 [(N+1), G] -> u64 [(N+1), row_words(G)], bit g%64 of word g/64 (row 0 = dummy item)."""
+    bits = np.asarray(bits, dtype=np.uint8)
+    n_rows, G = bits.shape
+    Wp = row_words(G)
+    padded = np.zeros((n_rows, Wp * 64), dtype=np.uint8)
+    padded[:, :G] = bits
+    return np.packbits(padded, axis=1, bitorder="little").view(np.uint64).reshape(n_rows, Wp)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceAbacus:
+    """GPU-resident item x group incidence bitmap (+ bp weights) and the hot-path queries on it."""
+
+    def __init__(self, n_items: int, n_groups: int, device: int = 0):
+        self._L = _native.lib()
+        self._h = C.c_void_p()
+        _native.check(self._L.pgx_abacus_create(C.byref(self._h), int(device), int(n_items), int(n_groups)))
+        self.n_items, self.n_groups, self.device = int(n_items), int(n_groups), int(device)
+        self.row_words = row_words(n_groups)
+        self._keep = []  # adopted device tensors kept alive
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.pgx_abacus_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- data ------------------------------------------------------------------------------------
+    def upload(self, bitmap: Optional[np.ndarray], weight: Optional[np.ndarray] = None):
+        """bitmap: u64 [(N+1), >= ceil(G/64)] node-major; weight: u32 [N+1] (bp lengths) or None."""
+        hw = 0
+        if bitmap is not None:
+            bitmap = np.ascontiguousarray(bitmap, dtype=np.uint64)
+            if bitmap.ndim != 2 or bitmap.shape[0] != self.n_items + 1:
+                raise ValueError("bitmap must have n_items + 1 rows")
+            hw = bitmap.shape[1]
+        if weight is not None:
+            weight = np.ascontiguousarray(weight, dtype=np.uint32)
+            if weight.shape != (self.n_items + 1,):
+                raise ValueError("weight must have n_items + 1 entries")
+        _native.check(self._L.pgx_abacus_upload(self._h, _ptr(bitmap), hw, _ptr(weight)))
+
+    def adopt_device(self, d_bitmap_ptr: int, d_weight_ptr: Optional[int] = None, keepalive=None):
+        """Use device buffers in place (bitmap with pgx_row_words(G) words per row)."""
+        _native.check(self._L.pgx_abacus_adopt_device(self._h, C.c_void_p(d_bitmap_ptr),
+                                                      C.c_void_p(d_weight_ptr) if d_weight_ptr else None))
+        self._keep = [keepalive]
+
+    def set_stream(self, cuda_stream_ptr: Optional[int]):
+        _native.check(self._L.pgx_abacus_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+    def clear(self):
+        _native.check(self._L.pgx_abacus_clear(self._h))
+
+    def scatter(self, items: np.ndarray, group_id: int, exclude: Optional[np.ndarray] = None):
+        """OR bit `group_id` into the rows of `items` (one path's ItemTable slice, src/util.rs:80-93)."""
+        items = np.ascontiguousarray(items, dtype=np.uint64)
+        ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.uint8)
+        if ex is not None and ex.shape != (self.n_items + 1,):
+            raise ValueError("exclude must have n_items + 1 entries")
+        _native.check(self._L.pgx_abacus_scatter(self._h, _ptr(items), items.size, int(group_id), _ptr(ex)))
+
+    def download(self) -> np.ndarray:
+        out = np.zeros((self.n_items + 1, self.row_words), dtype=np.uint64)
+        _native.check(self._L.pgx_abacus_download(self._h, _ptr(out), self.row_words))
+        return out
+
+    # -- hot path --------------------------------------------------------------------------------
+    def hist(self, count: bool = True, weight: bool = False, countable: bool = False):
+        """-> (hist_count u64[G+1] | None, hist_weight u64[G+1] | None, countable u32[N+1] | None)"""
+        G1 = self.n_groups + 1
+        hc = np.zeros(G1, dtype=np.uint64) if count else None
+        hw = np.zeros(G1, dtype=np.uint64) if weight else None
+        ct = np.zeros(self.n_items + 1, dtype=np.uint32) if countable else None
+        _native.check(self._L.pgx_hist(self._h, _ptr(hc), _ptr(hw), _ptr(ct)))
+        return hc, hw, ct
+
+    @staticmethod
+    def _cutoffs(cov_abs, quorum_thr, G):
+        cov = np.ascontiguousarray(cov_abs, dtype=np.uint32).reshape(-1)
+        thr = None
+        if quorum_thr is not None:
+            thr = np.ascontiguousarray(quorum_thr, dtype=np.uint32).reshape(-1)
+            if thr.size != cov.size * G:
+                raise ValueError("quorum_thr must have n_thresholds * n_groups entries")
+        return cov, thr
+
+    def ordered_growth(self, cov_abs: Sequence[int], quorum_thr=None, col_order=None, weighted: bool = False) -> np.ndarray:
+        """-> u64 [T, G] exact integer curves (AbacusByGroup::calc_growth for T threshold pairs)."""
+        G = self.n_groups
+        cov, thr = self._cutoffs(cov_abs, quorum_thr, G)
+        order = None if col_order is None else np.ascontiguousarray(col_order, dtype=np.uint32)
+        if order is not None and order.shape != (G,):
+            raise ValueError("col_order must have n_groups entries")
+        curve = np.zeros((cov.size, G), dtype=np.uint64)
+        _native.check(self._L.pgx_ordered_growth(self._h, cov.size, _ptr(cov), _ptr(thr), _ptr(order),
+                                                 int(bool(weighted)), _ptr(curve)))
+        return curve
+
+    def hist_ordered_growth(self, cov_abs, quorum_thr=None, weighted: bool = False, hist_count=True, hist_weight=False):
+        """one pass: -> (hist_count | None, hist_weight | None, curve u64[T, G])"""
+        G = self.n_groups
+        cov, thr = self._cutoffs(cov_abs, quorum_thr, G)
+        hc = np.zeros(G + 1, dtype=np.uint64) if hist_count else None
+        hw = np.zeros(G + 1, dtype=np.uint64) if hist_weight else None
+        curve = np.zeros((cov.size, G), dtype=np.uint64)
+        _native.check(self._L.pgx_hist_ordered_growth(self._h, _ptr(hc), _ptr(hw), cov.size, _ptr(cov), _ptr(thr),
+                                                      int(bool(weighted)), _ptr(curve)))
+        return hc, hw, curve
+
+    def permuted_growth(self, orders: np.ndarray, cov_abs, quorum_thr=None, weighted: bool = False) -> np.ndarray:
+        """orders: u32 [P, G], each row a permutation of the groups -> u64 [P, T, G]"""
+        G = self.n_groups
+        orders = np.ascontiguousarray(orders, dtype=np.uint32)
+        if orders.ndim != 2 or orders.shape[1] != G:
+            raise ValueError("orders must be [P, n_groups]")
+        cov, thr = self._cutoffs(cov_abs, quorum_thr, G)
+        curves = np.zeros((orders.shape[0], cov.size, G), dtype=np.uint64)
+        _native.check(self._L.pgx_permuted_growth(self._h, orders.shape[0], _ptr(orders), cov.size, _ptr(cov), _ptr(thr),
+                                                  int(bool(weighted)), _ptr(curves)))
+        return curves
+
+    def similarity(self, weighted: bool = False, row_begin: int = 0, row_end: Optional[int] = None):
+        """-> (inter u64[rows, G], len u64[G]); integer part of Similarity::set_table."""
+        G = self.n_groups
+        row_end = G if row_end is None else int(row_end)
+        inter = np.zeros((max(row_end - row_begin, 0), G), dtype=np.uint64)
+        ln = np.zeros(G, dtype=np.uint64)
+        _native.check(self._L.pgx_similarity(self._h, int(bool(weighted)), int(row_begin), row_end, _ptr(inter), _ptr(ln)))
+        return inter, ln
+
+    # -- reference-shaped convenience --------------------------------------------------------------
+    def calc_growth(self, t_coverage: Threshold, t_quorum: Threshold, count: str = "node") -> np.ndarray:
+        """AbacusByGroup::calc_growth(t_coverage, t_quorum, node_lens) -> Vec<f64> (abacus.rs:989-1032)."""
+        c, thr = growth_cutoffs(self.n_groups, t_coverage, t_quorum)
+        curve = self.ordered_growth([c], thr, weighted=(count == "bp"))
+        return curve[0].astype(np.float64)
+
+    # -- device-resident / async -------------------------------------------------------------------
+    def fused_out_words(self, n_thresholds: int) -> int:
+        return int(self._L.pgx_fused_out_words(self.n_groups, int(n_thresholds)))
+
+    def fused_pass_async(self, d_out_ptr: int, cov_abs, quorum_thr=None, weighted=False, hist_count=True,
+                         hist_weight=False):
+        cov, thr = self._cutoffs(cov_abs, quorum_thr, self.n_groups)
+        _native.check(self._L.pgx_fused_pass_async(self._h, int(bool(hist_count)), int(bool(hist_weight)), cov.size,
+                                                   _ptr(cov), _ptr(thr), int(bool(weighted)), C.c_void_p(d_out_ptr)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.pgx_launch_count(self._h))
+
+    def last_launch_info(self) -> str:
+        buf = C.create_string_buffer(512)
+        _native.check(self._L.pgx_last_launch_info(self._h, buf, 512))
+        return buf.value.decode()
+
+
+def curve_from_fused(out: np.ndarray, n_groups: int, n_thresholds: int):
+    """Split a fused-layout u64 buffer into (hist_count, hist_weight, curves[T, G])."""
+    G1 = n_groups + 1
+    hc, hw = out[:G1].copy(), out[G1:2 * G1].copy()
+    d = out[2 * G1:2 * G1 + n_thresholds * n_groups].reshape(n_thresholds, n_groups)
+    return hc, hw, np.cumsum(d, axis=1, dtype=np.uint64)

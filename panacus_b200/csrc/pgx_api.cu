@@ -1,0 +1,750 @@
+// pgx_api.cu -- the C ABI of libpanacus_b200 (see include/panacus_b200.h): handle management,
+// host<->device staging, threshold routing and the launch sequences of the hot-path kernels.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pgx_common.cuh"
+#include "pgx_internal.h"
+
+namespace pgx {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+}  // namespace pgx
+
+using namespace pgx;
+
+struct pgx_abacus {
+    int device = 0;
+    int sm_count = 148;
+    uint64_t n_items = 0, n_rows = 0;
+    uint32_t G = 0, W = 0, Wp = 0;
+
+    uint64_t *d_bitmap = nullptr;
+    bool own_bitmap = false;
+    uint32_t *d_weight = nullptr;  // nullptr = unit weights
+    bool own_weight = false;
+    uint32_t max_weight = 1;
+    bool max_weight_known = true;
+
+    uint32_t *d_countable = nullptr;  // N+1, lazily allocated
+    bool countable_valid = false;
+
+    uint64_t *d_gm = nullptr;  // group-major copy, lazily built
+    uint64_t gm_stride = 0;
+    bool gm_valid = false;
+    uint64_t *d_planes = nullptr;
+    uint32_t n_planes = 0;
+    bool planes_valid = false;
+
+    uint64_t *d_acc = nullptr;  // self-cleaning global accumulators of k_scan
+    size_t acc_words = 0;
+    unsigned int *d_ticket = nullptr;
+    unsigned int *d_err = nullptr;
+
+    uint32_t *d_thr = nullptr;  // quorum thresholds of the current call
+    size_t thr_cap = 0;
+    std::vector<uint32_t> thr_cache;
+    uint32_t *d_order = nullptr;
+    size_t order_cap = 0;
+    uint64_t *d_scratch = nullptr;  // generic device result buffer
+    size_t scratch_cap = 0;
+
+    uint64_t *h_pinned = nullptr;
+    size_t pinned_words = 0;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint64_t launches = 0;
+    std::string last_launch;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int ensure_pinned(pgx_abacus *a, size_t words) {
+    if (a->pinned_words >= words) return PGX_OK;
+    if (a->h_pinned) cudaFreeHost(a->h_pinned);
+    a->h_pinned = nullptr;
+    a->pinned_words = 0;
+    PGX_CUDA(cudaMallocHost(reinterpret_cast<void **>(&a->h_pinned), words * sizeof(uint64_t)));
+    a->pinned_words = words;
+    return PGX_OK;
+}
+
+template <typename T>
+int ensure_dev(T **ptr, size_t *cap, size_t count) {
+    if (*cap >= count && *ptr) return PGX_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(ptr), std::max<size_t>(count, 1) * sizeof(T)));
+    *cap = count;
+    return PGX_OK;
+}
+
+void invalidate_derived(pgx_abacus *a) {
+    a->countable_valid = false;
+    a->gm_valid = false;
+    a->planes_valid = false;
+}
+
+int check_handle(const pgx_abacus *a) {
+    if (!a) return fail(PGX_ERR_INVALID, "null handle");
+    if (!a->d_bitmap) return fail(PGX_ERR_STATE, "abacus has no bitmap");
+    return PGX_OK;
+}
+
+bool all_zero(const uint32_t *thr, uint32_t G) {
+    if (!thr) return true;
+    for (uint32_t g = 0; g < G; ++g)
+        if (thr[g]) return false;
+    return true;
+}
+
+int upload_thr(pgx_abacus *a, const std::vector<uint32_t> &thr) {
+    if (thr.empty()) return PGX_OK;
+    if (a->thr_cache == thr && a->d_thr) return PGX_OK;
+    int rc = ensure_dev(&a->d_thr, &a->thr_cap, thr.size());
+    if (rc) return rc;
+    PGX_CUDA(cudaMemcpyAsync(a->d_thr, thr.data(), thr.size() * 4u, cudaMemcpyHostToDevice, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));  // thr is a stack/vector buffer: finish before it goes away
+    a->thr_cache = thr;
+    return PGX_OK;
+}
+
+int validate_thresholds(const pgx_abacus *a, uint32_t T, const uint32_t *cov) {
+    if (T && !cov) return fail(PGX_ERR_INVALID, "cov_abs is null");
+    for (uint32_t t = 0; t < T; ++t)
+        if (cov[t] == 0) return fail(PGX_ERR_INVALID, "cov_abs entries must be >= 1 (abacus.rs:997 clamps)");
+    (void)a;
+    return PGX_OK;
+}
+
+// Launches k_scan for the thresholds ts[i0 .. i0+n) (global indices into cov/thr); n is reduced until
+// accumulators + pipeline fit in shared memory.  Returns the number of thresholds handled in *n_done.
+int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<uint32_t> &ts, size_t i0,
+                const uint32_t *cov, const uint32_t *thr, uint32_t *d_countable, uint64_t *d_out, size_t *n_done) {
+    const uint32_t G = a->G;
+    size_t n = std::min<size_t>(kMaxThresholds, ts.size() - i0);
+    ScanParams p;
+    int grid = 0;
+    for (;;) {
+        std::memset(&p, 0, sizeof(p));
+        p.bitmap = a->d_bitmap;
+        p.weight = a->d_weight;
+        p.acc = a->d_acc;
+        p.ticket = a->d_ticket;
+        p.out = d_out;
+        p.countable = d_countable;
+        p.n_rows = a->n_rows;
+        p.G = G;
+        p.W = a->W;
+        p.Wp = a->Wp;
+        p.flags = flags;
+        p.T = (uint32_t)n;
+        for (size_t k = 0; k < n; ++k) {
+            p.cov[k] = cov[ts[i0 + k]];
+            p.slot[k] = ts[i0 + k];
+        }
+        const int rc = plan_scan(p, quorum, a->sm_count, &grid);
+        if (rc == PGX_OK) break;
+        const size_t n_min = quorum ? 1 : 0;  // the fast kernel may run with hist only
+        if (rc != PGX_ERR_UNSUPPORTED || n <= n_min) return rc;
+        --n;
+    }
+    if (quorum) {
+        std::vector<uint32_t> packed(n * (size_t)G);
+        for (size_t k = 0; k < n; ++k) std::memcpy(packed.data() + k * G, thr + (size_t)ts[i0 + k] * G, (size_t)G * 4u);
+        const int rc = upload_thr(a, packed);
+        if (rc) return rc;
+        p.thr = a->d_thr;
+    }
+    const int rc = launch_scan(p, quorum, grid, a->stream);
+    if (rc) return rc;
+    a->launches++;
+    char buf[256];
+    snprintf(buf, sizeof buf, "k_scan<%s> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u",
+             quorum ? "quorum" : "fast", grid, kScanThreads, p.L.total, p.tile_items, p.stages, p.n_tiles, p.T);
+    a->last_launch = buf;
+    *n_done = n;
+    return PGX_OK;
+}
+
+// Fused pass for any number of thresholds; results in device memory `d_out` (fused layout with T
+// thresholds).  q = 0 thresholds ride along with the histogram in k_scan<fast>; the others go to
+// k_scan<quorum>.  Each launch takes as many thresholds as shared memory allows.
+int fused_pass(pgx_abacus *a, bool want_cnt, bool want_w, uint32_t T, const uint32_t *cov, const uint32_t *thr,
+               int weighted, uint32_t *d_countable, uint64_t *d_out) {
+    int rc = validate_thresholds(a, T, cov);
+    if (rc) return rc;
+    const uint32_t G = a->G;
+    std::vector<uint32_t> fast_t, gen_t;
+    for (uint32_t t = 0; t < T; ++t) (all_zero(thr ? thr + (size_t)t * G : nullptr, G) ? fast_t : gen_t).push_back(t);
+    const uint32_t wflag = weighted ? kWeighted : 0u;
+
+    bool hist_pending = want_cnt || want_w || (d_countable && gen_t.empty());
+    size_t i = 0;
+    while (hist_pending || i < fast_t.size()) {
+        const uint32_t flags = wflag | (hist_pending && want_cnt ? kHistCount : 0u) | (hist_pending && want_w ? kHistWeight : 0u);
+        size_t n = 0;
+        rc = scan_launch(a, false, flags, fast_t, i, cov, thr, hist_pending || gen_t.empty() ? d_countable : nullptr, d_out, &n);
+        if (rc) return rc;
+        if (!hist_pending && n == 0) return fail(PGX_ERR_UNSUPPORTED, "n_groups too large: no threshold fits in shared memory");
+        if (hist_pending) d_countable = nullptr;  // written once
+        hist_pending = false;
+        i += n;
+    }
+    i = 0;
+    while (i < gen_t.size()) {
+        size_t n = 0;
+        rc = scan_launch(a, true, wflag, gen_t, i, cov, thr, d_countable, d_out, &n);
+        if (rc) return rc;
+        d_countable = nullptr;
+        i += n;
+    }
+    return PGX_OK;
+}
+
+int ensure_countable(pgx_abacus *a) {
+    if (a->countable_valid) return PGX_OK;
+    if (!a->d_countable) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_countable), a->n_rows * 4u));
+    int rc = ensure_dev(&a->d_scratch, &a->scratch_cap, pgx_fused_out_words(a->G, 0));
+    if (rc) return rc;
+    rc = fused_pass(a, true, false, 0, nullptr, nullptr, 0, a->d_countable, a->d_scratch);
+    if (rc) return rc;
+    a->countable_valid = true;
+    return PGX_OK;
+}
+
+int ensure_gm(pgx_abacus *a) {
+    if (a->gm_valid) return PGX_OK;
+    a->gm_stride = gm_stride_words(a->n_rows);
+    if (!a->d_gm) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_gm), (size_t)a->G * a->gm_stride * 8u));
+    int rc = launch_transpose(a->d_bitmap, a->n_rows, a->G, a->Wp, a->d_gm, a->gm_stride, a->stream);
+    if (rc) return rc;
+    a->launches++;
+    a->gm_valid = true;
+    return PGX_OK;
+}
+
+__global__ void k_max_u32(const uint32_t *w, uint64_t n, unsigned int *out) {
+    unsigned int m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        m = max(m, w[i]);
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31u) == 0) atomicMax(out, m);
+}
+
+int ensure_planes(pgx_abacus *a) {
+    if (a->planes_valid) return PGX_OK;
+    if (!a->d_weight) {
+        a->n_planes = 0;
+        a->planes_valid = true;
+        return PGX_OK;
+    }
+    if (!a->max_weight_known) {
+        PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
+        k_max_u32<<<296, 256, 0, a->stream>>>(a->d_weight + 1, a->n_items, a->d_err);
+        PGX_CUDA(cudaGetLastError());
+        unsigned int m = 0;
+        PGX_CUDA(cudaMemcpyAsync(&m, a->d_err, 4, cudaMemcpyDeviceToHost, a->stream));
+        PGX_CUDA(cudaStreamSynchronize(a->stream));
+        PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
+        a->max_weight = m;
+        a->max_weight_known = true;
+    }
+    uint32_t np = 0;
+    while (np < 32u && (a->max_weight >> np)) ++np;
+    a->gm_stride = gm_stride_words(a->n_rows);
+    if (a->d_planes) cudaFree(a->d_planes);
+    a->d_planes = nullptr;
+    a->n_planes = np;
+    if (np) {
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_planes), (size_t)np * a->gm_stride * 8u));
+        int rc = launch_weight_planes(a->d_weight, a->n_rows, a->d_planes, a->gm_stride, np, a->stream);
+        if (rc) return rc;
+        a->launches++;
+    }
+    a->planes_valid = true;
+    return PGX_OK;
+}
+
+int is_permutation(const uint32_t *order, uint32_t G) {
+    std::vector<uint8_t> seen(G, 0);
+    for (uint32_t j = 0; j < G; ++j) {
+        if (order[j] >= G || seen[order[j]]) return 0;
+        seen[order[j]] = 1;
+    }
+    return 1;
+}
+
+// growth under explicit orders on the group-major copy; results (first differences) -> d_out
+int gm_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t T, const uint32_t *cov,
+              const uint32_t *thr, int weighted, uint64_t *curves /*host*/) {
+    const uint32_t G = a->G;
+    int rc = validate_thresholds(a, T, cov);
+    if (rc) return rc;
+    if (T == 0 || n_orders == 0) return PGX_OK;
+    if (!orders) return fail(PGX_ERR_INVALID, "orders is null");
+    for (uint32_t o = 0; o < n_orders; ++o)
+        if (!is_permutation(orders + (size_t)o * G, G)) return fail(PGX_ERR_INVALID, "order is not a permutation of 0..G-1");
+    bool need_cov = false;
+    for (uint32_t t = 0; t < T; ++t) need_cov |= cov[t] > 1u;
+    if (need_cov && (rc = ensure_countable(a))) return rc;
+    if ((rc = ensure_gm(a))) return rc;
+    if ((rc = ensure_dev(&a->d_order, &a->order_cap, (size_t)n_orders * G))) return rc;
+    PGX_CUDA(cudaMemcpyAsync(a->d_order, orders, (size_t)n_orders * G * 4u, cudaMemcpyHostToDevice, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+
+    const size_t out_words = (size_t)n_orders * T * G;
+    if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, out_words))) return rc;
+    if ((rc = ensure_pinned(a, out_words))) return rc;
+    PGX_CUDA(cudaMemsetAsync(a->d_scratch, 0, out_words * 8u, a->stream));
+
+    for (uint32_t t0 = 0; t0 < T;) {
+        uint32_t n = std::min<uint32_t>(kMaxThresholds, T - t0);
+        auto any_general = [&](uint32_t cnt) {
+            for (uint32_t k = 0; k < cnt; ++k)
+                if (!all_zero(thr ? thr + (size_t)(t0 + k) * G : nullptr, G)) return true;
+            return false;
+        };
+        while (n > 1 && gm_growth_smem_bytes(G, n, any_general(n)) > 200u * 1024u) --n;
+        GmGrowthParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.gm = a->d_gm;
+        p.gm_stride = a->gm_stride;
+        p.n_words = (a->n_rows + 63u) / 64u;
+        p.n_rows = a->n_rows;
+        p.weight = weighted ? a->d_weight : nullptr;
+        p.countable = a->d_countable;
+        p.G = G;
+        p.T = n;
+        p.weighted = weighted ? 1 : 0;
+        p.out_order_stride = (uint64_t)T * G;
+        std::vector<uint32_t> packed;
+        for (uint32_t k = 0; k < n; ++k) {
+            p.cov[k] = cov[t0 + k];
+            if (!all_zero(thr ? thr + (size_t)(t0 + k) * G : nullptr, G)) p.general_mask |= 1u << k;
+        }
+        if (p.general_mask) {
+            packed.assign((size_t)n * G, 0u);
+            for (uint32_t k = 0; k < n; ++k)
+                if ((p.general_mask >> k) & 1u)
+                    std::memcpy(packed.data() + (size_t)k * G, thr + (size_t)(t0 + k) * G, (size_t)G * 4u);
+            if ((rc = upload_thr(a, packed))) return rc;
+            p.thr = a->d_thr;
+        }
+        const uint32_t kBatch = 4096;  // orders per launch (gridDim.y)
+        for (uint32_t o0 = 0; o0 < n_orders; o0 += kBatch) {
+            p.n_orders = std::min<uint32_t>(kBatch, n_orders - o0);
+            p.order = a->d_order + (size_t)o0 * G;
+            p.out = a->d_scratch + (size_t)o0 * T * G + (size_t)t0 * G;
+            if ((rc = launch_gm_growth(p, a->sm_count, a->stream))) return rc;
+            a->launches++;
+        }
+        t0 += n;
+    }
+    a->last_launch = "k_gm_growth";
+    PGX_CUDA(cudaMemcpyAsync(a->h_pinned, a->d_scratch, out_words * 8u, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    // first differences -> curves (wrapping u64 prefix sums)
+    for (size_t c = 0; c < (size_t)n_orders * T; ++c) {
+        uint64_t run = 0;
+        for (uint32_t j = 0; j < G; ++j) {
+            run += a->h_pinned[c * G + j];
+            curves[c * G + j] = run;
+        }
+    }
+    return PGX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pgx_version(void) { return "panacus_b200 0.1.0 (sm_100a)"; }
+const char *pgx_last_error(void) { return g_last_error.c_str(); }
+
+int pgx_device_count(int *n) {
+    if (!n) return fail(PGX_ERR_INVALID, "null pointer");
+    *n = 0;
+    PGX_CUDA(cudaGetDeviceCount(n));
+    return PGX_OK;
+}
+
+uint32_t pgx_row_words(uint32_t n_groups) {
+    const uint32_t w = (n_groups + 63u) / 64u;
+    return w <= 1u ? 1u : (w + 1u) / 2u * 2u;
+}
+
+size_t pgx_fused_out_words(uint32_t n_groups, uint32_t n_thresholds) {
+    return 2u * ((size_t)n_groups + 1u) + (size_t)n_thresholds * n_groups;
+}
+
+int pgx_abacus_create(pgx_abacus **out, int device, uint64_t n_items, uint32_t n_groups) {
+    if (!out) return fail(PGX_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (n_groups == 0 || n_groups > (1u << 20)) return fail(PGX_ERR_INVALID, "n_groups must be in 1..2^20");
+    if (n_items >= 0xFFFFFFFFull - 1) return fail(PGX_ERR_UNSUPPORTED, "n_items must be < 2^32 - 2");
+    int ndev = 0;
+    PGX_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PGX_ERR_INVALID, "no such CUDA device");
+    pgx_abacus *a = new (std::nothrow) pgx_abacus();
+    if (!a) return fail(PGX_ERR_NOMEM, "out of host memory");
+    a->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) a->sm_count = prop.multiProcessorCount;
+    a->n_items = n_items;
+    a->n_rows = n_items + 1;
+    a->G = n_groups;
+    a->W = (n_groups + 63u) / 64u;
+    a->Wp = pgx_row_words(n_groups);
+    a->acc_words = pgx_fused_out_words(n_groups, kMaxThresholds);
+    auto bail = [&](int rc) {
+        pgx_abacus_destroy(a);
+        return rc;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&a->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(fail(PGX_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)));
+    a->stream = a->own_stream;
+    const size_t bm_bytes = (size_t)a->n_rows * a->Wp * 8u;
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&a->d_bitmap), bm_bytes)) != cudaSuccess)
+        return bail(fail(PGX_ERR_NOMEM, std::string("cudaMalloc bitmap: ") + cudaGetErrorString(e)));
+    a->own_bitmap = true;
+    if ((e = cudaMemsetAsync(a->d_bitmap, 0, bm_bytes, a->stream)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_acc), a->acc_words * 8u)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_ticket), 4)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_err), 4)) != cudaSuccess ||
+        (e = cudaMemsetAsync(a->d_acc, 0, a->acc_words * 8u, a->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(a->d_ticket, 0, 4, a->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(a->d_err, 0, 4, a->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(a->stream)) != cudaSuccess)
+        return bail(fail(PGX_ERR_CUDA, std::string("abacus setup: ") + cudaGetErrorString(e)));
+    *out = a;
+    return PGX_OK;
+}
+
+void pgx_abacus_destroy(pgx_abacus *a) {
+    if (!a) return;
+    DeviceGuard guard(a->device);
+    if (a->stream) cudaStreamSynchronize(a->stream);
+    if (a->own_bitmap && a->d_bitmap) cudaFree(a->d_bitmap);
+    if (a->own_weight && a->d_weight) cudaFree(a->d_weight);
+    cudaFree(a->d_countable);
+    cudaFree(a->d_gm);
+    cudaFree(a->d_planes);
+    cudaFree(a->d_acc);
+    cudaFree(a->d_ticket);
+    cudaFree(a->d_err);
+    cudaFree(a->d_thr);
+    cudaFree(a->d_order);
+    cudaFree(a->d_scratch);
+    if (a->h_pinned) cudaFreeHost(a->h_pinned);
+    if (a->own_stream) cudaStreamDestroy(a->own_stream);
+    cudaGetLastError();
+    delete a;
+}
+
+int pgx_abacus_set_stream(pgx_abacus *a, void *cuda_stream) {
+    if (!a) return fail(PGX_ERR_INVALID, "null handle");
+    DeviceGuard guard(a->device);
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    a->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : a->own_stream;
+    return PGX_OK;
+}
+
+int pgx_abacus_shape(const pgx_abacus *a, uint64_t *n_items, uint32_t *n_groups, uint32_t *row_words) {
+    if (!a) return fail(PGX_ERR_INVALID, "null handle");
+    if (n_items) *n_items = a->n_items;
+    if (n_groups) *n_groups = a->G;
+    if (row_words) *row_words = a->Wp;
+    return PGX_OK;
+}
+
+int pgx_abacus_upload(pgx_abacus *a, const uint64_t *bitmap, uint32_t host_row_words, const uint32_t *weight) {
+    if (!a) return fail(PGX_ERR_INVALID, "null handle");
+    DeviceGuard guard(a->device);
+    if (bitmap) {
+        if (host_row_words < a->W) return fail(PGX_ERR_INVALID, "host_row_words < ceil(n_groups/64)");
+        if (!a->own_bitmap) {
+            a->d_bitmap = nullptr;
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_bitmap), (size_t)a->n_rows * a->Wp * 8u));
+            a->own_bitmap = true;
+        }
+        if (host_row_words != a->Wp)
+            PGX_CUDA(cudaMemsetAsync(a->d_bitmap, 0, (size_t)a->n_rows * a->Wp * 8u, a->stream));
+        const size_t copy_w = std::min<uint32_t>(host_row_words, a->Wp);
+        PGX_CUDA(cudaMemcpy2DAsync(a->d_bitmap, (size_t)a->Wp * 8u, bitmap, (size_t)host_row_words * 8u, copy_w * 8u,
+                                   a->n_rows, cudaMemcpyHostToDevice, a->stream));
+        invalidate_derived(a);
+    }
+    if (weight) {
+        if (!a->own_weight || !a->d_weight) {
+            a->d_weight = nullptr;
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_weight), a->n_rows * 4u));
+            a->own_weight = true;
+        }
+        PGX_CUDA(cudaMemcpyAsync(a->d_weight, weight, a->n_rows * 4u, cudaMemcpyHostToDevice, a->stream));
+        uint32_t m = 0;
+        for (uint64_t i = 1; i < a->n_rows; ++i) m = std::max(m, weight[i]);
+        a->max_weight = m;
+        a->max_weight_known = true;
+        a->planes_valid = false;
+    }
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    return PGX_OK;
+}
+
+int pgx_abacus_adopt_device(pgx_abacus *a, uint64_t *d_bitmap, uint32_t *d_weight) {
+    if (!a) return fail(PGX_ERR_INVALID, "null handle");
+    if (!d_bitmap) return fail(PGX_ERR_INVALID, "d_bitmap is null");
+    if ((reinterpret_cast<uintptr_t>(d_bitmap) & 15u) || (reinterpret_cast<uintptr_t>(d_weight) & 15u))
+        return fail(PGX_ERR_INVALID, "device buffers must be 16-byte aligned");
+    DeviceGuard guard(a->device);
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if (a->own_bitmap && a->d_bitmap) cudaFree(a->d_bitmap);
+    if (a->own_weight && a->d_weight) cudaFree(a->d_weight);
+    a->d_bitmap = d_bitmap;
+    a->own_bitmap = false;
+    a->d_weight = d_weight;
+    a->own_weight = false;
+    a->max_weight_known = d_weight == nullptr;
+    a->max_weight = 1;
+    invalidate_derived(a);
+    return PGX_OK;
+}
+
+int pgx_abacus_clear(pgx_abacus *a) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    DeviceGuard guard(a->device);
+    PGX_CUDA(cudaMemsetAsync(a->d_bitmap, 0, (size_t)a->n_rows * a->Wp * 8u, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    invalidate_derived(a);
+    return PGX_OK;
+}
+
+int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, uint32_t group_id,
+                       const uint8_t *exclude) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (group_id >= a->G) return fail(PGX_ERR_INVALID, "group_id >= n_groups");
+    if (n_steps && !items) return fail(PGX_ERR_INVALID, "items is null");
+    DeviceGuard guard(a->device);
+    uint8_t *d_ex = nullptr;
+    if (exclude) {
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_ex), a->n_rows));
+        cudaError_t e = cudaMemcpyAsync(d_ex, exclude, a->n_rows, cudaMemcpyHostToDevice, a->stream);
+        if (e != cudaSuccess) {
+            cudaFree(d_ex);
+            return fail(PGX_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    const uint64_t kChunk = 1ull << 24;  // 16 Mi steps = 128 MB per staging copy
+    uint64_t *d_items = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_items), std::min<uint64_t>(kChunk, std::max<uint64_t>(n_steps, 1)) * 8u);
+    if (e != cudaSuccess) {
+        cudaFree(d_ex);
+        return fail(PGX_ERR_NOMEM, cudaGetErrorString(e));
+    }
+    rc = PGX_OK;
+    for (uint64_t s0 = 0; s0 < n_steps && rc == PGX_OK; s0 += kChunk) {
+        const uint64_t n = std::min<uint64_t>(kChunk, n_steps - s0);
+        e = cudaMemcpyAsync(d_items, items + s0, n * 8u, cudaMemcpyHostToDevice, a->stream);
+        if (e != cudaSuccess) {
+            rc = fail(PGX_ERR_CUDA, cudaGetErrorString(e));
+            break;
+        }
+        rc = launch_scatter(a->d_bitmap, a->Wp, a->n_rows, d_items, n, group_id, d_ex, a->d_err, a->stream);
+        a->launches++;
+        if (rc == PGX_OK && (e = cudaStreamSynchronize(a->stream)) != cudaSuccess) rc = fail(PGX_ERR_CUDA, cudaGetErrorString(e));
+    }
+    unsigned int err = 0;
+    if (rc == PGX_OK) {
+        e = cudaMemcpy(&err, a->d_err, 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(PGX_ERR_CUDA, cudaGetErrorString(e));
+        if (err) {
+            cudaMemset(a->d_err, 0, 4);
+            rc = fail(PGX_ERR_INVALID, "item id out of range 1..=n_items in scatter");
+        }
+    }
+    cudaFree(d_items);
+    cudaFree(d_ex);
+    invalidate_derived(a);
+    return rc;
+}
+
+int pgx_abacus_download(pgx_abacus *a, uint64_t *bitmap, uint32_t host_row_words) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (!bitmap || host_row_words < a->W) return fail(PGX_ERR_INVALID, "bad download buffer");
+    DeviceGuard guard(a->device);
+    if (host_row_words > a->Wp)
+        for (uint64_t i = 0; i < a->n_rows; ++i)
+            std::memset(bitmap + i * host_row_words + a->Wp, 0, (size_t)(host_row_words - a->Wp) * 8u);
+    const size_t copy_w = std::min<uint32_t>(host_row_words, a->Wp);
+    PGX_CUDA(cudaMemcpy2DAsync(bitmap, (size_t)host_row_words * 8u, a->d_bitmap, (size_t)a->Wp * 8u, copy_w * 8u,
+                               a->n_rows, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    return PGX_OK;
+}
+
+int pgx_hist_ordered_growth(pgx_abacus *a, uint64_t *hist_count, uint64_t *hist_weight, uint32_t n_thresholds,
+                            const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted, uint64_t *curve) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (n_thresholds && !curve) return fail(PGX_ERR_INVALID, "curve is null");
+    DeviceGuard guard(a->device);
+    const uint32_t G = a->G, G1 = G + 1u;
+    const size_t words = pgx_fused_out_words(G, n_thresholds);
+    if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, words))) return rc;
+    if ((rc = ensure_pinned(a, words))) return rc;
+    rc = fused_pass(a, hist_count != nullptr, hist_weight != nullptr, n_thresholds, cov_abs, quorum_thr, weighted, nullptr,
+                    a->d_scratch);
+    if (rc) return rc;
+    PGX_CUDA(cudaMemcpyAsync(a->h_pinned, a->d_scratch, words * 8u, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if (hist_count) std::memcpy(hist_count, a->h_pinned, (size_t)G1 * 8u);
+    if (hist_weight) std::memcpy(hist_weight, a->h_pinned + G1, (size_t)G1 * 8u);
+    for (uint32_t t = 0; t < n_thresholds; ++t) {
+        uint64_t run = 0;  // first differences -> curve (two's-complement wrapping sums)
+        const uint64_t *d = a->h_pinned + 2u * G1 + (size_t)t * G;
+        for (uint32_t j = 0; j < G; ++j) {
+            run += d[j];
+            curve[(size_t)t * G + j] = run;
+        }
+    }
+    return PGX_OK;
+}
+
+int pgx_hist(pgx_abacus *a, uint64_t *hist_count, uint64_t *hist_weight, uint32_t *countable) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    DeviceGuard guard(a->device);
+    const uint32_t G1 = a->G + 1u;
+    const size_t words = pgx_fused_out_words(a->G, 0);
+    if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, words))) return rc;
+    if ((rc = ensure_pinned(a, words))) return rc;
+    if (countable && !a->d_countable)
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_countable), a->n_rows * 4u));
+    rc = fused_pass(a, hist_count != nullptr || (!hist_weight && !countable), hist_weight != nullptr, 0, nullptr, nullptr, 0,
+                    countable ? a->d_countable : nullptr, a->d_scratch);
+    if (rc) return rc;
+    PGX_CUDA(cudaMemcpyAsync(a->h_pinned, a->d_scratch, words * 8u, cudaMemcpyDeviceToHost, a->stream));
+    if (countable) {
+        PGX_CUDA(cudaMemcpyAsync(countable, a->d_countable, a->n_rows * 4u, cudaMemcpyDeviceToHost, a->stream));
+        a->countable_valid = true;
+    }
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if (hist_count) std::memcpy(hist_count, a->h_pinned, (size_t)G1 * 8u);
+    if (hist_weight) std::memcpy(hist_weight, a->h_pinned + G1, (size_t)G1 * 8u);
+    return PGX_OK;
+}
+
+int pgx_ordered_growth(pgx_abacus *a, uint32_t n_thresholds, const uint32_t *cov_abs, const uint32_t *quorum_thr,
+                       const uint32_t *col_order, int weighted, uint64_t *curve) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (n_thresholds && !curve) return fail(PGX_ERR_INVALID, "curve is null");
+    if (!col_order) return pgx_hist_ordered_growth(a, nullptr, nullptr, n_thresholds, cov_abs, quorum_thr, weighted, curve);
+    DeviceGuard guard(a->device);
+    return gm_growth(a, 1, col_order, n_thresholds, cov_abs, quorum_thr, weighted, curve);
+}
+
+int pgx_permuted_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t n_thresholds,
+                        const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted, uint64_t *curves) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (n_thresholds && n_orders && !curves) return fail(PGX_ERR_INVALID, "curves is null");
+    DeviceGuard guard(a->device);
+    return gm_growth(a, n_orders, orders, n_thresholds, cov_abs, quorum_thr, weighted, curves);
+}
+
+int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint64_t *inter, uint64_t *len) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (row_begin > row_end || row_end > a->G) return fail(PGX_ERR_INVALID, "bad row range");
+    DeviceGuard guard(a->device);
+    const uint32_t G = a->G;
+    if ((rc = ensure_gm(a))) return rc;
+    const bool use_planes = weighted && a->d_weight;
+    if (use_planes && (rc = ensure_planes(a))) return rc;
+    const uint32_t rows = row_end - row_begin;
+    const size_t inter_words = (size_t)rows * G;
+    const size_t words = inter_words + G;
+    if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, words))) return rc;
+    if ((rc = ensure_pinned(a, words))) return rc;
+    PGX_CUDA(cudaMemsetAsync(a->d_scratch, 0, words * 8u, a->stream));
+    const uint64_t n_words = (a->n_rows + 63u) / 64u;
+    if (rows && inter) {
+        GmSimParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.gm = a->d_gm;
+        p.gm_stride = a->gm_stride;
+        p.n_words = n_words;
+        p.planes = use_planes ? a->d_planes : nullptr;
+        p.n_planes = use_planes ? a->n_planes : 0;
+        p.G = G;
+        p.row_begin = row_begin;
+        p.row_end = row_end;
+        p.inter = a->d_scratch;
+        if ((rc = launch_gm_similarity(p, a->sm_count, a->stream))) return rc;
+        a->launches++;
+        a->last_launch = "k_gm_similarity";
+    }
+    if (len) {
+        if ((rc = launch_gm_rowsum(a->d_gm, a->gm_stride, n_words, use_planes ? a->d_planes : nullptr,
+                                   use_planes ? a->n_planes : 0, G, a->d_scratch + inter_words, a->stream)))
+            return rc;
+        a->launches++;
+    }
+    PGX_CUDA(cudaMemcpyAsync(a->h_pinned, a->d_scratch, words * 8u, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if (rows && inter) std::memcpy(inter, a->h_pinned, inter_words * 8u);
+    if (len) std::memcpy(len, a->h_pinned + inter_words, (size_t)G * 8u);
+    return PGX_OK;
+}
+
+int pgx_fused_pass_async(pgx_abacus *a, int want_hist_count, int want_hist_weight, uint32_t n_thresholds,
+                         const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted, uint64_t *d_out) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (!d_out) return fail(PGX_ERR_INVALID, "d_out is null");
+    DeviceGuard guard(a->device);
+    return fused_pass(a, want_hist_count != 0, want_hist_weight != 0, n_thresholds, cov_abs, quorum_thr, weighted, nullptr,
+                      d_out);
+}
+
+uint64_t pgx_launch_count(const pgx_abacus *a) { return a ? a->launches : 0; }
+
+int pgx_last_launch_info(const pgx_abacus *a, char *buf, size_t buflen) {
+    if (!a || !buf || !buflen) return fail(PGX_ERR_INVALID, "bad arguments");
+    snprintf(buf, buflen, "%s", a->last_launch.c_str());
+    return PGX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,431 @@
+// pgx_gm.cu -- kernels over the group-major ("path-major") copy of the abacus bitmap:
+//   * k_transpose      node-major rows -> one bit-row per group (64 items per u64 word)
+//   * k_gm_growth      ordered growth under an arbitrary group order (permuted growth, any quorum):
+//                      OR-accumulate rows in the given order; bit-sliced per-item rank counters
+//                      compared against the per-position quorum threshold
+//                      (same arithmetic as AbacusByGroup::calc_growth, abacus.rs:989-1032, applied to
+//                      the abacus the reference would rebuild under `--order`, abacus.rs:324-326)
+//   * k_gm_similarity  all-pairs group intersections, AND + POPC over item words
+//                      (integer part of Similarity::set_table, src/analyses/similarity.rs:125-150)
+//   * k_weight_planes  bit-planes of the u32 item weights (bp-weighted intersections)
+//   * k_scatter        ItemTable slice -> bitmap bits (abacus.rs:719-744 de-duplication = idempotent OR)
+#include "pgx_common.cuh"
+#include "pgx_internal.h"
+
+namespace pgx {
+
+uint64_t gm_stride_words(uint64_t n_rows) {
+    const uint64_t w = (n_rows + 63u) / 64u;
+    return (w + 15u) / 16u * 16u;
+}
+
+namespace {
+
+// ---- transpose -----------------------------------------------------------------------------------
+// One warp turns 256 items x 64 groups (one u64 column of the node-major bitmap) into 64 group rows
+// x 8 u32 (32 contiguous bytes per row): 64 ballots per 32 items.
+__global__ void __launch_bounds__(256) k_transpose(const uint64_t *__restrict__ bitmap, uint64_t n_rows, uint32_t G,
+                                                   uint32_t W, uint32_t Wp, uint32_t *__restrict__ gm32,
+                                                   uint64_t gm_stride32) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t wc = blockIdx.y * 8u + warp;  // word column of the node-major row
+    if (wc >= W) return;
+    const uint64_t item0 = (uint64_t)blockIdx.x * 256u;
+    uint32_t keep0[8], keep1[8];
+#pragma unroll
+    for (int ib = 0; ib < 8; ++ib) {
+        const uint64_t item = item0 + (uint64_t)ib * 32u + lane;
+        uint64_t x = 0;
+        if (item != 0 && item < n_rows) x = __ldg(bitmap + item * Wp + wc);
+        const uint32_t xlo = (uint32_t)x, xhi = (uint32_t)(x >> 32);
+        uint32_t k0 = 0, k1 = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (xlo >> b) & 1u);
+            const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (xhi >> b) & 1u);
+            if (lane == (uint32_t)b) {
+                k0 = m0;
+                k1 = m1;
+            }
+        }
+        keep0[ib] = k0;
+        keep1[ib] = k1;
+    }
+    // lane b owns groups wc*64 + b and wc*64 + 32 + b; 8 u32 = items item0 .. item0+255
+    const uint64_t col32 = item0 / 32u;
+    const uint32_t g0 = wc * 64u + lane, g1 = g0 + 32u;
+    if (g0 < G) {
+        uint4 *dst = reinterpret_cast<uint4 *>(gm32 + (uint64_t)g0 * gm_stride32 + col32);
+        dst[0] = make_uint4(keep0[0], keep0[1], keep0[2], keep0[3]);
+        dst[1] = make_uint4(keep0[4], keep0[5], keep0[6], keep0[7]);
+    }
+    if (g1 < G) {
+        uint4 *dst = reinterpret_cast<uint4 *>(gm32 + (uint64_t)g1 * gm_stride32 + col32);
+        dst[0] = make_uint4(keep1[0], keep1[1], keep1[2], keep1[3]);
+        dst[1] = make_uint4(keep1[4], keep1[5], keep1[6], keep1[7]);
+    }
+}
+
+// ---- group-major growth -----------------------------------------------------------------------
+constexpr int kGmThreads = 256;
+constexpr int kRankPlanes = 21;  // supports G up to 2^20
+
+__device__ __forceinline__ uint64_t weighted_bits(uint64_t m, const uint32_t *__restrict__ wrow) {
+    uint64_t s = 0;
+    while (m) {
+        const uint32_t b = (uint32_t)__ffsll((long long)m) - 1u;
+        m &= m - 1;
+        s += __ldg(wrow + b);
+    }
+    return s;
+}
+
+__device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
+    // values are < 2^44 here (<= 64 weights of < 2^32 per lane ... summed over 32 lanes)
+    const uint32_t lo = (uint32_t)(v & 0xFFFFFFu), mid = (uint32_t)((v >> 24) & 0xFFFFFFu), hi = (uint32_t)(v >> 48);
+    const uint64_t slo = __reduce_add_sync(0xFFFFFFFFu, lo);
+    const uint64_t smid = __reduce_add_sync(0xFFFFFFFFu, mid);
+    const uint64_t shi = __reduce_add_sync(0xFFFFFFFFu, hi);
+    return slo + (smid << 24) + (shi << 48);
+}
+
+template <int P>  // number of rank bit-planes
+__global__ void __launch_bounds__(kGmThreads) k_gm_growth(const __grid_constant__ GmGrowthParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // smem: order[G] u32 | thr[T*G] u32 (if any general) | delta[T*G] u64
+    uint32_t *s_order = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *s_thr = s_order + p.G;
+    const uint32_t thr_words = p.general_mask ? p.T * p.G : 0u;
+    unsigned long long *s_delta =
+        reinterpret_cast<unsigned long long *>(smem_raw + (((size_t)(p.G + thr_words) * 4u + 15u) & ~(size_t)15u));
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t order_id = blockIdx.y;
+    const uint32_t *order = p.order + (size_t)order_id * p.G;
+    const uint32_t *thr = p.thr ? p.thr : nullptr;
+    for (uint32_t i = tid; i < p.G; i += kGmThreads) s_order[i] = order[i];
+    for (uint32_t i = tid; i < thr_words; i += kGmThreads) s_thr[i] = thr[i];
+    for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) s_delta[i] = 0ull;
+    __syncthreads();
+
+    const uint64_t wi = (uint64_t)blockIdx.x * kGmThreads + tid;
+    const bool active = wi < p.n_words;
+    const uint64_t wsafe = active ? wi : 0;
+    const uint32_t *wrow = p.weight ? p.weight + wsafe * 64u : nullptr;
+
+    // eligibility masks: item counted for threshold t only if its total coverage >= cov[t]
+    uint64_t elig[kMaxThresholds];
+#pragma unroll
+    for (int t = 0; t < kMaxThresholds; ++t) elig[t] = ~0ull;
+    bool need_cov = false;
+    for (uint32_t t = 0; t < p.T; ++t) need_cov |= p.cov[t] > 1u;
+    if (need_cov && active) {
+#pragma unroll
+        for (int t = 0; t < kMaxThresholds; ++t) elig[t] = 0ull;
+        for (uint32_t b = 0; b < 64u; ++b) {
+            const uint64_t item = wi * 64u + b;
+            const uint32_t c = (item < p.n_rows && item != 0) ? __ldg(p.countable + item) : 0u;
+#pragma unroll
+            for (int t = 0; t < kMaxThresholds; ++t)
+                if ((uint32_t)t < p.T && c >= p.cov[t]) elig[t] |= 1ull << b;
+        }
+    }
+    // weighted tail guard: items beyond n_rows never have bits set (transpose writes zeros)
+
+    uint64_t seen = 0;
+    uint64_t R[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) R[i] = 0ull;
+    uint64_t verdict[kMaxThresholds];
+#pragma unroll
+    for (int t = 0; t < kMaxThresholds; ++t) verdict[t] = 0ull;
+
+    const uint64_t *col = p.gm + wsafe;
+    for (uint32_t j = 0; j < p.G; ++j) {
+        const uint64_t b = active ? __ldg(col + (uint64_t)s_order[j] * p.gm_stride) : 0ull;
+        const uint64_t fresh = b & ~seen;
+        seen |= b;
+        if (p.general_mask) {  // R += b (bit-sliced ripple increment)
+            uint64_t carry = b;
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const uint64_t t2 = R[i] & carry;
+                R[i] ^= carry;
+                carry = t2;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kMaxThresholds; ++t) {
+            if ((uint32_t)t >= p.T) break;
+            uint64_t up, down;
+            if ((p.general_mask >> t) & 1u) {
+                // ge = (R >= K) per item, K = thr[t][j] (uniform): scan planes from the LSB
+                const uint32_t K = s_thr[t * p.G + j];
+                uint64_t ge = ~0ull;
+#pragma unroll
+                for (int i = 0; i < P; ++i) ge = ((K >> i) & 1u) ? (ge & R[i]) : (ge | R[i]);
+                if (K >> P) ge = 0ull;
+                const uint64_t vnew = (b & ge) | (~b & verdict[t]);
+                up = vnew & ~verdict[t];
+                down = verdict[t] & ~vnew;
+                verdict[t] = vnew;
+            } else {
+                up = fresh;
+                down = 0ull;
+            }
+            up &= elig[t];
+            down &= elig[t];
+            long long net;
+            if (p.weighted) {
+                const uint64_t su = warp_sum_u64(wrow ? weighted_bits(up, wrow) : (uint64_t)__popcll(up));
+                const uint64_t sd = warp_sum_u64(wrow ? weighted_bits(down, wrow) : (uint64_t)__popcll(down));
+                net = (long long)(su - sd);
+            } else {
+                const uint32_t su = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popcll(up));
+                const uint32_t sd = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popcll(down));
+                net = (long long)su - (long long)sd;
+            }
+            if (lane == 0 && net != 0) atomicAdd(&s_delta[t * p.G + j], (unsigned long long)net);
+        }
+    }
+    __syncthreads();
+    uint64_t *out = p.out + (size_t)order_id * p.out_order_stride;
+    for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) {
+        const unsigned long long v = s_delta[i];
+        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(out + i), v);
+    }
+}
+
+// ---- similarity -----------------------------------------------------------------------------------
+constexpr int kSimTile = 64;    // groups per tile edge
+constexpr int kSimKW = 32;      // item words per smem stage
+constexpr int kSimPad = kSimTile + 2;
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ GmSimParams p, uint32_t words_per_split) {
+    __shared__ uint64_t Xs[kSimKW][kSimPad];
+    __shared__ uint64_t Ys[kSimKW][kSimPad];
+    __shared__ uint64_t Ps[32][kSimKW];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tx = tid & 15u, ty = tid >> 4;
+    const uint32_t x0 = p.row_begin + blockIdx.y * kSimTile;  // output rows
+    const uint32_t y0 = blockIdx.x * kSimTile;                // output columns
+    const uint64_t k_begin = (uint64_t)blockIdx.z * words_per_split;
+    uint64_t k_end = k_begin + words_per_split;
+    if (k_end > p.n_words) k_end = p.n_words;
+
+    uint64_t acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+
+    for (uint64_t k0 = k_begin; k0 < k_end; k0 += kSimKW) {
+        // stage 64 x-rows and 64 y-rows x 32 words (coalesced along words), stored word-major
+        for (uint32_t e = tid; e < kSimTile * kSimKW; e += 256u) {
+            const uint32_t r = e / kSimKW, kw = e % kSimKW;
+            const uint64_t k = k0 + kw;
+            const uint32_t gx = x0 + r, gy = y0 + r;
+            Xs[kw][r] = (gx < p.row_end && k < k_end) ? __ldg(p.gm + (uint64_t)gx * p.gm_stride + k) : 0ull;
+            Ys[kw][r] = (gy < p.G && k < k_end) ? __ldg(p.gm + (uint64_t)gy * p.gm_stride + k) : 0ull;
+        }
+        if (WEIGHTED) {
+            for (uint32_t e = tid; e < p.n_planes * kSimKW; e += 256u) {
+                const uint32_t pl = e / kSimKW, kw = e % kSimKW;
+                const uint64_t k = k0 + kw;
+                Ps[pl][kw] = (k < k_end) ? __ldg(p.planes + (uint64_t)pl * p.gm_stride + k) : 0ull;
+            }
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (uint32_t kw = 0; kw < kSimKW; ++kw) {
+            uint64_t xv[4], yv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xv[i] = Xs[kw][ty * 4 + i];
+                yv[i] = Ys[kw][tx * 4 + i];
+            }
+            if (!WEIGHTED) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] += (uint64_t)__popcll(xv[i] & yv[j]);
+            } else {
+                for (uint32_t pl = 0; pl < p.n_planes; ++pl) {
+                    const uint64_t pw = Ps[pl][kw];
+                    if (!pw) continue;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] += (uint64_t)__popcll(xv[i] & yv[j] & pw) << pl;
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t gx = x0 + ty * 4 + i;
+        if (gx >= p.row_end) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t gy = y0 + tx * 4 + j;
+            if (gy < p.G && acc[i][j])
+                atomicAdd(reinterpret_cast<unsigned long long *>(p.inter + (uint64_t)(gx - p.row_begin) * p.G + gy),
+                          (unsigned long long)acc[i][j]);
+        }
+    }
+}
+
+// ---- per-group totals: len[g] = sum_i w_i [g in i] (similarity.rs:133-137) -------------------------
+__global__ void __launch_bounds__(256) k_gm_rowsum(const uint64_t *__restrict__ gm, uint64_t gm_stride,
+                                                   uint64_t n_words, const uint64_t *__restrict__ planes,
+                                                   uint32_t n_planes, uint64_t *__restrict__ len) {
+    const uint32_t g = blockIdx.x;
+    const uint64_t *row = gm + (uint64_t)g * gm_stride;
+    unsigned long long s = 0;
+    for (uint64_t k = threadIdx.x; k < n_words; k += 256u) {
+        const uint64_t x = __ldg(row + k);
+        if (!planes) {
+            s += (unsigned long long)__popcll(x);
+        } else if (x) {
+            for (uint32_t pl = 0; pl < n_planes; ++pl)
+                s += (unsigned long long)__popcll(x & __ldg(planes + (uint64_t)pl * gm_stride + k)) << pl;
+        }
+    }
+    __shared__ unsigned long long part[8];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31u) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; ++i) t += part[i];
+        len[g] = t;
+    }
+}
+
+// ---- weight bit-planes -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_weight_planes(const uint32_t *__restrict__ weight, uint64_t n_rows,
+                                                       uint32_t *__restrict__ planes32, uint64_t stride32,
+                                                       uint32_t n_planes, uint64_t n_items32) {
+    const uint64_t gw = ((uint64_t)blockIdx.x * 256u + threadIdx.x) >> 5;  // global warp = 32-item block
+    const uint32_t lane = threadIdx.x & 31u;
+    if (gw >= n_items32) return;
+    const uint64_t item = gw * 32u + lane;
+    const uint32_t w = (item != 0 && item < n_rows) ? __ldg(weight + item) : 0u;
+    for (uint32_t k = 0; k < n_planes; ++k) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, (w >> k) & 1u);
+        if (lane == 0) planes32[(uint64_t)k * stride32 + gw] = m;
+    }
+}
+
+// ---- scatter build ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows,
+                                                 const uint64_t *__restrict__ items, uint64_t n_steps,
+                                                 uint32_t group_id, const uint8_t *__restrict__ exclude,
+                                                 unsigned int *err) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t w = group_id >> 6;
+    const unsigned long long bit = 1ull << (group_id & 63u);
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_steps; s += stride) {
+        const uint64_t id = __ldg(items + s);
+        if (id == 0 || id >= n_rows) {
+            atomicOr(err, 1u);
+            continue;
+        }
+        if (exclude && __ldg(exclude + id)) continue;
+        unsigned long long *word = reinterpret_cast<unsigned long long *>(bitmap + id * Wp + w);
+        if (!(*word & bit)) atomicOr(word, bit);  // repeated visits of a group count once (abacus.rs:736-741)
+    }
+}
+
+size_t gm_growth_smem(const GmGrowthParams &p) { return gm_growth_smem_bytes(p.G, p.T, p.general_mask != 0); }
+
+template <int P>
+int launch_gm_growth_p(const GmGrowthParams &p, cudaStream_t stream) {
+    const size_t smem = gm_growth_smem(p);
+    if (smem > 232448u) return fail(PGX_ERR_UNSUPPORTED, "group-major growth: G*T too large for shared memory");
+    auto kern = k_gm_growth<P>;
+    PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((p.n_words + kGmThreads - 1) / kGmThreads), p.n_orders);
+    kern<<<grid, kGmThreads, smem, stream>>>(p);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+}  // namespace
+
+size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general) {
+    const size_t thr_words = any_general ? (size_t)T * G : 0u;
+    return (((size_t)(G + thr_words) * 4u + 15u) & ~(size_t)15u) + (size_t)T * G * 8u;
+}
+
+int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
+                     uint64_t gm_stride, cudaStream_t stream) {
+    const uint32_t W = (G + 63u) / 64u;
+    dim3 grid((unsigned)(gm_stride * 64u / 256u), (W + 7u) / 8u);
+    k_transpose<<<grid, 256, 0, stream>>>(bitmap, n_rows, G, W, Wp, reinterpret_cast<uint32_t *>(gm),
+                                          gm_stride * 2u);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+int launch_gm_growth(const GmGrowthParams &p, int /*sm_count*/, cudaStream_t stream) {
+    if (p.n_orders == 0 || p.n_orders > 65535u) return fail(PGX_ERR_INVALID, "n_orders must be in 1..65535 per launch");
+    if (p.G <= 255u) return launch_gm_growth_p<8>(p, stream);
+    if (p.G <= 4095u) return launch_gm_growth_p<12>(p, stream);
+    if (p.G <= 65535u) return launch_gm_growth_p<16>(p, stream);
+    return launch_gm_growth_p<kRankPlanes>(p, stream);
+}
+
+int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream) {
+    const uint32_t rows = p.row_end - p.row_begin;
+    if (rows == 0) return PGX_OK;
+    const uint32_t ty = (rows + kSimTile - 1) / kSimTile, tx = (p.G + kSimTile - 1) / kSimTile;
+    // split the item-word range so that the grid fills the GPU a few times over
+    uint64_t splits = ((uint64_t)sm_count * 8u + (uint64_t)tx * ty - 1) / ((uint64_t)tx * ty);
+    const uint64_t max_splits = (p.n_words + kSimKW - 1) / kSimKW;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535u) splits = 65535u;
+    uint64_t wps = (p.n_words + splits - 1) / splits;
+    wps = (wps + kSimKW - 1) / kSimKW * kSimKW;
+    splits = (p.n_words + wps - 1) / wps;
+    dim3 grid(tx, ty, (unsigned)splits);
+    if (p.planes) {
+        if (p.n_planes > 32u) return fail(PGX_ERR_INVALID, "n_planes > 32");
+        k_gm_similarity<true><<<grid, 256, 0, stream>>>(p, (uint32_t)wps);
+    } else {
+        k_gm_similarity<false><<<grid, 256, 0, stream>>>(p, (uint32_t)wps);
+    }
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+int launch_gm_rowsum(const uint64_t *gm, uint64_t gm_stride, uint64_t n_words, const uint64_t *planes,
+                     uint32_t n_planes, uint32_t G, uint64_t *len, cudaStream_t stream) {
+    k_gm_rowsum<<<G, 256, 0, stream>>>(gm, gm_stride, n_words, planes, n_planes, len);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+int launch_weight_planes(const uint32_t *weight, uint64_t n_rows, uint64_t *planes, uint64_t gm_stride,
+                         uint32_t n_planes, cudaStream_t stream) {
+    const uint64_t n_items32 = gm_stride * 2u;  // 32-item blocks covering the padded row
+    const uint64_t threads = n_items32 * 32u;
+    k_weight_planes<<<(unsigned)((threads + 255u) / 256u), 256, 0, stream>>>(
+        weight, n_rows, reinterpret_cast<uint32_t *>(planes), gm_stride * 2u, n_planes, n_items32);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+int launch_scatter(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, const uint64_t *d_items, uint64_t n_steps,
+                   uint32_t group_id, const uint8_t *d_exclude, unsigned int *d_err, cudaStream_t stream) {
+    if (n_steps == 0) return PGX_OK;
+    uint64_t blocks = (n_steps + 255u) / 256u;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    k_scatter<<<(unsigned)blocks, 256, 0, stream>>>(bitmap, Wp, n_rows, d_items, n_steps, group_id, d_exclude, d_err);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+}  // namespace pgx

@@ -1,0 +1,122 @@
+// pgx_internal.h -- interfaces between the translation units of libpanacus_b200 (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/panacus_b200.h"
+
+namespace pgx {
+
+constexpr int kMaxThresholds = 8;       // (coverage, quorum) pairs per launch
+constexpr int kConsumerWarps = 8;       // warps that scan items
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kScanThreads = kConsumerThreads + 32;  // + one TMA producer warp
+constexpr int kMaxStages = 8;
+
+enum ScanFlags : uint32_t {
+    kHistCount = 1u,   // accumulate hist_count
+    kHistWeight = 2u,  // accumulate hist_weight
+    kWeighted = 4u,    // growth deltas sum weight[i] instead of 1
+};
+
+// Byte offsets into the dynamic shared memory of k_scan (identical on host and device).
+struct ScanLayout {
+    uint32_t off_acc;        // start of the u32 accumulator region (zeroed at kernel start)
+    uint32_t acc_words;      // its length in u32
+    uint32_t off_hist_cnt;   // u32[G+1]
+    uint32_t off_hist_wlo;   // u32[G+1]
+    uint32_t off_hist_whi;   // u32[G+1]
+    uint32_t off_delta_lo;   // u32[T*G]  (counts when not weighted)
+    uint32_t off_delta_hi;   // u32[T*G]  (weighted only)
+    uint32_t off_thr;        // u32[T*G]  (quorum kernel only)
+    uint32_t off_stage0;     // first pipeline stage (128-byte aligned)
+    uint32_t stage_stride;   // bytes per stage
+    uint32_t off_stage_w;    // offset of the weight tile inside a stage
+    uint32_t total;          // dynamic shared memory bytes
+};
+
+struct ScanParams {
+    const uint64_t *bitmap;  // n_rows x Wp, node-major
+    const uint32_t *weight;  // n_rows, or nullptr (unit weights)
+    uint32_t *countable;     // n_rows, or nullptr
+    const uint32_t *thr;     // device T*G quorum thresholds (quorum kernel), else nullptr
+    uint64_t *acc;           // global accumulators (zero on entry, zero again on exit)
+    uint64_t *out;           // caller's fused-layout result buffer, written by the last CTA
+    unsigned int *ticket;    // CTA completion counter (zero on entry and exit)
+    uint64_t n_rows;         // N + 1
+    uint32_t G, W, Wp;
+    uint32_t T;
+    uint32_t cov[kMaxThresholds];
+    uint32_t slot[kMaxThresholds];  // threshold k's deltas go to out[2(G+1) + slot[k]*G ...]
+    uint32_t flags;
+    uint32_t tile_items;     // rows per pipeline stage (multiple of 4)
+    uint32_t stages;
+    uint32_t n_tiles;
+    uint64_t last_mask0, last_mask1;  // masks of the two words of the last 16-byte chunk of a row
+    ScanLayout L;
+};
+
+struct ScanPlan {
+    ScanParams p;
+    int grid;
+    int ctas_per_sm;
+};
+
+// Fills tile geometry, shared-memory layout and grid for one fused pass.  Returns PGX_OK or an error.
+int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out);
+// Enqueues the pass.  quorum = false: hist + first-set-bit growth (all thresholds have q = 0);
+// quorum = true: general thresholds (p.thr must be set), no hist.
+int launch_scan(const ScanParams &p, bool quorum, int grid, cudaStream_t stream);
+
+// ---- group-major ("path-major") side ----------------------------------------------------------
+// gm layout: G rows x gm_stride u64, bit (i % 64) of word (i / 64) of row g set iff item i is in
+// group g; gm_stride = ceil((N+1)/64) rounded up to a multiple of 16 words (128-byte rows).
+uint64_t gm_stride_words(uint64_t n_rows);
+int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
+                     uint64_t gm_stride, cudaStream_t stream);
+
+struct GmGrowthParams {
+    const uint64_t *gm;      // G x gm_stride
+    uint64_t gm_stride;
+    uint64_t n_words;        // ceil(n_rows / 64)
+    uint64_t n_rows;
+    const uint32_t *weight;  // n_rows or nullptr
+    const uint32_t *countable;  // n_rows (needed when any cov > 1)
+    const uint32_t *order;   // device: n_orders x G entries, group at position j
+    uint32_t n_orders;
+    const uint32_t *thr;     // device: T*G thresholds indexed by position, or nullptr (all q = 0)
+    uint64_t *out;           // device: first differences, order o at out + o*out_order_stride (zeroed by the launcher)
+    uint64_t out_order_stride;  // words between consecutive orders in out (>= T*G)
+    uint32_t G, T;
+    uint32_t cov[kMaxThresholds];
+    uint32_t general_mask;   // bit t set: threshold t needs the rank comparison (q > 0)
+    int weighted;
+};
+int launch_gm_growth(const GmGrowthParams &p, int sm_count, cudaStream_t stream);
+size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general);
+
+struct GmSimParams {
+    const uint64_t *gm;
+    uint64_t gm_stride;
+    uint64_t n_words;
+    const uint64_t *planes;  // weighted: n_planes x gm_stride weight bit-planes, else nullptr
+    uint32_t n_planes;
+    uint32_t G;
+    uint32_t row_begin, row_end;
+    uint64_t *inter;         // device (row_end-row_begin) x G, zeroed by the launcher
+};
+int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream);
+int launch_gm_rowsum(const uint64_t *gm, uint64_t gm_stride, uint64_t n_words, const uint64_t *planes,
+                     uint32_t n_planes, uint32_t G, uint64_t *len, cudaStream_t stream);
+int launch_weight_planes(const uint32_t *weight, uint64_t n_rows, uint64_t *planes, uint64_t gm_stride,
+                         uint32_t n_planes, cudaStream_t stream);
+
+// scatter build (ItemTable slice -> bitmap bits)
+int launch_scatter(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, const uint64_t *d_items, uint64_t n_steps,
+                   uint32_t group_id, const uint8_t *d_exclude, unsigned int *d_err, cudaStream_t stream);
+
+}  // namespace pgx

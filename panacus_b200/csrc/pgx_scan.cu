@@ -1,0 +1,426 @@
+// pgx_scan.cu -- the fused node-major pass: coverage histogram + ordered growth in one sweep over
+// the abacus bitmap.  Replaces AbacusByTotal::coverage + construct_hist[_bps]
+// (reference src/graph_broker/abacus.rs:719-787) and AbacusByGroup::calc_growth (abacus.rs:989-1032).
+//
+// Structure (one persistent CTA per SM slot, 8 scanning warps + 1 TMA producer warp):
+//   producer lane : 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of `tile_items` bitmap rows
+//                   (+ their u32 weights) into a ring of shared-memory stages, completion on mbarriers
+//   consumers     : one thread per item; 128-bit shared loads in a per-lane rotated chunk order
+//                   (bank-conflict free for any row width), popcount -> coverage, first set bit ->
+//                   growth column, 32-bit shared atomics into per-CTA accumulators
+//   epilogue      : per-CTA accumulators -> global u64 accumulators (RED.64); the last CTA snapshots
+//                   them into `out` and re-zeroes accumulators + ticket (self-cleaning, one launch)
+//
+// Integer-only, HBM-bandwidth-bound: algorithmic bytes per item = W*8 (+4 weighted).
+#include "pgx_common.cuh"
+#include "pgx_internal.h"
+
+namespace pgx {
+
+namespace {
+
+__device__ __forceinline__ uint32_t first_bit(uint64_t x) { return (uint32_t)__ffsll((long long)x) - 1u; }
+__device__ __forceinline__ uint32_t last_bit(uint64_t x) { return 63u - (uint32_t)__clzll((long long)x); }
+
+struct SmemAcc {
+    uint32_t *hist_cnt, *hist_wlo, *hist_whi, *delta_lo, *delta_hi;
+    const uint32_t *thr;
+};
+
+// ---- q = 0 path: hist bin + first-set-bit delta -------------------------------------------------
+__device__ __forceinline__ void account_fast(const ScanParams &p, const SmemAcc &s, uint64_t item, uint32_t cov,
+                                             uint32_t first, uint32_t wgt) {
+    if (p.countable) p.countable[item] = cov;
+    if (p.flags & kHistCount) atomicAdd(&s.hist_cnt[cov], 1u);
+    if (p.flags & kHistWeight) smem_add64(s.hist_wlo, s.hist_whi, cov, wgt, 0u);
+    if (cov == 0) return;
+    for (uint32_t t = 0; t < p.T; ++t) {
+        if (cov >= p.cov[t]) {
+            if (p.flags & kWeighted)
+                smem_add64(s.delta_lo + t * p.G, s.delta_hi + t * p.G, first, wgt, 0u);
+            else
+                atomicAdd(&s.delta_lo[t * p.G + first], 1u);
+        }
+    }
+}
+
+// word mask for natural-order readers: bits >= G and the padding word are ignored
+__device__ __forceinline__ uint64_t word_mask(const ScanParams &p, uint32_t w) {
+    if (w + 1 < p.W) return ~0ull;
+    if (w + 1 == p.W) return (p.G & 63u) ? ((1ull << (p.G & 63u)) - 1ull) : ~0ull;
+    return 0ull;
+}
+
+template <typename Reader>
+__device__ __forceinline__ void item_fast_natural(const ScanParams &p, const SmemAcc &s, uint64_t item,
+                                                  uint32_t wgt, Reader rd) {
+    uint32_t cov = 0, first = 0xFFFFFFFFu;
+    for (uint32_t w = 0; w < p.W; ++w) {
+        const uint64_t x = rd(w) & word_mask(p, w);
+        cov += __popcll(x);
+        if (x && first == 0xFFFFFFFFu) first = w * 64u + first_bit(x);
+    }
+    account_fast(p, s, item, cov, first, wgt);
+}
+
+// ---- general quorum path (abacus.rs:1004-1010 on the bitmap) --------------------------------------
+// For an item with bits b: at its k-th set bit (1-based) in column g the verdict becomes
+// (k >= thr[g]) and holds until the next set bit; the curve's first difference at g changes by
+// +-wgt whenever the verdict flips (it starts at "not counted").
+__device__ __forceinline__ void delta_add(const ScanParams &p, const SmemAcc &s, uint32_t t, uint32_t col,
+                                          uint32_t wgt, bool up) {
+    if (p.flags & kWeighted) {
+        if (up)
+            smem_add64(s.delta_lo + t * p.G, s.delta_hi + t * p.G, col, wgt, 0u);
+        else if (wgt)
+            smem_add64(s.delta_lo + t * p.G, s.delta_hi + t * p.G, col, 0u - wgt, 0xFFFFFFFFu);
+    } else {
+        atomicAdd(&s.delta_lo[t * p.G + col], up ? 1u : 0xFFFFFFFFu);
+    }
+}
+
+template <typename Reader>
+__device__ __forceinline__ void item_quorum_natural(const ScanParams &p, const SmemAcc &s, uint64_t item,
+                                                    uint32_t wgt, Reader rd) {
+    uint32_t cov = 0;
+    for (uint32_t w = 0; w < p.W; ++w) cov += __popcll(rd(w) & word_mask(p, w));
+    if (p.countable) p.countable[item] = cov;
+    uint32_t elig = 0;
+    for (uint32_t t = 0; t < p.T; ++t) elig |= (cov >= p.cov[t] ? 1u : 0u) << t;
+    if (cov == 0 || elig == 0) return;
+    uint32_t rank = 0, verdict = 0;  // verdict: bit t = item currently counted for threshold t
+    for (uint32_t w = 0; w < p.W; ++w) {
+        const uint64_t x = rd(w) & word_mask(p, w);
+        if (!x) continue;
+        const uint32_t c = __popcll(x), fb = first_bit(x), lb = last_bit(x), col0 = w * 64u;
+        for (uint32_t t = 0; t < p.T; ++t) {
+            if (!((elig >> t) & 1u)) continue;
+            const uint32_t *th = s.thr + t * p.G + col0;
+            bool prev = (verdict >> t) & 1u;
+            if (rank + 1 >= th[lb]) {  // every set bit of this word passes
+                if (!prev) delta_add(p, s, t, col0 + fb, wgt, true);
+                prev = true;
+            } else if (rank + c < th[fb]) {  // none passes
+                if (prev) delta_add(p, s, t, col0 + fb, wgt, false);
+                prev = false;
+            } else {
+                uint64_t y = x;
+                uint32_t k = rank;
+                while (y) {
+                    const uint32_t b = first_bit(y);
+                    y &= y - 1;
+                    ++k;
+                    const bool v = k >= th[b];
+                    if (v != prev) {
+                        delta_add(p, s, t, col0 + b, wgt, v);
+                        prev = v;
+                    }
+                }
+            }
+            verdict = (verdict & ~(1u << t)) | ((prev ? 1u : 0u) << t);
+        }
+        rank += c;
+    }
+}
+
+struct SmemRowReader {
+    uint32_t addr;
+    __device__ __forceinline__ uint64_t operator()(uint32_t w) const { return lds_u64(addr + w * 8u); }
+};
+struct GlobalRowReader {
+    const uint64_t *row;
+    __device__ __forceinline__ uint64_t operator()(uint32_t w) const { return __ldg(row + w); }
+};
+
+// ---- rotated-chunk fast path over a shared-memory row --------------------------------------------
+// A row is C = Wp/2 chunks of 16 bytes.  Lane i starts at chunk r(i) so that the 8 lanes of a
+// quarter-warp hit 8 different 16-byte bank groups for every row width:
+//   bank group of (i, c) = (i*C + c) mod 8;  with 2^a | C,  r(i) = (i >> (3-a')) & (2^a' - 1), a' = min(a,3).
+// popcount and first-set-bit are order independent, so the rotation costs nothing.
+template <int C_T>
+__device__ __forceinline__ void item_fast_smem(const ScanParams &p, const SmemAcc &s, uint64_t item, uint32_t wgt,
+                                               uint32_t row_addr, uint32_t li, uint32_t C_rt, uint32_t rot_shift,
+                                               uint32_t rot_mask) {
+    const uint32_t C = C_T > 0 ? (uint32_t)C_T : C_rt;
+    const uint32_t r = (li >> rot_shift) & rot_mask;
+    uint32_t cov = 0, first = 0xFFFFFFFFu;
+#pragma unroll(C_T > 0 ? C_T : 4)
+    for (uint32_t k = 0; k < C; ++k) {
+        uint32_t c = k + r;
+        if (c >= C) c -= C;
+        uint64_t x, y;
+        lds_v2_u64(row_addr + c * 16u, x, y);
+        if (c == C - 1) {
+            x &= p.last_mask0;
+            y &= p.last_mask1;
+        }
+        cov += __popcll(x) + __popcll(y);
+        if (x | y) {
+            const uint32_t fb = x ? first_bit(x) : 64u + first_bit(y);
+            first = min(first, c * 128u + fb);
+        }
+    }
+    account_fast(p, s, item, cov, first, wgt);
+}
+
+template <bool QUORUM, int C_T>
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    const uint32_t S = p.stages;
+    const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
+    const uint32_t stage0 = smem_u32(smem + p.L.off_stage0);
+    const uint32_t rowbytes = p.Wp * 8u;
+
+    SmemAcc s;
+    s.hist_cnt = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_cnt);
+    s.hist_wlo = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_wlo);
+    s.hist_whi = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_whi);
+    s.delta_lo = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_lo);
+    s.delta_hi = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_hi);
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(smem + p.L.off_thr);
+    s.thr = s_thr;
+
+    {
+        uint32_t *acc32 = reinterpret_cast<uint32_t *>(smem + p.L.off_acc);
+        for (uint32_t i = tid; i < p.L.acc_words; i += kScanThreads) acc32[i] = 0u;
+        if (QUORUM)
+            for (uint32_t i = tid; i < p.T * p.G; i += kScanThreads) s_thr[i] = p.thr[i];
+    }
+    if (tid == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(full0 + 8u * i, 1u);
+            mbar_init(empty0 + 8u * i, (uint32_t)kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == (uint32_t)kConsumerWarps) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t st = it % S, use = it / S;
+                if (use > 0) mbar_wait(empty0 + 8u * st, (use - 1u) & 1u);
+                const uint64_t row0 = (uint64_t)tile * p.tile_items;
+                const uint64_t left = p.n_rows - row0;
+                const uint32_t rows = left < p.tile_items ? (uint32_t)left : p.tile_items;
+                const uint32_t trows = rows & ~3u;  // TMA needs 16-byte multiples; <=3 tail rows read directly
+                const uint32_t full = full0 + 8u * st;
+                if (trows) {
+                    const uint32_t bytes_b = trows * rowbytes;
+                    const uint32_t bytes_w = p.weight ? trows * 4u : 0u;
+                    const uint32_t dst = stage0 + st * p.L.stage_stride;
+                    mbar_arrive_expect_tx(full, bytes_b + bytes_w);
+                    tma_bulk_g2s(dst, p.bitmap + row0 * p.Wp, bytes_b, full, pol);
+                    if (bytes_w) tma_bulk_g2s(dst + p.L.off_stage_w, p.weight + row0, bytes_w, full, pol);
+                } else {
+                    mbar_arrive(full);
+                }
+            }
+        }
+    } else {
+        // ===== consumers: one thread per item =====
+        const uint32_t C_rt = p.Wp >> 1;
+        uint32_t a = 0;
+        while (a < 3 && C_rt && !((C_rt >> a) & 1u)) ++a;  // a' = min(ctz(C), 3)
+        const uint32_t rot_shift = 3u - a, rot_mask = (1u << a) - 1u;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t st = it % S, use = it / S;
+            const uint64_t row0 = (uint64_t)tile * p.tile_items;
+            const uint64_t left = p.n_rows - row0;
+            const uint32_t rows = left < p.tile_items ? (uint32_t)left : p.tile_items;
+            const uint32_t trows = rows & ~3u;
+            const uint32_t base = stage0 + st * p.L.stage_stride;
+            const uint32_t wbase = base + p.L.off_stage_w;
+            mbar_wait(full0 + 8u * st, use & 1u);
+            for (uint32_t li = tid; li < rows; li += kConsumerThreads) {
+                const uint64_t item = row0 + li;
+                if (item == 0) {  // the reference's dummy item (abacus.rs:551, 1000-1002)
+                    if (p.countable) p.countable[0] = 0xFFFFFFFFu;
+                    continue;
+                }
+                if (li < trows) {
+                    uint32_t wgt = 1u;
+                    if (p.weight) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wgt) : "r"(wbase + li * 4u));
+                    const uint32_t row_addr = base + li * rowbytes;
+                    if (QUORUM) {
+                        item_quorum_natural(p, s, item, wgt, SmemRowReader{row_addr});
+                    } else if (C_T < 0) {  // 8-byte rows (G <= 64)
+                        const uint64_t x = lds_u64(row_addr) & p.last_mask0;
+                        account_fast(p, s, item, __popcll(x), x ? first_bit(x) : 0xFFFFFFFFu, wgt);
+                    } else {
+                        item_fast_smem<C_T>(p, s, item, wgt, row_addr, li, C_rt, rot_shift, rot_mask);
+                    }
+                } else {  // <= 3 tail rows of the last tile, straight from global memory
+                    const uint32_t wgt = p.weight ? __ldg(p.weight + item) : 1u;
+                    GlobalRowReader rd{p.bitmap + item * p.Wp};
+                    if (QUORUM)
+                        item_quorum_natural(p, s, item, wgt, rd);
+                    else
+                        item_fast_natural(p, s, item, wgt, rd);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8u * st);
+        }
+    }
+    __syncthreads();
+
+    // ===== epilogue: per-CTA accumulators -> global u64 accumulators =====
+    const uint32_t G1 = p.G + 1u;
+    for (uint32_t i = tid; i < G1; i += kScanThreads) {
+        if (p.flags & kHistCount) {
+            const uint32_t c = s.hist_cnt[i];
+            if (c) atomicAdd(reinterpret_cast<unsigned long long *>(p.acc + i), (unsigned long long)c);
+        }
+        if (p.flags & kHistWeight) {
+            const uint64_t v = ((uint64_t)s.hist_whi[i] << 32) | s.hist_wlo[i];
+            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(p.acc + G1 + i), (unsigned long long)v);
+        }
+    }
+    const uint32_t nd = p.T * p.G;
+    for (uint32_t i = tid; i < nd; i += kScanThreads) {
+        uint64_t v;
+        if (p.flags & kWeighted)
+            v = ((uint64_t)s.delta_hi[i] << 32) | s.delta_lo[i];
+        else
+            v = (uint64_t)(int64_t)(int32_t)s.delta_lo[i];  // signed per-CTA net flip count
+        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(p.acc + 2u * G1 + i), (unsigned long long)v);
+    }
+
+    // ===== last CTA: snapshot + re-zero (threadfence reduction pattern) =====
+    __shared__ uint32_t s_is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(p.ticket, 1u);
+        s_is_last = (t == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_is_last) {
+        __threadfence();
+        for (uint32_t i = tid; i < 2u * G1; i += kScanThreads) {
+            const bool wanted = (i < G1) ? (p.flags & kHistCount) : (p.flags & kHistWeight);
+            if (wanted) {
+                p.out[i] = __ldcg(p.acc + i);
+                p.acc[i] = 0ull;
+            }
+        }
+        for (uint32_t i = tid; i < nd; i += kScanThreads) {
+            const uint32_t t = i / p.G, j = i - t * p.G;
+            p.out[2u * G1 + p.slot[t] * p.G + j] = __ldcg(p.acc + 2u * G1 + i);
+            p.acc[2u * G1 + i] = 0ull;
+        }
+        if (tid == 0) *p.ticket = 0u;
+    }
+}
+
+inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; }
+
+template <bool QUORUM, int C_T>
+int launch_one(const ScanParams &p, int grid, cudaStream_t stream) {
+    auto kern = k_scan<QUORUM, C_T>;
+    PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.L.total));
+    kern<<<grid, kScanThreads, p.L.total, stream>>>(p);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+}  // namespace
+
+int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
+    if (p.G == 0 || p.G > (1u << 20)) return fail(PGX_ERR_UNSUPPORTED, "n_groups must be in 1..2^20");
+    if (p.T > (uint32_t)kMaxThresholds) return fail(PGX_ERR_INVALID, "too many thresholds per launch");
+    if (p.n_rows >= (1ull << 32)) return fail(PGX_ERR_UNSUPPORTED, "n_items must be < 2^32 - 1");
+    const uint32_t rowbytes = p.Wp * 8u;
+    const uint32_t G1 = p.G + 1u, TG = p.T * p.G;
+
+    // accumulators
+    ScanLayout &L = p.L;
+    uint32_t off = 2u * 8u * kMaxStages;  // full[] + empty[] mbarriers
+    L.off_acc = off;
+    L.off_hist_cnt = off;
+    off += (p.flags & kHistCount) ? G1 * 4u : 0u;
+    L.off_hist_wlo = off;
+    off += (p.flags & kHistWeight) ? G1 * 4u : 0u;
+    L.off_hist_whi = off;
+    off += (p.flags & kHistWeight) ? G1 * 4u : 0u;
+    L.off_delta_lo = off;
+    off += TG * 4u;
+    L.off_delta_hi = off;
+    off += (p.flags & kWeighted) ? TG * 4u : 0u;
+    L.acc_words = (off - L.off_acc) / 4u;
+    L.off_thr = off;
+    off += quorum ? TG * 4u : 0u;
+    off = align_up(off, 128u);
+    L.off_stage0 = off;
+
+    // tile geometry: ~32 KB of bitmap per stage, one item per consumer thread where rows allow
+    uint32_t tile = 32768u / rowbytes;
+    if (tile >= (uint32_t)kConsumerThreads) {
+        tile = tile / kConsumerThreads * kConsumerThreads;
+        if (tile > 2048u) tile = 2048u;
+    } else {
+        tile = (32768u / rowbytes) & ~3u;  // wide rows: fewer items than threads per stage
+        if (tile < 4u) tile = 4u;
+        if (tile * rowbytes > 98304u) return fail(PGX_ERR_UNSUPPORTED, "n_groups too large for the shared-memory pipeline");
+    }
+    p.tile_items = tile;
+    L.off_stage_w = align_up(tile * rowbytes, 128u);
+    L.stage_stride = L.off_stage_w + (p.weight ? align_up(tile * 4u, 128u) : 0u);
+
+    const uint32_t max_smem = 232448u;          // 227 KB opt-in limit per CTA
+    const uint32_t per_cta_2 = 232448u / 2u - 1024u;  // two CTAs per SM (1 KB reserved each)
+    int ctas = 2;
+    uint32_t stages = 0;
+    if (off + 3u * L.stage_stride <= per_cta_2) {
+        stages = (per_cta_2 - off) / L.stage_stride;
+    } else {
+        ctas = 1;
+        if (off + 2u * L.stage_stride > max_smem)
+            return fail(PGX_ERR_UNSUPPORTED, "accumulators + pipeline exceed shared memory for this G / T");
+        stages = (max_smem - off) / L.stage_stride;
+    }
+    if (stages > (uint32_t)kMaxStages) stages = kMaxStages;
+    p.stages = stages;
+    L.total = off + stages * L.stage_stride;
+
+    const uint64_t n_tiles = (p.n_rows + tile - 1u) / tile;
+    p.n_tiles = (uint32_t)n_tiles;
+    const uint64_t max_grid = (uint64_t)sm_count * ctas;
+    *grid_out = (int)(n_tiles < max_grid ? n_tiles : max_grid);
+
+    // masks for the two words of a row's last 16-byte chunk
+    const uint64_t lastmask = (p.G & 63u) ? ((1ull << (p.G & 63u)) - 1ull) : ~0ull;
+    if (p.Wp == 1u) {
+        p.last_mask0 = lastmask;
+        p.last_mask1 = 0ull;
+    } else if (p.W == p.Wp) {
+        p.last_mask0 = ~0ull;
+        p.last_mask1 = lastmask;
+    } else {  // odd W: last real word, then the padding word
+        p.last_mask0 = lastmask;
+        p.last_mask1 = 0ull;
+    }
+    return PGX_OK;
+}
+
+int launch_scan(const ScanParams &p, bool quorum, int grid, cudaStream_t stream) {
+    if (quorum) return launch_one<true, 0>(p, grid, stream);
+    if (p.Wp == 1u) return launch_one<false, -1>(p, grid, stream);
+    switch (p.Wp >> 1) {
+        case 1: return launch_one<false, 1>(p, grid, stream);
+        case 2: return launch_one<false, 2>(p, grid, stream);
+        case 4: return launch_one<false, 4>(p, grid, stream);
+        case 8: return launch_one<false, 8>(p, grid, stream);
+        case 16: return launch_one<false, 16>(p, grid, stream);
+        default: return launch_one<false, 0>(p, grid, stream);
+    }
+}
+
+}  // namespace pgx

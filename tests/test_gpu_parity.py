@@ -1,0 +1,318 @@
+"""GPU parity tests: every hot-path entry point of libpanacus_b200.so (through the C ABI) against the
+CPU oracle on the same inputs -- bit-exact (integer work).  Run with `-m gpu` on the B200 box."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import panacus_b200 as pb
+from panacus_b200 import synth
+from oracle import gfa_oracle as go
+from oracle import oracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KATS = json.load(open(os.path.join(GOLDEN, "kats.json")))
+
+PAIRS = [(1, 0.0), (2, 0.0), (1, 0.1), (2, 0.5), (4, 0.9), (1, 1.0), (3, 0.33)]
+
+
+def oracle_all(bitmap, G, weights, pairs):
+    """reference algorithm on the ItemTable derived from the bitmap -> dict of expected results"""
+    N = bitmap.shape[0] - 1
+    items, prefsum, op, og = po.bitmap_to_item_table(bitmap, G)
+    countable = po.abacus_by_total(N, items, prefsum, op, og)
+    r, c, v = po.csr_build(N, items, prefsum, op, og)
+    exp = {
+        "countable": countable,
+        "hist": po.construct_hist(countable, G),
+        "hist_bp": po.construct_hist_bps(countable, weights, G),
+        "r": r, "c": c,
+    }
+    for (cov, q) in pairs:
+        exp[("node", cov, q)] = po.calc_growth(r, c, G, po.absolute(cov), po.relative(q))
+        exp[("bp", cov, q)] = po.calc_growth(r, c, G, po.absolute(cov), po.relative(q), count_bp=True, node_lens=weights)
+    return exp
+
+
+def cutoffs(G, pairs):
+    cov = [max(1, c) for c, _ in pairs]
+    thr = np.stack([pb.quorum_thresholds(G, q) for _, q in pairs])
+    return cov, thr
+
+
+def check_table(bitmap, G, weights, pairs=PAIRS):
+    N = bitmap.shape[0] - 1
+    exp = oracle_all(bitmap, G, weights, list(pairs) + [(1, 0.0), (2, 0.0)])
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        hc, hw, ct = a.hist(count=True, weight=True, countable=True)
+        assert np.array_equal(ct, exp["countable"])
+        assert np.array_equal(hc, exp["hist"])
+        assert np.array_equal(hw, exp["hist_bp"])
+        cov, thr = cutoffs(G, pairs)
+        for weighted, key in ((False, "node"), (True, "bp")):
+            curves = a.ordered_growth(cov, thr, weighted=weighted)
+            for t, (c, q) in enumerate(pairs):
+                want = exp[(key, c, q)]
+                assert np.array_equal(curves[t].astype(np.float64), want), (key, c, q)
+        # fused hist + growth in one pass gives the same numbers
+        hc2, hw2, cv2 = a.hist_ordered_growth(cov, thr, weighted=True, hist_count=True, hist_weight=True)
+        assert np.array_equal(hc2, hc) and np.array_equal(hw2, hw)
+        assert np.array_equal(cv2, a.ordered_growth(cov, thr, weighted=True))
+        # q = 0 only (quorum_thr = NULL) uses the fast kernel alone
+        c0 = a.ordered_growth([1, 2], None, weighted=False)
+        assert np.array_equal(c0[0].astype(np.float64), exp[("node", 1, 0.0)])
+        assert np.array_equal(c0[1].astype(np.float64), exp[("node", 2, 0.0)])
+        # the reference-shaped convenience call
+        got = a.calc_growth(pb.Threshold.absolute(2), pb.Threshold.relative(0.5), "bp")
+        assert np.array_equal(got, exp[("bp", 2, 0.5)])
+    return exp
+
+
+# ---- reference fixtures ------------------------------------------------------------------------------
+
+def fixture_bitmap(gfa, count, **mask_kw):
+    g = go.parse_gfa(os.path.join(GOLDEN, gfa))
+    mask = go.make_mask(g, **mask_kw)
+    t = go.item_tables(g, mask, count)
+    op, og, names = go.path_order_arrays(mask, g)
+    G = len(names)
+    bits = np.zeros((t.n_items + 1, G), dtype=np.uint8)
+    for path_id, grp in zip(op, og):
+        ids = t.items[int(t.id_prefsum[int(path_id)]):int(t.id_prefsum[int(path_id) + 1])].astype(np.int64)
+        if t.exclude is not None:
+            ids = ids[t.exclude[ids] == 0]
+        bits[ids, int(grp)] = 1
+    if count == "edge":
+        weights = np.ones(t.n_items + 1, dtype=np.uint32)
+    else:
+        weights = np.array(g.node_lens, dtype=np.uint32)
+    return g, t, op, og, names, bits, weights
+
+
+@pytest.mark.parametrize("count", ["node", "bp", "edge"])
+def test_chrM_against_reference_goldens(count):
+    g, t, op, og, names, bits, weights = fixture_bitmap("chrM_test.gfa", count, groupby_sample=True)
+    k = KATS["chrM_groupby_sample"]
+    with pb.DeviceAbacus(t.n_items, len(names)) as a:
+        a.upload(pb.pack_bits(bits), weights)
+        hc, hw, ct = a.hist(count=True, weight=True, countable=True)
+        assert list(ct[1:]) == k["countable_" + count] and ct[0] == 0xFFFFFFFF
+        if count == "bp":
+            assert list(hw) == k["bp"]      # abacus.rs:1630
+        else:
+            assert list(hc) == k[count]     # abacus.rs:1525 / 1579
+        # ordered growth against the reference algorithm on the reference's own ItemTable
+        r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        cov, thr = cutoffs(len(names), PAIRS)
+        curves = a.ordered_growth(cov, thr, weighted=(count == "bp"))
+        for i, (cv, q) in enumerate(PAIRS):
+            want = po.calc_growth(r, c, len(names), po.absolute(cv), po.relative(q), count_bp=(count == "bp"),
+                                  node_lens=g.node_lens)
+            assert np.array_equal(curves[i].astype(np.float64), want), (cv, q)
+    if count == "node":
+        assert list(curves[0]) == [89, 106, 140, 154]
+
+
+@pytest.mark.parametrize("gfa", ["t_groups.gfa", "cdbg.gfa"])
+def test_small_fixtures(gfa):
+    for count in ("node", "bp", "edge"):
+        g, t, op, og, names, bits, weights = fixture_bitmap(gfa, count)
+        if t.n_items == 0:
+            continue
+        check_table(pb.pack_bits(bits), len(names), weights)
+
+
+def test_chrM_subset_and_exclude():
+    for kw in ({"subset": os.path.join(GOLDEN, "inclusion.bed1")},
+               {"exclude": os.path.join(GOLDEN, "exclusion.bed3")},
+               {"groupby_haplotype": True}):
+        g, t, op, og, names, bits, weights = fixture_bitmap("chrM_test.gfa", "node", **kw)
+        exp = check_table(pb.pack_bits(bits), len(names), weights, pairs=[(1, 0.0), (2, 0.5)])
+        # the bitmap built from (items, exclude) reproduces the reference's own coverage vector
+        want = po.abacus_by_total(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        assert np.array_equal(exp["countable"], want)
+
+
+# ---- random shapes: ragged widths, empty rows, full rows, every tile/tail combination -------------------
+
+SHAPES = [(1, 1), (2, 3), (3, 64), (4, 65), (5, 63), (255, 100), (256, 128), (257, 129), (1000, 256),
+          (1023, 300), (1030, 1024), (4099, 512), (515, 1100), (130, 2100), (70, 4500)]
+
+
+@pytest.mark.parametrize("N,G", SHAPES)
+def test_random_tables(N, G):
+    rng = np.random.default_rng(N * 7919 + G)
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=N * 31 + G)
+    # edge rows: empty, full, single first / last bit
+    if N >= 4:
+        bits[1] = 0
+        bits[2] = 1
+        bits[3] = 0
+        bits[3, 0] = 1
+        bits[4] = 0
+        bits[4, G - 1] = 1
+        bitmap = pb.pack_bits(bits)
+    weights[1:] = rng.integers(0, 100001, N)
+    if N >= 2:
+        weights[2] = 0xFFFFFFFF  # forces the 32-bit carry path of the shared-memory accumulators
+    check_table(bitmap, G, weights)
+
+
+def test_dense_and_sparse_variants():
+    for variant in ("dense", "sparse"):
+        bits, bitmap, weights = synth.numpy_table(3000, 200, seed=5, variant=variant)
+        check_table(bitmap, 200, weights)
+
+
+def test_garbage_in_padding_bits_is_ignored():
+    bits, bitmap, weights = synth.numpy_table(600, 70, seed=11)
+    exp = oracle_all(bitmap, 70, weights, [(1, 0.0), (2, 0.5)])
+    dirty = bitmap.copy()
+    dirty[:, 1] |= np.uint64(0xFFFFFFFFFFFFFFC0)  # bits 70..127
+    dirty[0, :] = np.uint64(0xFFFFFFFFFFFFFFFF)   # dummy row
+    with pb.DeviceAbacus(600, 70) as a:
+        a.upload(dirty, weights)
+        hc, hw, ct = a.hist(True, True, True)
+        assert np.array_equal(hc, exp["hist"]) and np.array_equal(hw, exp["hist_bp"])
+        cov, thr = cutoffs(70, [(1, 0.0), (2, 0.5)])
+        cv = a.ordered_growth(cov, thr)
+        assert np.array_equal(cv[0].astype(np.float64), exp[("node", 1, 0.0)])
+        assert np.array_equal(cv[1].astype(np.float64), exp[("node", 2, 0.5)])
+
+
+def test_many_thresholds_chunking():
+    bits, bitmap, weights = synth.numpy_table(900, 96, seed=3)
+    pairs = [(1 + (i % 5), [0.0, 0.25, 0.5, 0.75, 1.0][i % 5] if i % 2 else 0.0) for i in range(19)]
+    exp = oracle_all(bitmap, 96, weights, pairs)
+    with pb.DeviceAbacus(900, 96) as a:
+        a.upload(bitmap, weights)
+        cov, thr = cutoffs(96, pairs)
+        cv = a.ordered_growth(cov, thr, weighted=True)
+        for t, (c, q) in enumerate(pairs):
+            assert np.array_equal(cv[t].astype(np.float64), exp[("bp", c, q)]), (t, c, q)
+
+
+# ---- permuted growth (group-major kernels) -----------------------------------------------------------------
+
+@pytest.mark.parametrize("N,G", [(5, 3), (300, 64), (1000, 100), (2049, 257), (700, 1030)])
+def test_permuted_growth(N, G):
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=N + G)
+    orders = synth.random_orders(5, G, seed=99)
+    orders[0] = np.arange(G)  # identity: must equal the node-major kernels
+    pairs = [(1, 0.0), (2, 0.5), (4, 0.9)]
+    cov, thr = cutoffs(G, pairs)
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        for weighted in (False, True):
+            got = a.permuted_growth(orders, cov, thr, weighted=weighted)
+            assert np.array_equal(got[0], a.ordered_growth(cov, thr, weighted=weighted))
+            for p in range(orders.shape[0]):
+                pbits = bits[:, orders[p]]  # the abacus the reference rebuilds under --order
+                exp = oracle_all(pb.pack_bits(pbits), G, weights, pairs)
+                for t, (c, q) in enumerate(pairs):
+                    want = exp[("bp" if weighted else "node", c, q)]
+                    assert np.array_equal(got[p, t].astype(np.float64), want), (p, c, q, weighted)
+            one = a.ordered_growth(cov, thr, col_order=orders[3], weighted=weighted)
+            assert np.array_equal(one, got[3])
+
+
+# ---- similarity -------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("N,G", [(10, 2), (500, 64), (3000, 70), (1500, 130)])
+def test_similarity(N, G):
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=2 * N + G)
+    bits[1, :] = 1
+    bitmap = pb.pack_bits(bits)
+    exp = oracle_all(bitmap, G, weights, [])
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        for weighted in (False, True):
+            inter_o, len_o, table_o = po.similarity(exp["r"], exp["c"], G, count_bp=weighted, node_lens=weights)
+            inter, ln = a.similarity(weighted=weighted)
+            assert np.array_equal(inter, inter_o) and np.array_equal(ln, len_o)
+            # f32 Jaccard exactly as similarity.rs:153-163
+            table = inter.astype(np.float32) / (ln[:, None] + ln[None, :] - inter).astype(np.float32)
+            assert np.array_equal(table, table_o)
+            # row-block sharding (what each GPU computes in the 8-GPU configuration)
+            lo, hi = G // 3, max(G // 3 + 1, 2 * G // 3)
+            part, ln2 = a.similarity(weighted=weighted, row_begin=lo, row_end=hi)
+            assert np.array_equal(part, inter_o[lo:hi]) and np.array_equal(ln2, len_o)
+
+
+# ---- device-side build from ItemTables -------------------------------------------------------------------
+
+def test_scatter_build_matches_reference_incidence():
+    g, t, op, og, names, bits, weights = fixture_bitmap("chrM_test.gfa", "node", groupby_sample=True,
+                                                        exclude=os.path.join(GOLDEN, "exclusion.bed3"))
+    with pb.DeviceAbacus(t.n_items, len(names)) as a:
+        for path_id, grp in zip(op, og):
+            sl = t.items[int(t.id_prefsum[int(path_id)]):int(t.id_prefsum[int(path_id) + 1])]
+            a.scatter(sl, int(grp), t.exclude)
+        assert np.array_equal(a.download(), pb.pack_bits(bits))
+        hc, _, ct = a.hist(True, False, True)
+        want = po.abacus_by_total(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        assert np.array_equal(ct, want)
+        with pytest.raises(pb.PgxError):
+            a.scatter(np.array([t.n_items + 1], dtype=np.uint64), 0)
+
+
+def test_argument_errors():
+    with pytest.raises(pb.PgxError):
+        pb.DeviceAbacus(10, 0)
+    with pb.DeviceAbacus(10, 8) as a:
+        with pytest.raises(pb.PgxError):
+            a.ordered_growth([0], None)            # coverage cutoff must already be clamped to >= 1
+        with pytest.raises(pb.PgxError):
+            a.ordered_growth([1], None, col_order=np.zeros(8, dtype=np.uint32))  # not a permutation
+        with pytest.raises(pb.PgxError):
+            a.similarity(row_begin=5, row_end=3)
+        hc, _, _ = a.hist()                        # empty abacus: every item has coverage 0
+        assert hc[0] == 10 and hc[1:].sum() == 0
+
+
+# ---- full-size properties (BASELINE.json shapes; no CPU oracle at this size) ---------------------------------
+
+def test_full_size_properties():
+    import torch
+    N, G = 2_000_000, 1024
+    bitmap, weight = synth.torch_table(N, G, seed=synth.SEED_BASE + 1)
+    torch.cuda.synchronize()
+    with pb.DeviceAbacus(N, G) as a:
+        a.adopt_device(bitmap.data_ptr(), weight.data_ptr(), keepalive=(bitmap, weight))
+        pairs = [(1, 0.0), (2, 0.5), (4, 0.9)]
+        cov, thr = cutoffs(G, pairs)
+        hc, hw, cv = a.hist_ordered_growth(cov, thr, weighted=False, hist_count=True, hist_weight=True)
+        _, _, cvw = a.hist_ordered_growth(cov, thr, weighted=True, hist_count=False, hist_weight=False)
+        wsum = int(weight.to(torch.int64).sum().item())
+        assert int(hc.sum()) == N and int(hw.sum()) == wsum
+        # every item with >= 1 group is counted once all groups are in: curve end = N - hist[0]
+        assert int(cv[0, -1]) == N - int(hc[0]) and int(cvw[0, -1]) == wsum - int(hw[0])
+        assert (np.diff(cv[0].astype(np.int64)) >= 0).all()
+        # c = 2, q = 0.5 at the last column: all items with cov >= 2 whose final verdict holds; bounded by cov >= 2
+        assert int(cv[1, -1]) <= int(hc[2:].sum()) and int(cv[2, -1]) <= int(hc[4:].sum())
+        # popcount cross-check of the histogram against torch on the same device buffer
+        sub = bitmap[: 200_001]
+        bits = ((sub.unsqueeze(-1) >> torch.arange(64, device="cuda")) & 1).sum(dim=(1, 2))
+        ref_hist = torch.bincount(bits[1:], minlength=G + 1).cpu().numpy()
+        with pb.DeviceAbacus(200_000, G) as b:
+            b.adopt_device(sub.data_ptr(), None, keepalive=sub)
+            hb, _, _ = b.hist()
+            assert np.array_equal(hb.astype(np.int64), ref_hist)
+        # the group-major kernels (independent implementation) agree with the node-major pass
+        ident = np.arange(G, dtype=np.uint32)[None, :]
+        gm = a.permuted_growth(ident, cov, thr, weighted=True)
+        assert np.array_equal(gm[0], cvw)
+        # a sub-sample small enough for the CPU oracle, taken from the same device table
+        M = 20_000
+        host = bitmap[: M + 1].cpu().numpy().view(np.uint64)
+        wh = weight[: M + 1].cpu().numpy().view(np.uint32)
+        exp = oracle_all(host, G, wh, pairs)
+        with pb.DeviceAbacus(M, G) as b:
+            b.upload(host, wh)
+            cvs = b.ordered_growth(cov, thr, weighted=True)
+            for t, (c, q) in enumerate(pairs):
+                assert np.array_equal(cvs[t].astype(np.float64), exp[("bp", c, q)])
