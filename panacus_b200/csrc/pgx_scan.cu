@@ -12,6 +12,8 @@
 //                   them into `out` and re-zeroes accumulators + ticket (self-cleaning, one launch)
 //
 // Integer-only, HBM-bandwidth-bound: algorithmic bytes per item = W*8 (+4 weighted).
+#include <cstdlib>
+
 #include "pgx_common.cuh"
 #include "pgx_internal.h"
 
@@ -133,37 +135,58 @@ struct GlobalRowReader {
 };
 
 // ---- rotated-chunk fast path over a shared-memory row --------------------------------------------
-// A row is C = Wp/2 chunks of 16 bytes.  Lane i starts at chunk r(i) so that the 8 lanes of a
-// quarter-warp hit 8 different 16-byte bank groups for every row width:
-//   bank group of (i, c) = (i*C + c) mod 8;  with 2^a | C,  r(i) = (i >> (3-a')) & (2^a' - 1), a' = min(a,3).
-// popcount and first-set-bit are order independent, so the rotation costs nothing.
-template <int C_T>
+// A row is C = Wp/2 chunks of 16 bytes.  Lane i visits the chunks in a rotated order so that the 8
+// lanes of a quarter-warp hit 8 different 16-byte bank groups for every row width:
+//   bank group of (i, c) = (i*C + c) mod 8;  with 2^a | C,  r(i) = (i >> (3-a')) & (2^a' - 1), a' = min(a,3);
+//   chunk visited at step k: k ^ r(i) when C is a power of two, (k + r(i)) mod C otherwise.
+// popcount and "first non-empty chunk" are order independent, so the rotation costs nothing; the
+// first set bit is extracted once, after the loop, from the first non-empty chunk.
+template <int C_T, bool MASK>
 __device__ __forceinline__ void item_fast_smem(const ScanParams &p, const SmemAcc &s, uint64_t item, uint32_t wgt,
                                                uint32_t row_addr, uint32_t li, uint32_t C_rt, uint32_t rot_shift,
                                                uint32_t rot_mask) {
+    constexpr bool kXor = C_T > 0 && (C_T & (C_T - 1)) == 0;
     const uint32_t C = C_T > 0 ? (uint32_t)C_T : C_rt;
     const uint32_t r = (li >> rot_shift) & rot_mask;
-    uint32_t cov = 0, first = 0xFFFFFFFFu;
+    uint32_t cov = 0, firstc = 0xFFFFFFFFu;
 #pragma unroll(C_T > 0 ? C_T : 4)
     for (uint32_t k = 0; k < C; ++k) {
-        uint32_t c = k + r;
-        if (c >= C) c -= C;
+        uint32_t c;
+        if (kXor) {
+            c = k ^ r;
+        } else {
+            c = k + r;
+            if (c >= C) c -= C;
+        }
         uint64_t x, y;
         lds_v2_u64(row_addr + c * 16u, x, y);
-        if (c == C - 1) {
+        if (MASK && c == C - 1) {
             x &= p.last_mask0;
             y &= p.last_mask1;
         }
         cov += __popcll(x) + __popcll(y);
-        if (x | y) {
-            const uint32_t fb = x ? first_bit(x) : 64u + first_bit(y);
-            first = min(first, c * 128u + fb);
+        if ((x | y) != 0ull) firstc = min(firstc, c);
+    }
+    uint32_t first = 0xFFFFFFFFu;
+    if (cov) {
+        uint64_t x, y;
+        lds_v2_u64(row_addr + firstc * 16u, x, y);
+        if (MASK && firstc == C - 1) {
+            x &= p.last_mask0;
+            y &= p.last_mask1;
         }
+        first = firstc * 128u + (x ? first_bit(x) : 64u + first_bit(y));
     }
     account_fast(p, s, item, cov, first, wgt);
 }
 
-template <bool QUORUM, int C_T>
+// tuning overrides for experiments (PGX_SCAN_TILE / PGX_SCAN_STAGES / PGX_SCAN_CTAS), 0 = automatic
+uint32_t env_u32(const char *name) {
+    const char *v = getenv(name);
+    return v ? (uint32_t)strtoul(v, nullptr, 10) : 0u;
+}
+
+template <bool QUORUM, int C_T, bool MASK>
 __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t tid = threadIdx.x;
@@ -197,17 +220,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
     }
     __syncthreads();
 
+    const uint32_t last_tile = p.n_tiles - 1u;
+    // rows of the last tile (may be partial); every other tile is full
+    const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
+
     if (warp == (uint32_t)kConsumerWarps) {
         // ===== TMA producer =====
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
-            uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t st = it % S, use = it / S;
-                if (use > 0) mbar_wait(empty0 + 8u * st, (use - 1u) & 1u);
+            uint32_t st = 0, ph = 0;
+            bool ring_full = false;  // true once every stage has been used at least once
+            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
                 const uint64_t row0 = (uint64_t)tile * p.tile_items;
-                const uint64_t left = p.n_rows - row0;
-                const uint32_t rows = left < p.tile_items ? (uint32_t)left : p.tile_items;
+                const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
                 const uint32_t trows = rows & ~3u;  // TMA needs 16-byte multiples; <=3 tail rows read directly
                 const uint32_t full = full0 + 8u * st;
                 if (trows) {
@@ -220,6 +246,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                 } else {
                     mbar_arrive(full);
                 }
+                if (++st == S) {
+                    st = 0;
+                    ph ^= 1u;
+                    ring_full = true;
+                }
             }
         }
     } else {
@@ -228,16 +259,14 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         uint32_t a = 0;
         while (a < 3 && C_rt && !((C_rt >> a) & 1u)) ++a;  // a' = min(ctz(C), 3)
         const uint32_t rot_shift = 3u - a, rot_mask = (1u << a) - 1u;
-        uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t st = it % S, use = it / S;
+        uint32_t st = 0, ph = 0;
+        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const uint64_t row0 = (uint64_t)tile * p.tile_items;
-            const uint64_t left = p.n_rows - row0;
-            const uint32_t rows = left < p.tile_items ? (uint32_t)left : p.tile_items;
+            const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
             const uint32_t trows = rows & ~3u;
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const uint32_t wbase = base + p.L.off_stage_w;
-            mbar_wait(full0 + 8u * st, use & 1u);
+            mbar_wait(full0 + 8u * st, ph);
             for (uint32_t li = tid; li < rows; li += kConsumerThreads) {
                 const uint64_t item = row0 + li;
                 if (item == 0) {  // the reference's dummy item (abacus.rs:551, 1000-1002)
@@ -254,7 +283,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                         const uint64_t x = lds_u64(row_addr) & p.last_mask0;
                         account_fast(p, s, item, __popcll(x), x ? first_bit(x) : 0xFFFFFFFFu, wgt);
                     } else {
-                        item_fast_smem<C_T>(p, s, item, wgt, row_addr, li, C_rt, rot_shift, rot_mask);
+                        item_fast_smem<C_T, MASK>(p, s, item, wgt, row_addr, li, C_rt, rot_shift, rot_mask);
                     }
                 } else {  // <= 3 tail rows of the last tile, straight from global memory
                     const uint32_t wgt = p.weight ? __ldg(p.weight + item) : 1u;
@@ -267,6 +296,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8u * st);
+            if (++st == S) {
+                st = 0;
+                ph ^= 1u;
+            }
         }
     }
     __syncthreads();
@@ -304,17 +337,30 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
     __syncthreads();
     if (s_is_last) {
         __threadfence();
-        for (uint32_t i = tid; i < 2u * G1; i += kScanThreads) {
-            const bool wanted = (i < G1) ? (p.flags & kHistCount) : (p.flags & kHistWeight);
-            if (wanted) {
-                p.out[i] = __ldcg(p.acc + i);
-                p.acc[i] = 0ull;
+        // batched: issue kBatch independent L2 loads per thread before the dependent stores
+        constexpr uint32_t kBatch = 6;
+        const uint32_t total = 2u * G1 + nd;
+        for (uint32_t base = 0; base < total; base += kBatch * kScanThreads) {
+            uint64_t v[kBatch];
+#pragma unroll
+            for (uint32_t u = 0; u < kBatch; ++u) {
+                const uint32_t i = base + u * kScanThreads + tid;
+                v[u] = i < total ? __ldcg(p.acc + i) : 0ull;
             }
-        }
-        for (uint32_t i = tid; i < nd; i += kScanThreads) {
-            const uint32_t t = i / p.G, j = i - t * p.G;
-            p.out[2u * G1 + p.slot[t] * p.G + j] = __ldcg(p.acc + 2u * G1 + i);
-            p.acc[2u * G1 + i] = 0ull;
+#pragma unroll
+            for (uint32_t u = 0; u < kBatch; ++u) {
+                const uint32_t i = base + u * kScanThreads + tid;
+                if (i >= total) continue;
+                if (i < 2u * G1) {
+                    const bool wanted = (i < G1) ? (p.flags & kHistCount) : (p.flags & kHistWeight);
+                    if (!wanted) continue;
+                    p.out[i] = v[u];
+                } else {
+                    const uint32_t d = i - 2u * G1, t = d / p.G, j = d - t * p.G;
+                    p.out[2u * G1 + p.slot[t] * p.G + j] = v[u];
+                }
+                if (v[u]) p.acc[i] = 0ull;
+            }
         }
         if (tid == 0) *p.ticket = 0u;
     }
@@ -322,9 +368,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
 
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; }
 
-template <bool QUORUM, int C_T>
+template <bool QUORUM, int C_T, bool MASK>
 int launch_one(const ScanParams &p, int grid, cudaStream_t stream) {
-    auto kern = k_scan<QUORUM, C_T>;
+    auto kern = k_scan<QUORUM, C_T, MASK>;
     PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.L.total));
     kern<<<grid, kScanThreads, p.L.total, stream>>>(p);
     PGX_CUDA(cudaGetLastError());
@@ -360,32 +406,42 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     off = align_up(off, 128u);
     L.off_stage0 = off;
 
-    // tile geometry: ~32 KB of bitmap per stage, one item per consumer thread where rows allow
-    uint32_t tile = 32768u / rowbytes;
-    if (tile >= (uint32_t)kConsumerThreads) {
-        tile = tile / kConsumerThreads * kConsumerThreads;
-        if (tile > 2048u) tile = 2048u;
-    } else {
-        tile = (32768u / rowbytes) & ~3u;  // wide rows: fewer items than threads per stage
-        if (tile < 4u) tile = 4u;
+    // tile geometry (rows per stage, CTAs per SM, ring depth): measured optima on B200
+    // (tools/sweep_scan.py, profiles/r1_sweep_*.txt).  The quorum kernel keeps one item per thread.
+    uint32_t tile, want_ctas, want_stages;
+    const bool heavy = quorum || (p.flags & (kHistWeight | kWeighted)) != 0;  // more atomics per item
+    if (rowbytes >= 256u) {
+        tile = 256u, want_ctas = 1, want_stages = 3;
+        while (tile > 4u && tile * rowbytes > 65536u) tile >>= 1;
         if (tile * rowbytes > 98304u) return fail(PGX_ERR_UNSUPPORTED, "n_groups too large for the shared-memory pipeline");
+    } else if (rowbytes == 128u) {
+        if (heavy) tile = 256u, want_ctas = 2, want_stages = 2;
+        else tile = 512u, want_ctas = 1, want_stages = 3;
+    } else if (rowbytes >= 64u) {
+        tile = 256u, want_ctas = 2, want_stages = 4;
+    } else {
+        tile = 24576u / rowbytes / 256u * 256u;  // ~24 KB stages for narrow rows
+        if (tile > 3072u) tile = 3072u;
+        want_ctas = 2, want_stages = 3;
     }
+    if (const uint32_t t_env = env_u32("PGX_SCAN_TILE")) tile = (t_env + 3u) & ~3u;
     p.tile_items = tile;
     L.off_stage_w = align_up(tile * rowbytes, 128u);
     L.stage_stride = L.off_stage_w + (p.weight ? align_up(tile * 4u, 128u) : 0u);
 
-    const uint32_t max_smem = 232448u;          // 227 KB opt-in limit per CTA
-    const uint32_t per_cta_2 = 232448u / 2u - 1024u;  // two CTAs per SM (1 KB reserved each)
-    int ctas = 2;
+    const uint32_t max_smem = 232448u;  // 227 KB opt-in limit per CTA
+    if (const uint32_t c_env = env_u32("PGX_SCAN_CTAS")) want_ctas = c_env;
+    if (const uint32_t s_env = env_u32("PGX_SCAN_STAGES")) want_stages = s_env;
+    int ctas = (int)want_ctas;
     uint32_t stages = 0;
-    if (off + 3u * L.stage_stride <= per_cta_2) {
-        stages = (per_cta_2 - off) / L.stage_stride;
-    } else {
-        ctas = 1;
-        if (off + 2u * L.stage_stride > max_smem)
-            return fail(PGX_ERR_UNSUPPORTED, "accumulators + pipeline exceed shared memory for this G / T");
-        stages = (max_smem - off) / L.stage_stride;
+    for (; ctas >= 1; --ctas) {  // fall back to fewer CTAs per SM when the accumulators are large
+        const uint32_t budget = ctas == 1 ? max_smem : max_smem / (uint32_t)ctas - 1024u;
+        if (off + 2u * L.stage_stride > budget) continue;
+        stages = (budget - off) / L.stage_stride;
+        break;
     }
+    if (ctas < 1) return fail(PGX_ERR_UNSUPPORTED, "accumulators + pipeline exceed shared memory for this G / T");
+    if (stages > want_stages) stages = want_stages;
     if (stages > (uint32_t)kMaxStages) stages = kMaxStages;
     p.stages = stages;
     L.total = off + stages * L.stage_stride;
@@ -410,16 +466,22 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     return PGX_OK;
 }
 
+template <int C_T>
+int launch_fast(const ScanParams &p, int grid, cudaStream_t stream) {
+    const bool mask = p.last_mask0 != ~0ull || p.last_mask1 != ~0ull;
+    return mask ? launch_one<false, C_T, true>(p, grid, stream) : launch_one<false, C_T, false>(p, grid, stream);
+}
+
 int launch_scan(const ScanParams &p, bool quorum, int grid, cudaStream_t stream) {
-    if (quorum) return launch_one<true, 0>(p, grid, stream);
-    if (p.Wp == 1u) return launch_one<false, -1>(p, grid, stream);
+    if (quorum) return launch_one<true, 0, true>(p, grid, stream);
+    if (p.Wp == 1u) return launch_one<false, -1, true>(p, grid, stream);
     switch (p.Wp >> 1) {
-        case 1: return launch_one<false, 1>(p, grid, stream);
-        case 2: return launch_one<false, 2>(p, grid, stream);
-        case 4: return launch_one<false, 4>(p, grid, stream);
-        case 8: return launch_one<false, 8>(p, grid, stream);
-        case 16: return launch_one<false, 16>(p, grid, stream);
-        default: return launch_one<false, 0>(p, grid, stream);
+        case 1: return launch_fast<1>(p, grid, stream);
+        case 2: return launch_fast<2>(p, grid, stream);
+        case 4: return launch_fast<4>(p, grid, stream);
+        case 8: return launch_fast<8>(p, grid, stream);
+        case 16: return launch_fast<16>(p, grid, stream);
+        default: return launch_fast<0>(p, grid, stream);
     }
 }
 

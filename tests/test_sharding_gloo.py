@@ -1,0 +1,124 @@
+"""world_size-2 (and 3) gloo tests of the multi-GPU plumbing (panacus_b200/sharding.py) on CPU.
+The per-rank compute is a numpy stand-in with DeviceAbacus' method signatures (test double only); what is
+under test is the partitioning and the exchange: item-range all-reduce, order round-robin + all-gather,
+similarity row blocks + all-gather must reproduce the single-process result exactly."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from panacus_b200 import quorum_thresholds, sharding, synth
+
+
+class NumpyAbacus:
+    """Test double: same interface as panacus_b200.DeviceAbacus, dense numpy arithmetic."""
+
+    def __init__(self, bits, weight):
+        self.bits = bits.astype(np.int64)
+        self.bits[0] = 0
+        self.w = weight.astype(np.int64)
+        self.n_items, self.n_groups = bits.shape[0] - 1, bits.shape[1]
+
+    def _curve(self, bits, c, thr, weighted):
+        G = self.n_groups
+        total = bits.sum(1)
+        cnt = np.cumsum(bits, 1)
+        col = np.arange(G)[None, :]
+        last = np.maximum.accumulate(np.where(bits > 0, col, -1), axis=1)
+        ok = (last >= 0) & (cnt >= thr[np.clip(last, 0, G - 1)]) & (total[:, None] >= c)
+        w = self.w if weighted else np.ones_like(self.w)
+        return (ok * w[:, None]).sum(0).astype(np.uint64)
+
+    def hist_ordered_growth(self, cov_abs, quorum_thr=None, weighted=False, hist_count=True, hist_weight=False):
+        G = self.n_groups
+        cov = self.bits.sum(1)
+        hc = np.bincount(cov[1:], minlength=G + 1).astype(np.uint64)
+        hw = np.bincount(cov[1:], weights=self.w[1:], minlength=G + 1).astype(np.uint64) if hist_weight else None
+        T = len(cov_abs)
+        thr = np.zeros((T, G), dtype=np.int64) if quorum_thr is None else np.asarray(quorum_thr, dtype=np.int64).reshape(T, G)
+        cv = np.stack([self._curve(self.bits, cov_abs[t], thr[t], weighted) for t in range(T)])
+        return hc, hw, cv
+
+    def permuted_growth(self, orders, cov_abs, quorum_thr=None, weighted=False):
+        T, G = len(cov_abs), self.n_groups
+        thr = np.zeros((T, G), dtype=np.int64) if quorum_thr is None else np.asarray(quorum_thr, dtype=np.int64).reshape(T, G)
+        return np.stack([np.stack([self._curve(self.bits[:, o], cov_abs[t], thr[t], weighted) for t in range(T)])
+                         for o in orders]) if len(orders) else np.zeros((0, T, G), dtype=np.uint64)
+
+    def similarity(self, weighted=False, row_begin=0, row_end=None):
+        w = self.w if weighted else np.ones_like(self.w)
+        inter = (self.bits.T @ (self.bits * w[:, None])).astype(np.uint64)
+        return inter[row_begin:row_end], np.diag(inter).copy()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, G = 1501, 70
+        bits, bitmap, weight = synth.numpy_table(N, G, seed=123)
+        full = NumpyAbacus(bits, weight)
+        cov = [1, 2, 3]
+        thr = np.stack([quorum_thresholds(G, q) for q in (0.0, 0.5, 0.9)])
+        # --- item-range sharding + all-reduce
+        lo, hi = sharding.item_range(N, rank, world)
+        local_bits = np.concatenate([np.zeros((1, G), dtype=bits.dtype), bits[lo:hi]])
+        local_w = np.concatenate([np.zeros(1, dtype=weight.dtype), weight[lo:hi]])
+        bm_r, w_r, n_r = sharding.shard_rows(bitmap, weight, rank, world)
+        assert n_r == hi - lo and np.array_equal(w_r, local_w) and bm_r.shape[0] == n_r + 1
+        local = NumpyAbacus(local_bits, local_w)
+        hc, hw, cv = sharding.sharded_hist_ordered_growth(local, cov, thr, weighted=True, hist_weight=True)
+        hc0, hw0, cv0 = full.hist_ordered_growth(cov, thr, weighted=True, hist_weight=True)
+        assert np.array_equal(hc, hc0) and np.array_equal(hw, hw0) and np.array_equal(cv, cv0)
+        # u64 wrap-around survives the int64 transport
+        big = np.array([np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(1) << np.uint64(63)], dtype=np.uint64)
+        s = sharding.allreduce_u64(big)
+        want = (big.astype(object) * world) % (1 << 64)
+        assert [int(x) for x in s] == [int(x) for x in want]
+        # --- permutations round-robin + all-gather (5 orders over `world` ranks: ragged)
+        orders = synth.random_orders(5, G, seed=9)
+        pg = sharding.sharded_permuted_growth(full, orders, cov, thr, weighted=False)
+        assert np.array_equal(pg, full.permuted_growth(orders, cov, thr, weighted=False))
+        # --- similarity row blocks + all-gather
+        inter, ln = sharding.sharded_similarity(full, weighted=True)
+        inter0, ln0 = full.similarity(weighted=True)
+        assert np.array_equal(inter, inter0) and np.array_equal(ln, ln0)
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharding_over_gloo(world):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: "ok" for r in range(world)}
+
+
+def test_partitions_cover_everything_once():
+    for n, w in [(10, 3), (7, 8), (1000, 8), (1, 2)]:
+        ids = []
+        for r in range(w):
+            lo, hi = sharding.item_range(n, r, w)
+            ids += list(range(lo, hi))
+        assert ids == list(range(1, n + 1))
+        rows = []
+        for r in range(w):
+            lo, hi = sharding.row_block(n, r, w)
+            rows += list(range(lo, hi))
+        assert rows == list(range(n))
+        assert sorted(np.concatenate([sharding.order_indices(n, r, w) for r in range(w)]).tolist()) == list(range(n))
