@@ -219,6 +219,11 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     a.set_stream(stream.cuda_stream)
     T = 1
+    fused = world > 1 and args.exchange == "fused"
+    if fused:  # in-kernel all-reduce over NVLink peer memory: the step stays ONE kernel launch
+        from panacus_b200 import sharding
+        sharding.connect_fused_exchange(a)
+    nccl_exchange = world > 1 and not fused
     out = torch.zeros(a.fused_out_words(T), dtype=torch.int64, device=dev)
     cov = [1]
 
@@ -231,7 +236,7 @@ def run_ours(args):
         if flush is not None:
             flush.fill_(1)
         a.fused_pass_async(out.data_ptr(), cov, None, weighted=False, hist_count=True, hist_weight=False)
-        if world > 1:
+        if nccl_exchange:
             dist.all_reduce(out)  # the path's one exchange: sum of per-shard integer results
 
     for _ in range(max(args.warmup, 3)):
@@ -258,7 +263,7 @@ def run_ours(args):
         k_ev[i][0].record()
         a.fused_pass_async(out.data_ptr(), cov, None, weighted=False, hist_count=True, hist_weight=False)
         k_ev[i][1].record()
-        if world > 1:
+        if nccl_exchange:
             dist.all_reduce(out)
     e1.record()
     torch.cuda.synchronize()
@@ -271,18 +276,17 @@ def run_ours(args):
         total_ms = float(np.sum(kernel_ms))  # L2-flush writes are not part of the step
     else:
         total_ms = e0.elapsed_time(e1)
-    # keep the GPU under the same load a little longer so the clock sampler sees it
-    if sampler:
-        t_end = time.perf_counter() + 0.25
-        while time.perf_counter() < t_end:
-            a.fused_pass_async(out.data_ptr(), cov, None, weighted=False, hist_count=True, hist_weight=False)
-            torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-
     t_max = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     total_ms = float(t_max.item())
+    # keep every GPU under the same load a little longer so the clock sampler sees it (same count on all ranks:
+    # with the fused exchange every pass is collective)
+    n_extra = max(1, min(5000, int(250.0 / max(total_ms / args.steps, 1e-3))))
+    for _ in range(n_extra):
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
     ms_per_step = total_ms / args.steps
     cells_per_step = float(N) * G * world
     value = cells_per_step / (ms_per_step * 1e-3)
@@ -311,6 +315,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         host_np = host.numpy().view(np.uint64)
         b = pb.DeviceAbacus(N, G, device=local_rank)
+        if fused:
+            sharding.connect_fused_exchange(b)
         n_e2e = max(1, min(args.steps, args.e2e_steps))
         b.upload(host_np)  # warm-up (allocations, first-touch)
         b.hist_ordered_growth(cov, None, weighted=False)
@@ -360,7 +366,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": wl["name"], "n_items_per_gpu": N, "n_groups": G, "count": "node", "coverage": 1,
                        "quorum": 0, "sharding": "item ranges, one shard per GPU" if world > 1 else "single GPU",
-                       "exchange": "ncclAllReduce(int64 sum) of %d words per step" % out.numel() if world > 1 else "none",
+                       "exchange": ("none" if world == 1 else
+                                    "in-kernel all-reduce over NVLink peer memory (last CTA pushes %d u64 words to every rank)"
+                                    % out.numel() if fused else "ncclAllReduce(int64 sum) of %d words per step" % out.numel()),
                        "cache": "L2 flushed between steps (256 MB write)" if flush is not None
                                 else "input %.2f GB per GPU >> 126 MB L2, no flush" % (bitmap_bytes / 1e9)},
             "gbps_per_gpu": alg_bytes / (ms_per_step * 1e-3) / 1e9,
@@ -387,6 +395,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", choices=["fused", "nccl"], default="fused",
+                    help="N > 1: how the per-shard results are summed (fused = inside k_scan over NVLink peer memory)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

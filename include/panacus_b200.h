@@ -136,6 +136,21 @@ size_t pgx_fused_out_words(uint32_t n_groups, uint32_t n_thresholds);
 int pgx_fused_pass_async(pgx_abacus *a, int want_hist_count, int want_hist_weight, uint32_t n_thresholds,
                          const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted,
                          uint64_t *d_out);
+/* multi-GPU: fused exchange over NVLink peer memory --------------------------------------------------
+ * Item-range sharding (one process per GPU, each handle holds the rows of its item range): after
+ * pgx_exchange_connect, every fused pass (pgx_hist, pgx_ordered_growth without col_order,
+ * pgx_hist_ordered_growth, pgx_fused_pass_async) ends with an in-kernel all-reduce of the result
+ * vector: the last CTA of each rank stores its partial sums into every rank's exchange buffer with peer
+ * stores, signals, waits for all ranks and adds them up -- one kernel does the scan and the exchange.
+ * The calls are collective: all ranks must issue the same sequence of passes.
+ *   pgx_exchange_export  writes an opaque PGX_EXCHANGE_HANDLE_BYTES handle of this process' buffer
+ *                        (a cudaIpcMemHandle_t); gather the handles of all ranks with any transport.
+ *   pgx_exchange_connect maps the peers' buffers (world <= 8 GPUs of one NVLink domain). */
+#define PGX_EXCHANGE_HANDLE_BYTES 64
+int pgx_exchange_export(pgx_abacus *a, void *handle_out);
+int pgx_exchange_connect(pgx_abacus *a, uint32_t rank, uint32_t world, const void *all_handles);
+int pgx_exchange_disconnect(pgx_abacus *a);
+
 /* Number of kernel launches issued through this handle so far (for bench accounting). */
 uint64_t pgx_launch_count(const pgx_abacus *a);
 /* Name and launch geometry of the last hot-path kernel (for logs). */

@@ -20,7 +20,9 @@ EXPORTS = [
     "pgx_abacus_download", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
     "pgx_permuted_growth", "pgx_similarity", "pgx_fused_out_words", "pgx_fused_pass_async",
     "pgx_launch_count", "pgx_last_launch_info",
+    "pgx_exchange_export", "pgx_exchange_connect", "pgx_exchange_disconnect",
 ]
+EXCHANGE_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -80,6 +82,12 @@ def lib() -> C.CDLL:
     L.pgx_fused_out_words.argtypes = [C.c_uint32, C.c_uint32]
     L.pgx_fused_pass_async.restype = C.c_int
     L.pgx_fused_pass_async.argtypes = [vp, C.c_int, C.c_int, C.c_uint32, vp, vp, C.c_int, vp]
+    L.pgx_exchange_export.restype = C.c_int
+    L.pgx_exchange_export.argtypes = [vp, vp]
+    L.pgx_exchange_connect.restype = C.c_int
+    L.pgx_exchange_connect.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+    L.pgx_exchange_disconnect.restype = C.c_int
+    L.pgx_exchange_disconnect.argtypes = [vp]
     L.pgx_launch_count.restype = C.c_uint64
     L.pgx_launch_count.argtypes = [vp]
     L.pgx_last_launch_info.restype = C.c_int

@@ -243,6 +243,21 @@ class DeviceAbacus:
         _native.check(self._L.pgx_fused_pass_async(self._h, int(bool(hist_count)), int(bool(hist_weight)), cov.size,
                                                    _ptr(cov), _ptr(thr), int(bool(weighted)), C.c_void_p(d_out_ptr)))
 
+    # -- fused multi-GPU exchange (item-range sharding) ----------------------------------------------
+    def exchange_export(self) -> bytes:
+        buf = C.create_string_buffer(_native.EXCHANGE_HANDLE_BYTES)
+        _native.check(self._L.pgx_exchange_export(self._h, buf))
+        return buf.raw
+
+    def exchange_connect(self, rank: int, world: int, all_handles: bytes):
+        if len(all_handles) != world * _native.EXCHANGE_HANDLE_BYTES:
+            raise ValueError("all_handles must hold one handle per rank")
+        buf = C.create_string_buffer(all_handles, len(all_handles))
+        _native.check(self._L.pgx_exchange_connect(self._h, int(rank), int(world), buf))
+
+    def exchange_disconnect(self):
+        _native.check(self._L.pgx_exchange_disconnect(self._h))
+
     @property
     def launch_count(self) -> int:
         return int(self._L.pgx_launch_count(self._h))

@@ -63,6 +63,12 @@ struct pgx_abacus {
     uint64_t *h_pinned = nullptr;
     size_t pinned_words = 0;
 
+    // fused NVLink exchange (item-range sharding)
+    unsigned char *d_xchg = nullptr;  // [2][kMaxRanks][acc_words] u64 slots, then 2*kMaxRanks u32 flags
+    void *peer_base[kMaxRanks] = {};
+    Exchange x = {};
+    uint32_t epoch = 0;
+
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint64_t launches = 0;
     std::string last_launch;
@@ -163,6 +169,7 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
         p.W = a->W;
         p.Wp = a->Wp;
         p.flags = flags;
+        p.x = a->x;
         p.T = (uint32_t)n;
         for (size_t k = 0; k < n; ++k) {
             p.cov[k] = cov[ts[i0 + k]];
@@ -181,6 +188,7 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
         if (rc) return rc;
         p.thr = a->d_thr;
     }
+    if (a->x.world > 1u) p.x.epoch = ++a->epoch;  // collective sequence number (never 0)
     const int rc = launch_scan(p, quorum, grid, a->stream);
     if (rc) return rc;
     a->launches++;
@@ -452,6 +460,8 @@ void pgx_abacus_destroy(pgx_abacus *a) {
     if (!a) return;
     DeviceGuard guard(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
+    pgx_exchange_disconnect(a);
+    cudaFree(a->d_xchg);
     if (a->own_bitmap && a->d_bitmap) cudaFree(a->d_bitmap);
     if (a->own_weight && a->d_weight) cudaFree(a->d_weight);
     cudaFree(a->d_countable);
@@ -737,6 +747,71 @@ int pgx_fused_pass_async(pgx_abacus *a, int want_hist_count, int want_hist_weigh
     DeviceGuard guard(a->device);
     return fused_pass(a, want_hist_count != 0, want_hist_weight != 0, n_thresholds, cov_abs, quorum_thr, weighted, nullptr,
                       d_out);
+}
+
+static size_t xchg_data_bytes(const pgx_abacus *a) { return (size_t)2 * kMaxRanks * a->acc_words * 8u; }
+
+int pgx_exchange_export(pgx_abacus *a, void *handle_out) {
+    if (!a || !handle_out) return fail(PGX_ERR_INVALID, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PGX_EXCHANGE_HANDLE_BYTES, "handle size");
+    DeviceGuard guard(a->device);
+    if (!a->d_xchg) {
+        const size_t bytes = xchg_data_bytes(a) + 2u * kMaxRanks * 4u;
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_xchg), bytes));
+        PGX_CUDA(cudaMemset(a->d_xchg, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    PGX_CUDA(cudaIpcGetMemHandle(&h, a->d_xchg));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return PGX_OK;
+}
+
+int pgx_exchange_connect(pgx_abacus *a, uint32_t rank, uint32_t world, const void *all_handles) {
+    if (!a || !all_handles) return fail(PGX_ERR_INVALID, "bad arguments");
+    if (world < 1 || world > (uint32_t)kMaxRanks || rank >= world) return fail(PGX_ERR_INVALID, "bad rank / world (<= 8)");
+    if (!a->d_xchg) return fail(PGX_ERR_STATE, "call pgx_exchange_export first");
+    DeviceGuard guard(a->device);
+    pgx_exchange_disconnect(a);
+    Exchange x = {};
+    x.world = world;
+    x.rank = rank;
+    x.stride = (uint32_t)a->acc_words;
+    x.err = a->d_err;
+    for (uint32_t r = 0; r < world; ++r) {
+        unsigned char *base = nullptr;
+        if (r == rank) {
+            base = a->d_xchg;
+        } else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const unsigned char *>(all_handles) + (size_t)r * sizeof(h), sizeof(h));
+            void *ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                pgx_exchange_disconnect(a);
+                return fail(PGX_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            }
+            a->peer_base[r] = ptr;
+            base = static_cast<unsigned char *>(ptr);
+        }
+        x.data[r] = reinterpret_cast<uint64_t *>(base);
+        x.flag[r] = reinterpret_cast<uint32_t *>(base + xchg_data_bytes(a));
+    }
+    a->x = x;
+    return PGX_OK;
+}
+
+int pgx_exchange_disconnect(pgx_abacus *a) {
+    if (!a) return fail(PGX_ERR_INVALID, "null handle");
+    DeviceGuard guard(a->device);
+    if (a->stream) cudaStreamSynchronize(a->stream);
+    for (int r = 0; r < kMaxRanks; ++r) {
+        if (a->peer_base[r]) cudaIpcCloseMemHandle(a->peer_base[r]);
+        a->peer_base[r] = nullptr;
+    }
+    a->x = Exchange{};
+    cudaGetLastError();
+    return PGX_OK;
 }
 
 uint64_t pgx_launch_count(const pgx_abacus *a) { return a ? a->launches : 0; }

@@ -39,6 +39,18 @@ struct ScanLayout {
     uint32_t total;          // dynamic shared memory bytes
 };
 
+constexpr int kMaxRanks = 8;  // GPUs of one NVSwitch domain taking part in the fused exchange
+
+// In-kernel all-reduce of the KB-sized result vector over NVLink peer memory (world > 1): the last CTA
+// of every rank stores its vector into slot [epoch parity][rank] of every rank's buffer, raises a flag
+// there, waits for all ranks' flags in its own buffer and sums the slots.
+struct Exchange {
+    uint64_t *data[kMaxRanks];   // data[r]: rank r's buffer as mapped into this process (r == rank: local)
+    uint32_t *flag[kMaxRanks];   // flag[r]: rank r's flag words (2 * kMaxRanks u32)
+    unsigned int *err;           // set to 2 if a peer did not arrive within the timeout
+    uint32_t world, rank, epoch, stride;  // stride: u64 words per slot
+};
+
 struct ScanParams {
     const uint64_t *bitmap;  // n_rows x Wp, node-major
     const uint32_t *weight;  // n_rows, or nullptr (unit weights)
@@ -58,6 +70,7 @@ struct ScanParams {
     uint32_t n_tiles;
     uint64_t last_mask0, last_mask1;  // masks of the two words of the last 16-byte chunk of a row
     ScanLayout L;
+    Exchange x;              // x.world <= 1: no exchange
 };
 
 struct ScanPlan {

@@ -337,9 +337,19 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
     __syncthreads();
     if (s_is_last) {
         __threadfence();
-        // batched: issue kBatch independent L2 loads per thread before the dependent stores
-        constexpr uint32_t kBatch = 6;
         const uint32_t total = 2u * G1 + nd;
+        // accumulator index -> index in the caller's fused layout (0xFFFFFFFF: not requested)
+        auto out_index = [&](uint32_t i) -> uint32_t {
+            if (i < 2u * G1) {
+                const bool wanted = (i < G1) ? (p.flags & kHistCount) : (p.flags & kHistWeight);
+                return wanted ? i : 0xFFFFFFFFu;
+            }
+            const uint32_t d = i - 2u * G1, t = d / p.G, j = d - t * p.G;
+            return 2u * G1 + p.slot[t] * p.G + j;
+        };
+        constexpr uint32_t kBatch = 6;  // independent L2 loads in flight per thread
+        const bool xchg = p.x.world > 1u;
+        const uint32_t par = p.x.epoch & 1u;
         for (uint32_t base = 0; base < total; base += kBatch * kScanThreads) {
             uint64_t v[kBatch];
 #pragma unroll
@@ -351,15 +361,47 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             for (uint32_t u = 0; u < kBatch; ++u) {
                 const uint32_t i = base + u * kScanThreads + tid;
                 if (i >= total) continue;
-                if (i < 2u * G1) {
-                    const bool wanted = (i < G1) ? (p.flags & kHistCount) : (p.flags & kHistWeight);
-                    if (!wanted) continue;
-                    p.out[i] = v[u];
-                } else {
-                    const uint32_t d = i - 2u * G1, t = d / p.G, j = d - t * p.G;
-                    p.out[2u * G1 + p.slot[t] * p.G + j] = v[u];
+                const uint32_t oi = out_index(i);
+                if (oi == 0xFFFFFFFFu) continue;
+                if (!xchg) {
+                    p.out[oi] = v[u];
+                } else {  // push my partial result into slot [par][rank] of every rank (NVLink peer stores)
+                    const size_t off = (size_t)(par * kMaxRanks + p.x.rank) * p.x.stride + oi;
+                    for (uint32_t r = 0; r < p.x.world; ++r) p.x.data[r][off] = v[u];
                 }
                 if (v[u]) p.acc[i] = 0ull;
+            }
+        }
+        if (xchg) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid < p.x.world) {
+                // raise my flag at rank `tid`, then wait for rank `tid`'s flag here
+                uint32_t *remote = p.x.flag[tid] + par * kMaxRanks + p.x.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(p.x.epoch) : "memory");
+                const uint32_t *local = p.x.flag[p.x.rank] + par * kMaxRanks + tid;
+                uint64_t t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (;;) {
+                    uint32_t f;
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(local) : "memory");
+                    if (f == p.x.epoch) break;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived; flag the error, do not hang
+                        atomicExch(p.x.err, 2u);
+                        break;
+                    }
+                    __nanosleep(200);
+                }
+            }
+            __syncthreads();
+            const uint64_t *mine = p.x.data[p.x.rank] + (size_t)par * kMaxRanks * p.x.stride;
+            for (uint32_t i = tid; i < total; i += kScanThreads) {
+                const uint32_t oi = out_index(i);
+                if (oi == 0xFFFFFFFFu) continue;
+                uint64_t sum = 0;
+                for (uint32_t r = 0; r < p.x.world; ++r) sum += __ldcg(mine + (size_t)r * p.x.stride + oi);
+                p.out[oi] = sum;
             }
         }
         if (tid == 0) *p.ticket = 0u;

@@ -84,6 +84,23 @@ def allgather_rows(local: np.ndarray, counts: Sequence[int], device=None, group=
     return full.reshape((full.shape[0],) + tuple(local.shape[1:]))
 
 
+def connect_fused_exchange(abacus, group=None):
+    """Wire the in-kernel NVLink all-reduce of `abacus` (a DeviceAbacus holding this rank's item range) to
+    the other ranks of `group`: exchange the IPC handles with an all_gather, then map the peers."""
+    import torch
+    dist = _dist()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = abacus.exchange_export()
+    dev = torch.device("cuda", abacus.device) if dist.get_backend(group) == "nccl" else None
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8)
+    t = t.to(dev) if dev is not None else t
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    handles = b"".join(bytes(o.cpu().numpy().tobytes()) for o in outs)
+    abacus.exchange_connect(rank, world, handles)
+    dist.barrier(group=group)
+
+
 # ---- sharded queries (abacus = anything with DeviceAbacus' methods) -----------------------------------------
 
 def sharded_hist_ordered_growth(abacus, cov_abs, quorum_thr=None, weighted=False, hist_weight=False, device=None,
