@@ -242,8 +242,6 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
 
     # ---- timed region: K steps, device time via CUDA events on the launching stream ----
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -253,6 +251,9 @@ def run_ours(args):
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()  # all ranks enter the timed region together (the passes are collective)
+        torch.cuda.synchronize()
     profiling = os.environ.get("PGX_PROFILE_RANGE") == "1"
     if profiling:
         torch.cuda.cudart().cudaProfilerStart()
@@ -267,11 +268,17 @@ def run_ours(args):
             dist.all_reduce(out)
     e1.record()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     if profiling:
         torch.cuda.cudart().cudaProfilerStop()
     launches = a.launch_count - launches0
     res = out.cpu().numpy().view(np.uint64).copy()
     kernel_ms = [s.elapsed_time(e) for s, e in k_ev]
+    if os.environ.get("PGX_DEBUG_TIMES") == "1":
+        starts = [e0.elapsed_time(s) for s, _ in k_ev]
+        print(f"[rank {rank}] kernel_ms", [round(x, 3) for x in kernel_ms[:12]], "start offsets",
+              [round(x, 3) for x in starts[:12]], file=sys.stderr, flush=True)
     if flush is not None:
         total_ms = float(np.sum(kernel_ms))  # L2-flush writes are not part of the step
     else:
