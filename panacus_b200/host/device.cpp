@@ -1,0 +1,77 @@
+// device.cpp -- RAII wrapper over the C ABI (include/panacus_b200.h).  All counting happens in
+// libpanacus_b200.so; there is no host fallback.
+#include <cmath>
+
+#include "../../include/panacus_b200.h"
+#include "panacus_host.hpp"
+
+namespace panacus {
+
+namespace {
+void check(int rc, const char *what) {
+    if (rc != PGX_OK) throw Error(std::string(what) + ": " + pgx_last_error());
+}
+pgx_abacus *H(void *p) { return static_cast<pgx_abacus *>(p); }
+}  // namespace
+
+DeviceAbacus::DeviceAbacus(uint64_t n_items, uint32_t n_groups, int device) : n_items_(n_items), n_groups_(n_groups) {
+    pgx_abacus *h = nullptr;
+    check(pgx_abacus_create(&h, device, n_items, n_groups), "pgx_abacus_create");
+    h_ = h;
+}
+
+DeviceAbacus::~DeviceAbacus() { pgx_abacus_destroy(H(h_)); }
+
+void DeviceAbacus::build(const ItemTables &t, const std::vector<std::pair<uint64_t, std::string>> &path_order,
+                         std::vector<std::string> &group_names) {
+    // group id = rank of first appearance in counting order (abacus.rs:555-569, 816-829)
+    group_names.clear();
+    const uint8_t *ex = t.exclude.empty() ? nullptr : t.exclude.data();
+    for (auto &po : path_order) {
+        if (group_names.empty() || group_names.back() != po.second) group_names.push_back(po.second);
+        const uint32_t gid = (uint32_t)group_names.size() - 1;
+        const uint64_t b = t.id_prefsum[po.first], e = t.id_prefsum[po.first + 1];
+        if (e > b) check(pgx_abacus_scatter(H(h_), t.items.data() + b, e - b, gid, ex), "pgx_abacus_scatter");
+    }
+}
+
+void DeviceAbacus::set_weights(const std::vector<uint32_t> &w) {
+    if (w.size() != n_items_ + 1) throw Error("weight vector must have n_items + 1 entries");
+    check(pgx_abacus_upload(H(h_), nullptr, 0, w.data()), "pgx_abacus_upload(weights)");
+}
+
+void DeviceAbacus::hist(std::vector<uint64_t> *count, std::vector<uint64_t> *weight, std::vector<uint32_t> *countable) {
+    if (count) count->assign(n_groups_ + 1, 0);
+    if (weight) weight->assign(n_groups_ + 1, 0);
+    if (countable) countable->assign(n_items_ + 1, 0);
+    check(pgx_hist(H(h_), count ? count->data() : nullptr, weight ? weight->data() : nullptr,
+                   countable ? countable->data() : nullptr),
+          "pgx_hist");
+}
+
+std::vector<std::vector<double>> DeviceAbacus::calc_growth(const ThresholdContainer &aux, bool weighted) {
+    const uint32_t G = n_groups_, T = (uint32_t)aux.coverage.size();
+    std::vector<uint32_t> cov(T), thr((size_t)T * G);
+    for (uint32_t t = 0; t < T; ++t) {
+        cov[t] = (uint32_t)std::max<uint64_t>(1, aux.coverage[t].to_absolute(G));  // abacus.rs:997
+        const double q = std::max(0.0, aux.quorum[t].to_relative(G));              // abacus.rs:998
+        for (uint32_t g = 0; g < G; ++g) {
+            const double need = std::ceil(((double)g + 1.0) * q);  // abacus.rs:1010, same f64 expression
+            thr[(size_t)t * G + g] = need > 0.0 ? (uint32_t)need : 0u;
+        }
+    }
+    std::vector<uint64_t> curve((size_t)T * G);
+    check(pgx_ordered_growth(H(h_), T, cov.data(), thr.data(), nullptr, weighted ? 1 : 0, curve.data()), "pgx_ordered_growth");
+    std::vector<std::vector<double>> out(T, std::vector<double>(G));
+    for (uint32_t t = 0; t < T; ++t)
+        for (uint32_t g = 0; g < G; ++g) out[t][g] = (double)curve[(size_t)t * G + g];  // exact below 2^53
+    return out;
+}
+
+void DeviceAbacus::similarity(bool weighted, std::vector<uint64_t> &inter, std::vector<uint64_t> &len) {
+    inter.assign((size_t)n_groups_ * n_groups_, 0);
+    len.assign(n_groups_, 0);
+    check(pgx_similarity(H(h_), weighted ? 1 : 0, 0, n_groups_, inter.data(), len.data()), "pgx_similarity");
+}
+
+}  // namespace panacus

@@ -1,0 +1,726 @@
+// gfa.cpp -- GFA front end, PanSN path names, grouping / ordering, subset / exclude bookkeeping.
+// Semantics follow the reference (marschall-lab/panacus @ 395ba41); every function cites what it mirrors.
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <regex>
+#include <set>
+#include <sstream>
+
+#include "panacus_host.hpp"
+
+namespace panacus {
+
+namespace {
+
+constexpr uint64_t kUsizeMax = ~0ull;
+
+// whole file into memory (transparently gunzips, like io.rs:23-33)
+std::string slurp(const std::string &path) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) throw Error("cannot open " + path);
+    std::string data;
+    std::vector<char> buf(1 << 20);
+    int n;
+    while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)n);
+    const bool bad = n < 0;
+    gzclose(f);
+    if (bad) throw Error("read error in " + path);
+    return data;
+}
+
+std::vector<std::string> split(const std::string &s, char sep) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    for (;;) {
+        const size_t j = s.find(sep, i);
+        if (j == std::string::npos) {
+            out.push_back(s.substr(i));
+            break;
+        }
+        out.push_back(s.substr(i, j - i));
+        i = j + 1;
+    }
+    return out;
+}
+
+bool all_digits(const std::string &s) { return !s.empty() && std::all_of(s.begin(), s.end(), [](char c) { return c >= '0' && c <= '9'; }); }
+
+// ^(.+):([0-9]+)-([0-9]+)$  (graph.rs:17)
+bool match_coords(const std::string &s, std::string &name, uint64_t &a, uint64_t &b) {
+    const size_t colon = s.rfind(':');
+    if (colon == std::string::npos || colon == 0) return false;
+    const std::string tail = s.substr(colon + 1);
+    const size_t dash = tail.find('-');
+    if (dash == std::string::npos) return false;
+    const std::string x = tail.substr(0, dash), y = tail.substr(dash + 1);
+    if (!all_digits(x) || !all_digits(y)) return false;
+    name = s.substr(0, colon);
+    a = std::stoull(x);
+    b = std::stoull(y);
+    return true;
+}
+
+// ^([^#]+)(#[^#]+)?(#[^#].*)?$  (graph.rs:16) -> the matched groups, or empty if no match
+std::vector<std::string> match_pansn(const std::string &s) {
+    std::vector<std::string> segs;
+    size_t i = 0;
+    while (i < s.size() && s[i] != '#') ++i;
+    if (i == 0) return {};
+    segs.push_back(s.substr(0, i));
+    if (i == s.size()) return segs;
+    // group 2: '#' + one or more non-'#'
+    size_t j = i + 1;
+    while (j < s.size() && s[j] != '#') ++j;
+    if (j == i + 1) return {};  // "##" or trailing '#': neither group 2 nor group 3 can start here
+    segs.push_back(s.substr(i, j - i));
+    if (j == s.size()) return segs;
+    // group 3: '#' + a non-'#' + anything
+    if (j + 1 >= s.size() || s[j + 1] == '#') return {};
+    segs.push_back(s.substr(j));
+    return segs;
+}
+
+void merge_intervals(std::vector<std::pair<uint64_t, uint64_t>> &v) {
+    std::sort(v.begin(), v.end());
+    size_t i = 1;
+    while (i < v.size()) {
+        if (v[i - 1].second >= v[i].first) {
+            v[i - 1].second = std::max(v[i - 1].second, v[i].second);
+            v.erase(v.begin() + (long)i);
+        } else {
+            ++i;
+        }
+    }
+}
+
+using Intervals = std::vector<std::pair<uint64_t, uint64_t>>;
+
+bool intersects(const Intervals &v, std::pair<uint64_t, uint64_t> el) {  // util.rs:370-383
+    for (auto &iv : v)
+        if (iv.first <= el.second && iv.second >= el.first) return true;
+    return false;
+}
+bool is_contained(const Intervals &v, std::pair<uint64_t, uint64_t> el) {  // util.rs:385-398
+    for (auto &iv : v)
+        if (iv.first <= el.first && iv.second >= el.second) return true;
+    return false;
+}
+
+struct IntervalContainer {  // util.rs:199-310
+    std::map<uint64_t, Intervals> map;
+    void add(uint64_t id, uint64_t a, uint64_t b) {
+        auto &v = map[id];
+        v.emplace_back(a, b);
+        merge_intervals(v);
+    }
+    const Intervals *get(uint64_t id) const {
+        auto it = map.find(id);
+        return it == map.end() ? nullptr : &it->second;
+    }
+    bool contains(uint64_t id) const { return map.count(id) != 0; }
+    void remove(uint64_t id) { map.erase(id); }
+    uint64_t total_coverage(uint64_t id, const Intervals *exclude) const {  // util.rs:257-298 (wrapping usize)
+        const Intervals *iv = get(id);
+        if (!iv) return 0;
+        uint64_t res = 0;
+        if (!exclude) {
+            for (auto &x : *iv) res += x.second - x.first;
+            return res;
+        }
+        size_t i = 0;
+        for (auto &x : *iv) {
+            const uint64_t start = x.first, end = x.second;
+            while (i < exclude->size() && (*exclude)[i].second <= start) ++i;
+            if (i < exclude->size() && (*exclude)[i].first < end) {
+                res += std::min((*exclude)[i].first - 1, end) - start;
+                if ((*exclude)[i].second < end) res += end - (*exclude)[i].second + 1;
+            } else {
+                res += end - start;
+            }
+        }
+        return res;
+    }
+};
+
+struct ActiveTable {  // util.rs:117-197
+    std::vector<uint8_t> items;
+    bool with_annotation;
+    IntervalContainer annotation;
+    ActiveTable(size_t n, bool ann) : items(n, 0), with_annotation(ann) {}
+    void activate(uint64_t id) { items[id] = 1; }
+    void activate_n_annotate(uint64_t id, uint64_t item_len, uint64_t start, uint64_t end) {
+        if (end - start == item_len) {
+            items[id] = 1;
+            annotation.remove(id);
+        } else {
+            if (start <= end) annotation.add(id, start, end);
+            const Intervals *iv = annotation.get(id);
+            if (iv && !iv->empty() && (*iv)[0] == std::make_pair<uint64_t, uint64_t>(0, (uint64_t)item_len)) {
+                annotation.remove(id);
+                items[id] = 1;
+            }
+        }
+    }
+    Intervals get_active_intervals(uint64_t id, uint64_t item_len) const {
+        if (items[id]) return {{0, item_len}};
+        if (with_annotation) {
+            const Intervals *iv = annotation.get(id);
+            if (iv) return *iv;
+        }
+        return {};
+    }
+};
+
+std::map<std::string, Intervals> build_subpath_map(const std::vector<PathSegment> &segs) {  // abacus.rs:354-383
+    std::map<std::string, std::set<std::pair<uint64_t, uint64_t>>> tmp;
+    for (auto &x : segs) {
+        auto c = x.coords();
+        tmp[x.id()].insert(c ? *c : std::make_pair<uint64_t, uint64_t>(0, (uint64_t)kUsizeMax));
+    }
+    std::map<std::string, Intervals> out;
+    for (auto &kv : tmp) {
+        Intervals v(kv.second.begin(), kv.second.end());
+        merge_intervals(v);
+        out[kv.first] = v;
+    }
+    return out;
+}
+
+std::tuple<uint32_t, bool, uint32_t, bool> canonical_edge(uint32_t u, bool f1, uint32_t v, bool f2) {  // graph.rs:142-148
+    if (u > v || (u == v && !f1)) return {v, !f2, u, !f1};
+    return {u, f1, v, f2};
+}
+
+}  // namespace
+
+// ---- CountType / PathSegment ---------------------------------------------------------------------------
+
+std::string to_string(CountType c) {
+    switch (c) {
+        case CountType::Node: return "node";
+        case CountType::Bp: return "bp";
+        case CountType::Edge: return "edge";
+        default: return "all";
+    }
+}
+
+CountType count_type_from_str(const std::string &s0) {
+    std::string s = s0;
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    if (s == "node") return CountType::Node;
+    if (s == "bp") return CountType::Bp;
+    if (s == "edge") return CountType::Edge;
+    if (s == "all") return CountType::All;
+    throw Error("invalid count type '" + s0 + "' (expected node, bp, edge or all)");
+}
+
+PathSegment PathSegment::from_str(const std::string &s) {  // graph.rs:495-549
+    PathSegment p;
+    p.sample = s;
+    const std::vector<std::string> segs = match_pansn(s);
+    std::string name;
+    uint64_t a, b;
+    if (segs.size() == 3) {
+        p.sample = segs[0];
+        p.haplotype = segs[1].substr(1);
+        const std::string rest = segs[2].substr(1);
+        if (match_coords(rest, name, a, b)) {
+            p.seqid = name;
+            p.start = a;
+            p.end = b;
+        } else {
+            p.seqid = rest;
+        }
+    } else if (segs.size() == 2) {
+        p.sample = segs[0];
+        const std::string rest = segs[1].substr(1);
+        if (match_coords(rest, name, a, b)) {
+            p.haplotype = name;
+            p.start = a;
+            p.end = b;
+        } else {
+            p.haplotype = rest;
+        }
+    } else if (segs.size() == 1) {
+        if (match_coords(segs[0], name, a, b)) {
+            p.sample = name;
+            p.start = a;
+            p.end = b;
+        }
+    }
+    return p;
+}
+
+PathSegment PathSegment::from_str_start_end(const std::string &s, uint64_t a, uint64_t b) {
+    PathSegment p = from_str(s);
+    p.start = a;
+    p.end = b;
+    return p;
+}
+
+std::string PathSegment::id() const {  // graph.rs:558-579
+    if (haplotype) return sample + "#" + *haplotype + (seqid ? "#" + *seqid : "");
+    if (seqid) return sample + "#*#" + *seqid;
+    return sample;
+}
+
+PathSegment PathSegment::clear_coords() const {
+    PathSegment p = *this;
+    p.start.reset();
+    p.end.reset();
+    return p;
+}
+
+std::optional<std::pair<uint64_t, uint64_t>> PathSegment::coords() const {
+    if (start && end) return std::make_pair(*start, *end);
+    return std::nullopt;
+}
+
+std::string PathSegment::to_string() const {
+    auto c = coords();
+    if (c) return id() + ":" + std::to_string(c->first) + "-" + std::to_string(c->second);
+    return id();
+}
+
+bool PathSegment::operator<(const PathSegment &o) const {
+    return std::tie(sample, haplotype, seqid, start, end) < std::tie(o.sample, o.haplotype, o.seqid, o.start, o.end);
+}
+bool PathSegment::operator==(const PathSegment &o) const {
+    return std::tie(sample, haplotype, seqid, start, end) == std::tie(o.sample, o.haplotype, o.seqid, o.start, o.end);
+}
+
+// ---- GraphStorage::from_gfa (graph.rs:195-375, util.rs:368-410, 916-931, 1093-1142) ---------------------------
+
+GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges) {
+    GraphStorage g;
+    g.node_lens.push_back(0);
+    g.has_edges = with_edges;
+    const std::string data = slurp(path);
+    std::vector<std::pair<size_t, size_t>> lines;  // [begin, end) without the newline
+    for (size_t i = 0; i < data.size();) {
+        size_t j = data.find('\n', i);
+        if (j == std::string::npos) j = data.size();
+        if (j > i) lines.emplace_back(i, j);
+        i = j + 1;
+    }
+    auto field = [&](size_t b, size_t e, int k, size_t &fb, size_t &fe) -> bool {  // k-th TAB separated field
+        size_t s = b;
+        for (int c = 0; c < k; ++c) {
+            const void *t = memchr(data.data() + s, '\t', e - s);
+            if (!t) return false;
+            s = (size_t)((const char *)t - data.data()) + 1;
+        }
+        const void *t = memchr(data.data() + s, '\t', e - s);
+        fb = s;
+        fe = t ? (size_t)((const char *)t - data.data()) : e;
+        while (fe > fb && data[fe - 1] == '\r') --fe;
+        return true;
+    };
+    // pass 1: segments and path names (graph.rs:308-375)
+    for (auto &ln : lines) {
+        const char tag = data[ln.first];
+        size_t fb, fe;
+        if (tag == 'S') {
+            if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed S line");
+            std::string name = data.substr(fb, fe - fb);
+            if (g.node2id.count(name)) throw Error("Segment with ID " + name + " occurs multiple times in GFA");
+            g.node2id.emplace(std::move(name), (uint32_t)g.node2id.size() + 1);
+            size_t sb, se;
+            uint32_t len = 0;
+            if (field(ln.first, ln.second, 2, sb, se)) len = (uint32_t)(se - sb);
+            g.node_lens.push_back(len);
+        } else if (tag == 'P') {
+            if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed P line");
+            g.path_segments.push_back(PathSegment::from_str(data.substr(fb, fe - fb)));
+        } else if (tag == 'W') {
+            std::string f[6];
+            for (int k = 1; k <= 5; ++k) {
+                if (!field(ln.first, ln.second, k, fb, fe)) throw Error("malformed W line");
+                f[k] = data.substr(fb, fe - fb);
+            }
+            PathSegment p;  // util.rs:368-398
+            p.sample = f[1];
+            p.haplotype = f[2];
+            p.seqid = f[3];
+            if (f[4] != "*") p.start = std::stoull(f[4]);
+            if (f[5] != "*") p.end = std::stoull(f[5]);
+            g.path_segments.push_back(p);
+        }
+    }
+    auto node_id = [&](size_t b, size_t e) -> uint32_t {
+        auto it = g.node2id.find(data.substr(b, e - b));
+        if (it == g.node2id.end()) throw Error("unknown node " + data.substr(b, e - b));
+        return it->second;
+    };
+    // pass 1b: links (graph.rs:276-306)
+    if (with_edges) {
+        for (auto &ln : lines) {
+            if (data[ln.first] != 'L') continue;
+            size_t b1, e1, b2, e2, b3, e3, b4, e4;
+            if (!field(ln.first, ln.second, 1, b1, e1) || !field(ln.first, ln.second, 2, b2, e2) ||
+                !field(ln.first, ln.second, 3, b3, e3) || !field(ln.first, ln.second, 4, b4, e4))
+                throw Error("malformed L line");
+            auto e = canonical_edge(node_id(b1, e1), data[b2] == '+', node_id(b3, e3), data[b4] == '+');
+            if (!g.edge2id.count(e)) g.edge2id.emplace(e, (uint32_t)g.edge2id.size() + 1);
+        }
+    }
+    // pass 2: steps
+    for (auto &ln : lines) {
+        const char tag = data[ln.first];
+        size_t fb, fe;
+        if (tag == 'P') {
+            if (!field(ln.first, ln.second, 2, fb, fe)) throw Error("malformed P line");
+            std::vector<Step> steps;
+            size_t s = fb;
+            while (s < fe) {
+                const void *t = memchr(data.data() + s, ',', fe - s);
+                const size_t e = t ? (size_t)((const char *)t - data.data()) : fe;
+                if (e > s) steps.push_back({node_id(s, e - 1), data[e - 1] == '+'});
+                s = e + 1;
+            }
+            g.path_steps.push_back(std::move(steps));
+        } else if (tag == 'W') {
+            if (!field(ln.first, ln.second, 6, fb, fe)) throw Error("malformed W line");
+            std::vector<Step> steps;
+            size_t s = fb;
+            while (s < fe) {
+                const bool fwd = data[s] == '>';
+                size_t e = s + 1;
+                while (e < fe && data[e] != '>' && data[e] != '<') ++e;
+                if (e > s + 1) steps.push_back({node_id(s + 1, e), fwd});
+                s = e;
+            }
+            g.path_steps.push_back(std::move(steps));
+        }
+    }
+    return g;
+}
+
+// ---- BED / group files (io.rs:35-147) ------------------------------------------------------------------------------
+
+std::vector<PathSegment> parse_bed_to_path_segments(const std::string &path, bool use_block_info) {
+    std::ifstream in(path);
+    if (!in) throw Error("cannot open " + path);
+    std::vector<PathSegment> segs;
+    std::string line;
+    size_t i = 0;
+    while (std::getline(in, line)) {
+        ++i;
+        while (!line.empty() && (line.back() == '\r')) line.pop_back();
+        if (line.empty()) continue;
+        const std::vector<std::string> f = split(line, '\t');
+        const std::string &name = f[0];
+        if (name.rfind("browser ", 0) == 0 || name.rfind("track ", 0) == 0 || name[0] == '#') continue;
+        if (f.size() == 1) {
+            segs.push_back(PathSegment::from_str(name));
+        } else if (f.size() >= 3) {
+            const uint64_t start = std::stoull(f[1]), end = std::stoull(f[2]);
+            if (use_block_info && f.size() == 12) {
+                std::vector<uint64_t> sizes, starts;
+                for (auto &s : split(f[10], ','))
+                    if (all_digits(s)) sizes.push_back(std::stoull(s));
+                for (auto &s : split(f[11], ','))
+                    if (all_digits(s)) starts.push_back(std::stoull(s));
+                for (size_t k = 0; k < std::min(sizes.size(), starts.size()); ++k)
+                    segs.push_back(PathSegment::from_str_start_end(name, start + starts[k], start + starts[k] + sizes[k]));
+            } else {
+                segs.push_back(PathSegment::from_str_start_end(name, start, end));
+            }
+        } else {
+            throw Error("error in line " + std::to_string(i) + ": row must have either 1, 3, or 12 columns, but has 2");
+        }
+    }
+    return segs;
+}
+
+// ---- GraphMask ------------------------------------------------------------------------------------------------------
+
+namespace {
+
+std::map<PathSegment, std::string> load_groups(const GraphStorage &g, const GraphMaskParameters &p) {  // abacus.rs:242-308
+    std::map<PathSegment, std::string> res;
+    if (p.groupby_haplotype) {
+        for (auto &x : g.path_segments) res[x.clear_coords()] = x.sample + "#" + (x.haplotype ? *x.haplotype : "");
+        return res;
+    }
+    if (p.groupby_sample) {
+        for (auto &x : g.path_segments) res[x.clear_coords()] = x.sample;
+        return res;
+    }
+    if (!p.groupby.empty()) {
+        std::ifstream in(p.groupby);
+        if (!in) throw Error("cannot open " + p.groupby);
+        std::string line;
+        size_t i = 0;
+        while (std::getline(in, line)) {
+            ++i;
+            while (!line.empty() && line.back() == '\r') line.pop_back();
+            if (line.empty()) continue;
+            const auto cols = split(line, '\t');
+            if (cols.size() != 2) throw Error("error in line " + std::to_string(i) + ": table must have exactly two columns");
+            const PathSegment seg = PathSegment::from_str(cols[0]).clear_coords();
+            auto it = res.find(seg);
+            if (it != res.end() && it->second != cols[1])
+                throw Error("error in line " + std::to_string(i) + ": path " + seg.to_string() + " cannot be assigned to more than one group");
+            res.emplace(seg, cols[1]);
+        }
+        for (auto &x : g.path_segments) res.emplace(x.clear_coords(), x.id());
+        return res;
+    }
+    for (auto &x : g.path_segments) res[x.clear_coords()] = x.id();
+    return res;
+}
+
+std::optional<std::vector<PathSegment>> load_coord_list(const std::string &text, const std::vector<PathSegment> &paths) {
+    // abacus.rs:212-240: a file (BED / 1-column list) or, failing that, a regex over the path names
+    if (text.empty()) return std::nullopt;
+    std::ifstream probe(text);
+    if (probe.good()) return parse_bed_to_path_segments(text, true);
+    std::regex rx(text);
+    std::vector<PathSegment> out;
+    for (auto &p : paths)
+        if (std::regex_search(p.to_string(), rx)) out.push_back(p);
+    return out;
+}
+
+std::optional<std::vector<PathSegment>> complement_with_group_assignments(
+    const std::optional<std::vector<PathSegment>> &coords, const std::map<PathSegment, std::string> &groups) {  // abacus.rs:152-201
+    if (!coords) return std::nullopt;
+    std::map<std::string, std::vector<PathSegment>> group2paths;
+    for (auto &kv : groups) group2paths[kv.second].push_back(kv.first);
+    std::vector<PathSegment> out;
+    for (auto &p : *coords) {
+        if (groups.count(p.clear_coords())) {
+            out.push_back(p);
+        } else {
+            auto it = group2paths.find(p.id());
+            if (it != group2paths.end()) {
+                if (p.coords())
+                    throw Error("invalid coordinate \"" + p.to_string() + "\": group identifiers are not allowed to have start/stop information!");
+                out.insert(out.end(), it->second.begin(), it->second.end());
+            }
+            // unknown path / group: dropped (the reference only logs)
+        }
+    }
+    return out;
+}
+
+}  // namespace
+
+GraphMask GraphMask::from_graph(const GraphStorage &g, const GraphMaskParameters &p) {
+    GraphMask m;
+    m.groups = load_groups(g, p);
+    m.include_coords = complement_with_group_assignments(load_coord_list(p.positive_list, g.path_segments), m.groups);
+    m.exclude_coords = complement_with_group_assignments(load_coord_list(p.negative_list, g.path_segments), m.groups);
+    if (p.order && !p.order->empty()) {
+        m.order = complement_with_group_assignments(parse_bed_to_path_segments(*p.order, true), m.groups);
+        if (m.order && !m.order->empty()) {  // groups must not be fragmented (abacus.rs:114-127)
+            std::set<std::string> visited;
+            std::string cur = m.groups.at((*m.order)[0].clear_coords());
+            for (auto &seg : *m.order) {
+                const std::string &grp = m.groups.at(seg.clear_coords());
+                if (cur != grp && !visited.insert(grp).second)
+                    throw Error("order of paths contains fragmented groups: path " + seg.to_string() +
+                                " belongs to group that is interspersed by one or more other groups");
+                cur = grp;
+            }
+        }
+    }
+    return m;
+}
+
+std::vector<std::pair<uint64_t, std::string>> GraphMask::get_path_order(const std::vector<PathSegment> &paths) const {
+    // abacus.rs:310-347: all paths of a group are emitted together at the group's first position
+    std::map<std::string, std::vector<std::pair<uint64_t, std::string>>> group_to_paths;
+    for (size_t i = 0; i < paths.size(); ++i) {
+        const std::string &grp = groups.at(paths[i].clear_coords());
+        group_to_paths[grp].emplace_back((uint64_t)i, grp);
+    }
+    std::vector<PathSegment> ord;
+    if (order) {
+        ord = *order;
+    } else if (include_coords) {
+        ord = *include_coords;
+    } else {
+        std::set<PathSegment> ex;
+        if (exclude_coords) ex.insert(exclude_coords->begin(), exclude_coords->end());
+        for (auto &p : paths)
+            if (!ex.count(p)) ord.push_back(p);
+    }
+    std::vector<std::pair<uint64_t, std::string>> out;
+    for (auto &p : ord) {
+        auto git = groups.find(p.clear_coords());
+        if (git == groups.end()) continue;
+        auto it = group_to_paths.find(git->second);
+        if (it == group_to_paths.end()) continue;
+        out.insert(out.end(), it->second.begin(), it->second.end());
+        group_to_paths.erase(it);
+    }
+    return out;
+}
+
+// ---- ItemTable construction (graph_broker/util.rs:208-366, 569-790, 1186-1248; abacus.rs:1187-1229) ------------------
+
+namespace {
+
+void update_tables(const GraphStorage &g, const std::vector<Step> &steps, const Intervals &include, const Intervals &exclude,
+                   uint64_t offset, std::vector<uint64_t> &items, IntervalContainer *subset_covered, ActiveTable *exclude_table) {
+    // graph_broker/util.rs:569-721
+    size_t i = 0, j = 0;
+    uint64_t p = offset;
+    for (auto &st : steps) {
+        const uint64_t sid = st.node, l = g.node_lens[sid];
+        bool stop_here = false;
+        while (i < include.size() && include[i].first < p + l && !stop_here) {
+            if (include[i].second > p) {
+                uint64_t a = include[i].first > p ? include[i].first - p : 0, b;
+                if (include[i].second < p + l) {
+                    ++i;
+                    b = include[i - 1].second - p;
+                } else {
+                    stop_here = true;
+                    b = l;
+                }
+                if (!st.forward) {
+                    const uint64_t na = l - b, nb = l - a;
+                    a = na;
+                    b = nb;
+                }
+                items.push_back(sid);
+                if (subset_covered) {
+                    if (b - a == l) {
+                        if (subset_covered->contains(sid)) subset_covered->remove(sid);
+                    } else {
+                        subset_covered->add(sid, a, b);
+                    }
+                }
+            } else {
+                ++i;
+            }
+        }
+        stop_here = false;
+        while (j < exclude.size() && exclude[j].first < p + l && !stop_here) {
+            if (exclude[j].second > p) {
+                uint64_t a = exclude[j].first > p ? exclude[j].first - p : 0, b;
+                if (exclude[j].second < p + l) {
+                    ++j;
+                    b = exclude[j - 1].second - p;
+                } else {
+                    stop_here = true;
+                    b = l;
+                }
+                if (!st.forward) {
+                    const uint64_t na = l - b, nb = l - a;
+                    a = na;
+                    b = nb;
+                }
+                if (exclude_table) {
+                    if (exclude_table->with_annotation)
+                        exclude_table->activate_n_annotate(sid, l, a, b);
+                    else
+                        exclude_table->activate(sid);
+                }
+            } else {
+                ++j;
+            }
+        }
+        if (i >= include.size() && j >= exclude.size()) break;
+        p += l;
+    }
+}
+
+void update_tables_edgecount(const GraphStorage &g, const std::vector<Step> &steps, const Intervals &include,
+                             const Intervals &exclude, uint64_t offset, std::vector<uint64_t> &items, ActiveTable *exclude_table) {
+    // graph_broker/util.rs:723-790
+    size_t i = 0, j = 0;
+    uint64_t p = offset;
+    if (!steps.empty()) p += g.node_lens[steps[0].node];
+    for (size_t k = 0; k + 1 < steps.size(); ++k) {
+        const Step &s1 = steps[k], &s2 = steps[k + 1];
+        while (i < include.size() && include[i].second <= p) ++i;
+        while (j < exclude.size() && exclude[j].second <= p) ++j;
+        const uint64_t l = g.node_lens[s2.node];
+        auto it = g.edge2id.find(canonical_edge(s1.node, s1.forward, s2.node, s2.forward));
+        if (it == g.edge2id.end()) throw Error("path uses an edge that has no L line");
+        const uint64_t eid = it->second;
+        if (i < include.size() && include[i].first < p + l) items.push_back(eid);
+        if (exclude_table && j < exclude.size() && exclude[j].first < p + l)
+            exclude_table->activate(eid);
+        else if (i >= include.size() && j >= exclude.size())
+            break;
+        p += l;
+    }
+}
+
+}  // namespace
+
+ItemTables build_item_tables(const GraphStorage &g, const GraphMask &mask, CountType count) {
+    ItemTables t;
+    const bool edge = count == CountType::Edge;
+    t.n_items = edge ? g.edge_count() : g.node_count();
+    std::optional<IntervalContainer> subset_covered;
+    if (count == CountType::Bp && mask.include_coords) subset_covered.emplace();
+    std::optional<ActiveTable> exclude_table;
+    if (mask.exclude_coords) exclude_table.emplace(t.n_items + 1, count == CountType::Bp);
+    std::map<std::string, Intervals> include_map, exclude_map;
+    if (mask.include_coords) include_map = build_subpath_map(*mask.include_coords);
+    if (mask.exclude_coords) exclude_map = build_subpath_map(*mask.exclude_coords);
+    const Intervals complete = {{0, kUsizeMax}}, none = {};
+    t.id_prefsum.push_back(0);
+    for (size_t pi = 0; pi < g.path_segments.size(); ++pi) {
+        const PathSegment &seg = g.path_segments[pi];
+        const std::vector<Step> &steps = g.path_steps[pi];
+        const Intervals *inc = &complete, *exc = &none;
+        if (mask.include_coords) {
+            auto it = include_map.find(seg.id());
+            inc = it == include_map.end() ? &none : &it->second;
+        }
+        if (mask.exclude_coords) {
+            auto it = exclude_map.find(seg.id());
+            exc = it == exclude_map.end() ? &none : &it->second;
+        }
+        const auto c = seg.coords();
+        const uint64_t start = c ? c->first : 0, end = c ? c->second : kUsizeMax;
+        if (mask.include_coords && !intersects(*inc, {start, end}) && !intersects(*exc, {start, end})) {
+            t.id_prefsum.push_back(t.items.size());  // path neither subset nor excluded: skipped (util.rs:276-291)
+            continue;
+        }
+        if (!edge && (!mask.include_coords || is_contained(*inc, {start, end})) &&
+            (!mask.exclude_coords || is_contained(*exc, {start, end}))) {
+            // parse_path_seq_update_tables (util.rs:1186-1248): every step counts; if the path is on the
+            // exclude list, all of its items are flagged
+            const size_t first = t.items.size();
+            for (auto &s : steps) t.items.push_back(s.node);
+            if (!exc->empty() && exclude_table)
+                for (size_t k = first; k < t.items.size(); ++k) exclude_table->items[t.items[k]] = 1;
+        } else if (edge) {
+            update_tables_edgecount(g, steps, *inc, *exc, start, t.items, exclude_table ? &*exclude_table : nullptr);
+        } else {
+            update_tables(g, steps, *inc, *exc, start, t.items, subset_covered ? &*subset_covered : nullptr,
+                          exclude_table ? &*exclude_table : nullptr);
+        }
+        t.id_prefsum.push_back(t.items.size());
+    }
+    if (subset_covered) {  // quantify_uncovered_bps, abacus.rs:1187-1229
+        for (auto &kv : subset_covered->map) {
+            const uint64_t sid = kv.first;
+            if (exclude_table && exclude_table->items[sid]) continue;
+            const uint64_t l = g.node_lens[sid];
+            uint64_t covered;
+            if (exclude_table) {
+                const Intervals ex = exclude_table->get_active_intervals(sid, l);
+                covered = subset_covered->total_coverage(sid, &ex);
+            } else {
+                covered = subset_covered->total_coverage(sid, nullptr);
+            }
+            if (covered <= l) t.uncovered_bps[sid] = l - covered;
+        }
+    }
+    if (exclude_table) t.exclude = exclude_table->items;
+    return t;
+}
+
+}  // namespace panacus

@@ -1,0 +1,373 @@
+// main.cpp -- `panacus` command line for the hot-path subcommands, with the reference's flags:
+//   hist | growth | histgrowth | ordered-histgrowth | similarity
+// (src/commands/{hist,growth,histgrowth,ordered_histgrowth,similarity}.rs).  Counting runs on the GPU
+// through libpanacus_b200.so; parsing, grouping, thresholds, closed-form growth and TSV stay here.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <set>
+
+#include "panacus_host.hpp"
+
+using namespace panacus;
+
+namespace {
+
+struct Args {
+    std::string sub;
+    std::vector<std::string> positional;
+    std::map<std::string, std::string> opt;  // long name -> value ("1" for flags)
+    bool has(const std::string &k) const { return opt.count(k) != 0; }
+    std::string get(const std::string &k, const std::string &dflt = "") const {
+        auto it = opt.find(k);
+        return it == opt.end() ? dflt : it->second;
+    }
+};
+
+const std::map<char, std::string> kShort = {{'s', "subset"},  {'e', "exclude"},  {'g', "groupby"}, {'H', "groupby-haplotype"},
+                                             {'S', "groupby-sample"}, {'c', "count"}, {'l', "coverage"}, {'q', "quorum"},
+                                             {'a', "hist"},    {'O', "order"},    {'m', "method"},  {'t', "threads"},
+                                             {'v', "verbose"}};
+const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total"};
+
+Args parse_args(int argc, char **argv) {
+    Args a;
+    for (int i = 1; i < argc; ++i) {
+        std::string tok = argv[i];
+        std::string name, value;
+        bool have_value = false;
+        if (tok.rfind("--", 0) == 0) {
+            const size_t eq = tok.find('=');
+            name = tok.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+            if (eq != std::string::npos) {
+                value = tok.substr(eq + 1);
+                have_value = true;
+            }
+        } else if (tok.size() >= 2 && tok[0] == '-' && !(tok[1] >= '0' && tok[1] <= '9')) {
+            auto it = kShort.find(tok[1]);
+            if (it == kShort.end()) throw Error("unknown option " + tok);
+            name = it->second;
+            if (tok.size() > 2) {
+                if (kFlags.count(name)) {  // bundled flags, e.g. -SH
+                    a.opt[name] = "1";
+                    for (size_t k = 2; k < tok.size(); ++k) {
+                        auto jt = kShort.find(tok[k]);
+                        if (jt == kShort.end() || !kFlags.count(jt->second)) throw Error("unknown option in " + tok);
+                        a.opt[jt->second] = "1";
+                    }
+                    continue;
+                }
+                value = tok.substr(2);
+                have_value = true;
+            }
+        } else {
+            if (a.sub.empty())
+                a.sub = tok;
+            else
+                a.positional.push_back(tok);
+            continue;
+        }
+        if (kFlags.count(name)) {
+            a.opt[name] = "1";
+        } else {
+            if (!have_value) {
+                if (i + 1 >= argc) throw Error("option --" + name + " needs a value");
+                value = argv[++i];
+            }
+            a.opt[name] = value;
+        }
+    }
+    return a;
+}
+
+std::string argv_joined(int argc, char **argv) {
+    std::string s;
+    for (int i = 0; i < argc; ++i) {
+        if (i) s += ' ';
+        s += argv[i];
+    }
+    return s;
+}
+
+struct Run {
+    GraphStorage graph;
+    GraphMask mask;
+    std::vector<std::pair<uint64_t, std::string>> path_order;
+};
+
+Run load(const Args &a, const std::vector<CountType> &counts, bool with_order) {
+    bool edges = false;
+    for (auto c : counts) edges = edges || c == CountType::Edge;
+    Run r;
+    r.graph = GraphStorage::from_gfa(a.positional.at(0), edges);
+    GraphMaskParameters p;
+    p.groupby = a.get("groupby");
+    p.groupby_sample = a.has("groupby-sample");  // commands/hist.rs:44-50: -S wins over -H, both over -g
+    p.groupby_haplotype = !p.groupby_sample && a.has("groupby-haplotype");
+    if (p.groupby_sample || p.groupby_haplotype) p.groupby.clear();
+    p.positive_list = a.get("subset");
+    p.negative_list = a.get("exclude");
+    if (with_order && a.has("order")) p.order = a.get("order");
+    r.mask = GraphMask::from_graph(r.graph, p);
+    r.path_order = r.mask.get_path_order(r.graph.path_segments);
+    return r;
+}
+
+std::vector<CountType> expand(CountType c) {
+    if (c == CountType::All) return {CountType::Node, CountType::Bp, CountType::Edge};
+    return {c};
+}
+
+uint32_t count_groups(const std::vector<std::pair<uint64_t, std::string>> &po) {
+    uint32_t n = 0;
+    const std::string *last = nullptr;
+    for (auto &x : po) {
+        if (!last || *last != x.second) ++n;
+        last = &x.second;
+    }
+    return n;
+}
+
+// builds the device abacus for one count type; returns the group names in counting order
+std::unique_ptr<DeviceAbacus> make_abacus(const Run &r, CountType c, ItemTables &t, std::vector<std::string> &groups) {
+    t = build_item_tables(r.graph, r.mask, c);
+    const uint32_t G = count_groups(r.path_order);
+    if (G == 0) throw Error("no path left to count (check --subset / --exclude)");
+    auto ab = std::make_unique<DeviceAbacus>(t.n_items, G);
+    ab->build(t, r.path_order, groups);
+    return ab;
+}
+
+// Hist::from_abacus (graph_broker/hist.rs:39-49): coverage histogram of one count type
+Hist device_hist(const Run &r, CountType c) {
+    ItemTables t;
+    std::vector<std::string> groups;
+    auto ab = make_abacus(r, c, t, groups);
+    Hist h;
+    h.count = c;
+    if (c == CountType::Bp) {
+        ab->set_weights(r.graph.node_lens);
+        std::vector<uint32_t> countable;
+        ab->hist(nullptr, &h.coverage, t.uncovered_bps.empty() ? nullptr : &countable);
+        for (auto &kv : t.uncovered_bps) {  // abacus.rs:779-785
+            h.coverage[countable[kv.first]] -= kv.second;
+            h.coverage[0] += kv.second;
+        }
+    } else {
+        ab->hist(&h.coverage, nullptr, nullptr);
+    }
+    return h;
+}
+
+std::vector<double> as_f64(const std::vector<uint64_t> &v) { return std::vector<double>(v.begin(), v.end()); }
+
+int cmd_hist(const Args &a, const std::string &cmdline) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    const auto counts = expand(count);
+    const Run r = load(a, counts, false);
+    std::vector<std::vector<std::string>> headers = {{"panacus", "count", "", ""}};
+    std::vector<std::vector<double>> cols;
+    for (auto c : counts) {
+        const Hist h = device_hist(r, c);
+        cols.push_back(as_f64(h.coverage));
+        headers.push_back({"hist", to_string(c), "", ""});
+    }
+    std::cout << write_metadata_comments(cmdline, true) << write_table(headers, cols) << "\n";
+    return 0;
+}
+
+std::string growth_table(const std::vector<Hist> &hists, const ThresholdContainer &aux, bool add_hist) {
+    // analyses/growth.rs:33-102
+    std::vector<std::vector<std::string>> headers = {{"panacus", "count", "coverage", "quorum"}};
+    std::vector<std::vector<double>> cols;
+    if (add_hist)
+        for (auto &h : hists) {
+            cols.push_back(as_f64(h.coverage));
+            headers.push_back({"hist", to_string(h.count), "", ""});
+        }
+    for (auto &h : hists) {
+        for (auto &g : h.calc_all_growths(aux)) cols.push_back(g);
+        for (size_t k = 0; k < aux.coverage.size(); ++k)
+            headers.push_back({"growth", to_string(h.count), aux.coverage[k].get_string(), aux.quorum[k].get_string()});
+    }
+    return write_table(headers, cols);
+}
+
+bool ends_with(const std::string &s, const std::string &suf) {
+    return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth) {
+    const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
+    const std::string file = a.positional.at(0);
+    if (!histgrowth && ends_with(file, ".tsv")) {  // src/lib.rs:160-190: growth from a hist table, no graph
+        if (a.has("subset") || a.has("exclude") || a.has("groupby") || a.has("groupby-sample") || a.has("groupby-haplotype"))
+            throw Error("subset, exclude and groupby can only be used in graph mode (with a .gfa or .gfa.gz file)");
+        std::vector<std::string> comments;
+        const std::vector<Hist> hists = parse_hists(file, comments);
+        for (auto &c : comments) std::cout << c << "\n";
+        std::cout << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
+        return 0;
+    }
+    // `growth <gfa>` has no --count: node (graph_broker.rs:158-160); histgrowth takes -c
+    const CountType count = histgrowth ? count_type_from_str(a.get("count", "node")) : CountType::Node;
+    const auto counts = expand(count);
+    const Run r = load(a, counts, false);
+    std::vector<Hist> hists;
+    for (auto c : counts) hists.push_back(device_hist(r, c));
+    std::cout << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
+    return 0;
+}
+
+int cmd_ordered(const Args &a, const std::string &cmdline) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    if (count == CountType::All) throw Error("ordered-histgrowth does not accept count type 'all'");
+    const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
+    const Run r = load(a, {count}, true);
+    ItemTables t;
+    std::vector<std::string> groups;
+    auto ab = make_abacus(r, count, t, groups);
+    if (count == CountType::Bp) {  // weights = node_lens - uncovered_bps (abacus.rs:1016-1023)
+        std::vector<uint32_t> w = r.graph.node_lens;
+        for (auto &kv : t.uncovered_bps) w[kv.first] = kv.second > w[kv.first] ? 0u : w[kv.first] - (uint32_t)kv.second;
+        ab->set_weights(w);
+    }
+    std::vector<std::vector<double>> cols = ab->calc_growth(aux, count == CountType::Bp);
+    for (auto &c : cols) c.insert(c.begin(), std::nan(""));  // io.rs:580-583
+    std::vector<std::vector<std::string>> headers = {{"panacus", "count", "coverage", "quorum"}};
+    for (size_t k = 0; k < aux.coverage.size(); ++k)
+        headers.push_back({"ordered-growth", to_string(count), aux.coverage[k].get_string(), aux.quorum[k].get_string()});
+    std::cout << write_metadata_comments(cmdline, true) << write_ordered_table(headers, cols, groups) << "\n";
+    return 0;
+}
+
+// ---- similarity: Jaccard + hierarchical clustering order (analyses/similarity.rs:119-254) ---------------------------
+// The reference delegates the clustering to kodama 0.3.0 (not in the tree): this is a restatement of the
+// published Lance-Williams scheme with scipy/fastcluster-style step sorting; tie-breaking is unpinned.
+struct Step2 {
+    size_t c1, c2;
+    float d;
+};
+
+std::vector<size_t> cluster_leaf_order(const std::vector<std::vector<float>> &table, const std::string &method) {
+    const size_t n = table.size();
+    std::vector<size_t> leaves;
+    if (n < 2) {
+        for (size_t i = 0; i < n; ++i) leaves.push_back(i);
+        return leaves;
+    }
+    const bool squared = method == "ward" || method == "centroid" || method == "median";
+    std::vector<std::vector<double>> D(n, std::vector<double>(n, 0.0));
+    for (size_t i = 0; i < n; ++i)
+        for (size_t j = i + 1; j < n; ++j) {
+            float s = 0.f;  // euclidean distance between rows, f32 like similarity.rs:238-244
+            for (size_t k = 0; k < n; ++k) s += std::pow(table[i][k] - table[j][k], 2.0f);
+            const float d = std::sqrt(s);
+            D[i][j] = D[j][i] = squared ? (double)d * d : (double)d;
+        }
+    std::vector<bool> active(n, true);
+    std::vector<size_t> size(n, 1), label(n);
+    for (size_t i = 0; i < n; ++i) label[i] = i;
+    std::vector<Step2> steps;
+    for (size_t it = 0; it + 1 < n; ++it) {
+        size_t bi = 0, bj = 0;
+        double best = INFINITY;
+        for (size_t i = 0; i < n; ++i)
+            if (active[i])
+                for (size_t j = i + 1; j < n; ++j)
+                    if (active[j] && D[i][j] < best) best = D[i][j], bi = i, bj = j;
+        const double ni = (double)size[bi], nj = (double)size[bj];
+        for (size_t k = 0; k < n; ++k) {
+            if (!active[k] || k == bi || k == bj) continue;
+            const double dik = D[bi][k], djk = D[bj][k], nk = (double)size[k];
+            double d;
+            if (method == "single") d = std::min(dik, djk);
+            else if (method == "complete") d = std::max(dik, djk);
+            else if (method == "average") d = (ni * dik + nj * djk) / (ni + nj);
+            else if (method == "weighted") d = 0.5 * (dik + djk);
+            else if (method == "ward") d = ((ni + nk) * dik + (nj + nk) * djk - nk * best) / (ni + nj + nk);
+            else if (method == "median") d = 0.5 * dik + 0.5 * djk - 0.25 * best;
+            else d = (ni * dik + nj * djk) / (ni + nj) - ni * nj * best / ((ni + nj) * (ni + nj));  // centroid
+            D[bj][k] = D[k][bj] = d;
+        }
+        steps.push_back({label[bi], label[bj], (float)(squared ? std::sqrt(std::max(best, 0.0)) : best)});
+        active[bi] = false;
+        size[bj] += size[bi];
+        label[bj] = n + it;
+    }
+    std::stable_sort(steps.begin(), steps.end(), [](const Step2 &x, const Step2 &y) { return x.d < y.d; });
+    for (auto &s : steps) {  // get_order_from_dendrogram, similarity.rs:206-219
+        const size_t a = std::min(s.c1, s.c2), b = std::max(s.c1, s.c2);
+        if (a < n) leaves.push_back(a);
+        if (b < n) leaves.push_back(b);
+    }
+    return leaves;
+}
+
+int cmd_similarity(const Args &a, const std::string &cmdline) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    if (count == CountType::All) throw Error("similarity does not accept count type 'all'");
+    std::string method = a.get("method", "centroid");
+    std::transform(method.begin(), method.end(), method.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    const Run r = load(a, {count}, false);
+    ItemTables t;
+    std::vector<std::string> groups;
+    auto ab = make_abacus(r, count, t, groups);
+    if (count == CountType::Bp) ab->set_weights(r.graph.node_lens);  // no uncovered_bps correction here (similarity.rs:130-150)
+    std::vector<uint64_t> inter, len;
+    ab->similarity(count == CountType::Bp, inter, len);
+    const size_t G = groups.size();
+    std::vector<std::vector<float>> table(G, std::vector<float>(G));
+    for (size_t i = 0; i < G; ++i)
+        for (size_t j = 0; j < G; ++j)  // similarity.rs:153-163
+            table[i][j] = (float)inter[i * G + j] / (float)(len[i] + len[j] - inter[i * G + j]);
+    const std::vector<size_t> order = a.has("no-cluster") ? std::vector<size_t>() : cluster_leaf_order(table, method);
+    std::vector<size_t> perm(G);
+    for (size_t i = 0; i < G; ++i) perm[i] = i;
+    if (order.size() == G) perm = order;
+    std::string out = write_metadata_comments(cmdline, true);
+    out += "group";
+    for (size_t i = 0; i < G; ++i) out += "\t" + groups[perm[i]];
+    out += "\n";
+    for (size_t i = 0; i < G; ++i) {
+        out += groups[perm[i]];
+        for (size_t j = 0; j < G; ++j) out += "\t" + format_f32(table[perm[i]][perm[j]]);
+        out += "\n";
+    }
+    std::cout << out << "\n";
+    return 0;
+}
+
+void usage() {
+    std::cerr << "panacus (B200 hot path) -- usage: panacus <hist|growth|histgrowth|ordered-histgrowth|similarity> <GFA_FILE> [options]\n"
+                 "  -s, --subset FILE   -e, --exclude FILE   -g, --groupby FILE   -H, --groupby-haplotype   -S, --groupby-sample\n"
+                 "  -c, --count node|bp|edge|all   -l, --coverage LIST   -q, --quorum LIST   -a, --hist   -O, --order FILE\n"
+                 "  -m, --method single|complete|average|weighted|ward|centroid|median (similarity)   -t, --threads N\n";
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    try {
+        const Args a = parse_args(argc, argv);
+        if (a.sub.empty() || a.positional.empty()) {
+            usage();
+            return 2;
+        }
+        const std::string cmdline = argv_joined(argc, argv);
+        if (a.sub == "hist") return cmd_hist(a, cmdline);
+        if (a.sub == "growth") return cmd_growth(a, cmdline, false);
+        if (a.sub == "histgrowth") return cmd_growth(a, cmdline, true);
+        if (a.sub == "ordered-histgrowth") return cmd_ordered(a, cmdline);
+        if (a.sub == "similarity") return cmd_similarity(a, cmdline);
+        usage();
+        return 2;
+    } catch (const std::exception &e) {
+        std::cerr << "error: " << e.what() << "\n";
+        return 1;
+    }
+}

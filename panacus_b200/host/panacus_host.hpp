@@ -1,0 +1,155 @@
+// panacus_host.hpp -- C++ host layer above the C ABI (include/panacus_b200.h).
+//
+// The reference's host code is Rust; this image has no Rust toolchain, so the host side of the
+// drop-in is C++ with the reference's names and semantics for everything the hot path needs around
+// the GPU calls: GFA front end, path grouping / ordering, subset / exclude bookkeeping, thresholds,
+// the closed-form growth formulas (f64, host only) and the TSV writers.  Reference citations are
+// relative to marschall-lab/panacus @ 395ba41.
+#pragma once
+
+#include <cstdint>
+#include <map>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+namespace panacus {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ---- src/util.rs ------------------------------------------------------------------------------------
+enum class CountType { Node, Bp, Edge, All };  // util.rs:44-49
+std::string to_string(CountType c);
+CountType count_type_from_str(const std::string &s);  // case-insensitive, like clap's ignore_case
+
+struct Threshold {  // util.rs:327-364
+    bool is_relative = false;
+    double rel = 0.0;
+    uint64_t abs = 0;
+    static Threshold Relative(double v) { return {true, v, 0}; }
+    static Threshold Absolute(uint64_t v) { return {false, 0.0, v}; }
+    uint64_t to_absolute(uint64_t n) const;  // util.rs:351-356
+    double to_relative(uint64_t n) const;    // util.rs:358-363
+    std::string get_string() const;          // util.rs:344-349
+};
+
+struct ThresholdContainer {  // graph_broker/hist.rs:207-323
+    std::vector<Threshold> coverage, quorum;
+    static ThresholdContainer parse_params(const std::string &quorum, const std::string &coverage);
+};
+
+std::string format_f64(double v);  // Rust `{}` for f64 (shortest round trip, no exponent)
+std::string format_f32(float v);   // Rust `{}` for f32
+
+// ---- src/graph_broker/graph.rs ------------------------------------------------------------------------
+struct PathSegment {  // graph.rs:469-616
+    std::string sample;
+    std::optional<std::string> haplotype, seqid;
+    std::optional<uint64_t> start, end;
+
+    static PathSegment from_str(const std::string &s);                                  // graph.rs:495-549
+    static PathSegment from_str_start_end(const std::string &s, uint64_t a, uint64_t b);  // graph.rs:551-556
+    std::string id() const;                                                             // graph.rs:558-579
+    PathSegment clear_coords() const;                                                   // graph.rs:581-589
+    std::optional<std::pair<uint64_t, uint64_t>> coords() const;
+    std::string to_string() const;  // Display: id[:start-end]
+    bool operator<(const PathSegment &o) const;
+    bool operator==(const PathSegment &o) const;
+};
+
+struct Step {
+    uint32_t node;  // item id (1-based)
+    bool forward;
+};
+
+struct GraphStorage {  // graph.rs:150-375
+    std::unordered_map<std::string, uint32_t> node2id;
+    std::vector<uint32_t> node_lens;  // [0] = 0
+    std::vector<PathSegment> path_segments;
+    std::vector<std::vector<Step>> path_steps;  // steps of every P / W line, file order
+    std::map<std::tuple<uint32_t, bool, uint32_t, bool>, uint32_t> edge2id;  // canonical edge -> id (1-based)
+    bool has_edges = false;
+
+    uint64_t node_count() const { return node2id.size(); }
+    uint64_t edge_count() const { return edge2id.size(); }
+    static GraphStorage from_gfa(const std::string &path, bool with_edges);
+};
+
+// ---- src/graph_broker/abacus.rs: GraphMask ---------------------------------------------------------------
+struct GraphMaskParameters {
+    std::string groupby;  // file
+    bool groupby_haplotype = false, groupby_sample = false;
+    std::string positive_list, negative_list;  // --subset / --exclude: file or regex
+    std::optional<std::string> order;
+};
+
+struct GraphMask {  // abacus.rs:25-383
+    std::map<PathSegment, std::string> groups;
+    std::optional<std::vector<PathSegment>> include_coords, exclude_coords, order;
+
+    static GraphMask from_graph(const GraphStorage &g, const GraphMaskParameters &p);  // abacus.rs:55-150
+    // (path index, group name) in counting order; abacus.rs:310-347
+    std::vector<std::pair<uint64_t, std::string>> get_path_order(const std::vector<PathSegment> &paths) const;
+};
+
+std::vector<PathSegment> parse_bed_to_path_segments(const std::string &path, bool use_block_info);  // io.rs:35-115
+
+// ---- ItemTable + subset / exclude bookkeeping (src/util.rs:80-310, graph_broker/util.rs:208-790) -------------
+struct ItemTables {
+    std::vector<uint64_t> items;       // ItemTable.items
+    std::vector<uint64_t> id_prefsum;  // ItemTable.id_prefsum (P + 1)
+    std::vector<uint8_t> exclude;      // ActiveTable.items (N + 1) or empty
+    std::map<uint64_t, uint64_t> uncovered_bps;  // abacus.rs:1187-1229
+    uint64_t n_items = 0;
+};
+ItemTables build_item_tables(const GraphStorage &g, const GraphMask &mask, CountType count);
+
+// ---- closed-form growth (src/graph_broker/hist.rs:21-187), f64 on the host ------------------------------------
+struct Hist {
+    CountType count = CountType::Node;
+    std::vector<uint64_t> coverage;
+    std::vector<double> calc_growth(const Threshold &t_coverage, const Threshold &t_quorum) const;  // hist.rs:51-66
+    std::vector<std::vector<double>> calc_all_growths(const ThresholdContainer &aux) const;         // hist.rs:69-87
+};
+double choose(uint64_t n, uint64_t k);  // hist.rs:21-36
+
+// ---- TSV (src/io.rs:460-604, analyses/{hist,growth,similarity}.rs) ----------------------------------------------
+std::string write_table(const std::vector<std::vector<std::string>> &headers,
+                        const std::vector<std::vector<double>> &columns, uint64_t start_index = 0);
+std::string write_ordered_table(const std::vector<std::vector<std::string>> &headers,
+                                const std::vector<std::vector<double>> &columns, const std::vector<std::string> &index);
+std::string write_metadata_comments(const std::string &argv_joined, bool with_version);
+// hist-only TSV re-ingestion for `growth <file.tsv>` (io.rs:152-290)
+std::vector<Hist> parse_hists(const std::string &path, std::vector<std::string> &comments);
+
+// ---- device side (RAII over include/panacus_b200.h) ----------------------------------------------------------
+class DeviceAbacus {
+  public:
+    DeviceAbacus(uint64_t n_items, uint32_t n_groups, int device = 0);
+    ~DeviceAbacus();
+    DeviceAbacus(const DeviceAbacus &) = delete;
+    DeviceAbacus &operator=(const DeviceAbacus &) = delete;
+
+    // a5/a6 replacement: one scatter per path in counting order
+    void build(const ItemTables &t, const std::vector<std::pair<uint64_t, std::string>> &path_order,
+               std::vector<std::string> &group_names);
+    void set_weights(const std::vector<uint32_t> &w);
+    void hist(std::vector<uint64_t> *count, std::vector<uint64_t> *weight, std::vector<uint32_t> *countable);
+    // AbacusByGroup::calc_growth for all threshold pairs (abacus.rs:989-1032); f64 like the reference
+    std::vector<std::vector<double>> calc_growth(const ThresholdContainer &aux, bool weighted);
+    void similarity(bool weighted, std::vector<uint64_t> &inter, std::vector<uint64_t> &len);
+    uint32_t n_groups() const { return n_groups_; }
+    uint64_t n_items() const { return n_items_; }
+
+  private:
+    void *h_ = nullptr;
+    uint64_t n_items_;
+    uint32_t n_groups_;
+};
+
+}  // namespace panacus

@@ -1,0 +1,212 @@
+"""The `panacus` CLI of the C++ host layer (panacus_b200/bin/panacus) against the oracle's TSV, from the
+`panacus` header row on (the comment lines carry argv, like the reference's own R check skips them,
+test/integrated_test.R:20-24)."""
+import json
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import gfa_oracle as go
+from oracle import oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+BIN = os.path.join(ROOT, "panacus_b200", "bin", "panacus")
+
+
+def run_cli(*args, expect_ok=True):
+    assert os.path.exists(BIN), "build the host layer first (__graft_entry__.build())"
+    r = subprocess.run([BIN, *args], capture_output=True, text=True, timeout=300)
+    if expect_ok:
+        assert r.returncode == 0, r.stderr
+    return r
+
+
+def body(text):
+    """drop the comment lines and the trailing blank line"""
+    lines = [l for l in text.split("\n") if not l.startswith("#")]
+    while lines and lines[-1] == "":
+        lines.pop()
+    return "\n".join(lines) + "\n"
+
+
+# ---- CPU: `growth <hist.tsv>` needs no GPU; pins the product's closed-form growth to the reference goldens ----
+
+def test_growth_from_hist_tsv_chr22_golden(tmp_path):
+    d = json.load(open(os.path.join(GOLDEN, "chr22_histgrowth.json")))
+    counts = ["bp", "node", "edge"]
+    hist_tsv = tmp_path / "chr22.hist.tsv"
+    n = len(d["hist"]["bp"]["values"])
+    with open(hist_tsv, "w") as f:
+        f.write("# panacus hist chr22 (golden, docs/chr22.hprc-v1.0-pggb.histgrowth.html:267-269)\n")
+        f.write("panacus\t" + "\t".join("hist" for _ in counts) + "\n")
+        f.write("count\t" + "\t".join(counts) + "\n")
+        f.write("\t" * len(counts) + "\n" + "\t" * len(counts) + "\n")
+        for i in range(n):
+            f.write(str(i) + "\t" + "\t".join(str(d["hist"][c]["values"][i]) for c in counts) + "\n")
+    g = d["growth"]["bp"]
+    cov = ",".join(str(int(c)) for c in g["coverage"])
+    quo = ",".join(repr(float(q)) if float(q) not in (0.0, 1.0) else str(int(q)) for q in g["quorum"])
+    out = run_cli("growth", str(hist_tsv), "-l", cov, "-q", quo).stdout
+    rows = [l.split("\t") for l in body(out).strip().split("\n")]
+    assert rows[0][0] == "panacus" and rows[1][0] == "count"
+    T = len(g["coverage"])
+    for ci, c in enumerate(counts):
+        for t in range(T):
+            col = 1 + ci * T + t
+            assert rows[0][col] == "growth" and rows[1][col] == c
+            got = [r[col] for r in rows[4:]]
+            assert got[0] == "NaN"
+            assert [int(x) for x in got[1:]] == [int(v) for v in d["growth"][c]["curves"][t]], (c, t)
+    # the comment lines of the input table are carried over, then "# argv" (growth.rs:40-51)
+    assert out.startswith("# panacus hist chr22")
+
+
+def test_growth_from_hist_tsv_matches_oracle_table():
+    out = run_cli("growth", os.path.join(GOLDEN, "t_groups.hist.tsv"), "-q", "0,0.5,1", "-l", "1,1,2", "-a").stdout
+    cov, quo = po.parse_thresholds("0,0.5,1", "1,1,2")
+    assert body(out) == po.growth_table([("node", [5, 0, 10, 0, 0, 0, 0])], cov, quo, add_hist=True)
+
+
+def test_cli_errors():
+    r = run_cli("growth", os.path.join(GOLDEN, "t_groups.hist.tsv"), "-q", "1.5", expect_ok=False)
+    assert r.returncode != 0 and "within [0,1]" in r.stderr
+    r = run_cli("growth", os.path.join(GOLDEN, "t_groups.hist.tsv"), "-q", "0,0.5", "-l", "1,2,3", expect_ok=False)
+    assert r.returncode != 0 and "must match" in r.stderr
+    r = run_cli("growth", os.path.join(GOLDEN, "t_groups.hist.tsv"), "-S", expect_ok=False)
+    assert r.returncode != 0 and "graph mode" in r.stderr
+    r = run_cli("frobnicate", "x", expect_ok=False)
+    assert r.returncode == 2
+
+
+# ---- GPU: full subcommands on the reference's fixtures --------------------------------------------------------------
+
+def oracle_tables(gfa, count, **kw):
+    g = go.parse_gfa(os.path.join(GOLDEN, gfa))
+    mask = go.make_mask(g, **kw)
+    t = go.item_tables(g, mask, count)
+    op, og, names = go.path_order_arrays(mask, g)
+    return g, t, op, og, names
+
+
+def oracle_hist(gfa, count, **kw):
+    g, t, op, og, names = oracle_tables(gfa, count, **kw)
+    countable = po.abacus_by_total(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+    if count == "bp":
+        return po.construct_hist_bps(countable, g.node_lens, len(names), t.uncovered)
+    return po.construct_hist(countable, len(names))
+
+
+FLAG_SETS = [
+    ([], {}),
+    (["-S"], {"groupby_sample": True}),
+    (["-H"], {"groupby_haplotype": True}),
+    (["-g", os.path.join(GOLDEN, "test_groups.txt")], {"groupby_file": os.path.join(GOLDEN, "test_groups.txt")}),
+    (["-s", os.path.join(GOLDEN, "inclusion.bed1")], {"subset": os.path.join(GOLDEN, "inclusion.bed1")}),
+    (["-s", os.path.join(GOLDEN, "inclusion.bed3")], {"subset": os.path.join(GOLDEN, "inclusion.bed3")}),
+    (["-e", os.path.join(GOLDEN, "exclusion.bed3")], {"exclude": os.path.join(GOLDEN, "exclusion.bed3")}),
+    (["-S", "-s", os.path.join(GOLDEN, "inclusion_sub.bed1"), "-e", os.path.join(GOLDEN, "exclusion.bed3")],
+     {"groupby_sample": True, "subset": os.path.join(GOLDEN, "inclusion_sub.bed1"),
+      "exclude": os.path.join(GOLDEN, "exclusion.bed3")}),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags,kw", FLAG_SETS)
+def test_hist_chrM(flags, kw):
+    for count in ("node", "bp", "edge"):
+        out = run_cli("hist", os.path.join(GOLDEN, "chrM_test.gfa"), "-c", count, *flags).stdout
+        assert body(out) == po.hist_table([(count, oracle_hist("chrM_test.gfa", count, **kw))]), (count, flags)
+        assert out.split("\n")[1].startswith("# version")
+    out = run_cli("hist", os.path.join(GOLDEN, "chrM_test.gfa"), "-c", "all", *flags).stdout
+    want = po.hist_table([(c, oracle_hist("chrM_test.gfa", c, **kw)) for c in ("node", "bp", "edge")])
+    assert body(out) == want
+
+
+@pytest.mark.gpu
+def test_hist_chrM_reference_golden():
+    """BASELINE.json configs[0] family: the printed bp / node / edge hists are the reference's KATs."""
+    kats = json.load(open(os.path.join(GOLDEN, "kats.json")))["chrM_groupby_sample"]
+    out = run_cli("hist", os.path.join(GOLDEN, "chrM_test.gfa"), "-S", "-c", "all").stdout
+    rows = [l.split("\t") for l in body(out).strip().split("\n")][4:]
+    assert [int(r[1]) for r in rows] == kats["node"]
+    assert [int(r[2]) for r in rows] == kats["bp"]
+    assert [int(r[3]) for r in rows] == kats["edge"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gfa", ["chrM_test.gfa", "t_groups.gfa", "cdbg.gfa"])
+def test_histgrowth_and_growth(gfa):
+    path = os.path.join(GOLDEN, gfa)
+    cov, quo = po.parse_thresholds("0,0.5,1", "0,1,2")
+    for count in ("node", "bp", "edge"):
+        if gfa == "cdbg.gfa" and count == "edge":
+            continue
+        out = run_cli("histgrowth", path, "-c", count, "-q", "0,0.5,1", "-l", "0,1,2", "-a").stdout
+        want = po.growth_table([(count, oracle_hist(gfa, count))], cov, quo, add_hist=True)
+        assert body(out) == want, (gfa, count)
+    out = run_cli("growth", path, "-q", "0,0.5,1", "-l", "0,1,2").stdout
+    assert body(out) == po.growth_table([("node", oracle_hist(gfa, "node"))], cov, quo)
+    assert not any(l.startswith("# version") for l in out.split("\n"))  # growth.rs:48-51: no version line
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags,kw", FLAG_SETS)
+def test_ordered_histgrowth_chrM(flags, kw):
+    cov, quo = po.parse_thresholds("0,0.5,0.9,1", "1,2,1,1")
+    for count in ("node", "bp", "edge"):
+        g, t, op, og, names = oracle_tables("chrM_test.gfa", count, **kw)
+        r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        unc = None
+        if t.uncovered:
+            unc = np.zeros(t.n_items + 1, dtype=np.uint64)
+            for k, val in t.uncovered.items():
+                unc[k] = val
+        curves = [po.calc_growth(r, c, len(names), cc, qq, count_bp=(count == "bp"), node_lens=g.node_lens, uncovered=unc)
+                  for cc, qq in zip(cov, quo)]
+        want = po.ordered_growth_table(count, names, curves, cov, quo)
+        out = run_cli("ordered-histgrowth", os.path.join(GOLDEN, "chrM_test.gfa"), "-c", count, "-q", "0,0.5,0.9,1",
+                      "-l", "1,2,1,1", *flags).stdout
+        assert body(out) == want, (count, flags)
+
+
+@pytest.mark.gpu
+def test_ordered_histgrowth_with_order_file(tmp_path):
+    order = tmp_path / "order.txt"
+    order.write_text("HG00621\nchm13\nHG00438\ngrch38\n")
+    kw = {"groupby_sample": True, "order": str(order)}
+    g, t, op, og, names = oracle_tables("chrM_test.gfa", "node", **kw)
+    assert names == ["HG00621", "chm13", "HG00438", "grch38"]
+    r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+    cov, quo = po.parse_thresholds("0", "1")
+    want = po.ordered_growth_table("node", names, [po.calc_growth(r, c, 4, cov[0], quo[0])], cov, quo)
+    out = run_cli("ordered-histgrowth", os.path.join(GOLDEN, "chrM_test.gfa"), "-S", "-O", str(order)).stdout
+    assert body(out) == want
+    # t_groups in file order: the SURVEY appendix A example
+    out = run_cli("ordered-histgrowth", os.path.join(GOLDEN, "t_groups.gfa")).stdout
+    assert body(out) == ("panacus\tordered-growth\ncount\tnode\ncoverage\t1\nquorum\t0\n"
+                         "y#1\t2\ny#2\t5\ny#3\t8\ny#4\t9\ny#5\t10\nx\t10\n")
+
+
+@pytest.mark.gpu
+def test_similarity_values():
+    for count in ("node", "bp"):
+        g, t, op, og, names = oracle_tables("chrM_test.gfa", count, groupby_sample=True)
+        r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        inter, ln, table = po.similarity(r, c, len(names), count_bp=(count == "bp"), node_lens=g.node_lens)
+        out = run_cli("similarity", os.path.join(GOLDEN, "chrM_test.gfa"), "-S", "-c", count, "--no-cluster=1").stdout
+        rows = [l.split("\t") for l in body(out).strip().split("\n")]
+        assert rows[0] == ["group"] + names
+        for i, name in enumerate(names):
+            assert rows[1 + i][0] == name
+            assert [np.float32(x) for x in rows[1 + i][1:]] == [table[i, j] for j in range(len(names))]
+        # clustered output: same values, rows and columns permuted consistently
+        out = run_cli("similarity", os.path.join(GOLDEN, "chrM_test.gfa"), "-S", "-c", count).stdout
+        rows = [l.split("\t") for l in body(out).strip().split("\n")]
+        perm = [names.index(x) for x in rows[0][1:]]
+        assert sorted(perm) == list(range(len(names))) and [r[0] for r in rows[1:]] == rows[0][1:]
+        for i, pi in enumerate(perm):
+            assert [np.float32(x) for x in rows[1 + i][1:]] == [table[pi, pj] for pj in perm]
