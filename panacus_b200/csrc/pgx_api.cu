@@ -57,6 +57,7 @@ struct pgx_abacus {
     std::vector<uint32_t> thr_cache;
     uint32_t *d_order = nullptr;
     size_t order_cap = 0;
+    uint32_t *d_identity = nullptr;  // 0..G-1, for general-quorum growth in group order on the group-major copy
     uint64_t *d_scratch = nullptr;  // generic device result buffer
     size_t scratch_cap = 0;
 
@@ -148,6 +149,22 @@ int validate_thresholds(const pgx_abacus *a, uint32_t T, const uint32_t *cov) {
     return PGX_OK;
 }
 
+int ensure_countable(pgx_abacus *a);
+int ensure_gm(pgx_abacus *a);
+int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders, const std::vector<uint32_t> &ts,
+                     const uint32_t *cov, const uint32_t *thr, int weighted, uint64_t *d_out_base, uint64_t out_order_stride);
+
+// General-quorum thresholds in group order can run on either layout: k_scan<quorum> (node-major, one
+// thread per item, divergent) or k_gm_growth on the group-major copy (bit-sliced over 64 items per
+// thread, ~10x faster on large tables but needs the transposed copy).  PGX_QUORUM_PATH=scan|gm overrides.
+bool quorum_via_gm(const pgx_abacus *a) {
+    if (a->x.world > 1u) return false;  // the fused multi-GPU exchange lives in k_scan
+    const char *env = getenv("PGX_QUORUM_PATH");
+    if (env && !strcmp(env, "scan")) return false;
+    if (env && !strcmp(env, "gm")) return true;
+    return a->gm_valid || (size_t)a->n_rows * a->Wp * 8u >= (size_t)8 << 20;
+}
+
 // Launches k_scan for the thresholds ts[i0 .. i0+n) (global indices into cov/thr); n is reduced until
 // accumulators + pipeline fit in shared memory.  Returns the number of thresholds handled in *n_done.
 int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<uint32_t> &ts, size_t i0,
@@ -223,6 +240,24 @@ int fused_pass(pgx_abacus *a, bool want_cnt, bool want_w, uint32_t T, const uint
         if (hist_pending) d_countable = nullptr;  // written once
         hist_pending = false;
         i += n;
+    }
+    if (!gen_t.empty() && quorum_via_gm(a)) {
+        bool need_cov = false;
+        for (uint32_t t : gen_t) need_cov |= cov[t] > 1u;
+        if (need_cov && (rc = ensure_countable(a))) return rc;
+        if ((rc = ensure_gm(a))) return rc;
+        if (!a->d_identity) {
+            std::vector<uint32_t> id(G);
+            for (uint32_t g = 0; g < G; ++g) id[g] = g;
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_identity), (size_t)G * 4u));
+            PGX_CUDA(cudaMemcpyAsync(a->d_identity, id.data(), (size_t)G * 4u, cudaMemcpyHostToDevice, a->stream));
+            PGX_CUDA(cudaStreamSynchronize(a->stream));
+        }
+        uint64_t *base = d_out + 2u * ((size_t)G + 1u);
+        for (uint32_t t : gen_t) PGX_CUDA(cudaMemsetAsync(base + (size_t)t * G, 0, (size_t)G * 8u, a->stream));
+        if (d_countable && a->d_countable && d_countable != a->d_countable)
+            PGX_CUDA(cudaMemcpyAsync(d_countable, a->d_countable, a->n_rows * 4u, cudaMemcpyDeviceToDevice, a->stream));
+        return gm_growth_launch(a, 1, a->d_identity, gen_t, cov, thr, weighted, base, 0);
     }
     i = 0;
     while (i < gen_t.size()) {
@@ -308,7 +343,64 @@ int is_permutation(const uint32_t *order, uint32_t G) {
     return 1;
 }
 
-// growth under explicit orders on the group-major copy; results (first differences) -> d_out
+// Enqueues k_gm_growth for the thresholds `ts` (indices into cov / thr) under n_orders device-resident orders.
+// First differences of threshold ts[k], order o land at d_out_base + o*out_order_stride + ts[k]*G (pre-zeroed
+// by the caller).  Thresholds are taken in chunks that fit in shared memory.
+int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders, const std::vector<uint32_t> &ts,
+                     const uint32_t *cov, const uint32_t *thr, int weighted, uint64_t *d_out_base, uint64_t out_order_stride) {
+    const uint32_t G = a->G;
+    int rc;
+    for (size_t i0 = 0; i0 < ts.size();) {
+        size_t n = std::min<size_t>(kMaxThresholds, ts.size() - i0);
+        auto is_general = [&](size_t k) { return !all_zero(thr ? thr + (size_t)ts[i0 + k] * G : nullptr, G); };
+        auto any_general = [&](size_t cnt) {
+            for (size_t k = 0; k < cnt; ++k)
+                if (is_general(k)) return true;
+            return false;
+        };
+        while (n > 1 && gm_growth_smem_bytes(G, (uint32_t)n, any_general(n)) > 200u * 1024u) --n;
+        GmGrowthParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.gm = a->d_gm;
+        p.gm_stride = a->gm_stride;
+        p.n_words = (a->n_rows + 63u) / 64u;
+        p.n_rows = a->n_rows;
+        p.weight = weighted ? a->d_weight : nullptr;
+        p.countable = a->d_countable;
+        p.G = G;
+        p.T = (uint32_t)n;
+        p.weighted = weighted ? 1 : 0;
+        p.out_order_stride = out_order_stride;
+        for (size_t k = 0; k < n; ++k) {
+            p.cov[k] = cov[ts[i0 + k]];
+            p.slot[k] = ts[i0 + k];
+            if (is_general(k)) p.general_mask |= 1u << k;
+        }
+        if (p.general_mask) {
+            std::vector<uint32_t> packed(n * (size_t)G, 0u);
+            for (size_t k = 0; k < n; ++k)
+                if ((p.general_mask >> k) & 1u)
+                    std::memcpy(packed.data() + k * G, thr + (size_t)ts[i0 + k] * G, (size_t)G * 4u);
+            if ((rc = upload_thr(a, packed))) return rc;
+            p.thr = a->d_thr;
+        }
+        const uint32_t kBatch = 4096;  // orders per launch (gridDim.y)
+        for (uint32_t o0 = 0; o0 < n_orders; o0 += kBatch) {
+            p.n_orders = std::min<uint32_t>(kBatch, n_orders - o0);
+            p.order = d_orders + (size_t)o0 * G;
+            p.out = d_out_base + (size_t)o0 * out_order_stride;
+            if ((rc = launch_gm_growth(p, a->sm_count, a->stream))) return rc;
+            a->launches++;
+        }
+        char buf[160];
+        snprintf(buf, sizeof buf, "k_gm_growth orders=%u T=%zu general_mask=0x%x", n_orders, n, p.general_mask);
+        a->last_launch = buf;
+        i0 += n;
+    }
+    return PGX_OK;
+}
+
+// growth under explicit host orders on the group-major copy -> curves (host)
 int gm_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t T, const uint32_t *cov,
               const uint32_t *thr, int weighted, uint64_t *curves /*host*/) {
     const uint32_t G = a->G;
@@ -330,51 +422,9 @@ int gm_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t
     if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, out_words))) return rc;
     if ((rc = ensure_pinned(a, out_words))) return rc;
     PGX_CUDA(cudaMemsetAsync(a->d_scratch, 0, out_words * 8u, a->stream));
-
-    for (uint32_t t0 = 0; t0 < T;) {
-        uint32_t n = std::min<uint32_t>(kMaxThresholds, T - t0);
-        auto any_general = [&](uint32_t cnt) {
-            for (uint32_t k = 0; k < cnt; ++k)
-                if (!all_zero(thr ? thr + (size_t)(t0 + k) * G : nullptr, G)) return true;
-            return false;
-        };
-        while (n > 1 && gm_growth_smem_bytes(G, n, any_general(n)) > 200u * 1024u) --n;
-        GmGrowthParams p;
-        std::memset(&p, 0, sizeof(p));
-        p.gm = a->d_gm;
-        p.gm_stride = a->gm_stride;
-        p.n_words = (a->n_rows + 63u) / 64u;
-        p.n_rows = a->n_rows;
-        p.weight = weighted ? a->d_weight : nullptr;
-        p.countable = a->d_countable;
-        p.G = G;
-        p.T = n;
-        p.weighted = weighted ? 1 : 0;
-        p.out_order_stride = (uint64_t)T * G;
-        std::vector<uint32_t> packed;
-        for (uint32_t k = 0; k < n; ++k) {
-            p.cov[k] = cov[t0 + k];
-            if (!all_zero(thr ? thr + (size_t)(t0 + k) * G : nullptr, G)) p.general_mask |= 1u << k;
-        }
-        if (p.general_mask) {
-            packed.assign((size_t)n * G, 0u);
-            for (uint32_t k = 0; k < n; ++k)
-                if ((p.general_mask >> k) & 1u)
-                    std::memcpy(packed.data() + (size_t)k * G, thr + (size_t)(t0 + k) * G, (size_t)G * 4u);
-            if ((rc = upload_thr(a, packed))) return rc;
-            p.thr = a->d_thr;
-        }
-        const uint32_t kBatch = 4096;  // orders per launch (gridDim.y)
-        for (uint32_t o0 = 0; o0 < n_orders; o0 += kBatch) {
-            p.n_orders = std::min<uint32_t>(kBatch, n_orders - o0);
-            p.order = a->d_order + (size_t)o0 * G;
-            p.out = a->d_scratch + (size_t)o0 * T * G + (size_t)t0 * G;
-            if ((rc = launch_gm_growth(p, a->sm_count, a->stream))) return rc;
-            a->launches++;
-        }
-        t0 += n;
-    }
-    a->last_launch = "k_gm_growth";
+    std::vector<uint32_t> ts(T);
+    for (uint32_t t = 0; t < T; ++t) ts[t] = t;
+    if ((rc = gm_growth_launch(a, n_orders, a->d_order, ts, cov, thr, weighted, a->d_scratch, (uint64_t)T * G))) return rc;
     PGX_CUDA(cudaMemcpyAsync(a->h_pinned, a->d_scratch, out_words * 8u, cudaMemcpyDeviceToHost, a->stream));
     PGX_CUDA(cudaStreamSynchronize(a->stream));
     // first differences -> curves (wrapping u64 prefix sums)
@@ -472,6 +522,7 @@ void pgx_abacus_destroy(pgx_abacus *a) {
     cudaFree(a->d_err);
     cudaFree(a->d_thr);
     cudaFree(a->d_order);
+    cudaFree(a->d_identity);
     cudaFree(a->d_scratch);
     if (a->h_pinned) cudaFreeHost(a->h_pinned);
     if (a->own_stream) cudaStreamDestroy(a->own_stream);

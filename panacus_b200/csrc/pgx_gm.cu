@@ -22,21 +22,48 @@ uint64_t gm_stride_words(uint64_t n_rows) {
 namespace {
 
 // ---- transpose -----------------------------------------------------------------------------------
-// One warp turns 256 items x 64 groups (one u64 column of the node-major bitmap) into 64 group rows
-// x 8 u32 (32 contiguous bytes per row): 64 ballots per 32 items.
+// A CTA stages 256 items x 8 word-columns of the node-major bitmap in shared memory with coalesced
+// 128-bit loads (row pitch padded to 9 words: the column reads below are then 2-way = conflict free
+// for 64-bit accesses); warp w then turns word-column w into 64 group rows x 8 u32 (32 contiguous
+// bytes per row = one full sector per store): 64 ballots per 32 items.
+constexpr int kTrItems = 256, kTrCols = 8, kTrPitch = kTrCols + 1;
+
 __global__ void __launch_bounds__(256) k_transpose(const uint64_t *__restrict__ bitmap, uint64_t n_rows, uint32_t G,
                                                    uint32_t W, uint32_t Wp, uint32_t *__restrict__ gm32,
                                                    uint64_t gm_stride32) {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t wc = blockIdx.y * 8u + warp;  // word column of the node-major row
-    if (wc >= W) return;
-    const uint64_t item0 = (uint64_t)blockIdx.x * 256u;
+    __shared__ uint64_t tile[kTrItems * kTrPitch];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t item0 = (uint64_t)blockIdx.x * kTrItems;
+    const uint32_t wc0 = blockIdx.y * kTrCols;
+    const uint32_t ncols = min((uint32_t)kTrCols, Wp - wc0);  // word-columns staged by this CTA (Wp is even or 1)
+    if (ncols >= 2u && !(ncols & 1u)) {
+        const uint32_t chunks = ncols >> 1;  // 16-byte chunks per row
+        for (uint32_t e = tid; e < kTrItems * chunks; e += 256u) {
+            const uint32_t r = e / chunks, c = e - r * chunks;
+            const uint64_t item = item0 + r;
+            uint64_t x0 = 0, x1 = 0;
+            if (item != 0 && item < n_rows) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(bitmap + item * Wp + wc0) + c);
+                x0 = v.x;
+                x1 = v.y;
+            }
+            tile[r * kTrPitch + 2u * c] = x0;
+            tile[r * kTrPitch + 2u * c + 1u] = x1;
+        }
+    } else {
+        for (uint32_t e = tid; e < kTrItems * ncols; e += 256u) {
+            const uint32_t r = e / ncols, c = e - r * ncols;
+            const uint64_t item = item0 + r;
+            tile[r * kTrPitch + c] = (item != 0 && item < n_rows) ? __ldg(bitmap + item * Wp + wc0 + c) : 0ull;
+        }
+    }
+    __syncthreads();
+    const uint32_t wc = wc0 + warp;  // word column of the node-major row handled by this warp
+    if (warp >= ncols || wc >= W) return;
     uint32_t keep0[8], keep1[8];
 #pragma unroll
     for (int ib = 0; ib < 8; ++ib) {
-        const uint64_t item = item0 + (uint64_t)ib * 32u + lane;
-        uint64_t x = 0;
-        if (item != 0 && item < n_rows) x = __ldg(bitmap + item * Wp + wc);
+        const uint64_t x = tile[(ib * 32 + lane) * kTrPitch + warp];
         const uint32_t xlo = (uint32_t)x, xhi = (uint32_t)(x >> 32);
         uint32_t k0 = 0, k1 = 0;
 #pragma unroll
@@ -89,109 +116,138 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
     return slo + (smid << 24) + (shi << 48);
 }
 
-template <int P>  // number of rank bit-planes
-__global__ void __launch_bounds__(kGmThreads) k_gm_growth(const __grid_constant__ GmGrowthParams p) {
+// One thread owns 64 items (one u64 column of the group-major bitmap) and walks the groups in the given
+// order.  q = 0 thresholds: an item starts counting at its first group -> popcount of the newly seen
+// bits (HBM-bound; rows are prefetched kGmPrefetch steps ahead).  General thresholds: bit-sliced rank
+// counters R (P planes, one bit per item) are incremented by the row and compared against the uniform
+// per-position cutoff K = thr[t][j] with one 3-input LOP per plane; the verdict of an item only changes
+// at its own set bits (abacus.rs:1007-1010), and the curve's first difference is the net number (or
+// weight) of verdict flips.
+template <int P, bool GENERAL, int TMAX>  // P: rank bit-planes (2^P > G); TMAX: compile-time bound on p.T
+__global__ void __launch_bounds__(kGmThreads, GENERAL ? 3 : 4) k_gm_growth(const __grid_constant__ GmGrowthParams p) {
+    constexpr int kGmPrefetch = GENERAL ? 2 : 8;  // rows in flight per thread (the q = 0 kernel is HBM-bound)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // smem: order[G] u32 | thr[T*G] u32 (if any general) | delta[T*G] u64
     uint32_t *s_order = reinterpret_cast<uint32_t *>(smem_raw);
     uint32_t *s_thr = s_order + p.G;
-    const uint32_t thr_words = p.general_mask ? p.T * p.G : 0u;
+    const uint32_t thr_words = GENERAL ? p.T * p.G : 0u;
     unsigned long long *s_delta =
         reinterpret_cast<unsigned long long *>(smem_raw + (((size_t)(p.G + thr_words) * 4u + 15u) & ~(size_t)15u));
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t order_id = blockIdx.y;
     const uint32_t *order = p.order + (size_t)order_id * p.G;
-    const uint32_t *thr = p.thr ? p.thr : nullptr;
     for (uint32_t i = tid; i < p.G; i += kGmThreads) s_order[i] = order[i];
-    for (uint32_t i = tid; i < thr_words; i += kGmThreads) s_thr[i] = thr[i];
+    for (uint32_t i = tid; i < thr_words; i += kGmThreads) s_thr[i] = p.thr[i];
     for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) s_delta[i] = 0ull;
     __syncthreads();
 
     const uint64_t wi = (uint64_t)blockIdx.x * kGmThreads + tid;
     const bool active = wi < p.n_words;
     const uint64_t wsafe = active ? wi : 0;
-    const uint32_t *wrow = p.weight ? p.weight + wsafe * 64u : nullptr;
+    const uint32_t *wrow = (p.weighted && p.weight) ? p.weight + wsafe * 64u : nullptr;
 
     // eligibility masks: item counted for threshold t only if its total coverage >= cov[t]
-    uint64_t elig[kMaxThresholds];
+    uint64_t elig[TMAX];
 #pragma unroll
-    for (int t = 0; t < kMaxThresholds; ++t) elig[t] = ~0ull;
+    for (int t = 0; t < TMAX; ++t) elig[t] = ~0ull;
     bool need_cov = false;
     for (uint32_t t = 0; t < p.T; ++t) need_cov |= p.cov[t] > 1u;
     if (need_cov && active) {
 #pragma unroll
-        for (int t = 0; t < kMaxThresholds; ++t) elig[t] = 0ull;
+        for (int t = 0; t < TMAX; ++t) elig[t] = 0ull;
         for (uint32_t b = 0; b < 64u; ++b) {
             const uint64_t item = wi * 64u + b;
             const uint32_t c = (item < p.n_rows && item != 0) ? __ldg(p.countable + item) : 0u;
 #pragma unroll
-            for (int t = 0; t < kMaxThresholds; ++t)
+            for (int t = 0; t < TMAX; ++t)
                 if ((uint32_t)t < p.T && c >= p.cov[t]) elig[t] |= 1ull << b;
         }
     }
-    // weighted tail guard: items beyond n_rows never have bits set (transpose writes zeros)
 
     uint64_t seen = 0;
     uint64_t R[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) R[i] = 0ull;
-    uint64_t verdict[kMaxThresholds];
+    uint64_t verdict[TMAX];
 #pragma unroll
-    for (int t = 0; t < kMaxThresholds; ++t) verdict[t] = 0ull;
+    for (int t = 0; t < TMAX; ++t) verdict[t] = 0ull;
 
     const uint64_t *col = p.gm + wsafe;
-    for (uint32_t j = 0; j < p.G; ++j) {
-        const uint64_t b = active ? __ldg(col + (uint64_t)s_order[j] * p.gm_stride) : 0ull;
-        const uint64_t fresh = b & ~seen;
-        seen |= b;
-        if (p.general_mask) {  // R += b (bit-sliced ripple increment)
-            uint64_t carry = b;
+    auto load_row = [&](uint32_t j) -> uint64_t {
+        return (active && j < p.G) ? __ldg(col + (uint64_t)s_order[j] * p.gm_stride) : 0ull;
+    };
+    uint64_t nxt[kGmPrefetch];
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                const uint64_t t2 = R[i] & carry;
-                R[i] ^= carry;
-                carry = t2;
-            }
-        }
+    for (int u = 0; u < kGmPrefetch; ++u) nxt[u] = load_row((uint32_t)u);
+
+    for (uint32_t j0 = 0; j0 < p.G; j0 += kGmPrefetch) {
+        uint64_t cur[kGmPrefetch];
 #pragma unroll
-        for (int t = 0; t < kMaxThresholds; ++t) {
-            if ((uint32_t)t >= p.T) break;
-            uint64_t up, down;
-            if ((p.general_mask >> t) & 1u) {
-                // ge = (R >= K) per item, K = thr[t][j] (uniform): scan planes from the LSB
-                const uint32_t K = s_thr[t * p.G + j];
-                uint64_t ge = ~0ull;
+        for (int u = 0; u < kGmPrefetch; ++u) cur[u] = nxt[u];
 #pragma unroll
-                for (int i = 0; i < P; ++i) ge = ((K >> i) & 1u) ? (ge & R[i]) : (ge | R[i]);
-                if (K >> P) ge = 0ull;
-                const uint64_t vnew = (b & ge) | (~b & verdict[t]);
-                up = vnew & ~verdict[t];
-                down = verdict[t] & ~vnew;
-                verdict[t] = vnew;
-            } else {
-                up = fresh;
-                down = 0ull;
+        for (int u = 0; u < kGmPrefetch; ++u) nxt[u] = load_row(j0 + kGmPrefetch + (uint32_t)u);  // in flight during the math
+#pragma unroll
+        for (int u = 0; u < kGmPrefetch; ++u) {
+            const uint32_t j = j0 + (uint32_t)u;
+            if (j >= p.G) break;
+            const uint64_t b = cur[u];
+            const uint64_t fresh = b & ~seen;
+            seen |= b;
+            if (GENERAL) {  // R += b (bit-sliced ripple increment)
+                uint64_t carry = b;
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const uint64_t t2 = R[i] & carry;
+                    R[i] ^= carry;
+                    carry = t2;
+                }
             }
-            up &= elig[t];
-            down &= elig[t];
-            long long net;
-            if (p.weighted) {
-                const uint64_t su = warp_sum_u64(wrow ? weighted_bits(up, wrow) : (uint64_t)__popcll(up));
-                const uint64_t sd = warp_sum_u64(wrow ? weighted_bits(down, wrow) : (uint64_t)__popcll(down));
-                net = (long long)(su - sd);
-            } else {
-                const uint32_t su = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popcll(up));
-                const uint32_t sd = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popcll(down));
-                net = (long long)su - (long long)sd;
+#pragma unroll
+            for (int t = 0; t < TMAX; ++t) {
+                if ((uint32_t)t >= p.T) break;
+                uint64_t up, down = 0ull;
+                if (GENERAL && ((p.general_mask >> t) & 1u)) {
+                    // ge = (R >= K) per item, K uniform: scan the planes from the LSB,
+                    // ge <- K_i ? (ge & R_i) : (ge | R_i)  == one 3-input LOP with m = -K_i
+                    const uint32_t K = s_thr[t * p.G + j];
+                    uint64_t ge = ~0ull;
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        const uint64_t m = 0ull - (uint64_t)((K >> i) & 1u);
+                        ge = (m & (ge & R[i])) | (~m & (ge | R[i]));
+                    }
+                    if (K >> P) ge = 0ull;
+                    const uint64_t vnew = (b & ge) | (~b & verdict[t]);
+                    up = vnew & ~verdict[t];
+                    down = verdict[t] & ~vnew;
+                    verdict[t] = vnew;
+                } else {
+                    up = fresh;
+                }
+                up &= elig[t];
+                down &= elig[t];
+                long long net;
+                if (p.weighted) {
+                    const uint64_t su = warp_sum_u64(wrow ? weighted_bits(up, wrow) : (uint64_t)__popcll(up));
+                    uint64_t sd = 0;
+                    if (GENERAL) sd = warp_sum_u64(wrow ? weighted_bits(down, wrow) : (uint64_t)__popcll(down));
+                    net = (long long)(su - sd);
+                } else {
+                    const int diff = __popcll(up) - (GENERAL ? __popcll(down) : 0);
+                    net = (long long)__reduce_add_sync(0xFFFFFFFFu, diff);
+                }
+                if (lane == 0 && net != 0) atomicAdd(&s_delta[t * p.G + j], (unsigned long long)net);
             }
-            if (lane == 0 && net != 0) atomicAdd(&s_delta[t * p.G + j], (unsigned long long)net);
         }
     }
     __syncthreads();
     uint64_t *out = p.out + (size_t)order_id * p.out_order_stride;
     for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) {
         const unsigned long long v = s_delta[i];
-        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(out + i), v);
+        if (v) {
+            const uint32_t t = i / p.G, j = i - t * p.G;
+            atomicAdd(reinterpret_cast<unsigned long long *>(out + (size_t)p.slot[t] * p.G + j), v);
+        }
     }
 }
 
@@ -207,8 +263,19 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
     __shared__ uint64_t Ps[32][kSimKW];
     const uint32_t tid = threadIdx.x;
     const uint32_t tx = tid & 15u, ty = tid >> 4;
-    const uint32_t x0 = p.row_begin + blockIdx.y * kSimTile;  // output rows
-    const uint32_t y0 = blockIdx.x * kSimTile;                // output columns
+    uint32_t bx = blockIdx.x, by = blockIdx.y;
+    if (p.triangular) {  // full square requested: only tiles on or above the diagonal (bx >= by), mirrored afterwards
+        const uint32_t nt = (p.G + kSimTile - 1u) / kSimTile;  // tiles per edge; blockIdx.x enumerates the upper tiles
+        uint32_t lin = blockIdx.x;
+        by = 0;
+        while (lin >= nt - by) {
+            lin -= nt - by;
+            ++by;
+        }
+        bx = by + lin;
+    }
+    const uint32_t x0 = p.row_begin + by * kSimTile;  // output rows
+    const uint32_t y0 = bx * kSimTile;                // output columns
     const uint64_t k_begin = (uint64_t)blockIdx.z * words_per_split;
     uint64_t k_end = k_begin + words_per_split;
     if (k_end > p.n_words) k_end = p.n_words;
@@ -276,6 +343,12 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
     }
 }
 
+// lower triangle <- upper triangle (the intersection matrix is symmetric)
+__global__ void __launch_bounds__(256) k_sim_mirror(uint64_t *inter, uint32_t G) {
+    const uint32_t x = blockIdx.y * 16u + (threadIdx.x >> 4), y = blockIdx.x * 16u + (threadIdx.x & 15u);
+    if (x < G && y < G && y / kSimTile < x / kSimTile) inter[(uint64_t)x * G + y] = inter[(uint64_t)y * G + x];
+}
+
 // ---- per-group totals: len[g] = sum_i w_i [g in i] (similarity.rs:133-137) -------------------------
 __global__ void __launch_bounds__(256) k_gm_rowsum(const uint64_t *__restrict__ gm, uint64_t gm_stride,
                                                    uint64_t n_words, const uint64_t *__restrict__ planes,
@@ -340,11 +413,11 @@ __global__ void __launch_bounds__(256) k_scatter(uint64_t *bitmap, uint32_t Wp, 
 
 size_t gm_growth_smem(const GmGrowthParams &p) { return gm_growth_smem_bytes(p.G, p.T, p.general_mask != 0); }
 
-template <int P>
-int launch_gm_growth_p(const GmGrowthParams &p, cudaStream_t stream) {
+template <int P, bool GENERAL, int TMAX>
+int launch_gm_growth_t(const GmGrowthParams &p, cudaStream_t stream) {
     const size_t smem = gm_growth_smem(p);
     if (smem > 232448u) return fail(PGX_ERR_UNSUPPORTED, "group-major growth: G*T too large for shared memory");
-    auto kern = k_gm_growth<P>;
+    auto kern = k_gm_growth<P, GENERAL, TMAX>;
     PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((p.n_words + kGmThreads - 1) / kGmThreads), p.n_orders);
     kern<<<grid, kGmThreads, smem, stream>>>(p);
@@ -362,19 +435,29 @@ size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general) {
 int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
                      uint64_t gm_stride, cudaStream_t stream) {
     const uint32_t W = (G + 63u) / 64u;
-    dim3 grid((unsigned)(gm_stride * 64u / 256u), (W + 7u) / 8u);
+    dim3 grid((unsigned)(gm_stride * 64u / kTrItems), (W + kTrCols - 1u) / kTrCols);
     k_transpose<<<grid, 256, 0, stream>>>(bitmap, n_rows, G, W, Wp, reinterpret_cast<uint32_t *>(gm),
                                           gm_stride * 2u);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }
 
+template <int P, bool GENERAL>
+int launch_gm_growth_p(const GmGrowthParams &p, cudaStream_t stream) {
+    if (p.T <= 1u) return launch_gm_growth_t<P, GENERAL, 1>(p, stream);
+    if (p.T <= 2u) return launch_gm_growth_t<P, GENERAL, 2>(p, stream);
+    if (p.T <= 4u) return launch_gm_growth_t<P, GENERAL, 4>(p, stream);
+    return launch_gm_growth_t<P, GENERAL, kMaxThresholds>(p, stream);
+}
+
 int launch_gm_growth(const GmGrowthParams &p, int /*sm_count*/, cudaStream_t stream) {
     if (p.n_orders == 0 || p.n_orders > 65535u) return fail(PGX_ERR_INVALID, "n_orders must be in 1..65535 per launch");
-    if (p.G <= 255u) return launch_gm_growth_p<8>(p, stream);
-    if (p.G <= 4095u) return launch_gm_growth_p<12>(p, stream);
-    if (p.G <= 65535u) return launch_gm_growth_p<16>(p, stream);
-    return launch_gm_growth_p<kRankPlanes>(p, stream);
+    if (!p.general_mask) return launch_gm_growth_p<1, false>(p, stream);
+    if (p.G <= 255u) return launch_gm_growth_p<8, true>(p, stream);
+    if (p.G <= 1023u) return launch_gm_growth_p<10, true>(p, stream);
+    if (p.G <= 4095u) return launch_gm_growth_p<12, true>(p, stream);
+    if (p.G <= 65535u) return launch_gm_growth_p<16, true>(p, stream);
+    return launch_gm_growth_p<kRankPlanes, true>(p, stream);
 }
 
 int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream) {
@@ -391,13 +474,20 @@ int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream
     wps = (wps + kSimKW - 1) / kSimKW * kSimKW;
     splits = (p.n_words + wps - 1) / wps;
     dim3 grid(tx, ty, (unsigned)splits);
+    GmSimParams q = p;
+    q.triangular = (p.row_begin == 0 && p.row_end == p.G && tx == ty && tx > 1u) ? 1u : 0u;
+    if (q.triangular) grid = dim3(tx * (tx + 1u) / 2u, 1u, (unsigned)splits);
     if (p.planes) {
         if (p.n_planes > 32u) return fail(PGX_ERR_INVALID, "n_planes > 32");
-        k_gm_similarity<true><<<grid, 256, 0, stream>>>(p, (uint32_t)wps);
+        k_gm_similarity<true><<<grid, 256, 0, stream>>>(q, (uint32_t)wps);
     } else {
-        k_gm_similarity<false><<<grid, 256, 0, stream>>>(p, (uint32_t)wps);
+        k_gm_similarity<false><<<grid, 256, 0, stream>>>(q, (uint32_t)wps);
     }
     PGX_CUDA(cudaGetLastError());
+    if (q.triangular) {
+        k_sim_mirror<<<dim3((p.G + 15u) / 16u, (p.G + 15u) / 16u), 256, 0, stream>>>(p.inter, p.G);
+        PGX_CUDA(cudaGetLastError());
+    }
     return PGX_OK;
 }
 

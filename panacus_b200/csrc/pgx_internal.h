@@ -106,6 +106,7 @@ struct GmGrowthParams {
     uint64_t out_order_stride;  // words between consecutive orders in out (>= T*G)
     uint32_t G, T;
     uint32_t cov[kMaxThresholds];
+    uint32_t slot[kMaxThresholds];  // threshold k's first differences go to out + slot[k]*G
     uint32_t general_mask;   // bit t set: threshold t needs the rank comparison (q > 0)
     int weighted;
 };
@@ -120,6 +121,7 @@ struct GmSimParams {
     uint32_t n_planes;
     uint32_t G;
     uint32_t row_begin, row_end;
+    uint32_t triangular;     // set by the launcher: full square, compute upper tiles only and mirror
     uint64_t *inter;         // device (row_end-row_begin) x G, zeroed by the launcher
 };
 int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream);

@@ -53,11 +53,19 @@ def check_table(bitmap, G, weights, pairs=PAIRS):
         assert np.array_equal(hc, exp["hist"])
         assert np.array_equal(hw, exp["hist_bp"])
         cov, thr = cutoffs(G, pairs)
-        for weighted, key in ((False, "node"), (True, "bp")):
-            curves = a.ordered_growth(cov, thr, weighted=weighted)
-            for t, (c, q) in enumerate(pairs):
-                want = exp[(key, c, q)]
-                assert np.array_equal(curves[t].astype(np.float64), want), (key, c, q)
+        # general-quorum thresholds on both layouts: k_scan<quorum> (node-major) and k_gm_growth (group-major)
+        for path in ("scan", "gm"):
+            os.environ["PGX_QUORUM_PATH"] = path
+            try:
+                for weighted, key in ((False, "node"), (True, "bp")):
+                    curves = a.ordered_growth(cov, thr, weighted=weighted)
+                    for t, (c, q) in enumerate(pairs):
+                        want = exp[(key, c, q)]
+                        assert np.array_equal(curves[t].astype(np.float64), want), (path, key, c, q)
+                h3, w3, cv3 = a.hist_ordered_growth(cov, thr, weighted=True, hist_count=True, hist_weight=True)
+                assert np.array_equal(h3, hc) and np.array_equal(w3, hw) and np.array_equal(cv3, curves)
+            finally:
+                os.environ.pop("PGX_QUORUM_PATH", None)
         # fused hist + growth in one pass gives the same numbers
         hc2, hw2, cv2 = a.hist_ordered_growth(cov, thr, weighted=True, hist_count=True, hist_weight=True)
         assert np.array_equal(hc2, hc) and np.array_equal(hw2, hw)
