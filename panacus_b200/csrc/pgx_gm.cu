@@ -22,23 +22,36 @@ uint64_t gm_stride_words(uint64_t n_rows) {
 namespace {
 
 // ---- transpose -----------------------------------------------------------------------------------
-// A CTA stages 256 items x 8 word-columns of the node-major bitmap in shared memory with coalesced
-// 128-bit loads (row pitch padded to 9 words: the column reads below are then 2-way = conflict free
-// for 64-bit accesses); warp w then turns word-column w into 64 group rows x 8 u32 (32 contiguous
-// bytes per row = one full sector per store): 64 ballots per 32 items.
-constexpr int kTrItems = 256, kTrCols = 8, kTrPitch = kTrCols + 1;
+// A CTA stages 256 items x COLS word-columns of the node-major bitmap in shared memory with coalesced
+// 128-bit loads (row pitch padded by one word: the column reads below are then conflict free for 64-bit
+// accesses); warp w then turns word-column w into 64 group rows x 8 u32 (32 contiguous bytes per row =
+// one full sector per store).  The 32x32 bit blocks are transposed across the lanes of a warp with the
+// 5-stage shuffle butterfly (5 SHFL per block instead of 32 VOTE).
+constexpr int kTrItems = 256;
 
-__global__ void __launch_bounds__(256) k_transpose(const uint64_t *__restrict__ bitmap, uint64_t n_rows, uint32_t G,
-                                                   uint32_t W, uint32_t Wp, uint32_t *__restrict__ gm32,
-                                                   uint64_t gm_stride32) {
-    __shared__ uint64_t tile[kTrItems * kTrPitch];
+// lane r holds row r of a 32x32 bit matrix in x; on return lane c holds column c (bit r = old bit c of lane r)
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
+#pragma unroll
+    for (uint32_t j = 16u, m = 0x0000FFFFu; j != 0u; j >>= 1, m ^= (m << j)) {
+        const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y & m) << j));
+    }
+    return x;
+}
+
+template <int COLS>
+__global__ void __launch_bounds__(COLS * 32) k_transpose(const uint64_t *__restrict__ bitmap, uint64_t n_rows, uint32_t G,
+                                                         uint32_t W, uint32_t Wp, uint32_t *__restrict__ gm32,
+                                                         uint64_t gm_stride32) {
+    constexpr int kPitch = COLS + 1, kThreads = COLS * 32;
+    __shared__ uint64_t tile[kTrItems * kPitch];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t item0 = (uint64_t)blockIdx.x * kTrItems;
-    const uint32_t wc0 = blockIdx.y * kTrCols;
-    const uint32_t ncols = min((uint32_t)kTrCols, Wp - wc0);  // word-columns staged by this CTA (Wp is even or 1)
+    const uint32_t wc0 = blockIdx.y * COLS;
+    const uint32_t ncols = min((uint32_t)COLS, Wp - wc0);  // word-columns staged by this CTA (Wp is even or 1)
     if (ncols >= 2u && !(ncols & 1u)) {
         const uint32_t chunks = ncols >> 1;  // 16-byte chunks per row
-        for (uint32_t e = tid; e < kTrItems * chunks; e += 256u) {
+        for (uint32_t e = tid; e < kTrItems * chunks; e += kThreads) {
             const uint32_t r = e / chunks, c = e - r * chunks;
             const uint64_t item = item0 + r;
             uint64_t x0 = 0, x1 = 0;
@@ -47,14 +60,14 @@ __global__ void __launch_bounds__(256) k_transpose(const uint64_t *__restrict__ 
                 x0 = v.x;
                 x1 = v.y;
             }
-            tile[r * kTrPitch + 2u * c] = x0;
-            tile[r * kTrPitch + 2u * c + 1u] = x1;
+            tile[r * kPitch + 2u * c] = x0;
+            tile[r * kPitch + 2u * c + 1u] = x1;
         }
     } else {
-        for (uint32_t e = tid; e < kTrItems * ncols; e += 256u) {
+        for (uint32_t e = tid; e < kTrItems * ncols; e += kThreads) {
             const uint32_t r = e / ncols, c = e - r * ncols;
             const uint64_t item = item0 + r;
-            tile[r * kTrPitch + c] = (item != 0 && item < n_rows) ? __ldg(bitmap + item * Wp + wc0 + c) : 0ull;
+            tile[r * kPitch + c] = (item != 0 && item < n_rows) ? __ldg(bitmap + item * Wp + wc0 + c) : 0ull;
         }
     }
     __syncthreads();
@@ -63,20 +76,9 @@ __global__ void __launch_bounds__(256) k_transpose(const uint64_t *__restrict__ 
     uint32_t keep0[8], keep1[8];
 #pragma unroll
     for (int ib = 0; ib < 8; ++ib) {
-        const uint64_t x = tile[(ib * 32 + lane) * kTrPitch + warp];
-        const uint32_t xlo = (uint32_t)x, xhi = (uint32_t)(x >> 32);
-        uint32_t k0 = 0, k1 = 0;
-#pragma unroll
-        for (int b = 0; b < 32; ++b) {
-            const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (xlo >> b) & 1u);
-            const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (xhi >> b) & 1u);
-            if (lane == (uint32_t)b) {
-                k0 = m0;
-                k1 = m1;
-            }
-        }
-        keep0[ib] = k0;
-        keep1[ib] = k1;
+        const uint64_t x = tile[(ib * 32 + lane) * kPitch + warp];
+        keep0[ib] = transpose32((uint32_t)x, lane);
+        keep1[ib] = transpose32((uint32_t)(x >> 32), lane);
     }
     // lane b owns groups wc*64 + b and wc*64 + 32 + b; 8 u32 = items item0 .. item0+255
     const uint64_t col32 = item0 / 32u;
@@ -435,9 +437,13 @@ size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general) {
 int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
                      uint64_t gm_stride, cudaStream_t stream) {
     const uint32_t W = (G + 63u) / 64u;
-    dim3 grid((unsigned)(gm_stride * 64u / kTrItems), (W + kTrCols - 1u) / kTrCols);
-    k_transpose<<<grid, 256, 0, stream>>>(bitmap, n_rows, G, W, Wp, reinterpret_cast<uint32_t *>(gm),
-                                          gm_stride * 2u);
+    const unsigned gx = (unsigned)(gm_stride * 64u / kTrItems);
+    if (Wp >= 16u)  // 128-byte (or wider) rows: one CTA reads whole lines
+        k_transpose<16><<<dim3(gx, (W + 15u) / 16u), 512, 0, stream>>>(bitmap, n_rows, G, W, Wp,
+                                                                      reinterpret_cast<uint32_t *>(gm), gm_stride * 2u);
+    else
+        k_transpose<8><<<dim3(gx, (W + 7u) / 8u), 256, 0, stream>>>(bitmap, n_rows, G, W, Wp,
+                                                                    reinterpret_cast<uint32_t *>(gm), gm_stride * 2u);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }
