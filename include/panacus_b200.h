@@ -73,6 +73,14 @@ int pgx_abacus_adopt_device(pgx_abacus *a, uint64_t *d_bitmap, uint32_t *d_weigh
  * (abacus.rs:719-744, 859-899).  Ids are the reference's u64 ItemIdSize. */
 int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, uint32_t group_id,
                        const uint8_t *exclude);
+/* Whole-graph device-side build: the complete ItemTable (items[0..n_steps), id_prefsum[0..n_paths]) plus the
+ * counting order as a per-path group id (path_group[p] = group of path p, or -1 if the path is not counted:
+ * excluded / outside the subset / absent from the order, abacus.rs:310-347, 555-569).  One upload, one kernel:
+ * every step finds its path by binary search in id_prefsum and ORs its group's bit into the item's row.
+ * Replaces the per-path loops of item_table_to_abacus (abacus.rs:539-586) and both CSR passes
+ * (abacus.rs:859-986). */
+int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
+                     uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude);
 int pgx_abacus_clear(pgx_abacus *a);
 /* Device -> host copy of the bitmap in the packed host layout (host_row_words per row). */
 int pgx_abacus_download(pgx_abacus *a, uint64_t *bitmap, uint32_t host_row_words);

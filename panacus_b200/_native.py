@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libpanacus_b200.so")
 EXPORTS = [
     "pgx_version", "pgx_last_error", "pgx_device_count", "pgx_row_words",
     "pgx_abacus_create", "pgx_abacus_destroy", "pgx_abacus_set_stream", "pgx_abacus_shape",
-    "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_clear",
+    "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_build", "pgx_abacus_clear",
     "pgx_abacus_download", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
     "pgx_permuted_growth", "pgx_similarity", "pgx_fused_out_words", "pgx_fused_pass_async",
     "pgx_launch_count", "pgx_last_launch_info",
@@ -64,6 +64,8 @@ def lib() -> C.CDLL:
     L.pgx_abacus_adopt_device.argtypes = [vp, vp, vp]
     L.pgx_abacus_scatter.restype = C.c_int
     L.pgx_abacus_scatter.argtypes = [vp, vp, C.c_uint64, C.c_uint32, vp]
+    L.pgx_abacus_build.restype = C.c_int
+    L.pgx_abacus_build.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]
     L.pgx_abacus_clear.restype = C.c_int
     L.pgx_abacus_clear.argtypes = [vp]
     L.pgx_abacus_download.restype = C.c_int

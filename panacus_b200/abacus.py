@@ -157,6 +157,19 @@ class DeviceAbacus:
             raise ValueError("exclude must have n_items + 1 entries")
         _native.check(self._L.pgx_abacus_scatter(self._h, _ptr(items), items.size, int(group_id), _ptr(ex)))
 
+    def build(self, items: np.ndarray, id_prefsum: np.ndarray, path_group: np.ndarray, exclude: Optional[np.ndarray] = None):
+        """Whole ItemTable -> bitmap in one call; path_group[p] = group id of path p, or -1 if not counted."""
+        items = np.ascontiguousarray(items, dtype=np.uint64)
+        id_prefsum = np.ascontiguousarray(id_prefsum, dtype=np.uint64)
+        path_group = np.ascontiguousarray(path_group, dtype=np.int64)
+        if path_group.size + 1 != id_prefsum.size:
+            raise ValueError("id_prefsum must have one more entry than path_group")
+        ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.uint8)
+        if ex is not None and ex.shape != (self.n_items + 1,):
+            raise ValueError("exclude must have n_items + 1 entries")
+        _native.check(self._L.pgx_abacus_build(self._h, _ptr(items), items.size, _ptr(id_prefsum), path_group.size,
+                                               _ptr(path_group), _ptr(ex)))
+
     def download(self) -> np.ndarray:
         out = np.zeros((self.n_items + 1, self.row_words), dtype=np.uint64)
         _native.check(self._L.pgx_abacus_download(self._h, _ptr(out), self.row_words))

@@ -659,6 +659,59 @@ int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, u
     return rc;
 }
 
+int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
+                     uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (!id_prefsum || !path_group || (n_steps && !items)) return fail(PGX_ERR_INVALID, "null table pointer");
+    if (n_paths == 0) return n_steps ? fail(PGX_ERR_INVALID, "steps without paths") : (int)PGX_OK;
+    if (id_prefsum[0] != 0 || id_prefsum[n_paths] != n_steps) return fail(PGX_ERR_INVALID, "id_prefsum does not span the items");
+    for (uint64_t p = 0; p < n_paths; ++p)
+        if (id_prefsum[p] > id_prefsum[p + 1]) return fail(PGX_ERR_INVALID, "id_prefsum is not monotone");
+    DeviceGuard guard(a->device);
+    // device staging, freed on every exit path
+    struct Staging {
+        uint64_t *items = nullptr, *prefsum = nullptr;
+        int64_t *group = nullptr;
+        uint8_t *ex = nullptr;
+        ~Staging() {
+            cudaFree(items);
+            cudaFree(prefsum);
+            cudaFree(group);
+            cudaFree(ex);
+        }
+    } st;
+    const uint64_t kChunk = 1ull << 25;  // 32 Mi steps = 256 MB per staging copy
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.prefsum), (n_paths + 1) * 8u));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.group), n_paths * 8u));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.items), std::max<uint64_t>(std::min(kChunk, n_steps), 1) * 8u));
+    PGX_CUDA(cudaMemcpyAsync(st.prefsum, id_prefsum, (n_paths + 1) * 8u, cudaMemcpyHostToDevice, a->stream));
+    PGX_CUDA(cudaMemcpyAsync(st.group, path_group, n_paths * 8u, cudaMemcpyHostToDevice, a->stream));
+    if (exclude) {
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.ex), a->n_rows));
+        PGX_CUDA(cudaMemcpyAsync(st.ex, exclude, a->n_rows, cudaMemcpyHostToDevice, a->stream));
+    }
+    invalidate_derived(a);
+    for (uint64_t s0 = 0; s0 < n_steps; s0 += kChunk) {
+        const uint64_t n = std::min<uint64_t>(kChunk, n_steps - s0);
+        PGX_CUDA(cudaMemcpyAsync(st.items, items + s0, n * 8u, cudaMemcpyHostToDevice, a->stream));
+        if ((rc = launch_build(a->d_bitmap, a->Wp, a->n_rows, a->G, st.items, s0, n, st.prefsum, n_paths, st.group, st.ex,
+                               a->d_err, a->stream)))
+            return rc;
+        a->launches++;
+        PGX_CUDA(cudaStreamSynchronize(a->stream));  // the staging buffer is reused by the next chunk
+    }
+    unsigned int err = 0;
+    PGX_CUDA(cudaMemcpyAsync(&err, a->d_err, 4, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if (err) {
+        PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
+        return fail(PGX_ERR_INVALID, (err & 1u) ? "item id out of range 1..=n_items in the ItemTable" : "path_group entry >= n_groups");
+    }
+    a->last_launch = "k_build";
+    return PGX_OK;
+}
+
 int pgx_abacus_download(pgx_abacus *a, uint64_t *bitmap, uint32_t host_row_words) {
     int rc = check_handle(a);
     if (rc) return rc;

@@ -413,6 +413,39 @@ __global__ void __launch_bounds__(256) k_scatter(uint64_t *bitmap, uint32_t Wp, 
     }
 }
 
+// whole-ItemTable build: items[] holds steps [step0, step0 + n_steps) of the table
+__global__ void __launch_bounds__(256) k_build(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, uint32_t G,
+                                               const uint64_t *__restrict__ items, uint64_t step0, uint64_t n_steps,
+                                               const uint64_t *__restrict__ prefsum, uint64_t n_paths,
+                                               const int64_t *__restrict__ path_group,
+                                               const uint8_t *__restrict__ exclude, unsigned int *err) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_steps; k += stride) {
+        const uint64_t s = step0 + k;
+        // largest p with prefsum[p] <= s (empty paths share a boundary; the search lands on the owner)
+        uint64_t lo = 0, hi = n_paths;
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(prefsum + mid) <= s) lo = mid; else hi = mid;
+        }
+        const long long grp = __ldg(path_group + lo);
+        if (grp < 0) continue;
+        if ((unsigned long long)grp >= G) {
+            atomicOr(err, 4u);
+            continue;
+        }
+        const uint64_t id = __ldg(items + k);
+        if (id == 0 || id >= n_rows) {
+            atomicOr(err, 1u);
+            continue;
+        }
+        if (exclude && __ldg(exclude + id)) continue;
+        unsigned long long *word = reinterpret_cast<unsigned long long *>(bitmap + id * Wp + ((uint32_t)grp >> 6));
+        const unsigned long long bit = 1ull << ((uint32_t)grp & 63u);
+        if (!(*word & bit)) atomicOr(word, bit);
+    }
+}
+
 size_t gm_growth_smem(const GmGrowthParams &p) { return gm_growth_smem_bytes(p.G, p.T, p.general_mask != 0); }
 
 template <int P, bool GENERAL, int TMAX>
@@ -510,6 +543,18 @@ int launch_weight_planes(const uint32_t *weight, uint64_t n_rows, uint64_t *plan
     const uint64_t threads = n_items32 * 32u;
     k_weight_planes<<<(unsigned)((threads + 255u) / 256u), 256, 0, stream>>>(
         weight, n_rows, reinterpret_cast<uint32_t *>(planes), gm_stride * 2u, n_planes, n_items32);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+int launch_build(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, uint32_t G, const uint64_t *d_items, uint64_t step0,
+                 uint64_t n_steps, const uint64_t *d_prefsum, uint64_t n_paths, const int64_t *d_path_group,
+                 const uint8_t *d_exclude, unsigned int *d_err, cudaStream_t stream) {
+    if (n_steps == 0) return PGX_OK;
+    uint64_t blocks = (n_steps + 255u) / 256u;
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    k_build<<<(unsigned)blocks, 256, 0, stream>>>(bitmap, Wp, n_rows, G, d_items, step0, n_steps, d_prefsum, n_paths,
+                                                  d_path_group, d_exclude, d_err);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }

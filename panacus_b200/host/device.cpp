@@ -27,12 +27,13 @@ void DeviceAbacus::build(const ItemTables &t, const std::vector<std::pair<uint64
     // group id = rank of first appearance in counting order (abacus.rs:555-569, 816-829)
     group_names.clear();
     const uint8_t *ex = t.exclude.empty() ? nullptr : t.exclude.data();
+    std::vector<int64_t> path_group(t.id_prefsum.size() - 1, -1);  // -1: path not counted
     for (auto &po : path_order) {
         if (group_names.empty() || group_names.back() != po.second) group_names.push_back(po.second);
-        const uint32_t gid = (uint32_t)group_names.size() - 1;
-        const uint64_t b = t.id_prefsum[po.first], e = t.id_prefsum[po.first + 1];
-        if (e > b) check(pgx_abacus_scatter(H(h_), t.items.data() + b, e - b, gid, ex), "pgx_abacus_scatter");
+        path_group[po.first] = (int64_t)group_names.size() - 1;
     }
+    check(pgx_abacus_build(H(h_), t.items.data(), t.items.size(), t.id_prefsum.data(), path_group.size(), path_group.data(), ex),
+          "pgx_abacus_build");
 }
 
 void DeviceAbacus::set_weights(const std::vector<uint32_t> &w) {

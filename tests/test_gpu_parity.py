@@ -268,6 +268,42 @@ def test_scatter_build_matches_reference_incidence():
             a.scatter(np.array([t.n_items + 1], dtype=np.uint64), 0)
 
 
+def test_whole_table_build_matches_reference_incidence():
+    for kw in ({"groupby_sample": True}, {"groupby_haplotype": True, "exclude": os.path.join(GOLDEN, "exclusion.bed3")},
+               {"subset": os.path.join(GOLDEN, "inclusion.bed3")}):
+        for count in ("node", "edge"):
+            g, t, op, og, names, bits, weights = fixture_bitmap("chrM_test.gfa", count, **kw)
+            path_group = np.full(len(t.id_prefsum) - 1, -1, dtype=np.int64)  # paths outside the order are not counted
+            path_group[op.astype(np.int64)] = og.astype(np.int64)
+            with pb.DeviceAbacus(t.n_items, len(names)) as a:
+                a.build(t.items, t.id_prefsum, path_group, t.exclude)
+                assert np.array_equal(a.download(), pb.pack_bits(bits)), (kw, count)
+                _, _, ct = a.hist(True, False, True)
+                assert np.array_equal(ct, po.abacus_by_total(t.n_items, t.items, t.id_prefsum, op, og, t.exclude))
+    # random table with empty paths and repeated visits; one path left out
+    rng = np.random.default_rng(5)
+    N, P, G = 5000, 40, 13
+    lens = rng.integers(0, 800, P)
+    lens[[3, 4, 17]] = 0
+    items = rng.integers(1, N + 1, int(lens.sum())).astype(np.uint64)
+    prefsum = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    path_group = rng.integers(0, G, P).astype(np.int64)
+    path_group[7] = -1
+    want = np.zeros((N + 1, G), dtype=np.uint8)
+    for p in range(P):
+        if path_group[p] >= 0:
+            want[items[int(prefsum[p]):int(prefsum[p + 1])].astype(np.int64), path_group[p]] = 1
+    with pb.DeviceAbacus(N, G) as a:
+        a.build(items, prefsum, path_group)
+        assert np.array_equal(a.download(), pb.pack_bits(want))
+        with pytest.raises(pb.PgxError):
+            a.build(np.array([N + 1], dtype=np.uint64), np.array([0, 1], dtype=np.uint64), np.array([0], dtype=np.int64))
+        with pytest.raises(pb.PgxError):
+            a.build(np.array([1], dtype=np.uint64), np.array([0, 1], dtype=np.uint64), np.array([G], dtype=np.int64))
+        with pytest.raises(pb.PgxError):
+            a.build(np.array([1, 2], dtype=np.uint64), np.array([0, 1], dtype=np.uint64), np.array([0], dtype=np.int64))
+
+
 def test_argument_errors():
     with pytest.raises(pb.PgxError):
         pb.DeviceAbacus(10, 0)
