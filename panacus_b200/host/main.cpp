@@ -6,10 +6,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <map>
 #include <memory>
 #include <set>
+#include <sstream>
 
 #include "panacus_host.hpp"
 
@@ -165,7 +167,7 @@ Hist device_hist(const Run &r, CountType c) {
 
 std::vector<double> as_f64(const std::vector<uint64_t> &v) { return std::vector<double>(v.begin(), v.end()); }
 
-int cmd_hist(const Args &a, const std::string &cmdline) {
+int cmd_hist(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     const auto counts = expand(count);
     const Run r = load(a, counts, false);
@@ -176,7 +178,7 @@ int cmd_hist(const Args &a, const std::string &cmdline) {
         cols.push_back(as_f64(h.coverage));
         headers.push_back({"hist", to_string(c), "", ""});
     }
-    std::cout << write_metadata_comments(cmdline, true) << write_table(headers, cols) << "\n";
+    os << write_metadata_comments(cmdline, true) << write_table(headers, cols) << "\n";
     return 0;
 }
 
@@ -201,7 +203,7 @@ bool ends_with(const std::string &s, const std::string &suf) {
     return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
 }
 
-int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth) {
+int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth, std::ostream &os) {
     const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
     const std::string file = a.positional.at(0);
     if (!histgrowth && ends_with(file, ".tsv")) {  // src/lib.rs:160-190: growth from a hist table, no graph
@@ -209,8 +211,8 @@ int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth) {
             throw Error("subset, exclude and groupby can only be used in graph mode (with a .gfa or .gfa.gz file)");
         std::vector<std::string> comments;
         const std::vector<Hist> hists = parse_hists(file, comments);
-        for (auto &c : comments) std::cout << c << "\n";
-        std::cout << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
+        for (auto &c : comments) os << c << "\n";
+        os << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
         return 0;
     }
     // `growth <gfa>` has no --count: node (graph_broker.rs:158-160); histgrowth takes -c
@@ -219,11 +221,11 @@ int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth) {
     const Run r = load(a, counts, false);
     std::vector<Hist> hists;
     for (auto c : counts) hists.push_back(device_hist(r, c));
-    std::cout << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
+    os << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
     return 0;
 }
 
-int cmd_ordered(const Args &a, const std::string &cmdline) {
+int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     if (count == CountType::All) throw Error("ordered-histgrowth does not accept count type 'all'");
     const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
@@ -241,7 +243,7 @@ int cmd_ordered(const Args &a, const std::string &cmdline) {
     std::vector<std::vector<std::string>> headers = {{"panacus", "count", "coverage", "quorum"}};
     for (size_t k = 0; k < aux.coverage.size(); ++k)
         headers.push_back({"ordered-growth", to_string(count), aux.coverage[k].get_string(), aux.quorum[k].get_string()});
-    std::cout << write_metadata_comments(cmdline, true) << write_ordered_table(headers, cols, groups) << "\n";
+    os << write_metadata_comments(cmdline, true) << write_ordered_table(headers, cols, groups) << "\n";
     return 0;
 }
 
@@ -308,7 +310,7 @@ std::vector<size_t> cluster_leaf_order(const std::vector<std::vector<float>> &ta
     return leaves;
 }
 
-int cmd_similarity(const Args &a, const std::string &cmdline) {
+int cmd_similarity(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     if (count == CountType::All) throw Error("similarity does not accept count type 'all'");
     std::string method = a.get("method", "centroid");
@@ -338,7 +340,7 @@ int cmd_similarity(const Args &a, const std::string &cmdline) {
         for (size_t j = 0; j < G; ++j) out += "\t" + format_f32(table[perm[i]][perm[j]]);
         out += "\n";
     }
-    std::cout << out << "\n";
+    os << out << "\n";
     return 0;
 }
 
@@ -349,23 +351,58 @@ void usage() {
                  "  -m, --method single|complete|average|weighted|ward|centroid|median (similarity)   -t, --threads N\n";
 }
 
+int dispatch(int argc, char **argv, std::ostream &os) {
+    const Args a = parse_args(argc, argv);
+    if (a.sub.empty() || a.positional.empty()) {
+        usage();
+        return 2;
+    }
+    const std::string cmdline = argv_joined(argc, argv);
+    if (a.sub == "hist") return cmd_hist(a, cmdline, os);
+    if (a.sub == "growth") return cmd_growth(a, cmdline, false, os);
+    if (a.sub == "histgrowth") return cmd_growth(a, cmdline, true, os);
+    if (a.sub == "ordered-histgrowth") return cmd_ordered(a, cmdline, os);
+    if (a.sub == "similarity") return cmd_similarity(a, cmdline, os);
+    usage();
+    return 2;
+}
+
+// `panacus batch <file>`: one command line per row of <file> (whitespace separated, no quoting), all in
+// one process so the CUDA context is created once.  Output: "## batch <i> rc=<code>" then the command's
+// stdout.  Not part of the reference CLI; used by the test-suite and for scripted runs.
+int run_batch(const char *prog, const std::string &file) {
+    std::ifstream in(file);
+    if (!in) throw Error("cannot open " + file);
+    std::string line;
+    int idx = 0, worst = 0;
+    while (std::getline(in, line)) {
+        std::vector<std::string> tok = {prog};
+        std::stringstream ss(line);
+        std::string t;
+        while (ss >> t) tok.push_back(t);
+        if (tok.size() == 1) continue;
+        std::vector<char *> av;
+        for (auto &x : tok) av.push_back(const_cast<char *>(x.c_str()));
+        std::ostringstream out;
+        int rc;
+        try {
+            rc = dispatch((int)av.size(), av.data(), out);
+        } catch (const std::exception &e) {
+            rc = 1;
+            out << "error: " << e.what() << "\n";
+        }
+        std::cout << "## batch " << idx++ << " rc=" << rc << "\n" << out.str();
+        worst = std::max(worst, rc);
+    }
+    return worst;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
     try {
-        const Args a = parse_args(argc, argv);
-        if (a.sub.empty() || a.positional.empty()) {
-            usage();
-            return 2;
-        }
-        const std::string cmdline = argv_joined(argc, argv);
-        if (a.sub == "hist") return cmd_hist(a, cmdline);
-        if (a.sub == "growth") return cmd_growth(a, cmdline, false);
-        if (a.sub == "histgrowth") return cmd_growth(a, cmdline, true);
-        if (a.sub == "ordered-histgrowth") return cmd_ordered(a, cmdline);
-        if (a.sub == "similarity") return cmd_similarity(a, cmdline);
-        usage();
-        return 2;
+        if (argc == 3 && std::string(argv[1]) == "batch") return run_batch(argv[0], argv[2]);
+        return dispatch(argc, argv, std::cout);
     } catch (const std::exception &e) {
         std::cerr << "error: " << e.what() << "\n";
         return 1;

@@ -25,6 +25,21 @@ def run_cli(*args, expect_ok=True):
     return r
 
 
+def run_many(arglists, tmp_path):
+    """several commands in ONE process (`panacus batch`): the CUDA context is created once"""
+    f = tmp_path / "batch.txt"
+    f.write_text("".join(" ".join(a) + "\n" for a in arglists))
+    r = subprocess.run([BIN, "batch", str(f)], capture_output=True, text=True, timeout=600)
+    parts = r.stdout.split("## batch ")[1:]
+    assert len(parts) == len(arglists), (r.stdout[-500:], r.stderr[-500:])
+    outs = []
+    for i, part in enumerate(parts):
+        head, _, rest = part.partition("\n")
+        assert head == f"{i} rc=0", (head, rest[:300])
+        outs.append(rest)
+    return outs
+
+
 def body(text):
     """drop the comment lines and the trailing blank line"""
     lines = [l for l in text.split("\n") if not l.startswith("#")]
@@ -116,14 +131,15 @@ FLAG_SETS = [
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags,kw", FLAG_SETS)
-def test_hist_chrM(flags, kw):
-    for count in ("node", "bp", "edge"):
-        out = run_cli("hist", os.path.join(GOLDEN, "chrM_test.gfa"), "-c", count, *flags).stdout
+def test_hist_chrM(flags, kw, tmp_path):
+    gfa = os.path.join(GOLDEN, "chrM_test.gfa")
+    counts = ["node", "bp", "edge", "all"]
+    outs = run_many([["hist", gfa, "-c", c, *flags] for c in counts], tmp_path)
+    for count, out in zip(counts[:3], outs):
         assert body(out) == po.hist_table([(count, oracle_hist("chrM_test.gfa", count, **kw))]), (count, flags)
         assert out.split("\n")[1].startswith("# version")
-    out = run_cli("hist", os.path.join(GOLDEN, "chrM_test.gfa"), "-c", "all", *flags).stdout
     want = po.hist_table([(c, oracle_hist("chrM_test.gfa", c, **kw)) for c in ("node", "bp", "edge")])
-    assert body(out) == want
+    assert body(outs[3]) == want
 
 
 @pytest.mark.gpu
@@ -139,25 +155,28 @@ def test_hist_chrM_reference_golden():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("gfa", ["chrM_test.gfa", "t_groups.gfa", "cdbg.gfa"])
-def test_histgrowth_and_growth(gfa):
+def test_histgrowth_and_growth(gfa, tmp_path):
     path = os.path.join(GOLDEN, gfa)
     cov, quo = po.parse_thresholds("0,0.5,1", "0,1,2")
-    for count in ("node", "bp", "edge"):
-        if gfa == "cdbg.gfa" and count == "edge":
-            continue
-        out = run_cli("histgrowth", path, "-c", count, "-q", "0,0.5,1", "-l", "0,1,2", "-a").stdout
+    counts = [c for c in ("node", "bp", "edge") if not (gfa == "cdbg.gfa" and c == "edge")]
+    outs = run_many([["histgrowth", path, "-c", c, "-q", "0,0.5,1", "-l", "0,1,2", "-a"] for c in counts]
+                    + [["growth", path, "-q", "0,0.5,1", "-l", "0,1,2"]], tmp_path)
+    for count, out in zip(counts, outs):
         want = po.growth_table([(count, oracle_hist(gfa, count))], cov, quo, add_hist=True)
         assert body(out) == want, (gfa, count)
-    out = run_cli("growth", path, "-q", "0,0.5,1", "-l", "0,1,2").stdout
+    out = outs[-1]
     assert body(out) == po.growth_table([("node", oracle_hist(gfa, "node"))], cov, quo)
     assert not any(l.startswith("# version") for l in out.split("\n"))  # growth.rs:48-51: no version line
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags,kw", FLAG_SETS)
-def test_ordered_histgrowth_chrM(flags, kw):
+def test_ordered_histgrowth_chrM(flags, kw, tmp_path):
     cov, quo = po.parse_thresholds("0,0.5,0.9,1", "1,2,1,1")
-    for count in ("node", "bp", "edge"):
+    counts = ("node", "bp", "edge")
+    outs = run_many([["ordered-histgrowth", os.path.join(GOLDEN, "chrM_test.gfa"), "-c", c, "-q", "0,0.5,0.9,1",
+                      "-l", "1,2,1,1", *flags] for c in counts], tmp_path)
+    for count, out in zip(counts, outs):
         g, t, op, og, names = oracle_tables("chrM_test.gfa", count, **kw)
         r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
         unc = None
@@ -168,8 +187,6 @@ def test_ordered_histgrowth_chrM(flags, kw):
         curves = [po.calc_growth(r, c, len(names), cc, qq, count_bp=(count == "bp"), node_lens=g.node_lens, uncovered=unc)
                   for cc, qq in zip(cov, quo)]
         want = po.ordered_growth_table(count, names, curves, cov, quo)
-        out = run_cli("ordered-histgrowth", os.path.join(GOLDEN, "chrM_test.gfa"), "-c", count, "-q", "0,0.5,0.9,1",
-                      "-l", "1,2,1,1", *flags).stdout
         assert body(out) == want, (count, flags)
 
 
