@@ -227,3 +227,74 @@ def test_similarity_values():
         assert sorted(perm) == list(range(len(names))) and [r[0] for r in rows[1:]] == rows[0][1:]
         for i, pi in enumerate(perm):
             assert [np.float32(x) for x in rows[1 + i][1:]] == [table[pi, pj] for pj in perm]
+
+
+# ---- GPU: a generated GFA (P and W lines, PanSN names, links) end to end ---------------------------------------------
+
+def write_synthetic_gfa(path, n_nodes=3000, n_samples=7, seed=1):
+    rng = np.random.default_rng(seed)
+    lens = np.where(rng.random(n_nodes) < 0.5, 1, 1 + np.floor(np.exp(rng.normal(2.0, 1.5, n_nodes))).astype(int))
+    lines = ["H\tVN:Z:1.1"]
+    for i in range(n_nodes):
+        lines.append(f"S\ts{i + 1}\t" + "ACGT"[i % 4] * int(min(lens[i], 400)))
+    walks, links = [], set()
+    for s in range(n_samples):
+        for hap in (1, 2):
+            for contig in range(2):
+                n = int(rng.integers(50, 600))
+                start = int(rng.integers(0, n_nodes - 1))
+                nodes = [start]
+                for _ in range(n - 1):
+                    step = int(rng.choice([1, 1, 1, 2, 3, -1]))
+                    nodes.append(int(np.clip(nodes[-1] + step, 0, n_nodes - 1)))
+                ori = ["+" if rng.random() < 0.85 else "-" for _ in nodes]
+                for (a, oa), (b, ob) in zip(zip(nodes, ori), zip(nodes[1:], ori[1:])):
+                    links.add((a, oa, b, ob))
+                walks.append((f"smp{s}", hap, f"ctg{contig}", nodes, ori))
+    for a, oa, b, ob in sorted(links):
+        lines.append(f"L\ts{a + 1}\t{oa}\ts{b + 1}\t{ob}\t0M")
+    for k, (smp, hap, ctg, nodes, ori) in enumerate(walks):
+        if k % 3 == 0:  # W line
+            walk = "".join((">" if o == "+" else "<") + f"s{n + 1}" for n, o in zip(nodes, ori))
+            lines.append(f"W\t{smp}\t{hap}\t{ctg}\t0\t{len(nodes)}\t{walk}")
+        else:
+            steps = ",".join(f"s{n + 1}{o}" for n, o in zip(nodes, ori))
+            lines.append(f"P\t{smp}#{hap}#{ctg}\t{steps}\t*")
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+@pytest.mark.gpu
+def test_generated_gfa_end_to_end(tmp_path):
+    gfa = str(tmp_path / "synthetic.gfa")
+    write_synthetic_gfa(gfa)
+    cov, quo = po.parse_thresholds("0,0.3,0.8", "1,2,3")
+    cmds = [["hist", gfa, "-c", "all", "-H"], ["histgrowth", gfa, "-c", "bp", "-S", "-q", "0,0.3,0.8", "-l", "1,2,3"],
+            ["ordered-histgrowth", gfa, "-c", "bp", "-S", "-q", "0,0.3,0.8", "-l", "1,2,3"],
+            ["ordered-histgrowth", gfa, "-c", "edge", "-q", "0,0.3,0.8", "-l", "1,2,3"]]
+    outs = run_many(cmds, tmp_path)
+
+    def tables(count, **kw):
+        g = go.parse_gfa(gfa)
+        mask = go.make_mask(g, **kw)
+        t = go.item_tables(g, mask, count)
+        op, og, names = go.path_order_arrays(mask, g)
+        return g, t, op, og, names
+
+    hists = []
+    for count in ("node", "bp", "edge"):
+        g, t, op, og, names = tables(count, groupby_haplotype=True)
+        ct = po.abacus_by_total(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        hists.append((count, po.construct_hist_bps(ct, g.node_lens, len(names)) if count == "bp"
+                      else po.construct_hist(ct, len(names))))
+    assert body(outs[0]) == po.hist_table(hists)
+    g, t, op, og, names = tables("bp", groupby_sample=True)
+    ct = po.abacus_by_total(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+    assert body(outs[1]) == po.growth_table([("bp", po.construct_hist_bps(ct, g.node_lens, len(names)))], cov, quo)
+    r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+    curves = [po.calc_growth(r, c, len(names), cc, qq, count_bp=True, node_lens=g.node_lens) for cc, qq in zip(cov, quo)]
+    assert body(outs[2]) == po.ordered_growth_table("bp", names, curves, cov, quo)
+    g, t, op, og, names = tables("edge")
+    r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+    curves = [po.calc_growth(r, c, len(names), cc, qq) for cc, qq in zip(cov, quo)]
+    assert body(outs[3]) == po.ordered_growth_table("edge", names, curves, cov, quo)
+    assert len(names) == 28  # 7 samples x 2 haplotypes x 2 contigs, one group per path

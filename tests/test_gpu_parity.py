@@ -360,3 +360,54 @@ def test_full_size_properties():
             cvs = b.ordered_growth(cov, thr, weighted=True)
             for t, (c, q) in enumerate(pairs):
                 assert np.array_equal(cvs[t].astype(np.float64), exp[("bp", c, q)])
+
+
+def test_large_permuted_growth_and_similarity_properties():
+    """BASELINE.json configs 3 / 4 at (reduced but HBM-sized) shapes: size-independent invariants that tie the
+    group-major kernels to the pinned histogram path."""
+    import torch
+    N, G = 1_000_000, 512
+    bitmap, weight = synth.torch_table(N, G, seed=synth.SEED_BASE + 3)
+    torch.cuda.synchronize()
+    with pb.DeviceAbacus(N, G) as a:
+        a.adopt_device(bitmap.data_ptr(), weight.data_ptr(), keepalive=(bitmap, weight))
+        hc, hw, ct = a.hist(True, True, True)
+        pairs = [(1, 0.0), (2, 0.5), (4, 0.9)]
+        cov, thr = cutoffs(G, pairs)
+        orders = synth.random_orders(6, G, seed=synth.SEED_BASE + 3)
+        orders[0] = np.arange(G)
+        for weighted, h in ((False, hc), (True, hw)):
+            pg = a.permuted_growth(orders, cov, thr, weighted=weighted)
+            ref = a.ordered_growth(cov, thr, weighted=weighted)
+            assert np.array_equal(pg[0], ref)                      # identity order == group order
+            total = int(h[1:].sum())
+            for p in range(orders.shape[0]):
+                assert int(pg[p, 0, -1]) == total                   # union of all groups is order independent
+                assert (np.diff(pg[p, 0].astype(np.int64)) >= 0).all()
+                # last column of (c, q): items with coverage >= c whose final verdict holds; quorum only removes
+                assert int(pg[p, 1, -1]) <= int(h[2:].sum()) and int(pg[p, 2, -1]) <= int(h[4:].sum())
+            # q = 1.0: an item keeps counting exactly while its groups form a prefix of the order (the reference
+            # tests the quorum against the last group that contained the item, abacus.rs:1007-1010), so the curve
+            # is non-increasing after position 0 and never below the core (items present in every group)
+            thr1 = np.stack([pb.quorum_thresholds(G, 1.0)])
+            core = a.permuted_growth(orders[:3], [1], thr1, weighted=weighted)
+            for p in range(3):
+                assert (np.diff(core[p, 0].astype(np.int64)) <= 0).all() and int(core[p, 0, -1]) >= int(h[G])
+        # first point of every curve = size of the first group of that order = len[] of the similarity path
+        inter, ln = a.similarity(weighted=False)
+        pg = a.permuted_growth(orders, [1], None, weighted=False)
+        assert [int(pg[p, 0, 0]) for p in range(6)] == [int(ln[orders[p, 0]]) for p in range(6)]
+        # similarity invariants: symmetric, diagonal = len, bounded by min(len), total incidences match the hist
+        assert np.array_equal(inter, inter.T) and np.array_equal(np.diag(inter), ln)
+        assert (inter <= np.minimum(ln[:, None], ln[None, :])).all()
+        assert int(ln.sum()) == int((np.arange(G + 1, dtype=np.uint64) * hc).sum())
+        # sum over pairs = sum over items of coverage^2 (every item contributes cov x cov ordered pairs)
+        cov2 = np.bincount(ct[1:].astype(np.int64), minlength=G + 1).astype(object)
+        assert int(inter.astype(object).sum()) == int(sum(int(c) * int(c) * int(cov2[c]) for c in range(G + 1)))
+        interw, lnw = a.similarity(weighted=True)
+        wnp = weight.cpu().numpy().view(np.uint32).astype(np.int64)
+        ctn = ct.astype(np.int64)
+        assert int(lnw.astype(object).sum()) == int((wnp[1:] * ctn[1:]).sum())
+        assert int(interw.astype(object).sum()) == int((wnp[1:] * ctn[1:] * ctn[1:]).sum())
+        part, _ = a.similarity(weighted=True, row_begin=100, row_end=229)
+        assert np.array_equal(part, interw[100:229])
