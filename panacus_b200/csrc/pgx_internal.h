@@ -21,6 +21,7 @@ enum ScanFlags : uint32_t {
     kHistCount = 1u,   // accumulate hist_count
     kHistWeight = 2u,  // accumulate hist_weight
     kWeighted = 4u,    // growth deltas sum weight[i] instead of 1
+    kJoint = 8u,       // small G: one joint (coverage, first group) histogram, marginalised in the epilogue
 };
 
 // Byte offsets into the dynamic shared memory of k_scan (identical on host and device).
@@ -33,6 +34,9 @@ struct ScanLayout {
     uint32_t off_delta_lo;   // u32[T*G]  (counts when not weighted)
     uint32_t off_delta_hi;   // u32[T*G]  (weighted only)
     uint32_t off_thr;        // u32[T*G]  (quorum kernel only)
+    uint32_t off_joint_cnt;  // u32[(G+1)*G] joint histogram of counts      (kJoint)
+    uint32_t off_joint_wlo;  // u32[(G+1)*G] joint histogram of weights, low  (kJoint, weights in use)
+    uint32_t off_joint_whi;  //                                       high
     uint32_t off_stage0;     // first pipeline stage (128-byte aligned)
     uint32_t stage_stride;   // bytes per stage
     uint32_t off_stage_w;    // offset of the weight tile inside a stage
