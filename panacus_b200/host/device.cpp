@@ -41,6 +41,18 @@ void DeviceAbacus::set_weights(const std::vector<uint32_t> &w) {
     check(pgx_abacus_upload(H(h_), nullptr, 0, w.data()), "pgx_abacus_upload(weights)");
 }
 
+void DeviceAbacus::download(std::vector<uint64_t> &bitmap) const {
+    const uint32_t W = (n_groups_ + 63u) / 64u;
+    bitmap.assign((size_t)(n_items_ + 1) * W, 0);
+    check(pgx_abacus_download(H(h_), bitmap.data(), W), "pgx_abacus_download");
+}
+
+void DeviceAbacus::upload(const std::vector<uint64_t> &bitmap) {
+    const uint32_t W = (n_groups_ + 63u) / 64u;
+    if (bitmap.size() != (size_t)(n_items_ + 1) * W) throw Error("bitmap size does not match the abacus shape");
+    check(pgx_abacus_upload(H(h_), bitmap.data(), W, nullptr), "pgx_abacus_upload");
+}
+
 void DeviceAbacus::hist(std::vector<uint64_t> *count, std::vector<uint64_t> *weight, std::vector<uint32_t> *countable) {
     if (count) count->assign(n_groups_ + 1, 0);
     if (weight) weight->assign(n_groups_ + 1, 0);

@@ -134,33 +134,91 @@ uint32_t count_groups(const std::vector<std::pair<uint64_t, std::string>> &po) {
     return n;
 }
 
-// builds the device abacus for one count type; returns the group names in counting order
-std::unique_ptr<DeviceAbacus> make_abacus(const Run &r, CountType c, ItemTables &t, std::vector<std::string> &groups) {
-    t = build_item_tables(r.graph, r.mask, c);
+// One counted abacus on the device plus the host-side facts the analyses need around it; built from a GFA
+// (Run) or read back from a packed-abacus cache file.
+struct Counted {
+    CountType count = CountType::Node;
+    std::unique_ptr<DeviceAbacus> ab;
+    std::vector<std::string> groups;          // counting order
+    std::vector<uint32_t> weights;            // node_lens (node / bp), ones (edge)
+    std::map<uint64_t, uint64_t> uncovered;   // uncovered_bps
+};
+
+struct Source {
+    bool cached = false;
+    std::string path;
+    Run run;
+};
+
+bool ends_with(const std::string &s, const std::string &suf) {
+    return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+Source open_source(const Args &a, const std::vector<CountType> &counts, bool with_order) {
+    Source src;
+    src.path = a.positional.at(0);
+    src.cached = ends_with(src.path, ".pabm");
+    if (src.cached) {
+        for (const char *k : {"subset", "exclude", "groupby", "groupby-sample", "groupby-haplotype", "order"})
+            if (a.has(k)) throw Error(std::string("--") + k + " cannot be combined with a packed-abacus (.pabm) input: grouping, "
+                                      "subset and order are fixed when the cache is written");
+    } else {
+        src.run = load(a, counts, with_order);
+    }
+    return src;
+}
+
+Counted get_counted(const Source &src, CountType c, const Args &a) {
+    Counted k;
+    k.count = c;
+    if (src.cached) {
+        AbacusFile f = AbacusFile::load(src.path);
+        if (f.count != c)
+            throw Error("packed abacus " + src.path + " holds count type '" + to_string(f.count) + "', not '" + to_string(c) + "'");
+        k.groups = std::move(f.groups);
+        k.weights = std::move(f.weights);
+        k.uncovered = std::move(f.uncovered);
+        k.ab = std::make_unique<DeviceAbacus>(f.n_items, (uint32_t)k.groups.size());
+        k.ab->upload(f.bitmap);
+        return k;
+    }
+    const Run &r = src.run;
+    ItemTables t = build_item_tables(r.graph, r.mask, c);
     const uint32_t G = count_groups(r.path_order);
     if (G == 0) throw Error("no path left to count (check --subset / --exclude)");
-    auto ab = std::make_unique<DeviceAbacus>(t.n_items, G);
-    ab->build(t, r.path_order, groups);
-    return ab;
+    k.ab = std::make_unique<DeviceAbacus>(t.n_items, G);
+    k.ab->build(t, r.path_order, k.groups);
+    k.weights = c == CountType::Edge ? std::vector<uint32_t>(t.n_items + 1, 1u) : r.graph.node_lens;
+    if (c == CountType::Edge) k.weights[0] = 0;
+    k.uncovered = std::move(t.uncovered_bps);
+    if (a.has("save-abacus")) {  // <prefix>.<count>.pabm
+        AbacusFile f;
+        f.count = c;
+        f.n_items = t.n_items;
+        f.groups = k.groups;
+        f.weights = k.weights;
+        f.uncovered = k.uncovered;
+        k.ab->download(f.bitmap);
+        f.save(a.get("save-abacus") + "." + to_string(c) + ".pabm");
+    }
+    return k;
 }
 
 // Hist::from_abacus (graph_broker/hist.rs:39-49): coverage histogram of one count type
-Hist device_hist(const Run &r, CountType c) {
-    ItemTables t;
-    std::vector<std::string> groups;
-    auto ab = make_abacus(r, c, t, groups);
+Hist device_hist(const Source &src, CountType c, const Args &a) {
+    Counted k = get_counted(src, c, a);
     Hist h;
     h.count = c;
     if (c == CountType::Bp) {
-        ab->set_weights(r.graph.node_lens);
+        k.ab->set_weights(k.weights);
         std::vector<uint32_t> countable;
-        ab->hist(nullptr, &h.coverage, t.uncovered_bps.empty() ? nullptr : &countable);
-        for (auto &kv : t.uncovered_bps) {  // abacus.rs:779-785
+        k.ab->hist(nullptr, &h.coverage, k.uncovered.empty() ? nullptr : &countable);
+        for (auto &kv : k.uncovered) {  // abacus.rs:779-785
             h.coverage[countable[kv.first]] -= kv.second;
             h.coverage[0] += kv.second;
         }
     } else {
-        ab->hist(&h.coverage, nullptr, nullptr);
+        k.ab->hist(&h.coverage, nullptr, nullptr);
     }
     return h;
 }
@@ -170,11 +228,11 @@ std::vector<double> as_f64(const std::vector<uint64_t> &v) { return std::vector<
 int cmd_hist(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     const auto counts = expand(count);
-    const Run r = load(a, counts, false);
+    const Source src = open_source(a, counts, false);
     std::vector<std::vector<std::string>> headers = {{"panacus", "count", "", ""}};
     std::vector<std::vector<double>> cols;
     for (auto c : counts) {
-        const Hist h = device_hist(r, c);
+        const Hist h = device_hist(src, c, a);
         cols.push_back(as_f64(h.coverage));
         headers.push_back({"hist", to_string(c), "", ""});
     }
@@ -199,10 +257,6 @@ std::string growth_table(const std::vector<Hist> &hists, const ThresholdContaine
     return write_table(headers, cols);
 }
 
-bool ends_with(const std::string &s, const std::string &suf) {
-    return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
-}
-
 int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth, std::ostream &os) {
     const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
     const std::string file = a.positional.at(0);
@@ -218,9 +272,9 @@ int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth, std::
     // `growth <gfa>` has no --count: node (graph_broker.rs:158-160); histgrowth takes -c
     const CountType count = histgrowth ? count_type_from_str(a.get("count", "node")) : CountType::Node;
     const auto counts = expand(count);
-    const Run r = load(a, counts, false);
+    const Source src = open_source(a, counts, false);
     std::vector<Hist> hists;
-    for (auto c : counts) hists.push_back(device_hist(r, c));
+    for (auto c : counts) hists.push_back(device_hist(src, c, a));
     os << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
     return 0;
 }
@@ -229,16 +283,15 @@ int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     if (count == CountType::All) throw Error("ordered-histgrowth does not accept count type 'all'");
     const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
-    const Run r = load(a, {count}, true);
-    ItemTables t;
-    std::vector<std::string> groups;
-    auto ab = make_abacus(r, count, t, groups);
+    const Source src = open_source(a, {count}, true);
+    Counted k = get_counted(src, count, a);
+    const std::vector<std::string> &groups = k.groups;
     if (count == CountType::Bp) {  // weights = node_lens - uncovered_bps (abacus.rs:1016-1023)
-        std::vector<uint32_t> w = r.graph.node_lens;
-        for (auto &kv : t.uncovered_bps) w[kv.first] = kv.second > w[kv.first] ? 0u : w[kv.first] - (uint32_t)kv.second;
-        ab->set_weights(w);
+        std::vector<uint32_t> w = k.weights;
+        for (auto &kv : k.uncovered) w[kv.first] = kv.second > w[kv.first] ? 0u : w[kv.first] - (uint32_t)kv.second;
+        k.ab->set_weights(w);
     }
-    std::vector<std::vector<double>> cols = ab->calc_growth(aux, count == CountType::Bp);
+    std::vector<std::vector<double>> cols = k.ab->calc_growth(aux, count == CountType::Bp);
     for (auto &c : cols) c.insert(c.begin(), std::nan(""));  // io.rs:580-583
     std::vector<std::vector<std::string>> headers = {{"panacus", "count", "coverage", "quorum"}};
     for (size_t k = 0; k < aux.coverage.size(); ++k)
@@ -315,13 +368,12 @@ int cmd_similarity(const Args &a, const std::string &cmdline, std::ostream &os) 
     if (count == CountType::All) throw Error("similarity does not accept count type 'all'");
     std::string method = a.get("method", "centroid");
     std::transform(method.begin(), method.end(), method.begin(), [](unsigned char c) { return (char)std::tolower(c); });
-    const Run r = load(a, {count}, false);
-    ItemTables t;
-    std::vector<std::string> groups;
-    auto ab = make_abacus(r, count, t, groups);
-    if (count == CountType::Bp) ab->set_weights(r.graph.node_lens);  // no uncovered_bps correction here (similarity.rs:130-150)
+    const Source src = open_source(a, {count}, false);
+    Counted k = get_counted(src, count, a);
+    const std::vector<std::string> &groups = k.groups;
+    if (count == CountType::Bp) k.ab->set_weights(k.weights);  // no uncovered_bps correction here (similarity.rs:130-150)
     std::vector<uint64_t> inter, len;
-    ab->similarity(count == CountType::Bp, inter, len);
+    k.ab->similarity(count == CountType::Bp, inter, len);
     const size_t G = groups.size();
     std::vector<std::vector<float>> table(G, std::vector<float>(G));
     for (size_t i = 0; i < G; ++i)
@@ -348,7 +400,8 @@ void usage() {
     std::cerr << "panacus (B200 hot path) -- usage: panacus <hist|growth|histgrowth|ordered-histgrowth|similarity> <GFA_FILE> [options]\n"
                  "  -s, --subset FILE   -e, --exclude FILE   -g, --groupby FILE   -H, --groupby-haplotype   -S, --groupby-sample\n"
                  "  -c, --count node|bp|edge|all   -l, --coverage LIST   -q, --quorum LIST   -a, --hist   -O, --order FILE\n"
-                 "  -m, --method single|complete|average|weighted|ward|centroid|median (similarity)   -t, --threads N\n";
+                 "  -m, --method single|complete|average|weighted|ward|centroid|median (similarity)   -t, --threads N\n"
+                 "  --save-abacus PREFIX   write PREFIX.<count>.pabm (packed abacus); a .pabm file is accepted in place of the GFA\n";
 }
 
 int dispatch(int argc, char **argv, std::ostream &os) {

@@ -139,6 +139,9 @@ class DeviceAbacus {
     void build(const ItemTables &t, const std::vector<std::pair<uint64_t, std::string>> &path_order,
                std::vector<std::string> &group_names);
     void set_weights(const std::vector<uint32_t> &w);
+    // packed host copies of the bitmap ((n_items + 1) x ceil(G/64) u64), for the on-disk abacus cache
+    void download(std::vector<uint64_t> &bitmap) const;
+    void upload(const std::vector<uint64_t> &bitmap);
     void hist(std::vector<uint64_t> *count, std::vector<uint64_t> *weight, std::vector<uint32_t> *countable);
     // AbacusByGroup::calc_growth for all threshold pairs (abacus.rs:989-1032); f64 like the reference
     std::vector<std::vector<double>> calc_growth(const ThresholdContainer &aux, bool weighted);
@@ -150,6 +153,19 @@ class DeviceAbacus {
     void *h_ = nullptr;
     uint64_t n_items_;
     uint32_t n_groups_;
+};
+
+// ---- packed-abacus cache file (".pabm"): skip GFA parsing on repeated runs (the analogue of the
+// reference's hist-TSV reuse, io.rs:244-290) -----------------------------------------------------------------------
+struct AbacusFile {
+    CountType count = CountType::Node;
+    uint64_t n_items = 0;
+    std::vector<std::string> groups;          // counting order
+    std::vector<uint32_t> weights;            // node_lens (node / bp) or all ones (edge), n_items + 1
+    std::map<uint64_t, uint64_t> uncovered;   // uncovered_bps (bp with --subset)
+    std::vector<uint64_t> bitmap;             // (n_items + 1) x ceil(G/64), node-major
+    void save(const std::string &path) const;
+    static AbacusFile load(const std::string &path);
 };
 
 }  // namespace panacus

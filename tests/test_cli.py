@@ -298,3 +298,31 @@ def test_generated_gfa_end_to_end(tmp_path):
     curves = [po.calc_growth(r, c, len(names), cc, qq) for cc, qq in zip(cov, quo)]
     assert body(outs[3]) == po.ordered_growth_table("edge", names, curves, cov, quo)
     assert len(names) == 28  # 7 samples x 2 haplotypes x 2 contigs, one group per path
+
+
+@pytest.mark.gpu
+def test_packed_abacus_cache_round_trip(tmp_path):
+    """--save-abacus writes <prefix>.<count>.pabm; feeding the .pabm back gives byte-identical tables
+    (skip GFA parsing on repeated runs)."""
+    gfa = os.path.join(GOLDEN, "chrM_test.gfa")
+    prefix = str(tmp_path / "chrM")
+    sub = os.path.join(GOLDEN, "inclusion.bed3")
+    first = run_many([["hist", gfa, "-c", "all", "-S", "-s", sub, "--save-abacus", prefix],
+                      ["ordered-histgrowth", gfa, "-c", "bp", "-S", "-s", sub, "-q", "0,0.5", "-l", "1,2"],
+                      ["histgrowth", gfa, "-c", "edge", "-S", "-s", sub, "-q", "0,1", "-a"],
+                      ["similarity", gfa, "-c", "node", "-S", "-s", sub]], tmp_path)
+    for c in ("node", "bp", "edge"):
+        assert os.path.exists(f"{prefix}.{c}.pabm")
+    again = run_many([["hist", f"{prefix}.bp.pabm", "-c", "bp"],
+                      ["ordered-histgrowth", f"{prefix}.bp.pabm", "-c", "bp", "-q", "0,0.5", "-l", "1,2"],
+                      ["histgrowth", f"{prefix}.edge.pabm", "-c", "edge", "-q", "0,1", "-a"],
+                      ["similarity", f"{prefix}.node.pabm", "-c", "node"]], tmp_path)
+    all_rows = [l.split("\t") for l in body(first[0]).strip().split("\n")]
+    bp_rows = [l.split("\t") for l in body(again[0]).strip().split("\n")]
+    assert [r[2] for r in all_rows] == [r[1] for r in bp_rows]      # the bp column, incl. the uncovered_bps patch
+    for k in (1, 2, 3):
+        assert body(first[k]) == body(again[k])
+    r = run_cli("hist", f"{prefix}.bp.pabm", "-c", "node", expect_ok=False)
+    assert r.returncode != 0 and "holds count type" in r.stderr
+    r = run_cli("hist", f"{prefix}.bp.pabm", "-c", "bp", "-S", expect_ok=False)
+    assert r.returncode != 0 and "cannot be combined" in r.stderr
