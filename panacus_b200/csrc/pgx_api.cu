@@ -43,7 +43,12 @@ struct pgx_abacus {
     uint64_t *d_gm = nullptr;  // group-major copy, lazily built
     uint64_t gm_stride = 0;
     bool gm_valid = false;
-    uint64_t *d_planes = nullptr;
+    // weighted similarity: a second group-major copy with the items sorted by weight (descending), so that
+    // most 64-item words carry a single weight (one popcount pass) and high weight planes are empty
+    uint64_t *d_gm_w = nullptr;
+    uint32_t *d_perm = nullptr, *d_sorted_w = nullptr;
+    uint64_t *d_planes = nullptr, *d_uniform_w = nullptr;
+    uint32_t *d_plane_mask = nullptr;
     uint32_t n_planes = 0;
     bool planes_valid = false;
 
@@ -285,7 +290,7 @@ int ensure_gm(pgx_abacus *a) {
     if (a->gm_valid) return PGX_OK;
     a->gm_stride = gm_stride_words(a->n_rows);
     if (!a->d_gm) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_gm), (size_t)a->G * a->gm_stride * 8u));
-    int rc = launch_transpose(a->d_bitmap, a->n_rows, a->G, a->Wp, a->d_gm, a->gm_stride, a->stream);
+    int rc = launch_transpose(a->d_bitmap, a->n_rows, a->G, a->Wp, a->d_gm, a->gm_stride, nullptr, a->stream);
     if (rc) return rc;
     a->launches++;
     a->gm_valid = true;
@@ -321,15 +326,23 @@ int ensure_planes(pgx_abacus *a) {
     uint32_t np = 0;
     while (np < 32u && (a->max_weight >> np)) ++np;
     a->gm_stride = gm_stride_words(a->n_rows);
-    if (a->d_planes) cudaFree(a->d_planes);
+    cudaFree(a->d_planes);
     a->d_planes = nullptr;
     a->n_planes = np;
-    if (np) {
-        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_planes), (size_t)np * a->gm_stride * 8u));
-        int rc = launch_weight_planes(a->d_weight, a->n_rows, a->d_planes, a->gm_stride, np, a->stream);
-        if (rc) return rc;
-        a->launches++;
-    }
+    const size_t gm_bytes = (size_t)a->G * a->gm_stride * 8u;
+    if (!a->d_gm_w) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_gm_w), gm_bytes));
+    if (!a->d_perm) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_perm), a->n_rows * 4u));
+    if (!a->d_sorted_w) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_sorted_w), a->n_rows * 4u));
+    if (!a->d_uniform_w) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_uniform_w), a->gm_stride * 8u));
+    if (!a->d_plane_mask) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_plane_mask), a->gm_stride * 4u));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_planes), std::max<size_t>((size_t)np, 1) * a->gm_stride * 8u));
+    int rc = sort_items_by_weight(a->d_weight, a->n_rows, a->d_perm, a->d_sorted_w, a->stream);
+    if (rc) return rc;
+    if ((rc = launch_transpose(a->d_bitmap, a->n_rows, a->G, a->Wp, a->d_gm_w, a->gm_stride, a->d_perm, a->stream))) return rc;
+    if ((rc = launch_weight_planes(a->d_sorted_w, a->n_rows, a->d_planes, a->gm_stride, np, a->d_uniform_w, a->d_plane_mask, 0,
+                                   a->stream)))
+        return rc;
+    a->launches += 4;
     a->planes_valid = true;
     return PGX_OK;
 }
@@ -517,6 +530,11 @@ void pgx_abacus_destroy(pgx_abacus *a) {
     cudaFree(a->d_countable);
     cudaFree(a->d_gm);
     cudaFree(a->d_planes);
+    cudaFree(a->d_gm_w);
+    cudaFree(a->d_perm);
+    cudaFree(a->d_sorted_w);
+    cudaFree(a->d_uniform_w);
+    cudaFree(a->d_plane_mask);
     cudaFree(a->d_acc);
     cudaFree(a->d_ticket);
     cudaFree(a->d_err);
@@ -804,9 +822,12 @@ int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row
     if (row_begin > row_end || row_end > a->G) return fail(PGX_ERR_INVALID, "bad row range");
     DeviceGuard guard(a->device);
     const uint32_t G = a->G;
-    if ((rc = ensure_gm(a))) return rc;
     const bool use_planes = weighted && a->d_weight;
-    if (use_planes && (rc = ensure_planes(a))) return rc;
+    if (use_planes) {
+        if ((rc = ensure_planes(a))) return rc;  // weight-sorted group-major copy + planes
+    } else if ((rc = ensure_gm(a))) {
+        return rc;
+    }
     const uint32_t rows = row_end - row_begin;
     const size_t inter_words = (size_t)rows * G;
     const size_t words = inter_words + G;
@@ -817,10 +838,12 @@ int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row
     if (rows && inter) {
         GmSimParams p;
         std::memset(&p, 0, sizeof(p));
-        p.gm = a->d_gm;
+        p.gm = use_planes ? a->d_gm_w : a->d_gm;
         p.gm_stride = a->gm_stride;
         p.n_words = n_words;
         p.planes = use_planes ? a->d_planes : nullptr;
+        p.uniform_w = use_planes ? a->d_uniform_w : nullptr;
+        p.plane_mask = use_planes ? a->d_plane_mask : nullptr;
         p.n_planes = use_planes ? a->n_planes : 0;
         p.G = G;
         p.row_begin = row_begin;
@@ -831,8 +854,9 @@ int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row
         a->last_launch = "k_gm_similarity";
     }
     if (len) {
-        if ((rc = launch_gm_rowsum(a->d_gm, a->gm_stride, n_words, use_planes ? a->d_planes : nullptr,
-                                   use_planes ? a->n_planes : 0, G, a->d_scratch + inter_words, a->stream)))
+        if ((rc = launch_gm_rowsum(use_planes ? a->d_gm_w : a->d_gm, a->gm_stride, n_words, use_planes ? a->d_planes : nullptr,
+                                   use_planes ? a->n_planes : 0, use_planes ? a->d_uniform_w : nullptr, G,
+                                   a->d_scratch + inter_words, a->stream)))
             return rc;
         a->launches++;
     }

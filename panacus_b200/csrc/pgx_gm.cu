@@ -9,6 +9,8 @@
 //                      (integer part of Similarity::set_table, src/analyses/similarity.rs:125-150)
 //   * k_weight_planes  bit-planes of the u32 item weights (bp-weighted intersections)
 //   * k_scatter        ItemTable slice -> bitmap bits (abacus.rs:719-744 de-duplication = idempotent OR)
+#include <cub/device/device_radix_sort.cuh>
+
 #include "pgx_common.cuh"
 #include "pgx_internal.h"
 
@@ -42,7 +44,8 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
 template <int COLS>
 __global__ void __launch_bounds__(COLS * 32) k_transpose(const uint64_t *__restrict__ bitmap, uint64_t n_rows, uint32_t G,
                                                          uint32_t W, uint32_t Wp, uint32_t *__restrict__ gm32,
-                                                         uint64_t gm_stride32) {
+                                                         uint64_t gm_stride32, const uint32_t *__restrict__ perm) {
+    // perm != nullptr: bit position i of the output rows holds item perm[i] (weight-sorted copy for similarity)
     constexpr int kPitch = COLS + 1, kThreads = COLS * 32;
     __shared__ uint64_t tile[kTrItems * kPitch];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -53,7 +56,8 @@ __global__ void __launch_bounds__(COLS * 32) k_transpose(const uint64_t *__restr
         const uint32_t chunks = ncols >> 1;  // 16-byte chunks per row
         for (uint32_t e = tid; e < kTrItems * chunks; e += kThreads) {
             const uint32_t r = e / chunks, c = e - r * chunks;
-            const uint64_t item = item0 + r;
+            uint64_t item = item0 + r;
+            if (perm && item < n_rows) item = __ldg(perm + item);
             uint64_t x0 = 0, x1 = 0;
             if (item != 0 && item < n_rows) {
                 const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(bitmap + item * Wp + wc0) + c);
@@ -66,7 +70,8 @@ __global__ void __launch_bounds__(COLS * 32) k_transpose(const uint64_t *__restr
     } else {
         for (uint32_t e = tid; e < kTrItems * ncols; e += kThreads) {
             const uint32_t r = e / ncols, c = e - r * ncols;
-            const uint64_t item = item0 + r;
+            uint64_t item = item0 + r;
+            if (perm && item < n_rows) item = __ldg(perm + item);
             tile[r * kPitch + c] = (item != 0 && item < n_rows) ? __ldg(bitmap + item * Wp + wc0 + c) : 0ull;
         }
     }
@@ -263,6 +268,8 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
     __shared__ uint64_t Xs[kSimKW][kSimPad];
     __shared__ uint64_t Ys[kSimKW][kSimPad];
     __shared__ uint64_t Ps[32][kSimKW];
+    __shared__ uint64_t Us[kSimKW];   // (1 << 32) | w if all 64 items of the word share weight w, else 0
+    __shared__ uint32_t Ms[kSimKW];   // non-empty weight planes of the word
     const uint32_t tid = threadIdx.x;
     const uint32_t tx = tid & 15u, ty = tid >> 4;
     uint32_t bx = blockIdx.x, by = blockIdx.y;
@@ -303,6 +310,11 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
                 const uint64_t k = k0 + kw;
                 Ps[pl][kw] = (k < k_end) ? __ldg(p.planes + (uint64_t)pl * p.gm_stride + k) : 0ull;
             }
+            if (tid < kSimKW) {
+                const uint64_t k = k0 + tid;
+                Us[tid] = (k < k_end) ? __ldg(p.uniform_w + k) : (1ull << 32);
+                Ms[tid] = (k < k_end) ? __ldg(p.plane_mask + k) : 0u;
+            }
         }
         __syncthreads();
 #pragma unroll 4
@@ -319,13 +331,22 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[i][j] += (uint64_t)__popcll(xv[i] & yv[j]);
             } else {
-                for (uint32_t pl = 0; pl < p.n_planes; ++pl) {
-                    const uint64_t pw = Ps[pl][kw];
-                    if (!pw) continue;
+                const uint64_t u = Us[kw];
+                if (u) {  // items are sorted by weight: most words carry one weight -> a single popcount pass
+                    const uint64_t w = u & 0xFFFFFFFFull;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] += (uint64_t)__popcll(xv[i] & yv[j] & pw) << pl;
+                        for (int j = 0; j < 4; ++j) acc[i][j] += (uint64_t)__popcll(xv[i] & yv[j]) * w;
+                } else {
+                    for (uint32_t m = Ms[kw]; m; m &= m - 1u) {
+                        const uint32_t pl = (uint32_t)__ffs((int)m) - 1u;
+                        const uint64_t pw = Ps[pl][kw];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[i][j] += (uint64_t)__popcll(xv[i] & yv[j] & pw) << pl;
+                    }
                 }
             }
         }
@@ -354,7 +375,8 @@ __global__ void __launch_bounds__(256) k_sim_mirror(uint64_t *inter, uint32_t G)
 // ---- per-group totals: len[g] = sum_i w_i [g in i] (similarity.rs:133-137) -------------------------
 __global__ void __launch_bounds__(256) k_gm_rowsum(const uint64_t *__restrict__ gm, uint64_t gm_stride,
                                                    uint64_t n_words, const uint64_t *__restrict__ planes,
-                                                   uint32_t n_planes, uint64_t *__restrict__ len) {
+                                                   uint32_t n_planes, const uint64_t *__restrict__ uniform_w,
+                                                   uint64_t *__restrict__ len) {
     const uint32_t g = blockIdx.x;
     const uint64_t *row = gm + (uint64_t)g * gm_stride;
     unsigned long long s = 0;
@@ -363,8 +385,13 @@ __global__ void __launch_bounds__(256) k_gm_rowsum(const uint64_t *__restrict__ 
         if (!planes) {
             s += (unsigned long long)__popcll(x);
         } else if (x) {
-            for (uint32_t pl = 0; pl < n_planes; ++pl)
-                s += (unsigned long long)__popcll(x & __ldg(planes + (uint64_t)pl * gm_stride + k)) << pl;
+            const uint64_t u = uniform_w ? __ldg(uniform_w + k) : 0ull;
+            if (u) {
+                s += (unsigned long long)__popcll(x) * (u & 0xFFFFFFFFull);
+            } else {
+                for (uint32_t pl = 0; pl < n_planes; ++pl)
+                    s += (unsigned long long)__popcll(x & __ldg(planes + (uint64_t)pl * gm_stride + k)) << pl;
+            }
         }
     }
     __shared__ unsigned long long part[8];
@@ -379,17 +406,44 @@ __global__ void __launch_bounds__(256) k_gm_rowsum(const uint64_t *__restrict__ 
 }
 
 // ---- weight bit-planes -----------------------------------------------------------------------------
+// One warp per 64-item word of the (position-indexed) weight vector: plane k = bit k of every weight;
+// uniform_w[word] = (1 << 32) | w when all valid items of the word share the weight w; plane_mask[word] =
+// which planes are non-empty.  skip0: position 0 is the dummy item (natural order).
 __global__ void __launch_bounds__(256) k_weight_planes(const uint32_t *__restrict__ weight, uint64_t n_rows,
-                                                       uint32_t *__restrict__ planes32, uint64_t stride32,
-                                                       uint32_t n_planes, uint64_t n_items32) {
-    const uint64_t gw = ((uint64_t)blockIdx.x * 256u + threadIdx.x) >> 5;  // global warp = 32-item block
+                                                       uint64_t *__restrict__ planes, uint64_t stride,
+                                                       uint32_t n_planes, uint64_t n_words_padded,
+                                                       uint64_t *__restrict__ uniform_w, uint32_t *__restrict__ plane_mask,
+                                                       int skip0) {
+    const uint64_t word = ((uint64_t)blockIdx.x * 256u + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
-    if (gw >= n_items32) return;
-    const uint64_t item = gw * 32u + lane;
-    const uint32_t w = (item != 0 && item < n_rows) ? __ldg(weight + item) : 0u;
+    if (word >= n_words_padded) return;
+    const uint64_t i0 = word * 64u + lane, i1 = i0 + 32u;
+    const bool v0 = i0 < n_rows && !(skip0 && i0 == 0), v1 = i1 < n_rows;
+    const uint32_t w0 = v0 ? __ldg(weight + i0) : 0u, w1 = v1 ? __ldg(weight + i1) : 0u;
+    uint32_t mask = 0;
     for (uint32_t k = 0; k < n_planes; ++k) {
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, (w >> k) & 1u);
-        if (lane == 0) planes32[(uint64_t)k * stride32 + gw] = m;
+        const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (w0 >> k) & 1u), m1 = __ballot_sync(0xFFFFFFFFu, (w1 >> k) & 1u);
+        if (lane == 0) planes[(uint64_t)k * stride + word] = (uint64_t)m0 | ((uint64_t)m1 << 32);
+        if (m0 | m1) mask |= 1u << k;
+    }
+    // reference weight: the first valid item of the word
+    const uint32_t valid0 = __ballot_sync(0xFFFFFFFFu, v0), valid1 = __ballot_sync(0xFFFFFFFFu, v1);
+    uint32_t ref = 0;
+    if (valid0) ref = __shfl_sync(0xFFFFFFFFu, w0, __ffs((int)valid0) - 1);
+    else if (valid1) ref = __shfl_sync(0xFFFFFFFFu, w1, __ffs((int)valid1) - 1);
+    const bool same = __all_sync(0xFFFFFFFFu, (!v0 || w0 == ref) && (!v1 || w1 == ref));
+    if (lane == 0) {
+        if (uniform_w) uniform_w[word] = same ? ((1ull << 32) | ref) : 0ull;
+        if (plane_mask) plane_mask[word] = mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sort_keys(const uint32_t *__restrict__ weight, uint64_t n_rows,
+                                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    if (i < n_rows) {
+        keys[i] = i ? __ldg(weight + i) : 0u;  // the dummy item sorts with the zero weights
+        vals[i] = (uint32_t)i;
     }
 }
 
@@ -468,15 +522,15 @@ size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general) {
 }
 
 int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
-                     uint64_t gm_stride, cudaStream_t stream) {
+                     uint64_t gm_stride, const uint32_t *perm, cudaStream_t stream) {
     const uint32_t W = (G + 63u) / 64u;
     const unsigned gx = (unsigned)(gm_stride * 64u / kTrItems);
     if (Wp >= 16u)  // 128-byte (or wider) rows: one CTA reads whole lines
         k_transpose<16><<<dim3(gx, (W + 15u) / 16u), 512, 0, stream>>>(bitmap, n_rows, G, W, Wp,
-                                                                      reinterpret_cast<uint32_t *>(gm), gm_stride * 2u);
+                                                                      reinterpret_cast<uint32_t *>(gm), gm_stride * 2u, perm);
     else
         k_transpose<8><<<dim3(gx, (W + 7u) / 8u), 256, 0, stream>>>(bitmap, n_rows, G, W, Wp,
-                                                                    reinterpret_cast<uint32_t *>(gm), gm_stride * 2u);
+                                                                    reinterpret_cast<uint32_t *>(gm), gm_stride * 2u, perm);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }
@@ -531,19 +585,48 @@ int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream
 }
 
 int launch_gm_rowsum(const uint64_t *gm, uint64_t gm_stride, uint64_t n_words, const uint64_t *planes,
-                     uint32_t n_planes, uint32_t G, uint64_t *len, cudaStream_t stream) {
-    k_gm_rowsum<<<G, 256, 0, stream>>>(gm, gm_stride, n_words, planes, n_planes, len);
+                     uint32_t n_planes, const uint64_t *uniform_w, uint32_t G, uint64_t *len, cudaStream_t stream) {
+    k_gm_rowsum<<<G, 256, 0, stream>>>(gm, gm_stride, n_words, planes, n_planes, uniform_w, len);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }
 
 int launch_weight_planes(const uint32_t *weight, uint64_t n_rows, uint64_t *planes, uint64_t gm_stride,
-                         uint32_t n_planes, cudaStream_t stream) {
-    const uint64_t n_items32 = gm_stride * 2u;  // 32-item blocks covering the padded row
-    const uint64_t threads = n_items32 * 32u;
-    k_weight_planes<<<(unsigned)((threads + 255u) / 256u), 256, 0, stream>>>(
-        weight, n_rows, reinterpret_cast<uint32_t *>(planes), gm_stride * 2u, n_planes, n_items32);
+                         uint32_t n_planes, uint64_t *uniform_w, uint32_t *plane_mask, int skip0, cudaStream_t stream) {
+    const uint64_t threads = gm_stride * 32u;  // one warp per (padded) 64-item word
+    k_weight_planes<<<(unsigned)((threads + 255u) / 256u), 256, 0, stream>>>(weight, n_rows, planes, gm_stride, n_planes,
+                                                                           gm_stride, uniform_w, plane_mask, skip0);
     PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+// perm[i] = item at sorted position i (weights descending), sorted_w[i] = its weight
+int sort_items_by_weight(const uint32_t *weight, uint64_t n_rows, uint32_t *perm, uint32_t *sorted_w, cudaStream_t stream) {
+    uint32_t *keys = nullptr, *vals = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const int n = (int)n_rows;
+    auto cleanup = [&]() {
+        cudaFree(keys);
+        cudaFree(vals);
+        cudaFree(tmp);
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&keys), n_rows * 4u)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&vals), n_rows * 4u)) != cudaSuccess) {
+        cleanup();
+        return fail(PGX_ERR_NOMEM, cudaGetErrorString(e));
+    }
+    k_sort_keys<<<(unsigned)((n_rows + 255u) / 256u), 256, 0, stream>>>(weight, n_rows, keys, vals);
+    e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, keys, sorted_w, vals, perm, n, 0, 32, stream);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, keys, sorted_w, vals, perm, n, 0, 32, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cleanup();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PGX_ERR_CUDA, std::string("sort_items_by_weight: ") + cudaGetErrorString(e));
+    }
     return PGX_OK;
 }
 

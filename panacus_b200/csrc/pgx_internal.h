@@ -94,7 +94,8 @@ int launch_scan(const ScanParams &p, bool quorum, int grid, cudaStream_t stream)
 // group g; gm_stride = ceil((N+1)/64) rounded up to a multiple of 16 words (128-byte rows).
 uint64_t gm_stride_words(uint64_t n_rows);
 int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
-                     uint64_t gm_stride, cudaStream_t stream);
+                     uint64_t gm_stride, const uint32_t *perm /*nullptr = natural item order*/, cudaStream_t stream);
+int sort_items_by_weight(const uint32_t *weight, uint64_t n_rows, uint32_t *perm, uint32_t *sorted_w, cudaStream_t stream);
 
 struct GmGrowthParams {
     const uint64_t *gm;      // G x gm_stride
@@ -122,6 +123,8 @@ struct GmSimParams {
     uint64_t gm_stride;
     uint64_t n_words;
     const uint64_t *planes;  // weighted: n_planes x gm_stride weight bit-planes, else nullptr
+    const uint64_t *uniform_w;   // weighted: per word (1 << 32) | w if the word's items share one weight, else 0
+    const uint32_t *plane_mask;  // weighted: non-empty planes per word
     uint32_t n_planes;
     uint32_t G;
     uint32_t row_begin, row_end;
@@ -130,9 +133,9 @@ struct GmSimParams {
 };
 int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream);
 int launch_gm_rowsum(const uint64_t *gm, uint64_t gm_stride, uint64_t n_words, const uint64_t *planes,
-                     uint32_t n_planes, uint32_t G, uint64_t *len, cudaStream_t stream);
+                     uint32_t n_planes, const uint64_t *uniform_w, uint32_t G, uint64_t *len, cudaStream_t stream);
 int launch_weight_planes(const uint32_t *weight, uint64_t n_rows, uint64_t *planes, uint64_t gm_stride,
-                         uint32_t n_planes, cudaStream_t stream);
+                         uint32_t n_planes, uint64_t *uniform_w, uint32_t *plane_mask, int skip0, cudaStream_t stream);
 
 // scatter build (ItemTable slice -> bitmap bits)
 int launch_scatter(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, const uint64_t *d_items, uint64_t n_steps,
