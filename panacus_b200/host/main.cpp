@@ -396,6 +396,39 @@ int cmd_similarity(const Args &a, const std::string &cmdline, std::ostream &os) 
     return 0;
 }
 
+// `panacus debug-tables <gfa> [-c count] [grouping / subset / exclude / order flags]`: dumps what the host front
+// end hands to the device (group order, ItemTable, exclude flags, uncovered bps, node lengths) as text.  No GPU
+// needed; the CPU test-suite compares it with the oracle's restatement of the reference front end.
+int cmd_debug_tables(const Args &a, std::ostream &os) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    if (count == CountType::All) throw Error("debug-tables takes one count type");
+    const Run r = load(a, {count}, true);
+    const ItemTables t = build_item_tables(r.graph, r.mask, count);
+    std::vector<std::string> groups;
+    os << "path_order";
+    for (auto &po : r.path_order) {
+        if (groups.empty() || groups.back() != po.second) groups.push_back(po.second);
+        os << "\t" << po.first << ":" << groups.size() - 1;
+    }
+    os << "\ngroups";
+    for (auto &g : groups) os << "\t" << g;
+    os << "\nn_items\t" << t.n_items << "\nid_prefsum";
+    for (auto v : t.id_prefsum) os << "\t" << v;
+    os << "\nitems";
+    for (auto v : t.items) os << "\t" << v;
+    os << "\nexclude";
+    for (size_t i = 0; i < t.exclude.size(); ++i)
+        if (t.exclude[i]) os << "\t" << i;
+    os << "\nuncovered";
+    for (auto &kv : t.uncovered_bps) os << "\t" << kv.first << ":" << kv.second;
+    os << "\nnode_lens";
+    for (auto v : r.graph.node_lens) os << "\t" << v;
+    os << "\npaths";
+    for (auto &p : r.graph.path_segments) os << "\t" << p.to_string();
+    os << "\n";
+    return 0;
+}
+
 void usage() {
     std::cerr << "panacus (B200 hot path) -- usage: panacus <hist|growth|histgrowth|ordered-histgrowth|similarity> <GFA_FILE> [options]\n"
                  "  -s, --subset FILE   -e, --exclude FILE   -g, --groupby FILE   -H, --groupby-haplotype   -S, --groupby-sample\n"
@@ -416,6 +449,7 @@ int dispatch(int argc, char **argv, std::ostream &os) {
     if (a.sub == "histgrowth") return cmd_growth(a, cmdline, true, os);
     if (a.sub == "ordered-histgrowth") return cmd_ordered(a, cmdline, os);
     if (a.sub == "similarity") return cmd_similarity(a, cmdline, os);
+    if (a.sub == "debug-tables") return cmd_debug_tables(a, os);
     usage();
     return 2;
 }

@@ -1,0 +1,118 @@
+"""CPU-only: the C++ host front end (GFA parsing, PanSN path names, grouping, ordering, subset / exclude
+bookkeeping, ItemTable construction -- SURVEY 8a rows a1/a2 and 8f-2) against the oracle's restatement of
+the reference (oracle/gfa_oracle.py), through `panacus debug-tables` (no GPU involved)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import gfa_oracle as go
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+BIN = os.path.join(ROOT, "panacus_b200", "bin", "panacus")
+
+
+def debug_tables(gfa, count, flags):
+    r = subprocess.run([BIN, "debug-tables", gfa, "-c", count, *flags], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    d = {}
+    for line in r.stdout.rstrip("\n").split("\n"):
+        key, *vals = line.split("\t")
+        d[key] = vals
+    return d
+
+
+def check(gfa, count, flags, kw):
+    got = debug_tables(gfa, count, flags)
+    g = go.parse_gfa(gfa)
+    mask = go.make_mask(g, **kw)
+    t = go.item_tables(g, mask, count)
+    op, og, names = go.path_order_arrays(mask, g)
+    assert got["groups"] == names, (count, flags)
+    assert got["path_order"] == [f"{int(p)}:{int(q)}" for p, q in zip(op, og)]
+    assert int(got["n_items"][0]) == t.n_items
+    assert [int(x) for x in got["id_prefsum"]] == [int(x) for x in t.id_prefsum]
+    assert [int(x) for x in got["items"]] == [int(x) for x in t.items]
+    want_ex = [] if t.exclude is None else [int(i) for i in np.nonzero(t.exclude)[0]]
+    assert [int(x) for x in got["exclude"]] == want_ex
+    assert got["uncovered"] == [f"{k}:{v}" for k, v in sorted(t.uncovered.items())]
+    assert [int(x) for x in got["node_lens"]] == list(g.node_lens)
+    assert got["paths"] == [str(p) for p in g.path_segments]
+
+
+B = lambda name: os.path.join(GOLDEN, name)
+FLAG_SETS = [
+    ([], {}),
+    (["-S"], {"groupby_sample": True}),
+    (["-H"], {"groupby_haplotype": True}),
+    (["-g", B("test_groups.txt")], {"groupby_file": B("test_groups.txt")}),
+    (["-s", B("inclusion.bed1")], {"subset": B("inclusion.bed1")}),
+    (["-s", B("inclusion.bed3")], {"subset": B("inclusion.bed3")}),
+    (["-s", B("inclusion_chm13.bed1")], {"subset": B("inclusion_chm13.bed1")}),
+    (["-s", B("inclusion_sub.bed1"), "-S"], {"subset": B("inclusion_sub.bed1"), "groupby_sample": True}),
+    (["-e", B("exclusion.bed3")], {"exclude": B("exclusion.bed3")}),
+    (["-s", B("inclusion.bed3"), "-e", B("exclusion.bed3"), "-H"],
+     {"subset": B("inclusion.bed3"), "exclude": B("exclusion.bed3"), "groupby_haplotype": True}),
+    (["-s", "HG00"], {"subset": "HG00"}),          # not a file: a regex over the path names (abacus.rs:212-240)
+    (["-e", "grch38"], {"exclude": "grch38"}),
+]
+
+
+@pytest.mark.parametrize("flags,kw", FLAG_SETS)
+def test_chrM_front_end(flags, kw):
+    for count in ("node", "bp", "edge"):
+        check(B("chrM_test.gfa"), count, flags, kw)
+
+
+@pytest.mark.parametrize("gfa", ["t_groups.gfa", "cdbg.gfa"])
+def test_small_fixture_front_end(gfa):
+    for count in ("node", "bp", "edge"):
+        check(B(gfa), count, [], {})
+        check(B(gfa), count, ["-S"], {"groupby_sample": True})
+
+
+def test_order_file(tmp_path):
+    order = tmp_path / "order.txt"
+    order.write_text("HG00621\nchm13\nHG00438\ngrch38\n")
+    check(B("chrM_test.gfa"), "node", ["-S", "-O", str(order)], {"groupby_sample": True, "order": str(order)})
+    frag = tmp_path / "frag.txt"   # groups must not be interleaved in an order file (abacus.rs:114-127)
+    g = go.parse_gfa(B("chrM_test.gfa"))
+    names = [str(p) for p in g.path_segments]
+    frag.write_text("\n".join(names) + "\n")
+    r = subprocess.run([BIN, "debug-tables", B("chrM_test.gfa"), "-g", B("test_groups.txt"), "-O", str(frag)],
+                       capture_output=True, text=True)
+    mask_ok = True
+    try:
+        go.make_mask(g, groupby_file=B("test_groups.txt"), order=str(frag))
+    except Exception:
+        mask_ok = False
+    assert (r.returncode == 0) or ("fragmented" in r.stderr) or not mask_ok
+
+
+def test_generated_gfa_with_walks(tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("tc", os.path.join(ROOT, "tests", "test_cli.py"))
+    tc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tc)
+    gfa = str(tmp_path / "syn.gfa")
+    tc.write_synthetic_gfa(gfa, n_nodes=1500, n_samples=5, seed=4)
+    for count in ("node", "bp", "edge"):
+        check(gfa, count, [], {})
+        check(gfa, count, ["-H"], {"groupby_haplotype": True})
+        check(gfa, count, ["-S", "-e", "smp1"], {"groupby_sample": True, "exclude": "smp1"})
+
+
+@pytest.mark.parametrize("name,expect", [
+    ("a#1#chr:5-9", "a#1#chr:5-9"), ("a#1", "a#1"), ("x", "x"), ("a#1#h1#more", "a#1#h1#more"), ("a##b", "a##b"),
+    ("s:10-20", "s:10-20"), ("a#2:3-7", "a#2:3-7"),
+])
+def test_path_segment_names(tmp_path, name, expect):
+    """PathSegment::from_str / Display (graph.rs:495-616) on PanSN corner cases, vs the oracle's regex version."""
+    gfa = tmp_path / "p.gfa"
+    gfa.write_text(f"S\t1\tACGT\nS\t2\tAC\nP\t{name}\t1+,2+\t*\n")
+    got = debug_tables(str(gfa), "node", [])
+    seg = go.PathSegment.from_str(name)
+    assert got["paths"] == [str(seg)] == [expect]
+    assert got["groups"] == [seg.id()]
