@@ -634,47 +634,36 @@ int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, u
     if (group_id >= a->G) return fail(PGX_ERR_INVALID, "group_id >= n_groups");
     if (n_steps && !items) return fail(PGX_ERR_INVALID, "items is null");
     DeviceGuard guard(a->device);
-    uint8_t *d_ex = nullptr;
-    if (exclude) {
-        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_ex), a->n_rows));
-        cudaError_t e = cudaMemcpyAsync(d_ex, exclude, a->n_rows, cudaMemcpyHostToDevice, a->stream);
-        if (e != cudaSuccess) {
-            cudaFree(d_ex);
-            return fail(PGX_ERR_CUDA, cudaGetErrorString(e));
+    struct Staging {  // freed on every exit path
+        uint64_t *items = nullptr;
+        uint8_t *ex = nullptr;
+        ~Staging() {
+            cudaFree(items);
+            cudaFree(ex);
         }
+    } st;
+    if (exclude) {
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.ex), a->n_rows));
+        PGX_CUDA(cudaMemcpyAsync(st.ex, exclude, a->n_rows, cudaMemcpyHostToDevice, a->stream));
     }
     const uint64_t kChunk = 1ull << 24;  // 16 Mi steps = 128 MB per staging copy
-    uint64_t *d_items = nullptr;
-    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_items), std::min<uint64_t>(kChunk, std::max<uint64_t>(n_steps, 1)) * 8u);
-    if (e != cudaSuccess) {
-        cudaFree(d_ex);
-        return fail(PGX_ERR_NOMEM, cudaGetErrorString(e));
-    }
-    rc = PGX_OK;
-    for (uint64_t s0 = 0; s0 < n_steps && rc == PGX_OK; s0 += kChunk) {
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.items), std::min<uint64_t>(kChunk, std::max<uint64_t>(n_steps, 1)) * 8u));
+    invalidate_derived(a);
+    for (uint64_t s0 = 0; s0 < n_steps; s0 += kChunk) {
         const uint64_t n = std::min<uint64_t>(kChunk, n_steps - s0);
-        e = cudaMemcpyAsync(d_items, items + s0, n * 8u, cudaMemcpyHostToDevice, a->stream);
-        if (e != cudaSuccess) {
-            rc = fail(PGX_ERR_CUDA, cudaGetErrorString(e));
-            break;
-        }
-        rc = launch_scatter(a->d_bitmap, a->Wp, a->n_rows, d_items, n, group_id, d_ex, a->d_err, a->stream);
+        PGX_CUDA(cudaMemcpyAsync(st.items, items + s0, n * 8u, cudaMemcpyHostToDevice, a->stream));
+        if ((rc = launch_scatter(a->d_bitmap, a->Wp, a->n_rows, st.items, n, group_id, st.ex, a->d_err, a->stream))) return rc;
         a->launches++;
-        if (rc == PGX_OK && (e = cudaStreamSynchronize(a->stream)) != cudaSuccess) rc = fail(PGX_ERR_CUDA, cudaGetErrorString(e));
+        PGX_CUDA(cudaStreamSynchronize(a->stream));  // the staging buffer is reused by the next chunk
     }
     unsigned int err = 0;
-    if (rc == PGX_OK) {
-        e = cudaMemcpy(&err, a->d_err, 4, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = fail(PGX_ERR_CUDA, cudaGetErrorString(e));
-        if (err) {
-            cudaMemset(a->d_err, 0, 4);
-            rc = fail(PGX_ERR_INVALID, "item id out of range 1..=n_items in scatter");
-        }
+    PGX_CUDA(cudaMemcpyAsync(&err, a->d_err, 4, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if (err) {
+        PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
+        return fail(PGX_ERR_INVALID, "item id out of range 1..=n_items in scatter");
     }
-    cudaFree(d_items);
-    cudaFree(d_ex);
-    invalidate_derived(a);
-    return rc;
+    return PGX_OK;
 }
 
 int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,

@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(kGmThreads, GENERAL ? 3 : 4) k_gm_growth(const
     const uint32_t order_id = blockIdx.y;
     const uint32_t *order = p.order + (size_t)order_id * p.G;
     for (uint32_t i = tid; i < p.G; i += kGmThreads) s_order[i] = order[i];
-    for (uint32_t i = tid; i < thr_words; i += kGmThreads) s_thr[i] = p.thr[i];
+    if (GENERAL)
+        for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) s_thr[i] = p.thr[i];
     for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) s_delta[i] = 0ull;
     __syncthreads();
 

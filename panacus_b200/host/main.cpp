@@ -34,7 +34,7 @@ const std::map<char, std::string> kShort = {{'s', "subset"},  {'e', "exclude"}, 
                                              {'S', "groupby-sample"}, {'c', "count"}, {'l', "coverage"}, {'q', "quorum"},
                                              {'a', "hist"},    {'O', "order"},    {'m', "method"},  {'t', "threads"},
                                              {'v', "verbose"}};
-const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total"};
+const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json"};
 
 Args parse_args(int argc, char **argv) {
     Args a;
@@ -429,8 +429,199 @@ int cmd_debug_tables(const Args &a, std::ostream &os) {
     return 0;
 }
 
+// ---- report: the YAML front end (src/commands/report.rs, src/analysis_parameter.rs:82-258) -------------------------
+// The reference renders an HTML / JSON report; rendering is outside the hot path, so this front end runs the
+// same analyses on the same graph state and emits each analysis' TSV table under a "## run ... analysis ..." line.
+struct AnalysisSpec {
+    std::string type;  // Hist | Growth | OrderedGrowth | Similarity | (others: reported as unsupported)
+    std::map<std::string, std::string> kv;
+};
+struct RunSpec {
+    std::map<std::string, std::string> kv;  // graph, name, subset, exclude, grouping, grouping_file, nice
+    std::vector<AnalysisSpec> analyses;
+};
+
+std::string yaml_scalar(std::string v) {
+    size_t hash = std::string::npos;
+    bool in_s = false, in_d = false;
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (v[i] == '\'' && !in_d) in_s = !in_s;
+        if (v[i] == '"' && !in_s) in_d = !in_d;
+        if (v[i] == '#' && !in_s && !in_d && (i == 0 || v[i - 1] == ' ')) {
+            hash = i;
+            break;
+        }
+    }
+    if (hash != std::string::npos) v = v.substr(0, hash);
+    size_t a = 0, b = v.size();
+    while (a < b && std::isspace((unsigned char)v[a])) ++a;
+    while (b > a && std::isspace((unsigned char)v[b - 1])) --b;
+    v = v.substr(a, b - a);
+    if (v.size() >= 2 && ((v.front() == '"' && v.back() == '"') || (v.front() == '\'' && v.back() == '\''))) v = v.substr(1, v.size() - 2);
+    if (v == "null" || v == "~") v.clear();
+    return v;
+}
+
+void yaml_flow_map(const std::string &body, std::map<std::string, std::string> &kv) {  // {a: 1, b: "x,y"}
+    std::string cur;
+    std::vector<std::string> parts;
+    bool in_q = false;
+    for (char c : body) {
+        if (c == '"' || c == '\'') in_q = !in_q;
+        if (c == ',' && !in_q) {
+            parts.push_back(cur);
+            cur.clear();
+        } else {
+            cur += c;
+        }
+    }
+    if (!cur.empty()) parts.push_back(cur);
+    for (auto &part : parts) {
+        const size_t colon = part.find(':');
+        if (colon == std::string::npos) continue;
+        kv[yaml_scalar(part.substr(0, colon))] = yaml_scalar(part.substr(colon + 1));
+    }
+}
+
+std::vector<RunSpec> parse_report_yaml(const std::string &path) {
+    std::ifstream in(path);
+    if (!in) throw Error("cannot open " + path);
+    std::vector<RunSpec> runs;
+    std::string line;
+    bool in_analyses = false;
+    size_t lineno = 0;
+    while (std::getline(in, line)) {
+        ++lineno;
+        while (!line.empty() && (line.back() == '\r')) line.pop_back();
+        size_t indent = 0;
+        while (indent < line.size() && line[indent] == ' ') ++indent;
+        std::string body = line.substr(indent);
+        if (body.empty() || body[0] == '#') continue;
+        bool item = false;
+        if (body.rfind("- ", 0) == 0 || body == "-") {
+            item = true;
+            body = body.size() > 2 ? body.substr(2) : "";
+            indent += 2;
+        }
+        if (item && indent == 2) {  // a new run
+            runs.emplace_back();
+            in_analyses = false;
+        }
+        if (runs.empty()) throw Error("report YAML must be a list of runs (line " + std::to_string(lineno) + ")");
+        RunSpec &run = runs.back();
+        if (in_analyses && item) {  // "- !Hist" or "- !Hist {count_type: Bp}"
+            if (body.empty() || body[0] != '!') throw Error("expected an analysis tag like !Hist at line " + std::to_string(lineno));
+            AnalysisSpec spec;
+            const size_t sp = body.find_first_of(" {");
+            spec.type = body.substr(1, sp == std::string::npos ? std::string::npos : sp - 1);
+            const size_t lb = body.find('{'), rb = body.rfind('}');
+            if (lb != std::string::npos && rb != std::string::npos && rb > lb) yaml_flow_map(body.substr(lb + 1, rb - lb - 1), spec.kv);
+            run.analyses.push_back(spec);
+            continue;
+        }
+        const size_t colon = body.find(':');
+        if (colon == std::string::npos) throw Error("cannot parse YAML line " + std::to_string(lineno) + ": " + line);
+        const std::string key = yaml_scalar(body.substr(0, colon));
+        const std::string val = yaml_scalar(body.substr(colon + 1));
+        if (in_analyses && indent > 4 && !run.analyses.empty()) {  // block-style parameters of the last analysis
+            run.analyses.back().kv[key] = val;
+            continue;
+        }
+        in_analyses = false;
+        if (key == "analyses") {
+            in_analyses = true;
+        } else if (key == "grouping" && val.rfind("!Custom", 0) == 0) {
+            run.kv["grouping"] = "Custom";
+            run.kv["grouping_file"] = yaml_scalar(val.substr(7));
+        } else {
+            run.kv[key] = val;
+        }
+    }
+    return runs;
+}
+
+std::string lower(std::string s) {
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    return s;
+}
+
+int cmd_report(const Args &a0, std::ostream &os) {
+    const std::vector<RunSpec> runs = parse_report_yaml(a0.positional.at(0));
+    const bool dry = a0.has("dry-run");
+    int rc = 0;
+    for (size_t ri = 0; ri < runs.size(); ++ri) {
+        const RunSpec &run = runs[ri];
+        auto get = [&](const std::string &k) {
+            auto it = run.kv.find(k);
+            return it == run.kv.end() ? std::string() : it->second;
+        };
+        if (get("graph").empty()) throw Error("run " + std::to_string(ri) + " has no graph");
+        // count type of the run's histograms: union of the !Hist requests; two or more -> all (graph_broker.rs:150-160)
+        std::set<std::string> hist_counts;
+        for (auto &an : run.analyses)
+            if (an.type == "Hist") {
+                auto it = an.kv.find("count_type");
+                hist_counts.insert(lower(it == an.kv.end() ? "node" : it->second));
+            }
+        std::string run_count = "node";
+        if (hist_counts.size() == 1) run_count = *hist_counts.begin();
+        if (hist_counts.size() > 1) run_count = "all";
+        Args base;
+        base.positional.push_back(get("graph"));
+        if (!get("subset").empty()) base.opt["subset"] = get("subset");
+        if (!get("exclude").empty()) base.opt["exclude"] = get("exclude");
+        if (get("grouping") == "Sample") base.opt["groupby-sample"] = "1";
+        if (get("grouping") == "Haplotype") base.opt["groupby-haplotype"] = "1";
+        if (get("grouping") == "Custom") base.opt["groupby"] = get("grouping_file");
+        const std::string run_name = get("name").empty() ? get("graph") : get("name");
+        for (auto &an : run.analyses) {
+            Args a = base;
+            auto kv = [&](const std::string &k, const std::string &d) {
+                auto it = an.kv.find(k);
+                return it == an.kv.end() || it->second.empty() ? d : it->second;
+            };
+            os << "## run " << run_name << " analysis " << an.type << "\n";
+            const std::string cmdline = "panacus report " + a0.positional.at(0);
+            if (an.type == "Hist") {
+                a.sub = "hist";
+                a.opt["count"] = run_count;
+                if (!dry) rc |= cmd_hist(a, cmdline, os);
+            } else if (an.type == "Growth") {
+                a.sub = "histgrowth";
+                a.opt["count"] = run_count;
+                a.opt["coverage"] = kv("coverage", "1");
+                a.opt["quorum"] = kv("quorum", "0");
+                if (lower(kv("add_hist", "false")) == "true") a.opt["hist"] = "1";
+                if (!dry) rc |= cmd_growth(a, cmdline, true, os);
+            } else if (an.type == "OrderedGrowth") {
+                a.sub = "ordered-histgrowth";
+                a.opt["count"] = lower(kv("count_type", "node"));
+                a.opt["coverage"] = kv("coverage", "1");
+                a.opt["quorum"] = kv("quorum", "0");
+                if (!kv("order", "").empty()) a.opt["order"] = kv("order", "");
+                if (!dry) rc |= cmd_ordered(a, cmdline, os);
+            } else if (an.type == "Similarity") {
+                a.sub = "similarity";
+                a.opt["count"] = lower(kv("count_type", "node"));
+                a.opt["method"] = lower(kv("cluster_method", "centroid"));
+                if (!dry) rc |= cmd_similarity(a, cmdline, os);
+            } else {
+                os << "# analysis " << an.type << " is outside the accelerated hot path: not supported by this build\n";
+                continue;
+            }
+            if (dry) {
+                os << "# would run: " << a.sub << " " << a.positional[0];
+                for (auto &o : a.opt) os << " --" << o.first << (o.second == "1" && kFlags.count(o.first) ? "" : " " + o.second);
+                os << "\n";
+            }
+        }
+    }
+    return rc;
+}
+
 void usage() {
     std::cerr << "panacus (B200 hot path) -- usage: panacus <hist|growth|histgrowth|ordered-histgrowth|similarity> <GFA_FILE> [options]\n"
+                 "                                  panacus report <config.yaml> [--dry-run]   (tables as TSV; no HTML rendering)\n"
                  "  -s, --subset FILE   -e, --exclude FILE   -g, --groupby FILE   -H, --groupby-haplotype   -S, --groupby-sample\n"
                  "  -c, --count node|bp|edge|all   -l, --coverage LIST   -q, --quorum LIST   -a, --hist   -O, --order FILE\n"
                  "  -m, --method single|complete|average|weighted|ward|centroid|median (similarity)   -t, --threads N\n"
@@ -450,6 +641,7 @@ int dispatch(int argc, char **argv, std::ostream &os) {
     if (a.sub == "ordered-histgrowth") return cmd_ordered(a, cmdline, os);
     if (a.sub == "similarity") return cmd_similarity(a, cmdline, os);
     if (a.sub == "debug-tables") return cmd_debug_tables(a, os);
+    if (a.sub == "report") return cmd_report(a, os);
     usage();
     return 2;
 }

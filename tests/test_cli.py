@@ -326,3 +326,62 @@ def test_packed_abacus_cache_round_trip(tmp_path):
     assert r.returncode != 0 and "holds count type" in r.stderr
     r = run_cli("hist", f"{prefix}.bp.pabm", "-c", "bp", "-S", expect_ok=False)
     assert r.returncode != 0 and "cannot be combined" in r.stderr
+
+
+# ---- report: the YAML front end (commands/report.rs; tables as TSV, no HTML) ----------------------------------------
+
+REPORT_YAML = """# example in the style of src/commands/report.rs:55-62
+- graph: {chrM}
+  name: chrM            # optional
+  subset: ""
+  grouping: Sample
+  nice: false
+  analyses:
+    - !Hist
+      count_type: Bp
+    - !Growth
+      coverage: 1,1,2
+      quorum: 0,0.9,0
+    - !OrderedGrowth {{coverage: "1,2", quorum: "0,0.5", order: null, count_type: Node}}
+    - !Info
+- graph: {tg}
+  analyses:
+    - !Hist {{count_type: Node}}
+    - !Hist {{count_type: Edge}}
+    - !Growth {{add_hist: true}}
+"""
+
+
+def _write_report(tmp_path):
+    y = tmp_path / "report.yaml"
+    y.write_text(REPORT_YAML.format(chrM=os.path.join(GOLDEN, "chrM_test.gfa"), tg=os.path.join(GOLDEN, "t_groups.gfa")))
+    return str(y)
+
+
+def test_report_dry_run(tmp_path):
+    out = run_cli("report", _write_report(tmp_path), "--dry-run").stdout
+    lines = out.strip().split("\n")
+    assert lines[0] == "## run chrM analysis Hist" and "--count bp" in lines[1] and "--groupby-sample" in lines[1]
+    assert "histgrowth" in lines[3] and "--coverage 1,1,2" in lines[3] and "--quorum 0,0.9,0" in lines[3] and "--count bp" in lines[3]
+    assert "ordered-histgrowth" in lines[5] and "--count node" in lines[5] and "--order" not in lines[5]
+    assert "not supported" in lines[7]
+    # two different !Hist count types in one run -> every histogram of the run is built (graph_broker.rs:150-160)
+    assert "--count all" in lines[9] and "--count all" in lines[11] and "--hist" in lines[13]
+
+
+@pytest.mark.gpu
+def test_report_runs_the_same_tables_as_the_subcommands(tmp_path):
+    chrM, tg = os.path.join(GOLDEN, "chrM_test.gfa"), os.path.join(GOLDEN, "t_groups.gfa")
+    rep = run_cli("report", _write_report(tmp_path)).stdout
+    sections = [sec.split("\n", 1) for sec in rep.split("## run ")[1:]]
+    assert [h for h, _ in sections] == ["chrM analysis Hist", "chrM analysis Growth", "chrM analysis OrderedGrowth",
+                                        "chrM analysis Info", f"{tg} analysis Hist", f"{tg} analysis Hist",
+                                        f"{tg} analysis Growth"]
+    direct = run_many([["hist", chrM, "-S", "-c", "bp"], ["histgrowth", chrM, "-S", "-c", "bp", "-l", "1,1,2", "-q", "0,0.9,0"],
+                       ["ordered-histgrowth", chrM, "-S", "-c", "node", "-l", "1,2", "-q", "0,0.5"],
+                       ["hist", tg, "-c", "all"], ["histgrowth", tg, "-c", "all", "-a"]], tmp_path)
+    assert body(sections[0][1]) == body(direct[0])
+    assert body(sections[1][1]) == body(direct[1])
+    assert body(sections[2][1]) == body(direct[2])
+    assert body(sections[4][1]) == body(direct[3]) == body(sections[5][1])
+    assert body(sections[6][1]) == body(direct[4])
