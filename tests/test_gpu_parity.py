@@ -411,3 +411,25 @@ def test_large_permuted_growth_and_similarity_properties():
         assert int(interw.astype(object).sum()) == int((wnp[1:] * ctn[1:] * ctn[1:]).sum())
         part, _ = a.similarity(weighted=True, row_begin=100, row_end=229)
         assert np.array_equal(part, interw[100:229])
+
+
+@pytest.mark.parametrize("N,G", [(0, 5), (1, 1), (3, 20000), (40, 9000), (100, 65)])
+def test_extreme_shapes(N, G):
+    """no items at all, a single cell, very wide rows (row > one pipeline stage of 256 items), many thresholds"""
+    rng = np.random.default_rng(N + G)
+    bits = (rng.random((N + 1, G)) < 0.3).astype(np.uint8)
+    bits[0] = 0
+    weights = rng.integers(0, 1000, N + 1).astype(np.uint32)
+    pairs = [(1, 0.0), (2, 0.4), (1, 1.0)] if G > 1000 else [(1 + i % 3, [0.0, 0.2, 0.6, 1.0][i % 4]) for i in range(11)]
+    if N == 0:
+        with pb.DeviceAbacus(0, G) as a:
+            a.upload(pb.pack_bits(bits), weights)
+            hc, hw, ct = a.hist(True, True, True)
+            assert not hc.any() and not hw.any() and ct[0] == 0xFFFFFFFF
+            cov, thr = cutoffs(G, pairs)
+            assert not a.ordered_growth(cov, thr, weighted=True).any()
+            assert not a.permuted_growth(np.arange(G, dtype=np.uint32)[None, ::-1].copy(), cov, thr).any()
+            inter, ln = a.similarity()
+            assert not inter.any() and not ln.any()
+        return
+    check_table(pb.pack_bits(bits), G, weights, pairs=pairs)

@@ -54,6 +54,22 @@ for weighted in (False, True):
     report(f"permuted_growth {P} orders, 3 pairs (1,0)(2,.5)(4,.9)", ms, N=N, G=G, weighted=weighted, ms_per_order=round(ms / P, 4),
            gbps=round(P * alg / ms / 1e6, 1), frac_hbm=round(P * alg / ms / 1e6 / PEAK, 3))
 a.close(); del bitmap, weight
+# ---- device-side abacus build from an ItemTable vs the reference's host passes ----
+from oracle import oracle as po
+Nb, Gb = (100_000, 256) if quick else (400_000, 512)
+bits_b, bitmap_b, _ = synth.numpy_table(Nb, Gb, seed=9)
+items, prefsum, op, og = po.bitmap_to_item_table(bitmap_b, Gb)
+b = pb.DeviceAbacus(Nb, Gb)
+pg = np.arange(Gb, dtype=np.int64)
+b.build(items, prefsum, pg)
+assert np.array_equal(b.download(), bitmap_b)
+b.clear()
+ms = ev_time(lambda: b.build(items, prefsum, pg), reps=3)
+t0 = time.perf_counter(); po.abacus_by_total(Nb, items, prefsum, op, og); t_cov = time.perf_counter() - t0
+t0 = time.perf_counter(); po.csr_build(Nb, items, prefsum, op, og); t_csr = time.perf_counter() - t0
+report("pgx_abacus_build (H2D of the ItemTable + k_build)", ms, N=Nb, G=Gb, steps=int(items.size), steps_per_s=round(items.size / ms * 1e3 / 1e9, 2),
+       unit="G steps/s", cpu_coverage_pass_ms=round(t_cov * 1e3, 1), cpu_csr_build_ms=round(t_csr * 1e3, 1))
+b.close()
 # ---- config 4 shape: similarity 10M x 1024 ----
 N, G = (1_000_000, 1024) if quick else (10_000_000, 1024)
 bitmap, weight = synth.torch_table(N, G, seed=synth.SEED_BASE + 4)
