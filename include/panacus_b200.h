@@ -13,6 +13,10 @@
  *     (device pointer on the handle's device).  The caller owns every buffer it passes.
  *   - one handle is driven by one host thread at a time; handles on different devices are
  *     independent.
+ *   - shapes: n_items < 2^32 - 2; the histogram / growth kernels keep their per-CTA accumulators in shared
+ *     memory, which bounds n_groups to ~17,000 (both histograms in one call), ~26,000 (one of them), and the
+ *     number of thresholds per launch (more are split over several passes); larger shapes return
+ *     PGX_ERR_UNSUPPORTED.
  *   - item ids are 1..=n_items; row 0 of every per-item array is the reference's dummy item
  *     (src/graph_broker/graph.rs:323-324, abacus.rs:551,1000-1002) and is never counted.
  *

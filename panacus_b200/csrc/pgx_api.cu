@@ -237,9 +237,17 @@ int fused_pass(pgx_abacus *a, bool want_cnt, bool want_w, uint32_t T, const uint
     bool hist_pending = want_cnt || want_w || (d_countable && gen_t.empty());
     size_t i = 0;
     while (hist_pending || i < fast_t.size()) {
-        const uint32_t flags = wflag | (hist_pending && want_cnt ? kHistCount : 0u) | (hist_pending && want_w ? kHistWeight : 0u);
+        uint32_t flags = wflag | (hist_pending && want_cnt ? kHistCount : 0u) | (hist_pending && want_w ? kHistWeight : 0u);
         size_t n = 0;
         rc = scan_launch(a, false, flags, fast_t, i, cov, thr, hist_pending || gen_t.empty() ? d_countable : nullptr, d_out, &n);
+        if (rc == PGX_ERR_UNSUPPORTED && hist_pending && want_cnt && want_w) {
+            // very large G: both histograms do not fit in shared memory together -> one pass each
+            flags = wflag | kHistCount;
+            if ((rc = scan_launch(a, false, flags, fast_t, fast_t.size(), cov, thr, d_countable, d_out, &n))) return rc;
+            d_countable = nullptr;
+            flags = wflag | kHistWeight;
+            rc = scan_launch(a, false, flags, fast_t, i, cov, thr, nullptr, d_out, &n);
+        }
         if (rc) return rc;
         if (!hist_pending && n == 0) return fail(PGX_ERR_UNSUPPORTED, "n_groups too large: no threshold fits in shared memory");
         if (hist_pending) d_countable = nullptr;  // written once
@@ -372,8 +380,15 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
             return false;
         };
         while (n > 1 && gm_growth_smem_bytes(G, (uint32_t)n, any_general(n)) > 200u * 1024u) --n;
+        bool direct = false;
+        if (gm_growth_smem_bytes(G, (uint32_t)n, any_general(n)) > 200u * 1024u) {  // very large G: no smem staging of deltas
+            direct = true;
+            n = std::min<size_t>(kMaxThresholds, ts.size() - i0);
+            while (n > 1 && gm_growth_smem_bytes(G, (uint32_t)n, any_general(n), true) > 200u * 1024u) --n;
+        }
         GmGrowthParams p;
         std::memset(&p, 0, sizeof(p));
+        p.direct_out = direct ? 1u : 0u;
         p.gm = a->d_gm;
         p.gm_stride = a->gm_stride;
         p.n_words = (a->n_rows + 63u) / 64u;

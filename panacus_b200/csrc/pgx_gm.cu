@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(kGmThreads, GENERAL ? 3 : 4) k_gm_growth(const
     for (uint32_t i = tid; i < p.G; i += kGmThreads) s_order[i] = order[i];
     if (GENERAL)
         for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) s_thr[i] = p.thr[i];
-    for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) s_delta[i] = 0ull;
+    if (!p.direct_out)
+        for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) s_delta[i] = 0ull;
     __syncthreads();
 
     const uint64_t wi = (uint64_t)blockIdx.x * kGmThreads + tid;
@@ -244,11 +245,19 @@ __global__ void __launch_bounds__(kGmThreads, GENERAL ? 3 : 4) k_gm_growth(const
                     const int diff = __popcll(up) - (GENERAL ? __popcll(down) : 0);
                     net = (long long)__reduce_add_sync(0xFFFFFFFFu, diff);
                 }
-                if (lane == 0 && net != 0) atomicAdd(&s_delta[t * p.G + j], (unsigned long long)net);
+                if (lane == 0 && net != 0) {
+                    if (p.direct_out)
+                        atomicAdd(reinterpret_cast<unsigned long long *>(p.out + (size_t)order_id * p.out_order_stride +
+                                                                         (size_t)p.slot[t] * p.G + j),
+                                  (unsigned long long)net);
+                    else
+                        atomicAdd(&s_delta[t * p.G + j], (unsigned long long)net);
+                }
             }
         }
     }
     __syncthreads();
+    if (p.direct_out) return;
     uint64_t *out = p.out + (size_t)order_id * p.out_order_stride;
     for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) {
         const unsigned long long v = s_delta[i];
@@ -501,7 +510,7 @@ __global__ void __launch_bounds__(256) k_build(uint64_t *bitmap, uint32_t Wp, ui
     }
 }
 
-size_t gm_growth_smem(const GmGrowthParams &p) { return gm_growth_smem_bytes(p.G, p.T, p.general_mask != 0); }
+size_t gm_growth_smem(const GmGrowthParams &p) { return gm_growth_smem_bytes(p.G, p.T, p.general_mask != 0, p.direct_out != 0); }
 
 template <int P, bool GENERAL, int TMAX>
 int launch_gm_growth_t(const GmGrowthParams &p, cudaStream_t stream) {
@@ -517,9 +526,9 @@ int launch_gm_growth_t(const GmGrowthParams &p, cudaStream_t stream) {
 
 }  // namespace
 
-size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general) {
+size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general, bool direct_out) {
     const size_t thr_words = any_general ? (size_t)T * G : 0u;
-    return (((size_t)(G + thr_words) * 4u + 15u) & ~(size_t)15u) + (size_t)T * G * 8u;
+    return (((size_t)(G + thr_words) * 4u + 15u) & ~(size_t)15u) + (direct_out ? 0u : (size_t)T * G * 8u);
 }
 
 int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,

@@ -113,10 +113,11 @@ struct GmGrowthParams {
     uint32_t cov[kMaxThresholds];
     uint32_t slot[kMaxThresholds];  // threshold k's first differences go to out + slot[k]*G
     uint32_t general_mask;   // bit t set: threshold t needs the rank comparison (q > 0)
+    uint32_t direct_out;     // very large G: no shared-memory staging of the deltas, atomics go straight to `out`
     int weighted;
 };
 int launch_gm_growth(const GmGrowthParams &p, int sm_count, cudaStream_t stream);
-size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general);
+size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general, bool direct_out = false);
 
 struct GmSimParams {
     const uint64_t *gm;

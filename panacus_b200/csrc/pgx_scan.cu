@@ -518,7 +518,9 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     const bool heavy = quorum || (p.flags & (kHistWeight | kWeighted)) != 0;  // more atomics per item
     if (rowbytes >= 256u) {
         tile = 256u, want_ctas = 1, want_stages = 3;
-        while (tile > 4u && tile * rowbytes > 65536u) tile >>= 1;
+        // wide rows: fewer rows per stage; shrink further while accumulators + two stages do not fit
+        const uint32_t wbytes = p.weight ? 4u : 0u;
+        while (tile > 4u && (tile * rowbytes > 65536u || off + 2u * (tile * (rowbytes + wbytes) + 256u) > 232448u)) tile >>= 1;
         if (tile * rowbytes > 98304u) return fail(PGX_ERR_UNSUPPORTED, "n_groups too large for the shared-memory pipeline");
     } else if (rowbytes == 128u) {
         if (heavy) tile = 256u, want_ctas = 2, want_stages = 2;
