@@ -45,7 +45,7 @@ def cutoffs(G, pairs):
 
 def check_table(bitmap, G, weights, pairs=PAIRS):
     N = bitmap.shape[0] - 1
-    exp = oracle_all(bitmap, G, weights, list(pairs) + [(1, 0.0), (2, 0.0)])
+    exp = oracle_all(bitmap, G, weights, list(pairs) + [(1, 0.0), (2, 0.0), (2, 0.5)])
     with pb.DeviceAbacus(N, G) as a:
         a.upload(bitmap, weights)
         hc, hw, ct = a.hist(count=True, weight=True, countable=True)
