@@ -70,7 +70,7 @@ struct pgx_abacus {
     size_t pinned_words = 0;
 
     // fused NVLink exchange (item-range sharding)
-    unsigned char *d_xchg = nullptr;  // [2][kMaxRanks][acc_words] u64 slots, then 2*kMaxRanks u32 flags
+    unsigned char *d_xchg = nullptr;  // [2 parities][kMaxRanks][acc_words][2] u64 packets {epoch:32 | half:32}
     void *peer_base[kMaxRanks] = {};
     Exchange x = {};
     uint32_t epoch = 0;
@@ -881,14 +881,14 @@ int pgx_fused_pass_async(pgx_abacus *a, int want_hist_count, int want_hist_weigh
                       d_out);
 }
 
-static size_t xchg_data_bytes(const pgx_abacus *a) { return (size_t)2 * kMaxRanks * a->acc_words * 8u; }
+static size_t xchg_data_bytes(const pgx_abacus *a) { return (size_t)2 * kMaxRanks * a->acc_words * 16u; }  // 2 packets per word
 
 int pgx_exchange_export(pgx_abacus *a, void *handle_out) {
     if (!a || !handle_out) return fail(PGX_ERR_INVALID, "bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == PGX_EXCHANGE_HANDLE_BYTES, "handle size");
     DeviceGuard guard(a->device);
     if (!a->d_xchg) {
-        const size_t bytes = xchg_data_bytes(a) + 2u * kMaxRanks * 4u;
+        const size_t bytes = xchg_data_bytes(a);
         PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_xchg), bytes));
         PGX_CUDA(cudaMemset(a->d_xchg, 0, bytes));
     }
@@ -927,7 +927,6 @@ int pgx_exchange_connect(pgx_abacus *a, uint32_t rank, uint32_t world, const voi
             base = static_cast<unsigned char *>(ptr);
         }
         x.data[r] = reinterpret_cast<uint64_t *>(base);
-        x.flag[r] = reinterpret_cast<uint32_t *>(base + xchg_data_bytes(a));
     }
     a->x = x;
     return PGX_OK;

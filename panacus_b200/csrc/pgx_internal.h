@@ -46,13 +46,13 @@ struct ScanLayout {
 constexpr int kMaxRanks = 8;  // GPUs of one NVSwitch domain taking part in the fused exchange
 
 // In-kernel all-reduce of the KB-sized result vector over NVLink peer memory (world > 1): the last CTA
-// of every rank stores its vector into slot [epoch parity][rank] of every rank's buffer, raises a flag
-// there, waits for all ranks' flags in its own buffer and sums the slots.
+// of every rank stores its vector into slot [epoch parity][rank] of every rank's buffer as 8-byte
+// {epoch, half-word} packets (atomic stores: no flag / fence round trip), then spins on its own buffer
+// until every rank's packets carry the current epoch and sums them.
 struct Exchange {
     uint64_t *data[kMaxRanks];   // data[r]: rank r's buffer as mapped into this process (r == rank: local)
-    uint32_t *flag[kMaxRanks];   // flag[r]: rank r's flag words (2 * kMaxRanks u32)
     unsigned int *err;           // set to 2 if a peer did not arrive within the timeout
-    uint32_t world, rank, epoch, stride;  // stride: u64 words per slot
+    uint32_t world, rank, epoch, stride;  // stride: result words per slot (each word = 2 packets)
 };
 
 struct ScanParams {

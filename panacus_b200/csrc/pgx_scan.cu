@@ -413,42 +413,49 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                 if (oi == 0xFFFFFFFFu) continue;
                 if (!xchg) {
                     p.out[oi] = v[u];
-                } else {  // push my partial result into slot [par][rank] of every rank (NVLink peer stores)
-                    const size_t off = (size_t)(par * kMaxRanks + p.x.rank) * p.x.stride + oi;
-                    for (uint32_t r = 0; r < p.x.world; ++r) p.x.data[r][off] = v[u];
+                } else {
+                    // push my partial result into slot [par][rank] of every rank (NVLink peer stores).  Each u64 travels
+                    // as two 8-byte packets {epoch : 32 | half : 32}: an aligned 8-byte store is atomic, so the
+                    // receiver needs no separate flag, fence or barrier (the idea of NCCL's LL protocol)
+                    const size_t off = ((size_t)(par * kMaxRanks + p.x.rank) * p.x.stride + oi) * 2u;
+                    const uint64_t tag = (uint64_t)p.x.epoch << 32;
+                    const uint64_t lo = tag | (v[u] & 0xFFFFFFFFull), hi = tag | (v[u] >> 32);
+                    for (uint32_t r = 0; r < p.x.world; ++r) {
+                        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p.x.data[r] + off), "l"(lo) : "memory");
+                        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p.x.data[r] + off + 1), "l"(hi) : "memory");
+                    }
                 }
                 if (v[u]) p.acc[i] = 0ull;
             }
         }
         if (xchg) {
-            __threadfence_system();
-            __syncthreads();
-            if (tid < p.x.world) {
-                // raise my flag at rank `tid`, then wait for rank `tid`'s flag here
-                uint32_t *remote = p.x.flag[tid] + par * kMaxRanks + p.x.rank;
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(p.x.epoch) : "memory");
-                const uint32_t *local = p.x.flag[p.x.rank] + par * kMaxRanks + tid;
-                uint64_t t0, t1;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                for (;;) {
-                    uint32_t f;
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(local) : "memory");
-                    if (f == p.x.epoch) break;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                    if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived; flag the error, do not hang
-                        atomicExch(p.x.err, 2u);
-                        break;
-                    }
-                    __nanosleep(200);
-                }
-            }
-            __syncthreads();
-            const uint64_t *mine = p.x.data[p.x.rank] + (size_t)par * kMaxRanks * p.x.stride;
+            // every thread collects the words it pushed itself: spin until all ranks' packets carry this epoch
+            const uint64_t *mine = p.x.data[p.x.rank] + (size_t)par * kMaxRanks * p.x.stride * 2u;
+            uint64_t t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            bool dead = false;
             for (uint32_t i = tid; i < total; i += kScanThreads) {
                 const uint32_t oi = out_index(i);
                 if (oi == 0xFFFFFFFFu) continue;
                 uint64_t sum = 0;
-                for (uint32_t r = 0; r < p.x.world; ++r) sum += __ldcg(mine + (size_t)r * p.x.stride + oi);
+                for (uint32_t r = 0; r < p.x.world; ++r) {
+                    const uint64_t *q = mine + ((size_t)r * p.x.stride + oi) * 2u;
+                    uint64_t a, b;
+                    for (;;) {
+                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(a) : "l"(q) : "memory");
+                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(b) : "l"(q + 1) : "memory");
+                        if ((uint32_t)(a >> 32) == p.x.epoch && (uint32_t)(b >> 32) == p.x.epoch) break;
+                        if (dead) break;
+                        uint64_t t1;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                        if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived; flag the error, do not hang
+                            atomicExch(p.x.err, 2u);
+                            dead = true;
+                            break;
+                        }
+                    }
+                    sum += (a & 0xFFFFFFFFull) | (b << 32);
+                }
                 p.out[oi] = sum;
             }
         }
