@@ -437,25 +437,33 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             for (uint32_t i = tid; i < total; i += kScanThreads) {
                 const uint32_t oi = out_index(i);
                 if (oi == 0xFFFFFFFFu) continue;
-                uint64_t sum = 0;
-                for (uint32_t r = 0; r < p.x.world; ++r) {
-                    const uint64_t *q = mine + ((size_t)r * p.x.stride + oi) * 2u;
-                    uint64_t a, b;
-                    for (;;) {
-                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(a) : "l"(q) : "memory");
-                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(b) : "l"(q + 1) : "memory");
-                        if ((uint32_t)(a >> 32) == p.x.epoch && (uint32_t)(b >> 32) == p.x.epoch) break;
-                        if (dead) break;
-                        uint64_t t1;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                        if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived; flag the error, do not hang
-                            atomicExch(p.x.err, 2u);
-                            dead = true;
-                            break;
+                // all ranks' packets of this word are loaded together (one L2 round trip per attempt), then checked
+                uint64_t a[kMaxRanks], b[kMaxRanks];
+                for (;;) {
+#pragma unroll
+                    for (uint32_t r = 0; r < (uint32_t)kMaxRanks; ++r) {
+                        a[r] = b[r] = (uint64_t)p.x.epoch << 32;
+                        if (r < p.x.world) {
+                            const uint64_t *q = mine + ((size_t)r * p.x.stride + oi) * 2u;
+                            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a[r]), "=l"(b[r]) : "l"(q) : "memory");
                         }
                     }
-                    sum += (a & 0xFFFFFFFFull) | (b << 32);
+                    bool ok = true;
+#pragma unroll
+                    for (uint32_t r = 0; r < (uint32_t)kMaxRanks; ++r)
+                        ok = ok && (uint32_t)(a[r] >> 32) == p.x.epoch && (uint32_t)(b[r] >> 32) == p.x.epoch;
+                    if (ok || dead) break;
+                    uint64_t t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > 10000000000ull) {  // 10 s: a peer never arrived; flag the error, do not hang
+                        atomicExch(p.x.err, 2u);
+                        dead = true;
+                    }
                 }
+                uint64_t sum = 0;
+#pragma unroll
+                for (uint32_t r = 0; r < (uint32_t)kMaxRanks; ++r)
+                    if (r < p.x.world) sum += (a[r] & 0xFFFFFFFFull) | (b[r] << 32);
                 p.out[oi] = sum;
             }
         }
