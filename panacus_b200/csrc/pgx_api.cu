@@ -38,6 +38,7 @@ struct pgx_abacus {
     bool max_weight_known = true;
 
     uint32_t *d_countable = nullptr;  // N+1, lazily allocated
+    uint64_t *d_hist_tmp = nullptr;   // histogram by-product of the countable pass
     bool countable_valid = false;
 
     uint64_t *d_gm = nullptr;  // group-major copy, lazily built
@@ -286,9 +287,9 @@ int fused_pass(pgx_abacus *a, bool want_cnt, bool want_w, uint32_t T, const uint
 int ensure_countable(pgx_abacus *a) {
     if (a->countable_valid) return PGX_OK;
     if (!a->d_countable) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_countable), a->n_rows * 4u));
-    int rc = ensure_dev(&a->d_scratch, &a->scratch_cap, pgx_fused_out_words(a->G, 0));
-    if (rc) return rc;
-    rc = fused_pass(a, true, false, 0, nullptr, nullptr, 0, a->d_countable, a->d_scratch);
+    // the by-product histogram goes to its own buffer: d_scratch may hold a caller's partial results
+    if (!a->d_hist_tmp) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_hist_tmp), pgx_fused_out_words(a->G, 0) * 8u));
+    int rc = fused_pass(a, true, false, 0, nullptr, nullptr, 0, a->d_countable, a->d_hist_tmp);
     if (rc) return rc;
     a->countable_valid = true;
     return PGX_OK;
@@ -543,6 +544,7 @@ void pgx_abacus_destroy(pgx_abacus *a) {
     if (a->own_bitmap && a->d_bitmap) cudaFree(a->d_bitmap);
     if (a->own_weight && a->d_weight) cudaFree(a->d_weight);
     cudaFree(a->d_countable);
+    cudaFree(a->d_hist_tmp);
     cudaFree(a->d_gm);
     cudaFree(a->d_planes);
     cudaFree(a->d_gm_w);

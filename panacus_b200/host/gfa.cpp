@@ -8,6 +8,7 @@
 #include <regex>
 #include <set>
 #include <sstream>
+#include <string_view>
 
 #include "panacus_host.hpp"
 
@@ -189,9 +190,9 @@ std::map<std::string, Intervals> build_subpath_map(const std::vector<PathSegment
     return out;
 }
 
-std::tuple<uint32_t, bool, uint32_t, bool> canonical_edge(uint32_t u, bool f1, uint32_t v, bool f2) {  // graph.rs:142-148
-    if (u > v || (u == v && !f1)) return {v, !f2, u, !f1};
-    return {u, f1, v, f2};
+uint64_t canonical_edge(uint32_t u, bool f1, uint32_t v, bool f2) {  // graph.rs:142-148
+    if (u > v || (u == v && !f1)) return GraphStorage::edge_key(v, !f2, u, !f1);
+    return GraphStorage::edge_key(u, f1, v, f2);
 }
 
 }  // namespace
@@ -294,8 +295,14 @@ bool PathSegment::operator==(const PathSegment &o) const {
 
 // ---- GraphStorage::from_gfa (graph.rs:195-375, util.rs:368-410, 916-931, 1093-1142) ---------------------------
 
+uint64_t GraphStorage::edge_key(uint32_t u, bool fu, uint32_t v, bool fv) {
+    return ((uint64_t)((u << 1) | (fu ? 1u : 0u)) << 32) | (uint64_t)((v << 1) | (fv ? 1u : 0u));
+}
+
 GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges) {
     GraphStorage g;
+    // segment name -> id; keys are views into the file buffer (no allocation per lookup), local to the parse
+    std::unordered_map<std::string_view, uint32_t> node2id;
     g.node_lens.push_back(0);
     g.has_edges = with_edges;
     const std::string data = slurp(path);
@@ -325,9 +332,9 @@ GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges) {
         size_t fb, fe;
         if (tag == 'S') {
             if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed S line");
-            std::string name = data.substr(fb, fe - fb);
-            if (g.node2id.count(name)) throw Error("Segment with ID " + name + " occurs multiple times in GFA");
-            g.node2id.emplace(std::move(name), (uint32_t)g.node2id.size() + 1);
+            const std::string_view name(data.data() + fb, fe - fb);
+            if (!node2id.emplace(name, (uint32_t)node2id.size() + 1).second)
+                throw Error("Segment with ID " + std::string(name) + " occurs multiple times in GFA");
             size_t sb, se;
             uint32_t len = 0;
             if (field(ln.first, ln.second, 2, sb, se)) len = (uint32_t)(se - sb);
@@ -351,10 +358,11 @@ GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges) {
         }
     }
     auto node_id = [&](size_t b, size_t e) -> uint32_t {
-        auto it = g.node2id.find(data.substr(b, e - b));
-        if (it == g.node2id.end()) throw Error("unknown node " + data.substr(b, e - b));
+        auto it = node2id.find(std::string_view(data.data() + b, e - b));
+        if (it == node2id.end()) throw Error("unknown node " + data.substr(b, e - b));
         return it->second;
     };
+    if (node2id.size() >= (1u << 31)) throw Error("more than 2^31 segments are not supported");
     // pass 1b: links (graph.rs:276-306)
     if (with_edges) {
         for (auto &ln : lines) {
@@ -363,8 +371,8 @@ GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges) {
             if (!field(ln.first, ln.second, 1, b1, e1) || !field(ln.first, ln.second, 2, b2, e2) ||
                 !field(ln.first, ln.second, 3, b3, e3) || !field(ln.first, ln.second, 4, b4, e4))
                 throw Error("malformed L line");
-            auto e = canonical_edge(node_id(b1, e1), data[b2] == '+', node_id(b3, e3), data[b4] == '+');
-            if (!g.edge2id.count(e)) g.edge2id.emplace(e, (uint32_t)g.edge2id.size() + 1);
+            const uint64_t e = canonical_edge(node_id(b1, e1), data[b2] == '+', node_id(b3, e3), data[b4] == '+');
+            g.edge2id.emplace(e, (uint32_t)g.edge2id.size() + 1);  // no-op if the edge is already known
         }
     }
     // pass 2: steps

@@ -68,15 +68,16 @@ struct Step {
 };
 
 struct GraphStorage {  // graph.rs:150-375
-    std::unordered_map<std::string, uint32_t> node2id;
-    std::vector<uint32_t> node_lens;  // [0] = 0
+    std::vector<uint32_t> node_lens;  // [0] = 0; node ids are 1..=node_count() in S-line order (graph.rs:323-340)
     std::vector<PathSegment> path_segments;
     std::vector<std::vector<Step>> path_steps;  // steps of every P / W line, file order
-    std::map<std::tuple<uint32_t, bool, uint32_t, bool>, uint32_t> edge2id;  // canonical edge -> id (1-based)
+    // canonical edge (graph.rs:142-148) packed as ((u << 1 | fwd_u) << 32) | (v << 1 | fwd_v) -> id (1-based)
+    std::unordered_map<uint64_t, uint32_t> edge2id;
     bool has_edges = false;
 
-    uint64_t node_count() const { return node2id.size(); }
+    uint64_t node_count() const { return node_lens.size() - 1; }
     uint64_t edge_count() const { return edge2id.size(); }
+    static uint64_t edge_key(uint32_t u, bool fu, uint32_t v, bool fv);
     static GraphStorage from_gfa(const std::string &path, bool with_edges);
 };
 
