@@ -86,6 +86,19 @@ int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, u
 int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
                      uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude);
 int pgx_abacus_clear(pgx_abacus *a);
+/* AbacusByGroup's CSR {r, c, v} (abacus.rs:790-799) as built by compute_row_storage_space (abacus.rs:859-899) and
+ * compute_column_values (abacus.rs:901-986, report_values = true, src/graph_broker.rs:382), derived on the device:
+ *   r[0 .. n_items+1]  row offsets (n_items + 2 entries, r[0] = r[1] = 0: item 0 is the empty dummy row); from the
+ *                      row popcounts of the bitmap + a device-wide exclusive scan.  *nnz = r[n_items + 1].
+ *   c[0 .. nnz)        group ids of each row, ascending (the reference's GroupSize = u64): the set bits of the row
+ *   v[0 .. nnz)        occurrence count of each (item, group) incidence (CountSize = u32): one atomic add per ItemTable
+ *                      step; needs the same tables the bitmap was built from (pgx_abacus_build).  v may be NULL
+ *                      (then the table arguments are ignored), c may be NULL.
+ * Two calls because nnz is only known after the first.  Consumer in the reference: AbacusByGroup::to_tsv
+ * (abacus.rs:1056-1178), i.e. the `table` analysis (src/analyses/table.rs:14-35). */
+int pgx_abacus_csr_rows(pgx_abacus *a, uint64_t *r, uint64_t *nnz);
+int pgx_abacus_csr_fill(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
+                        uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude, uint64_t *c, uint32_t *v);
 /* Device -> host copy of the bitmap in the packed host layout (host_row_words per row). */
 int pgx_abacus_download(pgx_abacus *a, uint64_t *bitmap, uint32_t host_row_words);
 

@@ -549,3 +549,59 @@ def item_tables(g: Graph, mask: Mask, count: str) -> Tables:
     ex_arr = None if exclude_table is None else np.array(exclude_table.items, dtype=np.uint8)
     return Tables(np.array(items, dtype=np.uint64), np.array(prefsum, dtype=np.uint64), ex_arr,
                   uncovered, n_items)
+
+
+# ---- AbacusByGroup::to_tsv (abacus.rs:1056-1178): the `table` analysis ------------------------------------------
+
+def abacus_by_group_to_tsv(g: Graph, count: str, total: bool, groups, r, c, v, uncovered=None) -> str:
+    """Statement-by-statement restatement, including the edge branch indexing the occurrence counts with the
+    group index (`v[j as usize]`, abacus.rs:1166; IndexError where Rust would panic).  v = None <=> self.v is None."""
+    uncovered = uncovered or {}
+    id2node = [b""] * (g.node_count + 1)
+    for node, nid in g.node2id.items():
+        id2node[nid] = node
+    out = []
+    n_groups = len(groups)
+    if count in ("node", "bp"):
+        out.append("node" + ("\ttotal" if total else "".join("\t" + grp for grp in groups)) + "\n")
+        for i in range(1, len(r) - 1):  # tuple_windows().enumerate(), first entry ignored
+            start, end = int(r[i]), int(r[i + 1])
+            bp = int(g.node_lens[i]) - int(uncovered.get(i, 0)) if count == "bp" else 1
+            row = id2node[i].decode()
+            if total:
+                row += "\t%d" % (end - start)
+            else:
+                k = start
+                for j in range(n_groups):
+                    if k == end or j < int(c[k]):
+                        row += "\t0"
+                    elif j == int(c[k]):
+                        row += "\t%d" % (bp if v is None else int(v[k]) * bp)
+                        k += 1
+            out.append(row + "\n")
+    elif count == "edge":
+        if not g.edge2id:
+            return ""
+        sym = {"+": ">", "-": "<"}
+        id2edge = [None] * (g.edge_count + 1)
+        for edge, eid in g.edge2id.items():
+            id2edge[eid] = edge
+        out.append("edge" + ("\ttotal" if total else "".join("\t" + grp for grp in groups)) + "\n")
+        for i in range(1, len(r) - 1):
+            start, end = int(r[i]), int(r[i + 1])
+            u, o1, w, o2 = id2edge[i]
+            row = sym[o1] + id2node[u].decode() + sym[o2] + id2node[w].decode()
+            if total:
+                row += "\t%d" % (end - start)
+            else:
+                k = start
+                for j in range(n_groups):
+                    if k == end or j < int(c[k]):
+                        row += "\t0"
+                    elif j == int(c[k]):
+                        row += "\t1" if v is None else "\t%d" % int(v[j])  # sic: v[j], not v[k]
+                        k += 1
+            out.append(row + "\n")
+    else:
+        raise ValueError("inadmissible count type")
+    return "".join(out)

@@ -362,6 +362,17 @@ def ordered_growth_table(count: str, groups: Sequence[str], curves: Sequence[Seq
     return write_ordered_table(headers, cols, list(groups))
 
 
+def coverage_line_table(hists: Sequence[tuple[str, Iterable[int]]]) -> str:
+    """Body of analyses::coverage_line::generate_table after the comment lines (coverage_line.rs:23-57):
+    every hist without its row 0, index starting at 1."""
+    headers = [["panacus", "count", "", ""]]
+    cols = []
+    for count, h in hists:
+        cols.append([float(x) for x in list(h)[1:]])
+        headers.append(["hist", count, "", ""])
+    return write_table(headers, cols, 1)
+
+
 # ---- synthetic-input helpers ---------------------------------------------------------------
 
 def bitmap_to_item_table(bitmap: np.ndarray, n_groups: int):

@@ -17,7 +17,7 @@ EXPORTS = [
     "pgx_version", "pgx_last_error", "pgx_device_count", "pgx_row_words",
     "pgx_abacus_create", "pgx_abacus_destroy", "pgx_abacus_set_stream", "pgx_abacus_shape",
     "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_build", "pgx_abacus_clear",
-    "pgx_abacus_download", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
+    "pgx_abacus_download", "pgx_abacus_csr_rows", "pgx_abacus_csr_fill", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
     "pgx_permuted_growth", "pgx_similarity", "pgx_fused_out_words", "pgx_fused_pass_async",
     "pgx_launch_count", "pgx_last_launch_info",
     "pgx_exchange_export", "pgx_exchange_connect", "pgx_exchange_disconnect",
@@ -70,6 +70,10 @@ def lib() -> C.CDLL:
     L.pgx_abacus_clear.argtypes = [vp]
     L.pgx_abacus_download.restype = C.c_int
     L.pgx_abacus_download.argtypes = [vp, vp, C.c_uint32]
+    L.pgx_abacus_csr_rows.restype = C.c_int
+    L.pgx_abacus_csr_rows.argtypes = [vp, vp, u64p]
+    L.pgx_abacus_csr_fill.restype = C.c_int
+    L.pgx_abacus_csr_fill.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, vp, vp]
     L.pgx_hist.restype = C.c_int
     L.pgx_hist.argtypes = [vp, vp, vp, vp]
     L.pgx_ordered_growth.restype = C.c_int

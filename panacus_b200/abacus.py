@@ -175,6 +175,28 @@ class DeviceAbacus:
         _native.check(self._L.pgx_abacus_download(self._h, _ptr(out), self.row_words))
         return out
 
+    def csr(self, items=None, id_prefsum=None, path_group=None, exclude=None, values: bool = True):
+        """AbacusByGroup {r, c, v} (abacus.rs:790-799, 859-986) -> (r u64[N+2], c u64[nnz], v u32[nnz] | None).
+        v (occurrence counts) needs the ItemTable the bitmap was built from."""
+        r = np.zeros(self.n_items + 2, dtype=np.uint64)
+        nnz = C.c_uint64(0)
+        _native.check(self._L.pgx_abacus_csr_rows(self._h, _ptr(r), C.byref(nnz)))
+        c = np.zeros(nnz.value, dtype=np.uint64)
+        v = None
+        if values and items is not None:
+            items = np.ascontiguousarray(items, dtype=np.uint64)
+            id_prefsum = np.ascontiguousarray(id_prefsum, dtype=np.uint64)
+            path_group = np.ascontiguousarray(path_group, dtype=np.int64)
+            if path_group.size + 1 != id_prefsum.size:
+                raise ValueError("id_prefsum must have one more entry than path_group")
+            ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.uint8)
+            v = np.zeros(nnz.value, dtype=np.uint32)
+            _native.check(self._L.pgx_abacus_csr_fill(self._h, _ptr(items), items.size, _ptr(id_prefsum), path_group.size,
+                                                      _ptr(path_group), _ptr(ex), _ptr(c), _ptr(v)))
+        else:
+            _native.check(self._L.pgx_abacus_csr_fill(self._h, None, 0, None, 0, None, None, _ptr(c), None))
+        return r, c, v
+
     # -- hot path --------------------------------------------------------------------------------
     def hist(self, count: bool = True, weight: bool = False, countable: bool = False):
         """-> (hist_count u64[G+1] | None, hist_weight u64[G+1] | None, countable u32[N+1] | None)"""

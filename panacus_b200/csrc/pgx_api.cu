@@ -53,6 +53,9 @@ struct pgx_abacus {
     uint32_t n_planes = 0;
     bool planes_valid = false;
 
+    uint64_t *d_csr_r = nullptr;  // AbacusByGroup::r (N + 2 row offsets), lazily derived from the bitmap
+    bool csr_valid = false;
+
     uint64_t *d_acc = nullptr;  // self-cleaning global accumulators of k_scan
     size_t acc_words = 0;
     unsigned int *d_ticket = nullptr;
@@ -121,6 +124,7 @@ void invalidate_derived(pgx_abacus *a) {
     a->countable_valid = false;
     a->gm_valid = false;
     a->planes_valid = false;
+    a->csr_valid = false;
 }
 
 int check_handle(const pgx_abacus *a) {
@@ -545,6 +549,7 @@ void pgx_abacus_destroy(pgx_abacus *a) {
     if (a->own_weight && a->d_weight) cudaFree(a->d_weight);
     cudaFree(a->d_countable);
     cudaFree(a->d_hist_tmp);
+    cudaFree(a->d_csr_r);
     cudaFree(a->d_gm);
     cudaFree(a->d_planes);
     cudaFree(a->d_gm_w);
@@ -733,6 +738,94 @@ int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, con
         return fail(PGX_ERR_INVALID, (err & 1u) ? "item id out of range 1..=n_items in the ItemTable" : "path_group entry >= n_groups");
     }
     a->last_launch = "k_build";
+    return PGX_OK;
+}
+
+int pgx_abacus_csr_rows(pgx_abacus *a, uint64_t *r, uint64_t *nnz) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    DeviceGuard guard(a->device);
+    if (!a->csr_valid) {
+        if (!a->d_csr_r) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_csr_r), (a->n_rows + 1u) * 8u));
+        if ((rc = launch_csr_rows(a->d_bitmap, a->n_rows, a->G, a->W, a->Wp, a->d_csr_r, a->stream))) return rc;
+        a->launches += 2;
+        a->csr_valid = true;
+    }
+    if (r) PGX_CUDA(cudaMemcpyAsync(r, a->d_csr_r, (a->n_rows + 1u) * 8u, cudaMemcpyDeviceToHost, a->stream));
+    uint64_t total = 0;
+    PGX_CUDA(cudaMemcpyAsync(&total, a->d_csr_r + a->n_rows, 8u, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if (nnz) *nnz = total;
+    a->last_launch = "k_csr_row_len + scan";
+    return PGX_OK;
+}
+
+int pgx_abacus_csr_fill(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum, uint64_t n_paths,
+                        const int64_t *path_group, const uint8_t *exclude, uint64_t *c, uint32_t *v) {
+    int rc = check_handle(a);
+    if (rc) return rc;
+    if (v && (!id_prefsum || !path_group || (n_steps && !items))) return fail(PGX_ERR_INVALID, "null table pointer");
+    if (v && n_paths == 0 && n_steps) return fail(PGX_ERR_INVALID, "steps without paths");
+    if (v && n_paths && (id_prefsum[0] != 0 || id_prefsum[n_paths] != n_steps))
+        return fail(PGX_ERR_INVALID, "id_prefsum does not span the items");
+    uint64_t nnz = 0;
+    if ((rc = pgx_abacus_csr_rows(a, nullptr, &nnz))) return rc;
+    DeviceGuard guard(a->device);
+    struct Staging {  // freed on every exit path
+        uint64_t *c = nullptr, *items = nullptr, *prefsum = nullptr;
+        uint32_t *v = nullptr;
+        int64_t *group = nullptr;
+        uint8_t *ex = nullptr;
+        ~Staging() {
+            cudaFree(c);
+            cudaFree(items);
+            cudaFree(prefsum);
+            cudaFree(v);
+            cudaFree(group);
+            cudaFree(ex);
+        }
+    } st;
+    if (c && nnz) {
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.c), nnz * 8u));
+        if ((rc = launch_csr_cols(a->d_bitmap, a->n_rows, a->G, a->W, a->Wp, a->d_csr_r, st.c, a->stream))) return rc;
+        a->launches++;
+        PGX_CUDA(cudaMemcpyAsync(c, st.c, nnz * 8u, cudaMemcpyDeviceToHost, a->stream));
+        PGX_CUDA(cudaStreamSynchronize(a->stream));
+    }
+    if (v && nnz && n_paths) {
+        const uint64_t kChunk = 1ull << 25;  // 32 Mi steps = 256 MB per staging copy
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.v), nnz * 4u));
+        PGX_CUDA(cudaMemsetAsync(st.v, 0, nnz * 4u, a->stream));
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.prefsum), (n_paths + 1) * 8u));
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.group), n_paths * 8u));
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.items), std::max<uint64_t>(std::min(kChunk, n_steps), 1) * 8u));
+        PGX_CUDA(cudaMemcpyAsync(st.prefsum, id_prefsum, (n_paths + 1) * 8u, cudaMemcpyHostToDevice, a->stream));
+        PGX_CUDA(cudaMemcpyAsync(st.group, path_group, n_paths * 8u, cudaMemcpyHostToDevice, a->stream));
+        if (exclude) {
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.ex), a->n_rows));
+            PGX_CUDA(cudaMemcpyAsync(st.ex, exclude, a->n_rows, cudaMemcpyHostToDevice, a->stream));
+        }
+        for (uint64_t s0 = 0; s0 < n_steps; s0 += kChunk) {
+            const uint64_t n = std::min<uint64_t>(kChunk, n_steps - s0);
+            PGX_CUDA(cudaMemcpyAsync(st.items, items + s0, n * 8u, cudaMemcpyHostToDevice, a->stream));
+            if ((rc = launch_csr_vals(a->d_bitmap, a->n_rows, a->G, a->Wp, st.items, s0, n, st.prefsum, n_paths, st.group, st.ex,
+                                      a->d_csr_r, st.v, a->d_err, a->stream)))
+                return rc;
+            a->launches++;
+            PGX_CUDA(cudaStreamSynchronize(a->stream));  // the staging buffer is reused by the next chunk
+        }
+        unsigned int err = 0;
+        PGX_CUDA(cudaMemcpyAsync(&err, a->d_err, 4, cudaMemcpyDeviceToHost, a->stream));
+        PGX_CUDA(cudaMemcpyAsync(v, st.v, nnz * 4u, cudaMemcpyDeviceToHost, a->stream));
+        PGX_CUDA(cudaStreamSynchronize(a->stream));
+        if (err) {
+            PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
+            return fail(PGX_ERR_INVALID, (err & 8u)   ? "ItemTable step without its bit in the bitmap: the abacus was not built from this table"
+                                         : (err & 1u) ? "item id out of range 1..=n_items in the ItemTable"
+                                                      : "path_group entry >= n_groups");
+        }
+    }
+    a->last_launch = "k_csr_cols + k_csr_vals";
     return PGX_OK;
 }
 

@@ -147,4 +147,15 @@ int launch_build(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, uint32_t G, con
                  uint64_t n_steps, const uint64_t *d_prefsum, uint64_t n_paths, const int64_t *d_path_group,
                  const uint8_t *d_exclude, unsigned int *d_err, cudaStream_t stream);
 
+
+// AbacusByGroup CSR {r, c, v} from the bitmap (+ the ItemTable for the occurrence counts v); pgx_csr.cu
+int launch_csr_rows(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t W, uint32_t Wp, uint64_t *d_r /*n_rows + 1*/,
+                    cudaStream_t stream);  // synchronises the stream
+int launch_csr_cols(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t W, uint32_t Wp, const uint64_t *d_r,
+                    uint64_t *d_c, cudaStream_t stream);
+int launch_csr_vals(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, const uint64_t *d_items, uint64_t step0,
+                    uint64_t n_steps, const uint64_t *d_prefsum, uint64_t n_paths, const int64_t *d_path_group,
+                    const uint8_t *d_exclude, const uint64_t *d_r, uint32_t *d_v /*zeroed by the caller*/, unsigned int *d_err,
+                    cudaStream_t stream);
+
 }  // namespace pgx

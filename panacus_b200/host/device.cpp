@@ -36,6 +36,31 @@ void DeviceAbacus::build(const ItemTables &t, const std::vector<std::pair<uint64
           "pgx_abacus_build");
 }
 
+void DeviceAbacus::csr(const ItemTables &t, const std::vector<std::pair<uint64_t, std::string>> &path_order,
+                       std::vector<uint64_t> &r, std::vector<uint64_t> &c, std::vector<uint32_t> &v, bool want_v) {
+    r.assign(n_items_ + 2, 0);
+    uint64_t nnz = 0;
+    check(pgx_abacus_csr_rows(H(h_), r.data(), &nnz), "pgx_abacus_csr_rows");
+    c.assign(nnz, 0);
+    v.clear();
+    if (!want_v) {
+        check(pgx_abacus_csr_fill(H(h_), nullptr, 0, nullptr, 0, nullptr, nullptr, c.data(), nullptr), "pgx_abacus_csr_fill");
+        return;
+    }
+    v.assign(nnz, 0);
+    std::vector<int64_t> path_group(t.id_prefsum.size() - 1, -1);  // same numbering as build()
+    int64_t gid = -1;
+    const std::string *last = nullptr;
+    for (auto &po : path_order) {
+        if (!last || *last != po.second) ++gid;
+        last = &po.second;
+        path_group[po.first] = gid;
+    }
+    check(pgx_abacus_csr_fill(H(h_), t.items.data(), t.items.size(), t.id_prefsum.data(), path_group.size(), path_group.data(),
+                              t.exclude.empty() ? nullptr : t.exclude.data(), c.data(), v.data()),
+          "pgx_abacus_csr_fill");
+}
+
 void DeviceAbacus::set_weights(const std::vector<uint32_t> &w) {
     if (w.size() != n_items_ + 1) throw Error("weight vector must have n_items + 1 entries");
     check(pgx_abacus_upload(H(h_), nullptr, 0, w.data()), "pgx_abacus_upload(weights)");

@@ -299,7 +299,7 @@ uint64_t GraphStorage::edge_key(uint32_t u, bool fu, uint32_t v, bool fv) {
     return ((uint64_t)((u << 1) | (fu ? 1u : 0u)) << 32) | (uint64_t)((v << 1) | (fv ? 1u : 0u));
 }
 
-GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges) {
+GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bool with_names) {
     GraphStorage g;
     // segment name -> id; keys are views into the file buffer (no allocation per lookup), local to the parse
     std::unordered_map<std::string_view, uint32_t> node2id;
@@ -339,6 +339,10 @@ GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges) {
             uint32_t len = 0;
             if (field(ln.first, ln.second, 2, sb, se)) len = (uint32_t)(se - sb);
             g.node_lens.push_back(len);
+            if (with_names) {
+                if (g.node_names.empty()) g.node_names.emplace_back();
+                g.node_names.emplace_back(name);
+            }
         } else if (tag == 'P') {
             if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed P line");
             g.path_segments.push_back(PathSegment::from_str(data.substr(fb, fe - fb)));

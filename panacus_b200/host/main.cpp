@@ -1,5 +1,5 @@
 // main.cpp -- `panacus` command line for the hot-path subcommands, with the reference's flags:
-//   hist | growth | histgrowth | ordered-histgrowth | similarity
+//   hist | growth | histgrowth | ordered-histgrowth | similarity | table (+ coverage-line, report)
 // (src/commands/{hist,growth,histgrowth,ordered_histgrowth,similarity}.rs).  Counting runs on the GPU
 // through libpanacus_b200.so; parsing, grouping, thresholds, closed-form growth and TSV stay here.
 #include <algorithm>
@@ -101,11 +101,11 @@ struct Run {
     std::vector<std::pair<uint64_t, std::string>> path_order;
 };
 
-Run load(const Args &a, const std::vector<CountType> &counts, bool with_order) {
+Run load(const Args &a, const std::vector<CountType> &counts, bool with_order, bool with_names = false) {
     bool edges = false;
     for (auto c : counts) edges = edges || c == CountType::Edge;
     Run r;
-    r.graph = GraphStorage::from_gfa(a.positional.at(0), edges);
+    r.graph = GraphStorage::from_gfa(a.positional.at(0), edges, with_names);
     GraphMaskParameters p;
     p.groupby = a.get("groupby");
     p.groupby_sample = a.has("groupby-sample");  // commands/hist.rs:44-50: -S wins over -H, both over -g
@@ -154,7 +154,7 @@ bool ends_with(const std::string &s, const std::string &suf) {
     return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
 }
 
-Source open_source(const Args &a, const std::vector<CountType> &counts, bool with_order) {
+Source open_source(const Args &a, const std::vector<CountType> &counts, bool with_order, bool with_names = false) {
     Source src;
     src.path = a.positional.at(0);
     src.cached = ends_with(src.path, ".pabm");
@@ -163,7 +163,7 @@ Source open_source(const Args &a, const std::vector<CountType> &counts, bool wit
             if (a.has(k)) throw Error(std::string("--") + k + " cannot be combined with a packed-abacus (.pabm) input: grouping, "
                                       "subset and order are fixed when the cache is written");
     } else {
-        src.run = load(a, counts, with_order);
+        src.run = load(a, counts, with_order, with_names);
     }
     return src;
 }
@@ -396,6 +396,72 @@ int cmd_similarity(const Args &a, const std::string &cmdline, std::ostream &os) 
     return 0;
 }
 
+// `table` (src/commands/table.rs, analyses/table.rs:14-35 -> AbacusByGroup::to_tsv, abacus.rs:1056-1178): one row per
+// node / edge, one column per group (occurrence count x bp length) or the number of groups containing it (--total).
+// The reference registers the subcommand but has its CLI dispatch commented out (src/lib.rs:199-201); it is reachable
+// through the YAML report (`!Table`), where `order` is never applied (analysis_parameter.rs:251-253) -- the CLI here
+// honours -O as the subcommand's help text describes.
+int cmd_table(const Args &a, const std::string &cmdline, bool with_order, std::ostream &os) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    if (count == CountType::All) throw Error("table does not accept count type 'all'");
+    if (ends_with(a.positional.at(0), ".pabm"))
+        throw Error("table needs the graph itself (segment names and per-path occurrence counts), not a packed-abacus cache");
+    const bool total = a.has("total") || a.has("hist");  // -a is --total here (commands/table.rs:18), --hist elsewhere
+    const Run run = load(a, {count}, with_order, true);
+    ItemTables t = build_item_tables(run.graph, run.mask, count);
+    const uint32_t G = count_groups(run.path_order);
+    if (G == 0) throw Error("no path left to count (check --subset / --exclude)");
+    DeviceAbacus ab(t.n_items, G);
+    std::vector<std::string> groups;
+    ab.build(t, run.path_order, groups);
+    std::vector<uint64_t> r, c;
+    std::vector<uint32_t> v;
+    ab.csr(t, run.path_order, r, c, v, !total);
+    os << write_metadata_comments(cmdline, true)
+       << abacus_by_group_to_tsv(run.graph, count, total, groups, r, c, v, t.uncovered_bps) << "\n";
+    return 0;
+}
+
+// `panacus debug-table-tsv <gfa> --csr FILE [table flags]`: the to_tsv WRITER alone, fed with r / c / v read from a
+// text file (three lines of TAB separated integers) instead of the device -- a test hook like debug-tables, so that the
+// CPU test-suite can check the writer against the oracle's restatement without a GPU.  Nothing is counted here.
+int cmd_debug_table_tsv(const Args &a, std::ostream &os) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    const Run run = load(a, {count}, true, true);
+    const ItemTables t = build_item_tables(run.graph, run.mask, count);
+    std::vector<std::string> groups;
+    for (auto &po : run.path_order)
+        if (groups.empty() || groups.back() != po.second) groups.push_back(po.second);
+    std::ifstream in(a.get("csr"));
+    if (!in) throw Error("cannot open " + a.get("csr"));
+    std::vector<std::vector<uint64_t>> rows(3);
+    std::string line;
+    for (int k = 0; k < 3 && std::getline(in, line); ++k) {
+        std::stringstream ss(line);
+        uint64_t x;
+        while (ss >> x) rows[k].push_back(x);
+    }
+    const std::vector<uint32_t> v(rows[2].begin(), rows[2].end());
+    os << abacus_by_group_to_tsv(run.graph, count, a.has("total"), groups, rows[0], rows[1], v, t.uncovered_bps);
+    return 0;
+}
+
+// CoverageLine (analyses/coverage_line.rs:23-57): the run's histograms without row 0, index starting at 1
+int cmd_coverage_line(const Args &a, const std::string &cmdline, std::ostream &os) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    const auto counts = expand(count);
+    const Source src = open_source(a, counts, false);
+    std::vector<std::vector<std::string>> headers = {{"panacus", "count", "", ""}};
+    std::vector<std::vector<double>> cols;
+    for (auto c : counts) {  // the reference iterates a HashMap here: column order across count types is unspecified
+        const Hist h = device_hist(src, c, a);
+        cols.emplace_back(h.coverage.begin() + 1, h.coverage.end());
+        headers.push_back({"hist", to_string(c), "", ""});
+    }
+    os << write_metadata_comments(cmdline, true) << write_table(headers, cols, 1) << "\n";
+    return 0;
+}
+
 // `panacus debug-tables <gfa> [-c count] [grouping / subset / exclude / order flags]`: dumps what the host front
 // end hands to the device (group order, ItemTable, exclude flags, uncovered bps, node lengths) as text.  No GPU
 // needed; the CPU test-suite compares it with the oracle's restatement of the reference front end.
@@ -600,6 +666,15 @@ int cmd_report(const Args &a0, std::ostream &os) {
                 a.opt["quorum"] = kv("quorum", "0");
                 if (!kv("order", "").empty()) a.opt["order"] = kv("order", "");
                 if (!dry) rc |= cmd_ordered(a, cmdline, os);
+            } else if (an.type == "Table") {
+                a.sub = "table";
+                a.opt["count"] = lower(kv("count_type", "node"));
+                if (lower(kv("total", "false")) == "true") a.opt["total"] = "1";
+                if (!dry) rc |= cmd_table(a, cmdline, false, os);  // `order` is not applied by the reference here
+            } else if (an.type == "CoverageLine") {
+                a.sub = "coverage-line";
+                a.opt["count"] = run_count;  // prints the run's histograms (coverage_line.rs:39-47)
+                if (!dry) rc |= cmd_coverage_line(a, cmdline, os);
             } else if (an.type == "Similarity") {
                 a.sub = "similarity";
                 a.opt["count"] = lower(kv("count_type", "node"));
@@ -620,7 +695,7 @@ int cmd_report(const Args &a0, std::ostream &os) {
 }
 
 void usage() {
-    std::cerr << "panacus (B200 hot path) -- usage: panacus <hist|growth|histgrowth|ordered-histgrowth|similarity> <GFA_FILE> [options]\n"
+    std::cerr << "panacus (B200 hot path) -- usage: panacus <hist|growth|histgrowth|ordered-histgrowth|similarity|table|coverage-line> <GFA_FILE> [options]\n"
                  "                                  panacus report <config.yaml> [--dry-run]   (tables as TSV; no HTML rendering)\n"
                  "  -s, --subset FILE   -e, --exclude FILE   -g, --groupby FILE   -H, --groupby-haplotype   -S, --groupby-sample\n"
                  "  -c, --count node|bp|edge|all   -l, --coverage LIST   -q, --quorum LIST   -a, --hist   -O, --order FILE\n"
@@ -640,6 +715,9 @@ int dispatch(int argc, char **argv, std::ostream &os) {
     if (a.sub == "histgrowth") return cmd_growth(a, cmdline, true, os);
     if (a.sub == "ordered-histgrowth") return cmd_ordered(a, cmdline, os);
     if (a.sub == "similarity") return cmd_similarity(a, cmdline, os);
+    if (a.sub == "table") return cmd_table(a, cmdline, true, os);
+    if (a.sub == "coverage-line") return cmd_coverage_line(a, cmdline, os);
+    if (a.sub == "debug-table-tsv") return cmd_debug_table_tsv(a, os);
     if (a.sub == "debug-tables") return cmd_debug_tables(a, os);
     if (a.sub == "report") return cmd_report(a, os);
     usage();

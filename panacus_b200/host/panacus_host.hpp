@@ -74,11 +74,13 @@ struct GraphStorage {  // graph.rs:150-375
     // canonical edge (graph.rs:142-148) packed as ((u << 1 | fwd_u) << 32) | (v << 1 | fwd_v) -> id (1-based)
     std::unordered_map<uint64_t, uint32_t> edge2id;
     bool has_edges = false;
+    // segment names by id ([0] = ""), kept only when asked for (the `table` writer, abacus.rs:1067-1072)
+    std::vector<std::string> node_names;
 
     uint64_t node_count() const { return node_lens.size() - 1; }
     uint64_t edge_count() const { return edge2id.size(); }
     static uint64_t edge_key(uint32_t u, bool fu, uint32_t v, bool fv);
-    static GraphStorage from_gfa(const std::string &path, bool with_edges);
+    static GraphStorage from_gfa(const std::string &path, bool with_edges, bool with_names = false);
 };
 
 // ---- src/graph_broker/abacus.rs: GraphMask ---------------------------------------------------------------
@@ -125,6 +127,10 @@ std::string write_table(const std::vector<std::vector<std::string>> &headers,
 std::string write_ordered_table(const std::vector<std::vector<std::string>> &headers,
                                 const std::vector<std::vector<double>> &columns, const std::vector<std::string> &index);
 std::string write_metadata_comments(const std::string &argv_joined, bool with_version);
+// AbacusByGroup::to_tsv (abacus.rs:1056-1178): the per-item coverage table of the `table` analysis
+std::string abacus_by_group_to_tsv(const GraphStorage &g, CountType count, bool total, const std::vector<std::string> &groups,
+                                   const std::vector<uint64_t> &r, const std::vector<uint64_t> &c, const std::vector<uint32_t> &v,
+                                   const std::map<uint64_t, uint64_t> &uncovered_bps);
 // hist-only TSV re-ingestion for `growth <file.tsv>` (io.rs:152-290)
 std::vector<Hist> parse_hists(const std::string &path, std::vector<std::string> &comments);
 
@@ -147,6 +153,10 @@ class DeviceAbacus {
     // AbacusByGroup::calc_growth for all threshold pairs (abacus.rs:989-1032); f64 like the reference
     std::vector<std::vector<double>> calc_growth(const ThresholdContainer &aux, bool weighted);
     void similarity(bool weighted, std::vector<uint64_t> &inter, std::vector<uint64_t> &len);
+    // AbacusByGroup {r, c, v} (abacus.rs:790-799) of the abacus built from `t` under `path_order`; want_v = false skips
+    // the occurrence counts (the --total table never reads them, abacus.rs:1093-1096)
+    void csr(const ItemTables &t, const std::vector<std::pair<uint64_t, std::string>> &path_order, std::vector<uint64_t> &r,
+             std::vector<uint64_t> &c, std::vector<uint32_t> &v, bool want_v);
     uint32_t n_groups() const { return n_groups_; }
     uint64_t n_items() const { return n_items_; }
 

@@ -72,6 +72,96 @@ std::string write_metadata_comments(const std::string &argv_joined, bool with_ve
     return res;
 }
 
+// AbacusByGroup::to_tsv (abacus.rs:1056-1178)
+std::string abacus_by_group_to_tsv(const GraphStorage &g, CountType count, bool total, const std::vector<std::string> &groups,
+                                   const std::vector<uint64_t> &r, const std::vector<uint64_t> &c, const std::vector<uint32_t> &v,
+                                   const std::map<uint64_t, uint64_t> &uncovered_bps) {
+    if (g.node_names.size() != g.node_lens.size()) throw Error("table: the graph was loaded without segment names");
+    const uint64_t G = groups.size();
+    std::string out;
+    auto header = [&](const char *first) {
+        out += first;
+        if (total) {
+            out += "\ttotal";
+        } else {
+            for (auto &grp : groups) {
+                out += '\t';
+                out += grp;
+            }
+        }
+        out += '\n';
+    };
+    if (count == CountType::Node || count == CountType::Bp) {
+        header("node");
+        for (uint64_t i = 1; i + 1 < r.size(); ++i) {  // windows of r, first entry ignored (abacus.rs:1086-1088)
+            const uint64_t start = r[i], end = r[i + 1];
+            uint64_t bp = 1;
+            if (count == CountType::Bp) {
+                auto it = uncovered_bps.find(i);
+                bp = (uint64_t)g.node_lens[i] - (it == uncovered_bps.end() ? 0 : it->second);
+            }
+            out += g.node_names[i];
+            if (total) {
+                out += '\t';
+                out += std::to_string(end - start);
+                out += '\n';
+                continue;
+            }
+            uint64_t k = start;
+            for (uint64_t j = 0; j < G; ++j) {
+                if (k == end || j < c[k]) {
+                    out += "\t0";
+                } else if (j == c[k]) {
+                    out += '\t';
+                    out += std::to_string(v.empty() ? bp : (uint64_t)v[k] * bp);
+                    ++k;
+                }
+            }
+            out += '\n';
+        }
+        return out;
+    }
+    if (count != CountType::Edge) throw Error("inadmissible count type");
+    if (!g.has_edges) return out;  // abacus.rs:1121: no edge2id, nothing is written
+    std::vector<uint64_t> id2edge(g.edge_count() + 1, 0);
+    for (auto &kv : g.edge2id) id2edge[kv.second] = kv.first;
+    header("edge");
+    for (uint64_t i = 1; i + 1 < r.size(); ++i) {
+        const uint64_t start = r[i], end = r[i + 1];
+        const uint64_t key = id2edge[i];
+        const uint32_t a = (uint32_t)(key >> 32), b = (uint32_t)key;
+        out += (a & 1u) ? '>' : '<';
+        out += g.node_names[a >> 1];
+        out += (b & 1u) ? '>' : '<';
+        out += g.node_names[b >> 1];
+        if (total) {
+            out += '\t';
+            out += std::to_string(end - start);
+            out += '\n';
+            continue;
+        }
+        uint64_t k = start;
+        for (uint64_t j = 0; j < G; ++j) {
+            if (k == end || j < c[k]) {
+                out += "\t0";
+            } else if (j == c[k]) {
+                // the reference indexes the occurrence counts by the GROUP index here (`v[j as usize]`, abacus.rs:1166),
+                // not by the row cursor k; reproduced as is, including the out-of-bounds panic
+                if (v.empty()) {
+                    out += "\t1";
+                } else {
+                    if (j >= v.size()) throw Error("index out of bounds: the len is " + std::to_string(v.size()) + " but the index is " + std::to_string(j));
+                    out += '\t';
+                    out += std::to_string(v[j]);
+                }
+                ++k;
+            }
+        }
+        out += '\n';
+    }
+    return out;
+}
+
 std::vector<Hist> parse_hists(const std::string &path, std::vector<std::string> &comments) {  // io.rs:152-290
     std::ifstream in(path);
     if (!in) throw Error("cannot open " + path);

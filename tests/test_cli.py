@@ -328,6 +328,78 @@ def test_packed_abacus_cache_round_trip(tmp_path):
     assert r.returncode != 0 and "cannot be combined" in r.stderr
 
 
+# ---- table / coverage-line: AbacusByGroup::to_tsv and CoverageLine over the device-built CSR ------------
+
+TABLE_SETS = [
+    ("chrM_test.gfa", [], {}),
+    ("chrM_test.gfa", ["-S"], {"groupby_sample": True}),
+    ("chrM_test.gfa", ["-H", "-e", os.path.join(GOLDEN, "exclusion.bed3")],
+     {"groupby_haplotype": True, "exclude": os.path.join(GOLDEN, "exclusion.bed3")}),
+    ("chrM_test.gfa", ["-s", os.path.join(GOLDEN, "inclusion.bed3")], {"subset": os.path.join(GOLDEN, "inclusion.bed3")}),
+    ("t_groups.gfa", ["-g", os.path.join(GOLDEN, "test_groups.txt")], {"groupby_file": os.path.join(GOLDEN, "test_groups.txt")}),
+    ("cdbg.gfa", [], {}),
+]
+
+
+@pytest.mark.gpu
+def test_table_matches_oracle(tmp_path):
+    cmds, wants = [], []
+    for gfa, flags, kw in TABLE_SETS:
+        for count in ("node", "bp", "edge"):
+            g, t, op, og, names = oracle_tables(gfa, count, **kw)
+            r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+            for total in (False, True):
+                try:
+                    want = go.abacus_by_group_to_tsv(g, count, total, names, r, c, v, t.uncovered)
+                except IndexError:
+                    continue  # the reference panics on this input (v[j] out of bounds, abacus.rs:1166)
+                cmds.append(["table", os.path.join(GOLDEN, gfa), "-c", count, *flags, *(["-a"] if total else [])])
+                wants.append(want)
+    outs = run_many(cmds, tmp_path)
+    for cmd, out, want in zip(cmds, outs, wants):
+        assert out.split("\n")[1].startswith("# version"), cmd
+        assert body(out) == want, cmd
+    # -O changes the column order of the table like it does for ordered-histgrowth
+    order = tmp_path / "order.txt"
+    g, t, op, og, names = oracle_tables("chrM_test.gfa", "node")
+    order.write_text("\n".join(reversed(names)) + "\n")
+    g, t, op, og, names2 = oracle_tables("chrM_test.gfa", "node", order=str(order))
+    assert names2 == list(reversed(names))
+    r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+    out = run_cli("table", os.path.join(GOLDEN, "chrM_test.gfa"), "-O", str(order)).stdout
+    assert body(out) == go.abacus_by_group_to_tsv(g, "node", False, names2, r, c, v, t.uncovered)
+
+
+TABLE_YAML = """- graph: {chrM}
+  grouping: Haplotype
+  analyses:
+    - !Hist {{count_type: Bp}}
+    - !CoverageLine {{count_type: Bp, reference: x}}
+    - !Table {{count_type: Bp, total: false}}
+    - !Table
+      count_type: Node
+      total: true
+"""
+
+
+@pytest.mark.gpu
+def test_report_table_and_coverage_line(tmp_path):
+    chrM = os.path.join(GOLDEN, "chrM_test.gfa")
+    y = tmp_path / "t.yaml"
+    y.write_text(TABLE_YAML.format(chrM=chrM))
+    rep = run_cli("report", str(y)).stdout
+    sections = [sec.split("\n", 1) for sec in rep.split("## run ")[1:]]
+    assert [h for h, _ in sections] == [f"{chrM} analysis Hist", f"{chrM} analysis CoverageLine", f"{chrM} analysis Table",
+                                        f"{chrM} analysis Table"]
+    hist = oracle_hist("chrM_test.gfa", "bp", groupby_haplotype=True)
+    assert body(sections[0][1]) == po.hist_table([("bp", hist)])
+    assert body(sections[1][1]) == po.coverage_line_table([("bp", hist)])
+    for sec, count, total in ((sections[2], "bp", False), (sections[3], "node", True)):
+        g, t, op, og, names = oracle_tables("chrM_test.gfa", count, groupby_haplotype=True)
+        r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        assert body(sec[1]) == go.abacus_by_group_to_tsv(g, count, total, names, r, c, v, t.uncovered)
+
+
 # ---- report: the YAML front end (commands/report.rs; tables as TSV, no HTML) ----------------------------------------
 
 REPORT_YAML = """# example in the style of src/commands/report.rs:55-62

@@ -304,6 +304,49 @@ def test_whole_table_build_matches_reference_incidence():
             a.build(np.array([1, 2], dtype=np.uint64), np.array([0, 1], dtype=np.uint64), np.array([0], dtype=np.int64))
 
 
+def test_csr_build_matches_reference_r_c_v():
+    """AbacusByGroup {r, c, v}: device CSR (bitmap popcounts + scan, bit positions, one atomic per step) against the
+    reference's two cursor passes (abacus.rs:859-986) restated in oracle/."""
+    for kw in ({}, {"groupby_sample": True}, {"groupby_haplotype": True, "exclude": os.path.join(GOLDEN, "exclusion.bed3")},
+               {"subset": os.path.join(GOLDEN, "inclusion.bed3")}):
+        for count in ("node", "edge"):
+            g, t, op, og, names, bits, weights = fixture_bitmap("chrM_test.gfa", count, **kw)
+            path_group = np.full(len(t.id_prefsum) - 1, -1, dtype=np.int64)
+            path_group[op.astype(np.int64)] = og.astype(np.int64)
+            r0, c0, v0 = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+            with pb.DeviceAbacus(t.n_items, len(names)) as a:
+                a.build(t.items, t.id_prefsum, path_group, t.exclude)
+                r, c, v = a.csr(t.items, t.id_prefsum, path_group, t.exclude)
+                assert np.array_equal(r, r0) and np.array_equal(c, c0) and np.array_equal(v, v0), (kw, count)
+                r2, c2, v2 = a.csr(values=False)
+                assert np.array_equal(r2, r0) and np.array_equal(c2, c0) and v2 is None
+    # random table: many paths per group, G > 64 (multi-word ranks), repeated visits, empty paths, one path left out
+    rng = np.random.default_rng(11)
+    for N, P, G in ((3000, 60, 13), (2000, 300, 150), (1, 3, 2)):
+        lens = rng.integers(0, 400, P)
+        lens[rng.integers(0, P, 3)] = 0
+        items = rng.integers(1, N + 1, int(lens.sum())).astype(np.uint64)
+        prefsum = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        path_group = np.sort(rng.integers(0, G, P)).astype(np.int64)  # a group's paths are contiguous (abacus.rs:310-347)
+        path_group[P // 2] = -1
+        exclude = (rng.random(N + 1) < 0.05).astype(np.uint8)
+        keep = np.flatnonzero(path_group >= 0)
+        op, og = keep.astype(np.uint64), path_group[keep].astype(np.uint64)
+        for ex in (None, exclude):
+            r0, c0, v0 = po.csr_build(N, items, prefsum, op, og, ex)
+            with pb.DeviceAbacus(N, G) as a:
+                a.build(items, prefsum, path_group, ex)
+                r, c, v = a.csr(items, prefsum, path_group, ex)
+                assert np.array_equal(r, r0) and np.array_equal(c, c0) and np.array_equal(v, v0), (N, P, G, ex is None)
+                assert int(v.sum()) == sum(int(lens[p]) for p in keep) - (0 if ex is None else
+                                                                           int(sum(ex[items[int(prefsum[p]):int(prefsum[p + 1])].astype(np.int64)].sum() for p in keep)))
+    # a table the bitmap was not built from is refused
+    with pb.DeviceAbacus(10, 4) as a:
+        a.build(np.array([1, 2], dtype=np.uint64), np.array([0, 2], dtype=np.uint64), np.array([0], dtype=np.int64))
+        with pytest.raises(pb.PgxError):
+            a.csr(np.array([3], dtype=np.uint64), np.array([0, 1], dtype=np.uint64), np.array([1], dtype=np.int64))
+
+
 def test_argument_errors():
     with pytest.raises(pb.PgxError):
         pb.DeviceAbacus(10, 0)

@@ -116,3 +116,36 @@ def test_path_segment_names(tmp_path, name, expect):
     seg = go.PathSegment.from_str(name)
     assert got["paths"] == [str(seg)] == [expect]
     assert got["groups"] == [seg.id()]
+
+
+# ---- the `table` writer (AbacusByGroup::to_tsv, abacus.rs:1056-1178) fed with the oracle's r / c / v -----------------
+
+@pytest.mark.parametrize("gfa", ["chrM_test.gfa", "t_groups.gfa", "cdbg.gfa"])
+def test_table_writer_matches_oracle(gfa, tmp_path):
+    from oracle import oracle as po
+    path = B(gfa)
+    sets = [([], {}), (["-S"], {"groupby_sample": True})]
+    if gfa == "chrM_test.gfa":
+        sets += [(["-s", B("inclusion.bed3")], {"subset": B("inclusion.bed3")}),
+                 (["-e", B("exclusion.bed3"), "-H"], {"exclude": B("exclusion.bed3"), "groupby_haplotype": True})]
+    for flags, kw in sets:
+        for count in ("node", "bp", "edge"):
+            g = go.parse_gfa(path)
+            mask = go.make_mask(g, **kw)
+            t = go.item_tables(g, mask, count)
+            op, og, names = go.path_order_arrays(mask, g)
+            r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+            csr = tmp_path / "csr.txt"
+            csr.write_text("\n".join("\t".join(str(int(x)) for x in a) for a in (r, c, v)) + "\n")
+            for total in (False, True):
+                try:
+                    want = go.abacus_by_group_to_tsv(g, count, total, names, r, c, v, t.uncovered)
+                except IndexError:
+                    want = None  # the reference panics here (v[j] with j >= nnz, abacus.rs:1166)
+                p = subprocess.run([BIN, "debug-table-tsv", path, "-c", count, "--csr", str(csr), *flags,
+                                    *(["--total"] if total else [])], capture_output=True, text=True, timeout=120)
+                if want is None:
+                    assert p.returncode != 0 and "index out of bounds" in p.stderr
+                else:
+                    assert p.returncode == 0, p.stderr
+                    assert p.stdout == want, (gfa, flags, count, total)
