@@ -114,10 +114,17 @@ struct GmGrowthParams {
     uint32_t slot[kMaxThresholds];  // threshold k's first differences go to out + slot[k]*G
     uint32_t general_mask;   // bit t set: threshold t needs the rank comparison (q > 0)
     uint32_t direct_out;     // very large G: no shared-memory staging of the deltas, atomics go straight to `out`
+    uint32_t has_fast;       // k_gm_quorum only: cov / slot index T is a q = 0 threshold computed in the same pass
     int weighted;
 };
 int launch_gm_growth(const GmGrowthParams &p, int sm_count, cudaStream_t stream);
 size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general, bool direct_out = false);
+// table-driven general-quorum kernel (pgx_quorum.cu): T <= kGmQuorumMaxT general thresholds (+ one q = 0) per launch
+constexpr uint32_t kGmQuorumMaxT = 4;
+constexpr size_t kGmQuorumSmemMax = 227u * 1024u;
+int gm_quorum_planes(uint32_t G);  // rank bit-planes the kernel is instantiated with for G groups (0: unsupported)
+size_t gm_quorum_smem_bytes(uint32_t G, uint32_t T, bool weighted);
+int launch_gm_quorum(const GmGrowthParams &p, cudaStream_t stream);
 
 struct GmSimParams {
     const uint64_t *gm;

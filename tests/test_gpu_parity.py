@@ -206,8 +206,12 @@ def test_many_thresholds_chunking():
 
 # ---- permuted growth (group-major kernels) -----------------------------------------------------------------
 
+@pytest.mark.parametrize("kernel", ["table", "old"])
 @pytest.mark.parametrize("N,G", [(5, 3), (300, 64), (1000, 100), (2049, 257), (700, 1030)])
-def test_permuted_growth(N, G):
+def test_permuted_growth(N, G, kernel, monkeypatch):
+    """general thresholds on k_gm_quorum (mask table in shared memory; default) and on k_gm_growth<P,true> (PGX_GM_QUORUM=old)"""
+    if kernel == "old":
+        monkeypatch.setenv("PGX_GM_QUORUM", "old")
     bits, bitmap, weights = synth.numpy_table(N, G, seed=N + G)
     orders = synth.random_orders(5, G, seed=99)
     orders[0] = np.arange(G)  # identity: must equal the node-major kernels
@@ -217,6 +221,8 @@ def test_permuted_growth(N, G):
         a.upload(bitmap, weights)
         for weighted in (False, True):
             got = a.permuted_growth(orders, cov, thr, weighted=weighted)
+            if kernel == "table" and G > 1:
+                assert "k_gm_quorum" in a.last_launch_info()
             assert np.array_equal(got[0], a.ordered_growth(cov, thr, weighted=weighted))
             for p in range(orders.shape[0]):
                 pbits = bits[:, orders[p]]  # the abacus the reference rebuilds under --order
@@ -226,6 +232,26 @@ def test_permuted_growth(N, G):
                     assert np.array_equal(got[p, t].astype(np.float64), want), (p, c, q, weighted)
             one = a.ordered_growth(cov, thr, col_order=orders[3], weighted=weighted)
             assert np.array_equal(one, got[3])
+
+
+def test_permuted_growth_many_mixed_thresholds():
+    """3 q = 0 thresholds (one rides along with k_gm_quorum, two go to the HBM-bound kernel) + 7 general ones (two launches
+    of <= 4), interleaved, with coverage cutoffs; caller-supplied cutoffs beyond G + 1 never count"""
+    N, G = 1500, 90
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=77)
+    pairs = [(1, 0.0), (2, 0.25), (1, 1.0), (2, 0.0), (3, 0.5), (1, 0.05), (5, 0.9), (3, 0.0), (2, 0.75), (1, 0.6)]
+    cov, thr = cutoffs(G, pairs)
+    orders = synth.random_orders(3, G, seed=5)
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        for weighted in (False, True):
+            got = a.permuted_growth(orders, cov, thr, weighted=weighted)
+            for p in range(orders.shape[0]):
+                exp = oracle_all(pb.pack_bits(bits[:, orders[p]]), G, weights, pairs)
+                for t, (c, q) in enumerate(pairs):
+                    assert np.array_equal(got[p, t].astype(np.float64), exp[("bp" if weighted else "node", c, q)]), (p, c, q)
+        never = np.full((1, G), 2 ** 31, dtype=np.uint32)
+        assert not a.permuted_growth(orders[:1], [1], never).any()
 
 
 # ---- similarity -------------------------------------------------------------------------------------------
