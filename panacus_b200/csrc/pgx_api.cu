@@ -1015,9 +1015,11 @@ int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row
         p.row_begin = row_begin;
         p.row_end = row_end;
         p.inter = a->d_scratch;
+        const char *env = getenv("PGX_SIM");  // "plain": one POPC per item word and pair; default: carry-save pairs of words
+        p.csa = (!use_planes && !(env && !strcmp(env, "plain"))) ? 1u : 0u;
         if ((rc = launch_gm_similarity(p, a->sm_count, a->stream))) return rc;
         a->launches++;
-        a->last_launch = "k_gm_similarity";
+        a->last_launch = use_planes ? "k_gm_similarity<weighted>" : p.csa ? "k_gm_similarity<csa>" : "k_gm_similarity<plain>";
     }
     if (len) {
         if ((rc = launch_gm_rowsum(use_planes ? a->d_gm_w : a->d_gm, a->gm_stride, n_words, use_planes ? a->d_planes : nullptr,

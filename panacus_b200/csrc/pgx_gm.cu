@@ -273,8 +273,25 @@ constexpr int kSimTile = 64;    // groups per tile edge
 constexpr int kSimKW = 32;      // item words per smem stage
 constexpr int kSimPad = kSimTile + 2;
 
-template <bool WEIGHTED>
+// one LOP3 each (nvcc splits the three-term majority into two ops)
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// CSA (unweighted only): the AND words of two consecutive item words go through a carry-save adder per group pair
+// (ones' = ones ^ a1 ^ a2, carry = maj(ones, a1, a2)); only the carry word is popcounted (weight 2) and the `ones`
+// word once at the very end.  Halves the POPC count -- the kernel's bound, 16 lanes/clk/SM against 64 for LOP3 -- for
+// 4 extra logic ops per pair and two words, which roughly balances the two pipes.
+template <bool WEIGHTED, bool CSA>
 __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ GmSimParams p, uint32_t words_per_split) {
+    static_assert(!(WEIGHTED && CSA), "the carry-save variant counts unweighted intersections");
     __shared__ uint64_t Xs[kSimKW][kSimPad];
     __shared__ uint64_t Ys[kSimKW][kSimPad];
     __shared__ uint64_t Ps[32][kSimKW];
@@ -300,10 +317,18 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
     if (k_end > p.n_words) k_end = p.n_words;
 
     uint64_t acc[4][4];
+    uint32_t ones_lo[CSA ? 4 : 1][CSA ? 4 : 1], ones_hi[CSA ? 4 : 1][CSA ? 4 : 1];  // CSA: pending weight-1 bits per pair
+    uint32_t twos[CSA ? 4 : 1][CSA ? 4 : 1];  // CSA: number of carries (weight 2); < 2^31 for any n_items < 2^32
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+        for (int j = 0; j < 4; ++j) {
+            acc[i][j] = 0ull;
+            if (CSA) {
+                ones_lo[i][j] = ones_hi[i][j] = 0u;
+                twos[i][j] = 0u;
+            }
+        }
 
     for (uint64_t k0 = k_begin; k0 < k_end; k0 += kSimKW) {
         // stage 64 x-rows and 64 y-rows x 32 words (coalesced along words), stored word-major
@@ -327,6 +352,31 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
             }
         }
         __syncthreads();
+        if (CSA) {
+#pragma unroll 2
+            for (uint32_t kw = 0; kw < kSimKW; kw += 2) {
+                uint64_t xa[4], ya[4], xb[4], yb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    xa[i] = Xs[kw][ty * 4 + i];
+                    ya[i] = Ys[kw][tx * 4 + i];
+                    xb[i] = Xs[kw + 1][ty * 4 + i];
+                    yb[i] = Ys[kw + 1][tx * 4 + i];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t a1 = xa[i] & ya[j], a2 = xb[i] & yb[j];
+                        const uint32_t a1l = (uint32_t)a1, a1h = (uint32_t)(a1 >> 32), a2l = (uint32_t)a2, a2h = (uint32_t)(a2 >> 32);
+                        twos[i][j] += (uint32_t)(__popc(lop3_maj(ones_lo[i][j], a1l, a2l)) + __popc(lop3_maj(ones_hi[i][j], a1h, a2h)));
+                        ones_lo[i][j] = lop3_xor3(ones_lo[i][j], a1l, a2l);
+                        ones_hi[i][j] = lop3_xor3(ones_hi[i][j], a1h, a2h);
+                    }
+            }
+            __syncthreads();
+            continue;
+        }
 #pragma unroll 4
         for (uint32_t kw = 0; kw < kSimKW; ++kw) {
             uint64_t xv[4], yv[4];
@@ -361,6 +411,12 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
             }
         }
         __syncthreads();
+    }
+    if (CSA) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 2ull * twos[i][j] + (uint64_t)(__popc(ones_lo[i][j]) + __popc(ones_hi[i][j]));
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -582,9 +638,11 @@ int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream
     if (q.triangular) grid = dim3(tx * (tx + 1u) / 2u, 1u, (unsigned)splits);
     if (p.planes) {
         if (p.n_planes > 32u) return fail(PGX_ERR_INVALID, "n_planes > 32");
-        k_gm_similarity<true><<<grid, 256, 0, stream>>>(q, (uint32_t)wps);
+        k_gm_similarity<true, false><<<grid, 256, 0, stream>>>(q, (uint32_t)wps);
+    } else if (p.csa) {
+        k_gm_similarity<false, true><<<grid, 256, 0, stream>>>(q, (uint32_t)wps);
     } else {
-        k_gm_similarity<false><<<grid, 256, 0, stream>>>(q, (uint32_t)wps);
+        k_gm_similarity<false, false><<<grid, 256, 0, stream>>>(q, (uint32_t)wps);
     }
     PGX_CUDA(cudaGetLastError());
     if (q.triangular) {

@@ -256,8 +256,12 @@ def test_permuted_growth_many_mixed_thresholds():
 
 # ---- similarity -------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("N,G", [(10, 2), (500, 64), (3000, 70), (1500, 130)])
-def test_similarity(N, G):
+@pytest.mark.parametrize("variant", ["csa", "plain"])
+@pytest.mark.parametrize("N,G", [(10, 2), (500, 64), (3000, 70), (1500, 130), (70000, 40)])
+def test_similarity(N, G, variant, monkeypatch):
+    """unweighted intersections on the carry-save kernel (default) and on the plain AND + POPC kernel (PGX_SIM=plain)"""
+    if variant == "plain":
+        monkeypatch.setenv("PGX_SIM", "plain")
     bits, bitmap, weights = synth.numpy_table(N, G, seed=2 * N + G)
     bits[1, :] = 1
     bitmap = pb.pack_bits(bits)
@@ -268,6 +272,8 @@ def test_similarity(N, G):
             inter_o, len_o, table_o = po.similarity(exp["r"], exp["c"], G, count_bp=weighted, node_lens=weights)
             inter, ln = a.similarity(weighted=weighted)
             assert np.array_equal(inter, inter_o) and np.array_equal(ln, len_o)
+            if not weighted:
+                assert a.last_launch_info() == f"k_gm_similarity<{variant}>"
             # f32 Jaccard exactly as similarity.rs:153-163
             table = inter.astype(np.float32) / (ln[:, None] + ln[None, :] - inter).astype(np.float32)
             assert np.array_equal(table, table_o)
