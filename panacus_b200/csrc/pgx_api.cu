@@ -360,6 +360,11 @@ int ensure_planes(pgx_abacus *a) {
     return PGX_OK;
 }
 
+bool gm_grid_col_fastest() {
+    const char *env = getenv("PGX_GM_GRID");
+    return env && !strcmp(env, "col");
+}
+
 int is_permutation(const uint32_t *order, uint32_t G) {
     std::vector<uint8_t> seen(G, 0);
     for (uint32_t j = 0; j < G; ++j) {
@@ -405,6 +410,7 @@ int gm_growth_launch_legacy(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_
         p.T = (uint32_t)n;
         p.weighted = weighted ? 1 : 0;
         p.out_order_stride = out_order_stride;
+        p.col_fastest = gm_grid_col_fastest() ? 1u : 0u;
         for (size_t k = 0; k < n; ++k) {
             p.cov[k] = cov[ts[i0 + k]];
             p.slot[k] = ts[i0 + k];
@@ -469,6 +475,7 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
         p.T = (uint32_t)n;
         p.weighted = weighted ? 1 : 0;
         p.out_order_stride = out_order_stride;
+        p.col_fastest = gm_grid_col_fastest() ? 1u : 0u;
         p.general_mask = (1u << n) - 1u;
         std::vector<uint32_t> packed(n * (size_t)G);
         for (size_t k = 0; k < n; ++k) {

@@ -141,7 +141,11 @@ __global__ void __launch_bounds__(kGmThreads, GENERAL ? 3 : 4) k_gm_growth(const
     unsigned long long *s_delta =
         reinterpret_cast<unsigned long long *>(smem_raw + (((size_t)(p.G + thr_words) * 4u + 15u) & ~(size_t)15u));
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const uint32_t order_id = blockIdx.y;
+    // 1-D grid, order fastest: the CTAs resident at any time cover a few 64-item columns under many orders, so all but
+    // the first read of a column block hit L2 (the group-major copy of a large table does not fit it as a whole)
+    const uint32_t n_col_blocks = (uint32_t)((p.n_words + kGmThreads - 1) / kGmThreads);
+    const uint32_t order_id = p.col_fastest ? blockIdx.x / n_col_blocks : blockIdx.x % p.n_orders;
+    const uint64_t col_block = p.col_fastest ? blockIdx.x % n_col_blocks : blockIdx.x / p.n_orders;
     const uint32_t *order = p.order + (size_t)order_id * p.G;
     for (uint32_t i = tid; i < p.G; i += kGmThreads) s_order[i] = order[i];
     if (GENERAL)
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(kGmThreads, GENERAL ? 3 : 4) k_gm_growth(const
         for (uint32_t i = tid; i < p.T * p.G; i += kGmThreads) s_delta[i] = 0ull;
     __syncthreads();
 
-    const uint64_t wi = (uint64_t)blockIdx.x * kGmThreads + tid;
+    const uint64_t wi = col_block * kGmThreads + tid;
     const bool active = wi < p.n_words;
     const uint64_t wsafe = active ? wi : 0;
     const uint32_t *wrow = (p.weighted && p.weight) ? p.weight + wsafe * 64u : nullptr;
@@ -574,8 +578,9 @@ int launch_gm_growth_t(const GmGrowthParams &p, cudaStream_t stream) {
     if (smem > 232448u) return fail(PGX_ERR_UNSUPPORTED, "group-major growth: G*T too large for shared memory");
     auto kern = k_gm_growth<P, GENERAL, TMAX>;
     PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((p.n_words + kGmThreads - 1) / kGmThreads), p.n_orders);
-    kern<<<grid, kGmThreads, smem, stream>>>(p);
+    const uint64_t blocks = (p.n_words + kGmThreads - 1) / kGmThreads * p.n_orders;
+    if (blocks > 0x7FFFFFFFull) return fail(PGX_ERR_UNSUPPORTED, "group-major growth: too many column blocks x orders in one launch");
+    kern<<<(unsigned)blocks, kGmThreads, smem, stream>>>(p);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }

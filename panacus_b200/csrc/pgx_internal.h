@@ -114,6 +114,8 @@ struct GmGrowthParams {
     uint32_t slot[kMaxThresholds];  // threshold k's first differences go to out + slot[k]*G
     uint32_t general_mask;   // bit t set: threshold t needs the rank comparison (q > 0)
     uint32_t direct_out;     // very large G: no shared-memory staging of the deltas, atomics go straight to `out`
+    uint32_t col_fastest;    // grid mapping: 0 = consecutive CTAs take the same column block under different orders (L2 reuse),
+                             // 1 = consecutive CTAs walk the column blocks of one order (PGX_GM_GRID=col; for measurements)
     uint32_t has_fast;       // k_gm_quorum only: cov / slot index T is a q = 0 threshold computed in the same pass
     int weighted;
 };

@@ -62,7 +62,10 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
     uint32_t *s_dhi = s_dlo + (size_t)(T + 1) * p.G;            // [T + 1][G] high words (WEIGHTED only)
     const bool has_fast = p.has_fast != 0u;                     // threshold index T: a q = 0 threshold riding along
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const uint32_t order_id = blockIdx.y;
+    // 1-D grid, order fastest (see k_gm_growth): co-resident CTAs share their column blocks through L2
+    const uint32_t n_col_blocks = (uint32_t)((p.n_words + kQThreads - 1) / kQThreads);
+    const uint32_t order_id = p.col_fastest ? blockIdx.x / n_col_blocks : blockIdx.x % p.n_orders;
+    const uint64_t col_block = p.col_fastest ? blockIdx.x % n_col_blocks : blockIdx.x / p.n_orders;
     const uint32_t *order = p.order + (size_t)order_id * p.G;
     for (uint32_t i = tid; i < p.G; i += kQThreads) s_order[i] = order[i];
     for (uint32_t i = tid; i < p.G * T; i += kQThreads) {
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
     for (uint32_t i = tid; i < p.G * (T + 1) * (WEIGHTED ? 2u : 1u); i += kQThreads) s_dlo[i] = 0u;
     __syncthreads();
 
-    const uint64_t wi = (uint64_t)blockIdx.x * kQThreads + tid;
+    const uint64_t wi = col_block * kQThreads + tid;
     const bool active = wi < p.n_words;
     const uint64_t wsafe = active ? wi : 0;
     const uint32_t *wrow = (WEIGHTED && p.weight) ? p.weight + wsafe * 64u : nullptr;
@@ -204,8 +207,9 @@ int launch_q(const GmGrowthParams &p, cudaStream_t stream) {
     const size_t smem = gm_quorum_smem_bytes(p.G, T, WEIGHTED);
     auto kern = k_gm_quorum<P, T, WEIGHTED>;
     PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((p.n_words + kQThreads - 1) / kQThreads), p.n_orders);
-    kern<<<grid, kQThreads, smem, stream>>>(p);
+    const uint64_t blocks = (p.n_words + kQThreads - 1) / kQThreads * p.n_orders;
+    if (blocks > 0x7FFFFFFFull) return fail(PGX_ERR_UNSUPPORTED, "k_gm_quorum: too many column blocks x orders in one launch");
+    kern<<<(unsigned)blocks, kQThreads, smem, stream>>>(p);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }

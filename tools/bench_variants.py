@@ -61,6 +61,21 @@ for pairs in ([(1, 0.0), (2, 0.5), (4, 0.9)], [(2, 0.5)], [(1, 0.1), (2, 0.5), (
         report(what="permuted_growth", N=N, G=G, orders=P, pairs=pairs, weighted=weighted, old_ms=round(res["old"][1], 3),
                table_ms=round(res["table"][1], 3), speedup=round(res["old"][1] / res["table"][1], 2), identical=same,
                launch=res["table"][2])
+# q = 0 only (HBM-bound k_gm_growth<.,false>): grid mapping, column-fastest (old) vs order-fastest (L2 reuse across orders)
+alg = N * ((G + 63) // 64) * 8
+for weighted in (False, True):
+    res = {}
+    for name, val in (("col", "col"), ("order", None)):
+        out, ms = with_env("PGX_GM_GRID", val, lambda: timed(lambda: a.permuted_growth(orders, [1], None, weighted=weighted)))
+        res[name] = (out, ms)
+    report(what="permuted_growth q=0 grid mapping", N=N, G=G, orders=P, weighted=weighted, col_fastest_ms=round(res["col"][1], 3),
+           order_fastest_ms=round(res["order"][1], 3), identical=bool(np.array_equal(res["col"][0], res["order"][0])),
+           algorithmic_gbps_order_fastest=round(P * alg / res["order"][1] / 1e6, 1))
+cov3, thr3 = cutoffs(G, [(1, 0.0), (2, 0.5), (4, 0.9)])
+out_c, ms_c = with_env("PGX_GM_GRID", "col", lambda: timed(lambda: a.permuted_growth(orders, cov3, thr3)))
+out_o, ms_o = timed(lambda: a.permuted_growth(orders, cov3, thr3))
+report(what="permuted_growth 3 pairs grid mapping (k_gm_quorum)", N=N, G=G, orders=P, col_fastest_ms=round(ms_c, 3),
+       order_fastest_ms=round(ms_o, 3), identical=bool(np.array_equal(out_c, out_o)))
 # group order, one pass (what ordered-histgrowth with a quorum runs on large tables)
 cov, thr = cutoffs(G, [(1, 0.0), (2, 0.5), (4, 0.9)])
 for weighted in (False, True):
