@@ -1,22 +1,31 @@
 #!/bin/bash
-# One gpurun call: GPU parity suite, old-vs-new kernel comparison, the bench line and an ncu launch list.
-# Everything lands in gpurun_out/ (merged back by gpurun).  Each step has its own timeout so that a slow
-# step cannot starve the ones after it.
+# One gpurun call: GPU parity suite, old-vs-new kernel comparison, the bench line, smoke, secondary timings and an
+# ncu launch list.  Everything lands in gpurun_out/ (merged back by gpurun).  The steps share one deadline
+# (BUDGET_S seconds from the start, default 600) so that the call ends on its own, most important step first.
 set -u
-mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+START=$(date +%s)
+BUDGET_S=${BUDGET_S:-600}
+left() { echo $(( START + BUDGET_S - $(date +%s) )); }
+step() {  # step <name> <max seconds> <command...>
+    local name=$1 max=$2; shift 2
+    local l; l=$(left)
+    if [ "$l" -lt 20 ]; then echo "== $name: skipped (deadline)"; return; fi
+    [ "$l" -lt "$max" ] && max=$l
+    local t0; t0=$(date +%s)
+    timeout "$max" "$@"
+    echo "== $name rc=$? in $(( $(date +%s) - t0 )) s (limit $max)"
+}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-( time timeout 420 python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider ) > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-( time timeout 240 python tools/bench_variants.py ) > gpurun_out/bench_variants.txt 2> gpurun_out/bench_variants.err
-echo "variants rc=$?"; cat gpurun_out/bench_variants.txt
-( time timeout 200 python bench.py --steps 50 --warmup 5 ) > gpurun_out/bench_target.json 2> gpurun_out/bench_target.err
-echo "bench rc=$?"; tail -c 600 gpurun_out/bench_target.json
-( time timeout 120 python -c "import __graft_entry__ as g; g.smoke()" ) > gpurun_out/smoke.log 2>&1
-echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
-( time timeout 240 python tools/bench_aux.py ) > gpurun_out/bench_aux.txt 2> gpurun_out/bench_aux.err
-echo "aux rc=$?"
-timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv \
-    --log-file gpurun_out/launches_variants.csv python tools/bench_variants.py --quick > gpurun_out/ncu_variants.log 2>&1
-echo "ncu rc=$?"
+step pytest 360 bash -c 'python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log'
+tail -4 gpurun_out/pytest_gpu.log
+step variants 180 bash -c 'python tools/bench_variants.py > gpurun_out/bench_variants.txt 2> gpurun_out/bench_variants.err'
+cat gpurun_out/bench_variants.txt; tail -3 gpurun_out/bench_variants.err
+step bench 180 bash -c 'python bench.py --steps 50 --warmup 5 > gpurun_out/bench_target.json 2> gpurun_out/bench_target.err'
+tail -c 400 gpurun_out/bench_target.json
+step smoke 90 bash -c 'python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1'
+tail -1 gpurun_out/smoke.log
+step aux 200 bash -c 'python tools/bench_aux.py > gpurun_out/bench_aux.txt 2> gpurun_out/bench_aux.err'
+step ncu 150 bash -c 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_gm\|k_scan\|k_transpose -c 80 --csv --log-file gpurun_out/launches_variants.csv python tools/bench_variants.py --quick > gpurun_out/ncu_variants.log 2>&1'
+echo "total $(( $(date +%s) - START )) s"
