@@ -440,42 +440,62 @@ int gm_growth_launch_legacy(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_
     return PGX_OK;
 }
 
-// Growth on the group-major copy for the thresholds `ts` under n_orders device-resident orders (results as above).
-// General thresholds (q > 0) run on the table-driven k_gm_quorum, up to kGmQuorumMaxT per launch, and one q = 0
-// threshold rides along with the first of those launches; any further q = 0 thresholds take the HBM-bound
-// k_gm_growth<.,false>.  Shapes whose mask table does not fit in shared memory (very large G) and
-// PGX_GM_QUORUM=old use k_gm_growth<P,true> for everything.
+// Growth on the group-major copy for the thresholds `ts` under n_orders device-resident orders (results as above),
+// on k_gm_quorum: general thresholds (q > 0) up to kGmQuorumMaxT per launch, one q = 0 threshold riding along with the
+// first of those launches, any further q = 0 thresholds in T = 0 launches of up to four.  bp-weighted runs use the
+// weight-sorted group-major copy (ensure_planes).  Shapes whose tables do not fit in shared memory (very large G) and
+// PGX_GM_QUORUM=old use the first-generation k_gm_growth for everything.
 int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders, const std::vector<uint32_t> &ts,
                      const uint32_t *cov, const uint32_t *thr, int weighted, uint64_t *d_out_base, uint64_t out_order_stride) {
     const uint32_t G = a->G;
+    const bool w = weighted != 0;
     std::vector<uint32_t> fast, gen;
     for (uint32_t t : ts) (all_zero(thr ? thr + (size_t)t * G : nullptr, G) ? fast : gen).push_back(t);
     const char *env = getenv("PGX_GM_QUORUM");
-    const bool table_kernel = !(env && !strcmp(env, "old")) && !gen.empty() && gm_quorum_planes(G) > 0 &&
-                              gm_quorum_smem_bytes(G, 1, weighted != 0) <= kGmQuorumSmemMax;
-    if (!table_kernel) return gm_growth_launch_legacy(a, n_orders, d_orders, ts, cov, thr, weighted, d_out_base, out_order_stride);
+    const bool fits = gen.empty() ? gm_quorum_smem_bytes(G, 0, 1, w) <= kGmQuorumSmemMax
+                                  : (gm_quorum_planes(G) > 0 && gm_quorum_smem_bytes(G, 1, 1, w) <= kGmQuorumSmemMax);
+    if ((env && !strcmp(env, "old")) || !fits || ts.empty())
+        return gm_growth_launch_legacy(a, n_orders, d_orders, ts, cov, thr, weighted, d_out_base, out_order_stride);
     int rc;
-    if (fast.size() > 1) {
-        const std::vector<uint32_t> rest(fast.begin() + 1, fast.end());
-        if ((rc = gm_growth_launch_legacy(a, n_orders, d_orders, rest, cov, thr, weighted, d_out_base, out_order_stride))) return rc;
-    }
+    const bool sorted = w && a->d_weight != nullptr;  // weight-sorted item order: uniform-weight columns are the rule
+    if (sorted && (rc = ensure_planes(a))) return rc;
+    GmGrowthParams base;
+    std::memset(&base, 0, sizeof(base));
+    base.gm = sorted ? a->d_gm_w : a->d_gm;
+    base.gm_stride = a->gm_stride;
+    base.n_words = (a->n_rows + 63u) / 64u;
+    base.n_rows = a->n_rows;
+    base.weight = sorted ? a->d_sorted_w : nullptr;
+    base.perm = sorted ? a->d_perm : nullptr;
+    base.uniform_w = sorted ? a->d_uniform_w : nullptr;
+    base.countable = a->d_countable;
+    base.G = G;
+    base.weighted = w ? 1 : 0;
+    base.out_order_stride = out_order_stride;
+    base.col_fastest = gm_grid_col_fastest() ? 1u : 0u;
+    auto run = [&](GmGrowthParams &p) -> int {
+        const uint32_t kBatch = 4096;  // orders per launch
+        for (uint32_t o0 = 0; o0 < n_orders; o0 += kBatch) {
+            p.n_orders = std::min<uint32_t>(kBatch, n_orders - o0);
+            p.order = d_orders + (size_t)o0 * G;
+            p.out = d_out_base + (size_t)o0 * out_order_stride;
+            const int r = launch_gm_quorum(p, a->stream);
+            if (r) return r;
+            a->launches++;
+        }
+        char buf[192];
+        snprintf(buf, sizeof buf, "k_gm_quorum<P=%d> orders=%u T=%u q0=%u%s smem=%zu", p.T ? gm_quorum_planes(G) : 0, n_orders, p.T,
+                 p.n_fast, sorted ? " weight-sorted" : "", gm_quorum_smem_bytes(G, p.T, gm_quorum_fast_slots(p.T, p.n_fast), w));
+        a->last_launch = buf;
+        return PGX_OK;
+    };
+    size_t f0 = 0;  // q = 0 thresholds already placed
     for (size_t i0 = 0; i0 < gen.size();) {
         size_t n = std::min<size_t>(kGmQuorumMaxT, gen.size() - i0);
         // two CTAs per SM when possible (<= 112 KB of shared memory each), otherwise whatever still fits
-        while (n > 1 && gm_quorum_smem_bytes(G, (uint32_t)n, weighted != 0) > 112u * 1024u) --n;
-        GmGrowthParams p;
-        std::memset(&p, 0, sizeof(p));
-        p.gm = a->d_gm;
-        p.gm_stride = a->gm_stride;
-        p.n_words = (a->n_rows + 63u) / 64u;
-        p.n_rows = a->n_rows;
-        p.weight = weighted ? a->d_weight : nullptr;
-        p.countable = a->d_countable;
-        p.G = G;
+        while (n > 1 && gm_quorum_smem_bytes(G, (uint32_t)n, 1, w) > 112u * 1024u) --n;
+        GmGrowthParams p = base;
         p.T = (uint32_t)n;
-        p.weighted = weighted ? 1 : 0;
-        p.out_order_stride = out_order_stride;
-        p.col_fastest = gm_grid_col_fastest() ? 1u : 0u;
         p.general_mask = (1u << n) - 1u;
         std::vector<uint32_t> packed(n * (size_t)G);
         for (size_t k = 0; k < n; ++k) {
@@ -483,26 +503,29 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
             p.slot[k] = gen[i0 + k];
             std::memcpy(packed.data() + k * G, thr + (size_t)gen[i0 + k] * G, (size_t)G * 4u);
         }
-        if (i0 == 0 && !fast.empty()) {
-            p.has_fast = 1u;
+        if (f0 < fast.size() && f0 == 0) {
+            p.n_fast = 1u;
             p.cov[n] = cov[fast[0]];
             p.slot[n] = fast[0];
+            f0 = 1;
         }
         if ((rc = upload_thr(a, packed))) return rc;
         p.thr = a->d_thr;
-        const uint32_t kBatch = 4096;  // orders per launch (gridDim.y)
-        for (uint32_t o0 = 0; o0 < n_orders; o0 += kBatch) {
-            p.n_orders = std::min<uint32_t>(kBatch, n_orders - o0);
-            p.order = d_orders + (size_t)o0 * G;
-            p.out = d_out_base + (size_t)o0 * out_order_stride;
-            if ((rc = launch_gm_quorum(p, a->stream))) return rc;
-            a->launches++;
-        }
-        char buf[160];
-        snprintf(buf, sizeof buf, "k_gm_quorum<P=%d> orders=%u T=%zu%s smem=%zu", gm_quorum_planes(G), n_orders, n,
-                 p.has_fast ? "+1 (q=0)" : "", gm_quorum_smem_bytes(G, (uint32_t)n, weighted != 0));
-        a->last_launch = buf;
+        if ((rc = run(p))) return rc;
         i0 += n;
+    }
+    while (f0 < fast.size()) {  // q = 0 thresholds that did not ride along: up to four per pass
+        size_t n = std::min<size_t>(4, fast.size() - f0);
+        while (n > 1 && gm_quorum_smem_bytes(G, 0, gm_quorum_fast_slots(0, (uint32_t)n), w) > kGmQuorumSmemMax) --n;
+        GmGrowthParams p = base;
+        p.T = 0;
+        p.n_fast = (uint32_t)n;
+        for (size_t k = 0; k < n; ++k) {
+            p.cov[k] = cov[fast[f0 + k]];
+            p.slot[k] = fast[f0 + k];
+        }
+        if ((rc = run(p))) return rc;
+        f0 += n;
     }
     return PGX_OK;
 }

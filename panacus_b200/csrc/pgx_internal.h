@@ -116,7 +116,9 @@ struct GmGrowthParams {
     uint32_t direct_out;     // very large G: no shared-memory staging of the deltas, atomics go straight to `out`
     uint32_t col_fastest;    // grid mapping: 0 = consecutive CTAs take the same column block under different orders (L2 reuse),
                              // 1 = consecutive CTAs walk the column blocks of one order (PGX_GM_GRID=col; for measurements)
-    uint32_t has_fast;       // k_gm_quorum only: cov / slot index T is a q = 0 threshold computed in the same pass
+    uint32_t n_fast;         // k_gm_quorum only: cov / slot index T .. T+n_fast-1 are q = 0 thresholds of the same pass
+    const uint32_t *perm;       // k_gm_quorum, weighted: gm / weight are in weight-sorted item order, perm[pos] = item
+    const uint64_t *uniform_w;  // k_gm_quorum, weighted: (1 << 32) | w per column whose items all weigh w, else 0
     int weighted;
 };
 int launch_gm_growth(const GmGrowthParams &p, int sm_count, cudaStream_t stream);
@@ -125,7 +127,8 @@ size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general, bool direc
 constexpr uint32_t kGmQuorumMaxT = 4;
 constexpr size_t kGmQuorumSmemMax = 227u * 1024u;
 int gm_quorum_planes(uint32_t G);  // rank bit-planes the kernel is instantiated with for G groups (0: unsupported)
-size_t gm_quorum_smem_bytes(uint32_t G, uint32_t T, bool weighted);
+size_t gm_quorum_smem_bytes(uint32_t G, uint32_t T, uint32_t NF, bool weighted);
+uint32_t gm_quorum_fast_slots(uint32_t T, uint32_t n_fast);  // NF of the instantiation that serves (T, n_fast)
 int launch_gm_quorum(const GmGrowthParams &p, cudaStream_t stream);
 
 struct GmSimParams {

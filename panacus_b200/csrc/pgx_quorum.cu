@@ -9,11 +9,15 @@
 //   * the per-plane cutoff masks come from a shared-memory table built once per CTA ([position][threshold][plane],
 //     16-byte rows read with LDS.128 on the otherwise idle LSU pipe) instead of being rebuilt from K in every lane;
 //   * T general thresholds and the weighted mode are template parameters: no per-threshold branches.  One q = 0
-//     threshold may ride along (p.has_fast: "item counts from its first group on", a popcount of the seen mask, a few
-//     ops per position); further q = 0 thresholds go to the HBM-bound k_gm_growth<.,false> in their own launch;
+//     threshold may ride along (p.n_fast: "item counts from its first group on", a popcount of the seen mask, a few
+//     ops per position); further q = 0 thresholds run in a T = 0 launch of their own;
 //   * counting nodes: a thread tracks popc(verdict) and adds the change, one REDUX per warp and position and a
 //     native 32-bit shared atomic (64-bit shared atomics are CAS loops on sm_100);
-//   * summing bp: the net weight of the flipped bits, reduced as three 24/24/16-bit pieces of its two's complement.
+//   * summing bp: runs on the weight-sorted group-major copy (the one similarity uses): most 64-item words then carry
+//     a single weight w and their contribution is (change of the popcount) x w; only mixed words walk the flipped
+//     bits.  The per-lane net is reduced as three 24/24/16-bit pieces of its two's complement (3 REDUX).
+//   * T = 0 instantiations (q = 0 thresholds only, up to NF of them differing in their coverage cutoff) replace the
+//     first-generation k_gm_growth<.,false> for permuted union growth: same loop without ranks, deeper prefetch.
 #include "pgx_common.cuh"
 #include "pgx_internal.h"
 #include "pgx_rank.cuh"
@@ -51,16 +55,18 @@ __device__ __forceinline__ long long warp_sum_i64(long long v) {
     return (long long)(slo + (smid << 24) + ((unsigned long long)shi << 48));
 }
 
-template <int P, int T, bool WEIGHTED>
-__global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(const __grid_constant__ GmGrowthParams p) {
+// T general thresholds (cov / slot index 0 .. T-1) and p.n_fast <= NF thresholds with q = 0 (index T .. T+n_fast-1).
+template <int P, int T, int NF, bool WEIGHTED>
+__global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k_gm_quorum(const __grid_constant__ GmGrowthParams p) {
     constexpr int PP = RankMaskWords<P>::value;
-    constexpr int kPrefetch = 2;  // rows in flight per thread (the loop is ALU-bound, not HBM-bound)
+    constexpr int TT = T > 0 ? T : 1;  // array extents (no zero-length arrays)
+    constexpr int kPrefetch = T == 0 ? 8 : 2;  // rows in flight per thread: q = 0 only is memory-bound, ranks are ALU-bound
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem_raw);  // [G][T][PP]
     uint32_t *s_order = s_mask + (size_t)p.G * T * PP;          // [G]
-    uint32_t *s_dlo = s_order + p.G;                            // [T + 1][G] first differences (low or only word)
-    uint32_t *s_dhi = s_dlo + (size_t)(T + 1) * p.G;            // [T + 1][G] high words (WEIGHTED only)
-    const bool has_fast = p.has_fast != 0u;                     // threshold index T: a q = 0 threshold riding along
+    uint32_t *s_dlo = s_order + p.G;                            // [T + NF][G] first differences (low or only word)
+    uint32_t *s_dhi = s_dlo + (size_t)(T + NF) * p.G;           // [T + NF][G] high words (WEIGHTED only)
+    const uint32_t n_fast = p.n_fast < (uint32_t)NF ? p.n_fast : (uint32_t)NF;  // q = 0 thresholds (warp-uniform)
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     // 1-D grid, order fastest (see k_gm_growth): co-resident CTAs share their column blocks through L2
     const uint32_t n_col_blocks = (uint32_t)((p.n_words + kQThreads - 1) / kQThreads);
@@ -72,30 +78,41 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
         const uint32_t j = i / T, t = i - j * T;
         rank_mask_row<P>(__ldg(p.thr + (size_t)t * p.G + j), p.G, s_mask + (size_t)i * PP);
     }
-    for (uint32_t i = tid; i < p.G * (T + 1) * (WEIGHTED ? 2u : 1u); i += kQThreads) s_dlo[i] = 0u;
+    for (uint32_t i = tid; i < p.G * (T + NF) * (WEIGHTED ? 2u : 1u); i += kQThreads) s_dlo[i] = 0u;
     __syncthreads();
 
     const uint64_t wi = col_block * kQThreads + tid;
     const bool active = wi < p.n_words;
     const uint64_t wsafe = active ? wi : 0;
+    // WEIGHTED with weights: p.gm is the weight-sorted copy -- bit b of column wi is item p.perm[wi * 64 + b], p.weight
+    // holds the weights in that order and p.uniform_w[wi] = (1 << 32) | w when all items of the column weigh w
     const uint32_t *wrow = (WEIGHTED && p.weight) ? p.weight + wsafe * 64u : nullptr;
+    bool uniform = WEIGHTED && !p.weight;  // unit weights
+    uint32_t uw = 1u;
+    if (WEIGHTED && p.weight && p.uniform_w) {
+        const unsigned long long u = active ? __ldg(reinterpret_cast<const unsigned long long *>(p.uniform_w) + wi) : (1ull << 32);
+        uniform = (u >> 32) != 0ull;
+        uw = (uint32_t)u;
+    }
 
     // eligibility: an item counts for threshold t only if its total coverage >= cov[t] (abacus.rs:1003)
-    uint32_t elo[T + 1], ehi[T + 1];
+    uint32_t elo[T + NF], ehi[T + NF];
 #pragma unroll
-    for (int t = 0; t <= T; ++t) elo[t] = ehi[t] = ~0u;
+    for (int t = 0; t < T + NF; ++t) elo[t] = ehi[t] = ~0u;
     bool need_cov = false;
 #pragma unroll
-    for (int t = 0; t <= T; ++t) need_cov |= (t < T || has_fast) && p.cov[t] > 1u;
+    for (int t = 0; t < T + NF; ++t) need_cov |= (uint32_t)t < (uint32_t)T + n_fast && p.cov[t] > 1u;
     if (need_cov) {
 #pragma unroll
-        for (int t = 0; t <= T; ++t) elo[t] = ehi[t] = 0u;
+        for (int t = 0; t < T + NF; ++t) elo[t] = ehi[t] = 0u;
         if (active) {
             for (uint32_t b = 0; b < 64u; ++b) {
-                const uint64_t item = wi * 64u + b;
-                const uint32_t c = (item < p.n_rows && item != 0) ? __ldg(p.countable + item) : 0u;
+                const uint64_t pos = wi * 64u + b;
+                uint64_t item = pos;
+                if (p.perm && pos < p.n_rows) item = __ldg(p.perm + pos);
+                const uint32_t c = (pos < p.n_rows && item != 0) ? __ldg(p.countable + item) : 0u;
 #pragma unroll
-                for (int t = 0; t <= T; ++t)
+                for (int t = 0; t < T + NF; ++t)
                     if (c >= p.cov[t]) {
                         if (b < 32u) elo[t] |= 1u << b; else ehi[t] |= 1u << (b - 32u);
                     }
@@ -105,12 +122,12 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
 
     RankColumn<P> R;
     R.clear();
-    uint32_t vlo[T], vhi[T];
-    int cnt[T + 1];
+    uint32_t vlo[TT], vhi[TT];
+    int cnt[T + NF];
 #pragma unroll
-    for (int t = 0; t < T; ++t) vlo[t] = vhi[t] = 0u;
+    for (int t = 0; t < TT; ++t) vlo[t] = vhi[t] = 0u;
 #pragma unroll
-    for (int t = 0; t <= T; ++t) cnt[t] = 0;
+    for (int t = 0; t < T + NF; ++t) cnt[t] = 0;
     uint32_t slo = 0u, shi = 0u;  // items seen so far (q = 0 threshold)
 
     const uint64_t *col = p.gm + wsafe;
@@ -132,27 +149,39 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
             const uint32_t j = j0 + (uint32_t)u;
             if (j >= p.G) break;
             const uint32_t blo = (uint32_t)cur[u], bhi = (uint32_t)(cur[u] >> 32);
-            R.add(blo, bhi);
-            if (has_fast) {  // warp-uniform: an item starts counting at its first group and never stops (q = 0)
-                if (!WEIGHTED) {
-                    slo |= blo;
-                    shi |= bhi;
-                    const int c = __popc(slo & elo[T]) + __popc(shi & ehi[T]);
-                    const int net = __reduce_add_sync(0xFFFFFFFFu, c - cnt[T]);
-                    cnt[T] = c;
-                    if (lane == 0 && net != 0) atomicAdd(reinterpret_cast<int *>(s_dlo) + T * p.G + j, net);
-                } else {
-                    const uint32_t flo = blo & ~slo & elo[T], fhi = bhi & ~shi & ehi[T];
-                    slo |= blo;
-                    shi |= bhi;
-                    long long mine = 0;
-                    if (flo | fhi) mine = weight_of_bits(flo, fhi, wrow);
-                    const long long net = warp_sum_i64(mine);
-                    if (lane == 0 && net != 0)
-                        smem_add64(s_dlo, s_dhi, T * p.G + j, (uint32_t)(unsigned long long)net,
-                                   (uint32_t)((unsigned long long)net >> 32));
+            if (T > 0) R.add(blo, bhi);
+            if (T == 0 || n_fast != 0u) {  // warp-uniform: an item starts counting at its first group and never stops (q = 0)
+                const uint32_t olo = slo, ohi = shi;
+                slo |= blo;
+                shi |= bhi;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    if ((uint32_t)f >= n_fast) break;
+                    int d = 0;
+                    if (!WEIGHTED || uniform) {
+                        const int c = __popc(slo & elo[T + f]) + __popc(shi & ehi[T + f]);
+                        d = c - cnt[T + f];
+                        cnt[T + f] = c;
+                    }
+                    if (!WEIGHTED) {
+                        const int net = __reduce_add_sync(0xFFFFFFFFu, d);
+                        if (lane == 0 && net != 0) atomicAdd(reinterpret_cast<int *>(s_dlo) + (T + f) * p.G + j, net);
+                    } else {
+                        long long mine;
+                        if (uniform) {  // every item of the column weighs uw
+                            mine = (long long)d * (long long)uw;
+                        } else {
+                            const uint32_t flo = blo & ~olo & elo[T + f], fhi = bhi & ~ohi & ehi[T + f];
+                            mine = (flo | fhi) ? weight_of_bits(flo, fhi, wrow) : 0ll;
+                        }
+                        const long long net = warp_sum_i64(mine);
+                        if (lane == 0 && net != 0)
+                            smem_add64(s_dlo, s_dhi, (T + f) * p.G + j, (uint32_t)(unsigned long long)net,
+                                       (uint32_t)((unsigned long long)net >> 32));
+                    }
                 }
             }
+            if (T == 0) continue;
             const uint4 *row = reinterpret_cast<const uint4 *>(s_mask + (size_t)j * (T * PP));
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -174,11 +203,17 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
                     cnt[t] = c;
                     if (lane == 0 && net != 0) atomicAdd(reinterpret_cast<int *>(s_dlo) + t * p.G + j, net);
                 } else {
-                    const uint32_t ulo = nlo & ~vlo[t] & elo[t], uhi = nhi & ~vhi[t] & ehi[t];
-                    const uint32_t dlo = vlo[t] & ~nlo & elo[t], dhi = vhi[t] & ~nhi & ehi[t];
                     long long mine = 0;
-                    if (ulo | uhi) mine += weight_of_bits(ulo, uhi, wrow);
-                    if (dlo | dhi) mine -= weight_of_bits(dlo, dhi, wrow);
+                    if (uniform) {  // every item of the column weighs uw: (change of the count) x uw
+                        const int c = __popc(nlo & elo[t]) + __popc(nhi & ehi[t]);
+                        mine = (long long)(c - cnt[t]) * (long long)uw;
+                        cnt[t] = c;
+                    } else {
+                        const uint32_t ulo = nlo & ~vlo[t] & elo[t], uhi = nhi & ~vhi[t] & ehi[t];
+                        const uint32_t dlo = vlo[t] & ~nlo & elo[t], dhi = vhi[t] & ~nhi & ehi[t];
+                        if (ulo | uhi) mine += weight_of_bits(ulo, uhi, wrow);
+                        if (dlo | dhi) mine -= weight_of_bits(dlo, dhi, wrow);
+                    }
                     const long long net = warp_sum_i64(mine);
                     if (lane == 0 && net != 0)
                         smem_add64(s_dlo, s_dhi, t * p.G + j, (uint32_t)(unsigned long long)net,
@@ -191,7 +226,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
     }
     __syncthreads();
     uint64_t *out = p.out + (size_t)order_id * p.out_order_stride;
-    for (uint32_t i = tid; i < p.G * (T + (has_fast ? 1u : 0u)); i += kQThreads) {
+    for (uint32_t i = tid; i < p.G * ((uint32_t)T + n_fast); i += kQThreads) {
         unsigned long long v;
         if (WEIGHTED) v = (unsigned long long)s_dlo[i] | ((unsigned long long)s_dhi[i] << 32);
         else v = (unsigned long long)(long long)(int)s_dlo[i];  // signed count -> two's-complement u64
@@ -202,10 +237,10 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
     }
 }
 
-template <int P, int T, bool WEIGHTED>
+template <int P, int T, int NF, bool WEIGHTED>
 int launch_q(const GmGrowthParams &p, cudaStream_t stream) {
-    const size_t smem = gm_quorum_smem_bytes(p.G, T, WEIGHTED);
-    auto kern = k_gm_quorum<P, T, WEIGHTED>;
+    const size_t smem = gm_quorum_smem_bytes(p.G, T, NF, WEIGHTED);
+    auto kern = k_gm_quorum<P, T, NF, WEIGHTED>;
     PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t blocks = (p.n_words + kQThreads - 1) / kQThreads * p.n_orders;
     if (blocks > 0x7FFFFFFFull) return fail(PGX_ERR_UNSUPPORTED, "k_gm_quorum: too many column blocks x orders in one launch");
@@ -217,17 +252,24 @@ int launch_q(const GmGrowthParams &p, cudaStream_t stream) {
 template <int P, bool WEIGHTED>
 int launch_q_t(const GmGrowthParams &p, cudaStream_t stream) {
     switch (p.T) {
-        case 1: return launch_q<P, 1, WEIGHTED>(p, stream);
-        case 2: return launch_q<P, 2, WEIGHTED>(p, stream);
-        case 3: return launch_q<P, 3, WEIGHTED>(p, stream);
-        case 4: return launch_q<P, 4, WEIGHTED>(p, stream);
-        default: return fail(PGX_ERR_INVALID, "k_gm_quorum takes 1..4 thresholds per launch");
+        case 1: return launch_q<P, 1, 1, WEIGHTED>(p, stream);
+        case 2: return launch_q<P, 2, 1, WEIGHTED>(p, stream);
+        case 3: return launch_q<P, 3, 1, WEIGHTED>(p, stream);
+        case 4: return launch_q<P, 4, 1, WEIGHTED>(p, stream);
+        default: return fail(PGX_ERR_INVALID, "k_gm_quorum takes 1..4 general thresholds per launch");
     }
 }
 
 template <int P>
 int launch_q_p(const GmGrowthParams &p, cudaStream_t stream) {
     return p.weighted ? launch_q_t<P, true>(p, stream) : launch_q_t<P, false>(p, stream);
+}
+
+template <bool WEIGHTED>
+int launch_q0(const GmGrowthParams &p, cudaStream_t stream) {  // q = 0 thresholds only
+    if (p.n_fast <= 1u) return launch_q<1, 0, 1, WEIGHTED>(p, stream);
+    if (p.n_fast <= 2u) return launch_q<1, 0, 2, WEIGHTED>(p, stream);
+    return launch_q<1, 0, 4, WEIGHTED>(p, stream);
 }
 
 }  // namespace
@@ -239,18 +281,24 @@ int gm_quorum_planes(uint32_t G) {
     return 0;
 }
 
-size_t gm_quorum_smem_bytes(uint32_t G, uint32_t T, bool weighted) {
-    const int P = gm_quorum_planes(G);
-    return ((size_t)G * T * (size_t)((P + 3) & ~3) + G + (size_t)(T + 1u) * G * (weighted ? 2u : 1u)) * 4u;
+// NF: q = 0 slots of the instantiation (1 next to general thresholds; 1, 2 or 4 when T = 0)
+size_t gm_quorum_smem_bytes(uint32_t G, uint32_t T, uint32_t NF, bool weighted) {
+    const int P = T ? gm_quorum_planes(G) : 0;
+    return ((size_t)G * T * (size_t)((P + 3) & ~3) + G + (size_t)(T + NF) * G * (weighted ? 2u : 1u)) * 4u;
 }
 
-// Thresholds 0 .. p.T-1 (p.T <= 4) must be general ones (p.thr holds T x G cutoffs by position); with p.has_fast,
-// cov / slot index p.T describes one q = 0 threshold computed in the same pass.  p.direct_out is not supported.
+uint32_t gm_quorum_fast_slots(uint32_t T, uint32_t n_fast) { return T ? 1u : (n_fast <= 1u ? 1u : n_fast <= 2u ? 2u : 4u); }
+
+// Thresholds 0 .. p.T-1 (p.T <= 4) must be general ones (p.thr holds T x G cutoffs by position); cov / slot index
+// p.T .. p.T+p.n_fast-1 describe q = 0 thresholds computed in the same pass (at most 1 when p.T > 0, at most 4 when
+// p.T = 0).  p.direct_out is not supported.
 int launch_gm_quorum(const GmGrowthParams &p, cudaStream_t stream) {
     if (p.n_orders == 0 || p.n_orders > 65535u) return fail(PGX_ERR_INVALID, "n_orders must be in 1..65535 per launch");
-    if (!p.thr || p.direct_out || p.T == 0) return fail(PGX_ERR_INVALID, "k_gm_quorum: bad parameters");
-    if (gm_quorum_smem_bytes(p.G, p.T, p.weighted != 0) > kGmQuorumSmemMax)
-        return fail(PGX_ERR_UNSUPPORTED, "k_gm_quorum: mask table does not fit in shared memory");
+    if (p.direct_out || (p.T == 0 && p.n_fast == 0) || (p.T && !p.thr) || p.n_fast > (p.T ? 1u : 4u) || p.T > kGmQuorumMaxT)
+        return fail(PGX_ERR_INVALID, "k_gm_quorum: bad parameters");
+    if (gm_quorum_smem_bytes(p.G, p.T, gm_quorum_fast_slots(p.T, p.n_fast), p.weighted != 0) > kGmQuorumSmemMax)
+        return fail(PGX_ERR_UNSUPPORTED, "k_gm_quorum: tables do not fit in shared memory");
+    if (p.T == 0) return p.weighted ? launch_q0<true>(p, stream) : launch_q0<false>(p, stream);
     switch (gm_quorum_planes(p.G)) {
         case 7: return launch_q_p<7>(p, stream);
         case 8: return launch_q_p<8>(p, stream);

@@ -254,6 +254,29 @@ def test_permuted_growth_many_mixed_thresholds():
         assert not a.permuted_growth(orders[:1], [1], never).any()
 
 
+@pytest.mark.parametrize("N,G", [(1500, 90), (4000, 300)])
+def test_permuted_growth_q0_only(N, G):
+    """q = 0 thresholds only (the permutation-sampled union / coverage >= c growth): T = 0 launches of k_gm_quorum with
+    1, 2 and 4 + 1 thresholds differing in their coverage cutoff; bp sums on the weight-sorted copy, with weights that
+    leave both single-weight and mixed 64-item columns"""
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=N)
+    rng = np.random.default_rng(N)
+    weights = np.where(rng.random(N + 1) < 0.6, 1, rng.integers(1, 2 ** 32, N + 1, dtype=np.uint64)).astype(np.uint32)
+    weights[0] = 0
+    orders = synth.random_orders(3, G, seed=11)
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        for covs in ([1], [2, 1], [1, 2, 3, 4, 5]):
+            pairs = [(c, 0.0) for c in covs]
+            for weighted in (False, True):
+                got = a.permuted_growth(orders, covs, None, weighted=weighted)
+                assert "k_gm_quorum" in a.last_launch_info() and "T=0" in a.last_launch_info()
+                for p in range(orders.shape[0]):
+                    exp = oracle_all(pb.pack_bits(bits[:, orders[p]]), G, weights, pairs)
+                    for t, (c, q) in enumerate(pairs):
+                        assert np.array_equal(got[p, t].astype(np.float64), exp[("bp" if weighted else "node", c, q)]), (p, c, weighted)
+
+
 # ---- similarity -------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("variant", ["csa", "plain"])
