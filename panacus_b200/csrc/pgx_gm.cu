@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
     if (k_end > p.n_words) k_end = p.n_words;
 
     uint64_t acc[4][4];
+    const uint32_t one = p.csa;  // == 1 whenever CSA is instantiated
     uint32_t ones_lo[CSA ? 4 : 1][CSA ? 4 : 1], ones_hi[CSA ? 4 : 1][CSA ? 4 : 1];  // CSA: pending weight-1 bits per pair
     uint32_t twos[CSA ? 4 : 1][CSA ? 4 : 1];  // CSA: number of carries (weight 2); < 2^31 for any n_items < 2^32
 #pragma unroll
@@ -373,7 +374,10 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
                     for (int j = 0; j < 4; ++j) {
                         const uint64_t a1 = xa[i] & ya[j], a2 = xb[i] & yb[j];
                         const uint32_t a1l = (uint32_t)a1, a1h = (uint32_t)(a1 >> 32), a2l = (uint32_t)a2, a2h = (uint32_t)(a2 >> 32);
-                        twos[i][j] += (uint32_t)(__popc(lop3_maj(ones_lo[i][j], a1l, a2l)) + __popc(lop3_maj(ones_hi[i][j], a1h, a2h)));
+                        // accumulate with IMAD (x * 1 + acc, multiplier from a kernel parameter so it stays a multiply): the
+                        // FMA pipe is idle here while LOP3 saturates the ALU pipe an IADD3 would share
+                        twos[i][j] = (uint32_t)__popc(lop3_maj(ones_lo[i][j], a1l, a2l)) * one + twos[i][j];
+                        twos[i][j] = (uint32_t)__popc(lop3_maj(ones_hi[i][j], a1h, a2h)) * one + twos[i][j];
                         ones_lo[i][j] = lop3_xor3(ones_lo[i][j], a1l, a2l);
                         ones_hi[i][j] = lop3_xor3(ones_hi[i][j], a1h, a2h);
                     }

@@ -18,6 +18,8 @@
 //     bits.  The per-lane net is reduced as three 24/24/16-bit pieces of its two's complement (3 REDUX).
 //   * T = 0 instantiations (q = 0 thresholds only, up to NF of them differing in their coverage cutoff) replace the
 //     first-generation k_gm_growth<.,false> for permuted union growth: same loop without ranks, deeper prefetch.
+#include <type_traits>
+
 #include "pgx_common.cuh"
 #include "pgx_internal.h"
 #include "pgx_rank.cuh"
@@ -44,6 +46,12 @@ __device__ __forceinline__ long long weight_of_bits(uint32_t lo, uint32_t hi, co
     return s;
 }
 
+// native 32-bit shared-memory reduction by the calling lane (wrapping add: signed values as two's complement); inline PTX
+// keeps ptxas from wrapping it into its vote / elect / popc aggregation sequence, the caller already is one elected lane
+__device__ __forceinline__ void red_shared_add_u32(uint32_t *addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(addr)), "r"(v) : "memory");
+}
+
 // exact warp sum of signed 64-bit values with |v| < 2^47: v = hi * 2^48 + mid * 2^24 + lo (hi signed)
 __device__ __forceinline__ long long warp_sum_i64(long long v) {
     const unsigned long long u = (unsigned long long)v;
@@ -63,9 +71,10 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
     constexpr int kPrefetch = T == 0 ? 8 : 2;  // rows in flight per thread: q = 0 only is memory-bound, ranks are ALU-bound
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem_raw);  // [G][T][PP]
-    uint32_t *s_order = s_mask + (size_t)p.G * T * PP;          // [G]
-    uint32_t *s_dlo = s_order + p.G;                            // [T + NF][G] first differences (low or only word)
-    uint32_t *s_dhi = s_dlo + (size_t)(T + NF) * p.G;           // [T + NF][G] high words (WEIGHTED only)
+    // byte offset of the row added at position j (+ 8 entries repeating the last row: the prefetch needs no bounds check)
+    unsigned long long *s_off = reinterpret_cast<unsigned long long *>(s_mask + (size_t)p.G * T * PP);  // [G + 8]
+    uint32_t *s_dlo = reinterpret_cast<uint32_t *>(s_off + p.G + 8u);  // [T + NF][G] first differences (low or only word)
+    uint32_t *s_dhi = s_dlo + (size_t)(T + NF) * p.G;                  // [T + NF][G] high words (WEIGHTED only)
     const uint32_t n_fast = p.n_fast < (uint32_t)NF ? p.n_fast : (uint32_t)NF;  // q = 0 thresholds (warp-uniform)
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     // 1-D grid, order fastest (see k_gm_growth): co-resident CTAs share their column blocks through L2
@@ -73,7 +82,8 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
     const uint32_t order_id = p.col_fastest ? blockIdx.x / n_col_blocks : blockIdx.x % p.n_orders;
     const uint64_t col_block = p.col_fastest ? blockIdx.x % n_col_blocks : blockIdx.x / p.n_orders;
     const uint32_t *order = p.order + (size_t)order_id * p.G;
-    for (uint32_t i = tid; i < p.G; i += kQThreads) s_order[i] = order[i];
+    for (uint32_t i = tid; i < p.G + 8u; i += kQThreads)
+        s_off[i] = (unsigned long long)order[i < p.G ? i : p.G - 1u] * p.gm_stride * 8ull;
     for (uint32_t i = tid; i < p.G * T; i += kQThreads) {
         const uint32_t j = i / T, t = i - j * T;
         rank_mask_row<P>(__ldg(p.thr + (size_t)t * p.G + j), p.G, s_mask + (size_t)i * PP);
@@ -130,25 +140,34 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
     for (int t = 0; t < T + NF; ++t) cnt[t] = 0;
     uint32_t slo = 0u, shi = 0u;  // items seen so far (q = 0 threshold)
 
-    const uint64_t *col = p.gm + wsafe;
-    auto load_row = [&](uint32_t j) -> uint64_t {
-        return (active && j < p.G) ? __ldg(col + (uint64_t)s_order[j] * p.gm_stride) : 0ull;
-    };
-    uint64_t nxt[kPrefetch];
+    // threads past the last column read column 0 like everybody else; their eligibility masks are cleared below, so
+    // they never count
+    const unsigned char *col = reinterpret_cast<const unsigned char *>(p.gm + wsafe);
+    auto load_row = [&](uint32_t j) -> uint64_t { return __ldg(reinterpret_cast<const unsigned long long *>(col + s_off[j])); };
+    if (!active) {
 #pragma unroll
-    for (int u = 0; u < kPrefetch; ++u) nxt[u] = load_row((uint32_t)u);
+        for (int t = 0; t < T + NF; ++t) elo[t] = ehi[t] = 0u;
+    }
+    uint64_t ring[kPrefetch];  // slot u holds row j0 + u; refilled with row j0 + kPrefetch + u as soon as it is consumed
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u) ring[u] = load_row((uint32_t)u);
 
-    for (uint32_t j0 = 0; j0 < p.G; j0 += kPrefetch) {
-        uint64_t cur[kPrefetch];
+    // The warp sum of position j is parked in lane j % 32; every 32 positions each lane adds its value to the CTA's
+    // shared first differences -- one conflict-free reduction per 32 positions instead of an elected-lane one per position.
+    typename std::conditional<WEIGHTED, long long, int>::type park[T + NF];
 #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) cur[u] = nxt[u];
-#pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) nxt[u] = load_row(j0 + kPrefetch + (uint32_t)u);
+    for (int t = 0; t < T + NF; ++t) park[t] = 0;
+    for (uint32_t jb = 0; jb < p.G; jb += 32u) {
+      const uint32_t jend = jb + 32u < p.G ? jb + 32u : p.G;
+      for (uint32_t j0 = jb; j0 < jend; j0 += kPrefetch) {
 #pragma unroll
         for (int u = 0; u < kPrefetch; ++u) {
             const uint32_t j = j0 + (uint32_t)u;
-            if (j >= p.G) break;
-            const uint32_t blo = (uint32_t)cur[u], bhi = (uint32_t)(cur[u] >> 32);
+            if (j >= jend) break;
+            const bool my_slot = lane == j - jb;
+            const uint64_t rowbits = ring[u];
+            ring[u] = load_row(j + kPrefetch);
+            const uint32_t blo = (uint32_t)rowbits, bhi = (uint32_t)(rowbits >> 32);
             if (T > 0) R.add(blo, bhi);
             if (T == 0 || n_fast != 0u) {  // warp-uniform: an item starts counting at its first group and never stops (q = 0)
                 const uint32_t olo = slo, ohi = shi;
@@ -165,7 +184,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
                     }
                     if (!WEIGHTED) {
                         const int net = __reduce_add_sync(0xFFFFFFFFu, d);
-                        if (lane == 0 && net != 0) atomicAdd(reinterpret_cast<int *>(s_dlo) + (T + f) * p.G + j, net);
+                        if (my_slot) park[T + f] = net;
                     } else {
                         long long mine;
                         if (uniform) {  // every item of the column weighs uw
@@ -175,9 +194,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
                             mine = (flo | fhi) ? weight_of_bits(flo, fhi, wrow) : 0ll;
                         }
                         const long long net = warp_sum_i64(mine);
-                        if (lane == 0 && net != 0)
-                            smem_add64(s_dlo, s_dhi, (T + f) * p.G + j, (uint32_t)(unsigned long long)net,
-                                       (uint32_t)((unsigned long long)net >> 32));
+                        if (my_slot) park[T + f] = net;
                     }
                 }
             }
@@ -201,7 +218,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
                     const int c = __popc(nlo & elo[t]) + __popc(nhi & ehi[t]);
                     const int net = __reduce_add_sync(0xFFFFFFFFu, c - cnt[t]);
                     cnt[t] = c;
-                    if (lane == 0 && net != 0) atomicAdd(reinterpret_cast<int *>(s_dlo) + t * p.G + j, net);
+                    if (my_slot) park[t] = net;
                 } else {
                     long long mine = 0;
                     if (uniform) {  // every item of the column weighs uw: (change of the count) x uw
@@ -215,14 +232,25 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
                         if (dlo | dhi) mine -= weight_of_bits(dlo, dhi, wrow);
                     }
                     const long long net = warp_sum_i64(mine);
-                    if (lane == 0 && net != 0)
-                        smem_add64(s_dlo, s_dhi, t * p.G + j, (uint32_t)(unsigned long long)net,
-                                   (uint32_t)((unsigned long long)net >> 32));
+                    if (my_slot) park[t] = net;
                 }
                 vlo[t] = nlo;
                 vhi[t] = nhi;
             }
         }
+      }
+      if (jb + lane < jend) {  // lane l holds the warp sums of position jb + l
+#pragma unroll
+          for (int t = 0; t < T + NF; ++t) {
+              if ((uint32_t)t >= (uint32_t)T + n_fast) break;
+              if (WEIGHTED) {
+                  const unsigned long long v = (unsigned long long)park[t];
+                  if (v) smem_add64(s_dlo, s_dhi, t * p.G + jb + lane, (uint32_t)v, (uint32_t)(v >> 32));
+              } else {
+                  red_shared_add_u32(s_dlo + t * p.G + jb + lane, (uint32_t)park[t]);
+              }
+          }
+      }
     }
     __syncthreads();
     uint64_t *out = p.out + (size_t)order_id * p.out_order_stride;
@@ -235,6 +263,190 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
             atomicAdd(reinterpret_cast<unsigned long long *>(out + (size_t)p.slot[t] * p.G + j), v);
         }
     }
+}
+
+// ---- q = 0 thresholds only: "an item counts from its first group on" (abacus.rs:1007-1010 with ceil((c+1)*0) = 0) ----------
+// The permutation-sampled union / coverage >= c growth.  No ranks: a thread keeps the `seen` mask of 128 items (two
+// adjacent u64 columns, one 16-byte load per row) and adds the change of popc(seen & eligible) at every position.  With
+// several orders in flight the column blocks are served from L2 (one DRAM pass for all orders), so the loop is
+// issue-bound: two columns per thread halve the per-item share of the row lookup, the REDUX and the shared atomic.
+// NF thresholds (p.n_fast <= NF of them in use) differ only in their coverage cutoff; COV = any cutoff > 1.
+template <int NF, bool WEIGHTED, bool COV>
+__global__ void __launch_bounds__(kQThreads, (NF >= 4 || (WEIGHTED && NF >= 2)) ? 2 : 3) k_gm_union(const __grid_constant__ GmGrowthParams p) {
+    constexpr int kPrefetch = 8;  // divides 32 (the parking scheme below)
+    constexpr int NE = COV ? NF : 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // byte offset of the row added at position j; kPrefetch extra entries repeat the last row so that the prefetch
+    // needs no bounds predicate
+    unsigned long long *s_off = reinterpret_cast<unsigned long long *>(smem_raw);  // [G + kPrefetch]
+    uint32_t *s_dlo = reinterpret_cast<uint32_t *>(s_off + p.G + kPrefetch);       // [NF][G]
+    uint32_t *s_dhi = s_dlo + (size_t)NF * p.G;                                    // [NF][G] (WEIGHTED only)
+    const uint32_t n_fast = p.n_fast < (uint32_t)NF ? p.n_fast : (uint32_t)NF;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint64_t n_pairs = (p.n_words + 1u) / 2u;  // pairs of columns
+    const uint32_t n_col_blocks = (uint32_t)((n_pairs + kQThreads - 1) / kQThreads);
+    const uint32_t order_id = p.col_fastest ? blockIdx.x / n_col_blocks : blockIdx.x % p.n_orders;
+    const uint64_t col_block = p.col_fastest ? blockIdx.x % n_col_blocks : blockIdx.x / p.n_orders;
+    const uint32_t *order = p.order + (size_t)order_id * p.G;
+    for (uint32_t i = tid; i < p.G + kPrefetch; i += kQThreads)
+        s_off[i] = (unsigned long long)order[i < p.G ? i : p.G - 1u] * p.gm_stride * 8ull;
+    for (uint32_t i = tid; i < p.G * NF * (WEIGHTED ? 2u : 1u); i += kQThreads) s_dlo[i] = 0u;
+    __syncthreads();
+
+    const uint64_t pi = col_block * kQThreads + tid;
+    const bool active = pi < n_pairs;
+    const uint64_t w0 = active ? pi * 2u : 0;  // first column of the pair (the rows are padded with zero words to 128 bytes)
+    // weight-sorted copy (see k_gm_quorum): per column, (1 << 32) | w when all its items weigh w
+    const uint32_t *wrow = (WEIGHTED && p.weight) ? p.weight + w0 * 64u : nullptr;
+    bool uni[2] = {WEIGHTED && !p.weight, WEIGHTED && !p.weight};
+    uint32_t uw[2] = {1u, 1u};
+    if (WEIGHTED && p.weight && p.uniform_w) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool in = active && w0 + h < p.n_words;
+            const unsigned long long u = in ? __ldg(reinterpret_cast<const unsigned long long *>(p.uniform_w) + w0 + h) : (1ull << 32);
+            uni[h] = (u >> 32) != 0ull;
+            uw[h] = (uint32_t)u;
+        }
+    }
+    uint32_t elig[NE][4];  // [threshold][32-item quarter]
+    if (COV) {
+#pragma unroll
+        for (int f = 0; f < NE; ++f)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) elig[f][q] = 0u;
+        if (active) {
+            for (uint32_t b = 0; b < 128u; ++b) {
+                const uint64_t pos = w0 * 64u + b;
+                uint64_t item = pos;
+                if (p.perm && pos < p.n_rows) item = __ldg(p.perm + pos);
+                const uint32_t c = (pos < p.n_rows && item != 0) ? __ldg(p.countable + item) : 0u;
+#pragma unroll
+                for (int f = 0; f < NE; ++f)
+                    if (c >= p.cov[f]) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if ((b >> 5) == (uint32_t)q) elig[f][q] |= 1u << (b & 31u);
+                    }
+            }
+        }
+    }
+    uint32_t seen[4] = {0u, 0u, 0u, 0u};
+    int cnt[NF][2];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) cnt[f][0] = cnt[f][1] = 0;
+
+    // threads past the last pair read pair 0 (w0 = 0) like everybody else and contribute nothing (see `live` below)
+    const unsigned char *col = reinterpret_cast<const unsigned char *>(p.gm + w0);
+    auto load_row = [&](uint32_t j) -> uint4 { return __ldg(reinterpret_cast<const uint4 *>(col + s_off[j])); };
+    const int live = active ? 1 : 0;
+    uint4 ring[kPrefetch];  // slot u holds row j0 + u; it is refilled with row j0 + kPrefetch + u as soon as it is consumed
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u) ring[u] = load_row((uint32_t)u);
+    // warp sums are parked in lane j % 32 and added to shared memory once per 32 positions (see k_gm_quorum)
+    typename std::conditional<WEIGHTED, long long, int>::type park[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) park[f] = 0;
+    for (uint32_t jb = 0; jb < p.G; jb += 32u) {
+      const uint32_t jend = jb + 32u < p.G ? jb + 32u : p.G;
+      for (uint32_t j0 = jb; j0 < jend; j0 += kPrefetch) {
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u) {
+            const uint32_t j = j0 + (uint32_t)u;
+            if (j >= jend) break;
+            const bool my_slot = lane == j - jb;
+            const uint32_t b[4] = {ring[u].x, ring[u].y, ring[u].z, ring[u].w};
+            uint32_t old[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                old[q] = seen[q];
+                seen[q] |= b[q];
+            }
+            if (!WEIGHTED) ring[u] = load_row(j + kPrefetch);  // the slot is consumed: refill it (no register copies)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                if (f > 0 && (uint32_t)f >= n_fast) break;  // n_fast >= 1
+                const int fe = COV ? f : 0;
+                int d[2] = {0, 0};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!WEIGHTED || uni[h]) {
+                        const int c = COV ? __popc(seen[2 * h] & elig[fe][2 * h]) + __popc(seen[2 * h + 1] & elig[fe][2 * h + 1])
+                                          : __popc(seen[2 * h]) + __popc(seen[2 * h + 1]);
+                        d[h] = c - cnt[f][h];
+                        cnt[f][h] = c;
+                    }
+                }
+                if (!WEIGHTED) {
+                    const int net = __reduce_add_sync(0xFFFFFFFFu, (d[0] + d[1]) * live);
+                    if (my_slot) park[f] = net;
+                } else {
+                    long long mine = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (!live) break;
+                        if (uni[h]) {
+                            mine += (long long)d[h] * (long long)uw[h];
+                        } else {
+                            uint32_t flo = b[2 * h] & ~old[2 * h], fhi = b[2 * h + 1] & ~old[2 * h + 1];
+                            if (COV) {
+                                flo &= elig[fe][2 * h];
+                                fhi &= elig[fe][2 * h + 1];
+                            }
+                            if (flo | fhi) mine += weight_of_bits(flo, fhi, wrow + 64 * h);
+                        }
+                    }
+                    const long long net = warp_sum_i64(mine);
+                    if (my_slot) park[f] = net;
+                }
+            }
+            if (WEIGHTED) ring[u] = load_row(j + kPrefetch);  // mixed-weight columns still needed the row above
+        }
+      }
+      if (jb + lane < jend) {
+#pragma unroll
+          for (int f = 0; f < NF; ++f) {
+              if (f > 0 && (uint32_t)f >= n_fast) break;
+              if (WEIGHTED) {
+                  const unsigned long long v = (unsigned long long)park[f];
+                  if (v) smem_add64(s_dlo, s_dhi, f * p.G + jb + lane, (uint32_t)v, (uint32_t)(v >> 32));
+              } else {
+                  red_shared_add_u32(s_dlo + f * p.G + jb + lane, (uint32_t)park[f]);
+              }
+          }
+      }
+    }
+    __syncthreads();
+    uint64_t *out = p.out + (size_t)order_id * p.out_order_stride;
+    for (uint32_t i = tid; i < p.G * n_fast; i += kQThreads) {
+        unsigned long long v;
+        if (WEIGHTED) v = (unsigned long long)s_dlo[i] | ((unsigned long long)s_dhi[i] << 32);
+        else v = (unsigned long long)s_dlo[i];  // counts only grow for q = 0
+        if (v) {
+            const uint32_t f = i / p.G, j = i - f * p.G;
+            atomicAdd(reinterpret_cast<unsigned long long *>(out + (size_t)p.slot[f] * p.G + j), v);
+        }
+    }
+}
+
+template <int NF, bool WEIGHTED, bool COV>
+int launch_union(const GmGrowthParams &p, cudaStream_t stream) {
+    const size_t smem = ((size_t)p.G + 8u) * 8u + (size_t)NF * p.G * (WEIGHTED ? 2u : 1u) * 4u;  // 8 = kPrefetch of k_gm_union
+    auto kern = k_gm_union<NF, WEIGHTED, COV>;
+    PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t n_pairs = (p.n_words + 1u) / 2u;
+    const uint64_t blocks = (n_pairs + kQThreads - 1) / kQThreads * p.n_orders;
+    if (blocks > 0x7FFFFFFFull) return fail(PGX_ERR_UNSUPPORTED, "k_gm_union: too many column blocks x orders in one launch");
+    kern<<<(unsigned)blocks, kQThreads, smem, stream>>>(p);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+template <bool WEIGHTED, bool COV>
+int launch_union_n(const GmGrowthParams &p, cudaStream_t stream) {
+    if (p.n_fast <= 1u) return launch_union<1, WEIGHTED, COV>(p, stream);
+    if (p.n_fast <= 2u) return launch_union<2, WEIGHTED, COV>(p, stream);
+    return launch_union<4, WEIGHTED, COV>(p, stream);
 }
 
 template <int P, int T, int NF, bool WEIGHTED>
@@ -284,7 +496,7 @@ int gm_quorum_planes(uint32_t G) {
 // NF: q = 0 slots of the instantiation (1 next to general thresholds; 1, 2 or 4 when T = 0)
 size_t gm_quorum_smem_bytes(uint32_t G, uint32_t T, uint32_t NF, bool weighted) {
     const int P = T ? gm_quorum_planes(G) : 0;
-    return ((size_t)G * T * (size_t)((P + 3) & ~3) + G + (size_t)(T + NF) * G * (weighted ? 2u : 1u)) * 4u;
+    return ((size_t)G * T * (size_t)((P + 3) & ~3) + 2u * ((size_t)G + 8u) + (size_t)(T + NF) * G * (weighted ? 2u : 1u)) * 4u;
 }
 
 uint32_t gm_quorum_fast_slots(uint32_t T, uint32_t n_fast) { return T ? 1u : (n_fast <= 1u ? 1u : n_fast <= 2u ? 2u : 4u); }
@@ -298,6 +510,12 @@ int launch_gm_quorum(const GmGrowthParams &p, cudaStream_t stream) {
         return fail(PGX_ERR_INVALID, "k_gm_quorum: bad parameters");
     if (gm_quorum_smem_bytes(p.G, p.T, gm_quorum_fast_slots(p.T, p.n_fast), p.weighted != 0) > kGmQuorumSmemMax)
         return fail(PGX_ERR_UNSUPPORTED, "k_gm_quorum: tables do not fit in shared memory");
+    if (p.T == 0 && !p.union_via_quorum) {  // q = 0 only: the two-column k_gm_union
+        bool cov = false;
+        for (uint32_t f = 0; f < p.n_fast; ++f) cov |= p.cov[f] > 1u;
+        if (p.weighted) return cov ? launch_union_n<true, true>(p, stream) : launch_union_n<true, false>(p, stream);
+        return cov ? launch_union_n<false, true>(p, stream) : launch_union_n<false, false>(p, stream);
+    }
     if (p.T == 0) return p.weighted ? launch_q0<true>(p, stream) : launch_q0<false>(p, stream);
     switch (gm_quorum_planes(p.G)) {
         case 7: return launch_q_p<7>(p, stream);
