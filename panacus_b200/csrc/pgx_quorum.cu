@@ -68,7 +68,7 @@ template <int P, int T, int NF, bool WEIGHTED>
 __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k_gm_quorum(const __grid_constant__ GmGrowthParams p) {
     constexpr int PP = RankMaskWords<P>::value;
     constexpr int TT = T > 0 ? T : 1;  // array extents (no zero-length arrays)
-    constexpr int kPrefetch = T == 0 ? 8 : 2;  // rows in flight per thread: q = 0 only is memory-bound, ranks are ALU-bound
+    constexpr int kPrefetch = T == 0 ? 8 : 4;  // rows in flight per thread (divides 32); a single order streams from DRAM, many orders from L2
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem_raw);  // [G][T][PP]
     // byte offset of the row added at position j (+ 8 entries repeating the last row: the prefetch needs no bounds check)
