@@ -473,10 +473,6 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
     base.weighted = w ? 1 : 0;
     base.out_order_stride = out_order_stride;
     base.col_fastest = gm_grid_col_fastest() ? 1u : 0u;
-    {
-        const char *u = getenv("PGX_GM_UNION");
-        base.union_via_quorum = (u && !strcmp(u, "quorum")) ? 1u : 0u;
-    }
     auto run = [&](GmGrowthParams &p) -> int {
         const uint32_t kBatch = 4096;  // orders per launch
         for (uint32_t o0 = 0; o0 < n_orders; o0 += kBatch) {
@@ -488,7 +484,7 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
             a->launches++;
         }
         char buf[192];
-        if (p.T == 0 && !p.union_via_quorum)
+        if (p.T == 0)
             snprintf(buf, sizeof buf, "k_gm_union orders=%u T=0 q0=%u%s", n_orders, p.n_fast, sorted ? " weight-sorted" : "");
         else
             snprintf(buf, sizeof buf, "k_gm_quorum<P=%d> orders=%u T=%u q0=%u%s smem=%zu", p.T ? gm_quorum_planes(G) : 0, n_orders,

@@ -116,8 +116,7 @@ struct GmGrowthParams {
     uint32_t direct_out;     // very large G: no shared-memory staging of the deltas, atomics go straight to `out`
     uint32_t col_fastest;    // grid mapping: 0 = consecutive CTAs take the same column block under different orders (L2 reuse),
                              // 1 = consecutive CTAs walk the column blocks of one order (PGX_GM_GRID=col; for measurements)
-    uint32_t union_via_quorum;  // T = 0: use the one-column k_gm_quorum<1,0,..> instead of k_gm_union (PGX_GM_UNION=quorum)
-    uint32_t n_fast;         // k_gm_quorum only: cov / slot index T .. T+n_fast-1 are q = 0 thresholds of the same pass
+    uint32_t n_fast;         // k_gm_quorum / k_gm_union: cov / slot index T .. T+n_fast-1 are q = 0 thresholds of the pass
     const uint32_t *perm;       // k_gm_quorum, weighted: gm / weight are in weight-sorted item order, perm[pos] = item
     const uint64_t *uniform_w;  // k_gm_quorum, weighted: (1 << 32) | w per column whose items all weigh w, else 0
     int weighted;

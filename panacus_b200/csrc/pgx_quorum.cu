@@ -1,23 +1,27 @@
-// pgx_quorum.cu -- k_gm_quorum: ordered growth for general quorum thresholds (q > 0) under an arbitrary group
-// order, on the group-major copy of the bitmap.  Same arithmetic as AbacusByGroup::calc_growth
-// (src/graph_broker/abacus.rs:989-1032) applied to the abacus the reference would rebuild under `--order`
-// (abacus.rs:324-326); the thresholds are the host's f64 `ceil((j + 1) * q)` per position (abacus.rs:1010).
+// pgx_quorum.cu -- ordered growth under arbitrary group orders on the group-major copy of the bitmap:
+//   k_gm_quorum  general quorum thresholds (q > 0), optionally with one q = 0 threshold riding along
+//   k_gm_union   q = 0 thresholds only (the permutation-sampled union / coverage >= c growth)
+// Same arithmetic as AbacusByGroup::calc_growth (src/graph_broker/abacus.rs:989-1032) applied to the abacus the
+// reference would rebuild under `--order` (abacus.rs:324-326); the thresholds are the host's f64 `ceil((j + 1) * q)`
+// per position (abacus.rs:1010).
 //
-// One thread owns 64 items and walks the groups in order, keeping their ranks in P bit-planes (pgx_rank.cuh).
-// Integer-ALU bound by construction (~4P + 2PT logic ops per 64 items and position for T thresholds), so the
-// inner loop is kept to the plane operations themselves:
+// k_gm_quorum: one thread owns 64 items and walks the groups in order, keeping their ranks in P bit-planes
+// (pgx_rank.cuh).  Integer-ALU bound by construction (~4P + 2PT logic ops per 64 items and position for T thresholds),
+// so the inner loop is kept to the plane operations themselves:
 //   * the per-plane cutoff masks come from a shared-memory table built once per CTA ([position][threshold][plane],
 //     16-byte rows read with LDS.128 on the otherwise idle LSU pipe) instead of being rebuilt from K in every lane;
 //   * T general thresholds and the weighted mode are template parameters: no per-threshold branches.  One q = 0
 //     threshold may ride along (p.n_fast: "item counts from its first group on", a popcount of the seen mask, a few
-//     ops per position); further q = 0 thresholds run in a T = 0 launch of their own;
-//   * counting nodes: a thread tracks popc(verdict) and adds the change, one REDUX per warp and position and a
-//     native 32-bit shared atomic (64-bit shared atomics are CAS loops on sm_100);
-//   * summing bp: runs on the weight-sorted group-major copy (the one similarity uses): most 64-item words then carry
-//     a single weight w and their contribution is (change of the popcount) x w; only mixed words walk the flipped
-//     bits.  The per-lane net is reduced as three 24/24/16-bit pieces of its two's complement (3 REDUX).
-//   * T = 0 instantiations (q = 0 thresholds only, up to NF of them differing in their coverage cutoff) replace the
-//     first-generation k_gm_growth<.,false> for permuted union growth: same loop without ranks, deeper prefetch.
+//     ops per position); further q = 0 thresholds run on k_gm_union;
+//   * counting nodes: a thread tracks popc(verdict & eligible) and adds the change; one REDUX per warp and position,
+//     whose result is parked in lane (position % 32) and added to the CTA's shared first differences once per 32
+//     positions -- one conflict-free native 32-bit shared reduction instead of an elected-lane atomic per position
+//     (and no 64-bit shared atomics, which are CAS loops on sm_100);
+//   * summing bp: runs on the weight-sorted group-major copy (the one similarity uses): most 64-item columns then carry
+//     a single weight w and their contribution is (change of the popcount) x w; only mixed columns walk the flipped
+//     bits.  The per-lane net is reduced as three 24/24/16-bit pieces of its two's complement (3 REDUX);
+//   * the byte offsets of the rows (order[j] x row pitch) are pre-multiplied in shared memory and padded by repeats of
+//     the last row: a row load is LDS.64 + one 64-bit add + LDG, without bounds predicates.
 #include <type_traits>
 
 #include "pgx_common.cuh"
@@ -65,10 +69,10 @@ __device__ __forceinline__ long long warp_sum_i64(long long v) {
 
 // T general thresholds (cov / slot index 0 .. T-1) and p.n_fast <= NF thresholds with q = 0 (index T .. T+n_fast-1).
 template <int P, int T, int NF, bool WEIGHTED>
-__global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k_gm_quorum(const __grid_constant__ GmGrowthParams p) {
+__global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(const __grid_constant__ GmGrowthParams p) {
+    static_assert(T >= 1 && T <= (int)kGmQuorumMaxT && NF == 1, "1..4 general thresholds and at most one q = 0 rider");
     constexpr int PP = RankMaskWords<P>::value;
-    constexpr int TT = T > 0 ? T : 1;  // array extents (no zero-length arrays)
-    constexpr int kPrefetch = T == 0 ? 8 : 4;  // rows in flight per thread (divides 32); a single order streams from DRAM, many orders from L2
+    constexpr int kPrefetch = 4;  // rows in flight per thread (divides 32); a single order streams from DRAM, many orders from L2
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem_raw);  // [G][T][PP]
     // byte offset of the row added at position j (+ 8 entries repeating the last row: the prefetch needs no bounds check)
@@ -132,10 +136,10 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
 
     RankColumn<P> R;
     R.clear();
-    uint32_t vlo[TT], vhi[TT];
+    uint32_t vlo[T], vhi[T];
     int cnt[T + NF];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) vlo[t] = vhi[t] = 0u;
+    for (int t = 0; t < T; ++t) vlo[t] = vhi[t] = 0u;
 #pragma unroll
     for (int t = 0; t < T + NF; ++t) cnt[t] = 0;
     uint32_t slo = 0u, shi = 0u;  // items seen so far (q = 0 threshold)
@@ -168,8 +172,8 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
             const uint64_t rowbits = ring[u];
             ring[u] = load_row(j + kPrefetch);
             const uint32_t blo = (uint32_t)rowbits, bhi = (uint32_t)(rowbits >> 32);
-            if (T > 0) R.add(blo, bhi);
-            if (T == 0 || n_fast != 0u) {  // warp-uniform: an item starts counting at its first group and never stops (q = 0)
+            R.add(blo, bhi);
+            if (n_fast != 0u) {  // warp-uniform: an item starts counting at its first group and never stops (q = 0)
                 const uint32_t olo = slo, ohi = shi;
                 slo |= blo;
                 shi |= bhi;
@@ -198,7 +202,6 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : (T == 0 ? 3 : 2)) k
                     }
                 }
             }
-            if (T == 0) continue;
             const uint4 *row = reinterpret_cast<const uint4 *>(s_mask + (size_t)j * (T * PP));
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -477,13 +480,6 @@ int launch_q_p(const GmGrowthParams &p, cudaStream_t stream) {
     return p.weighted ? launch_q_t<P, true>(p, stream) : launch_q_t<P, false>(p, stream);
 }
 
-template <bool WEIGHTED>
-int launch_q0(const GmGrowthParams &p, cudaStream_t stream) {  // q = 0 thresholds only
-    if (p.n_fast <= 1u) return launch_q<1, 0, 1, WEIGHTED>(p, stream);
-    if (p.n_fast <= 2u) return launch_q<1, 0, 2, WEIGHTED>(p, stream);
-    return launch_q<1, 0, 4, WEIGHTED>(p, stream);
-}
-
 }  // namespace
 
 int gm_quorum_planes(uint32_t G) {
@@ -510,13 +506,12 @@ int launch_gm_quorum(const GmGrowthParams &p, cudaStream_t stream) {
         return fail(PGX_ERR_INVALID, "k_gm_quorum: bad parameters");
     if (gm_quorum_smem_bytes(p.G, p.T, gm_quorum_fast_slots(p.T, p.n_fast), p.weighted != 0) > kGmQuorumSmemMax)
         return fail(PGX_ERR_UNSUPPORTED, "k_gm_quorum: tables do not fit in shared memory");
-    if (p.T == 0 && !p.union_via_quorum) {  // q = 0 only: the two-column k_gm_union
+    if (p.T == 0) {  // q = 0 only: k_gm_union
         bool cov = false;
         for (uint32_t f = 0; f < p.n_fast; ++f) cov |= p.cov[f] > 1u;
         if (p.weighted) return cov ? launch_union_n<true, true>(p, stream) : launch_union_n<true, false>(p, stream);
         return cov ? launch_union_n<false, true>(p, stream) : launch_union_n<false, false>(p, stream);
     }
-    if (p.T == 0) return p.weighted ? launch_q0<true>(p, stream) : launch_q0<false>(p, stream);
     switch (gm_quorum_planes(p.G)) {
         case 7: return launch_q_p<7>(p, stream);
         case 8: return launch_q_p<8>(p, stream);

@@ -254,15 +254,15 @@ def test_permuted_growth_many_mixed_thresholds():
         assert not a.permuted_growth(orders[:1], [1], never).any()
 
 
-@pytest.mark.parametrize("kernel", ["union", "quorum"])
+@pytest.mark.parametrize("kernel", ["union", "old"])
 @pytest.mark.parametrize("N,G", [(1500, 90), (4000, 300), (70, 33), (16500, 40)])
 def test_permuted_growth_q0_only(N, G, kernel, monkeypatch):
     """q = 0 thresholds only (the permutation-sampled union / coverage >= c growth): k_gm_union (two columns per thread;
-    default) and the T = 0 instantiations of k_gm_quorum (PGX_GM_UNION=quorum), with 1, 2 and 4 + 1 thresholds differing
+    default) and the first-generation k_gm_growth<.,false> (PGX_GM_QUORUM=old), with 1, 2 and 4 + 1 thresholds differing
     in their coverage cutoff; bp sums on the weight-sorted copy, with weights that leave both single-weight and mixed
     64-item columns; odd and even numbers of columns, more than one CTA per order"""
-    if kernel == "quorum":
-        monkeypatch.setenv("PGX_GM_UNION", "quorum")
+    if kernel == "old":
+        monkeypatch.setenv("PGX_GM_QUORUM", "old")
     bits, bitmap, weights = synth.numpy_table(N, G, seed=N)
     rng = np.random.default_rng(N)
     weights = np.where(rng.random(N + 1) < 0.6, 1, rng.integers(1, 2 ** 32, N + 1, dtype=np.uint64)).astype(np.uint32)
@@ -274,7 +274,7 @@ def test_permuted_growth_q0_only(N, G, kernel, monkeypatch):
             pairs = [(c, 0.0) for c in covs]
             for weighted in (False, True):
                 got = a.permuted_growth(orders, covs, None, weighted=weighted)
-                assert ("k_gm_union" if kernel == "union" else "k_gm_quorum") in a.last_launch_info() and "T=0" in a.last_launch_info()
+                assert ("k_gm_union" if kernel == "union" else "k_gm_growth") in a.last_launch_info()
                 for p in range(orders.shape[0]):
                     exp = oracle_all(pb.pack_bits(bits[:, orders[p]]), G, weights, pairs)
                     for t, (c, q) in enumerate(pairs):
