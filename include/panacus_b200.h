@@ -150,6 +150,12 @@ int pgx_permuted_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders
  * (similarity.rs:153-163) and the clustering stay on the host. */
 int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint64_t *inter,
                    uint64_t *len);
+/* Same for the part of the rows on and right of the diagonal: only inter[(x-row_begin)*G + y] with y >= row_begin is
+ * computed, the columns left of row_begin are returned as zero.  The matrix is symmetric, so the ranks of a multi-GPU
+ * run can split the upper triangle instead of whole rows (panacus_b200/sharding.py: two folded row blocks per rank)
+ * and mirror it after the all-gather -- about half the work of row blocks. */
+int pgx_similarity_upper(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint64_t *inter,
+                         uint64_t *len);
 
 /* asynchronous / device-resident variants (used for kernel-only timing and multi-GPU reduction) -- */
 /* Enqueues the fused pass on the handle's stream and leaves the raw accumulators in device memory:

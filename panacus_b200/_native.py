@@ -18,7 +18,7 @@ EXPORTS = [
     "pgx_abacus_create", "pgx_abacus_destroy", "pgx_abacus_set_stream", "pgx_abacus_shape",
     "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_build", "pgx_abacus_clear",
     "pgx_abacus_download", "pgx_abacus_csr_rows", "pgx_abacus_csr_fill", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
-    "pgx_permuted_growth", "pgx_similarity", "pgx_fused_out_words", "pgx_fused_pass_async",
+    "pgx_permuted_growth", "pgx_similarity", "pgx_similarity_upper", "pgx_fused_out_words", "pgx_fused_pass_async",
     "pgx_launch_count", "pgx_last_launch_info",
     "pgx_exchange_export", "pgx_exchange_connect", "pgx_exchange_disconnect",
 ]
@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
     L.pgx_permuted_growth.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_int, vp]
     L.pgx_similarity.restype = C.c_int
     L.pgx_similarity.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp]
+    L.pgx_similarity_upper.restype = C.c_int
+    L.pgx_similarity_upper.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, vp, vp]
     L.pgx_fused_out_words.restype = C.c_size_t
     L.pgx_fused_out_words.argtypes = [C.c_uint32, C.c_uint32]
     L.pgx_fused_pass_async.restype = C.c_int

@@ -252,13 +252,15 @@ class DeviceAbacus:
                                                   int(bool(weighted)), _ptr(curves)))
         return curves
 
-    def similarity(self, weighted: bool = False, row_begin: int = 0, row_end: Optional[int] = None):
-        """-> (inter u64[rows, G], len u64[G]); integer part of Similarity::set_table."""
+    def similarity(self, weighted: bool = False, row_begin: int = 0, row_end: Optional[int] = None, upper: bool = False):
+        """-> (inter u64[rows, G], len u64[G]); integer part of Similarity::set_table.  upper: only the columns
+        >= row_begin are computed (the others are zero): the matrix is symmetric (pgx_similarity_upper)."""
         G = self.n_groups
         row_end = G if row_end is None else int(row_end)
         inter = np.zeros((max(row_end - row_begin, 0), G), dtype=np.uint64)
         ln = np.zeros(G, dtype=np.uint64)
-        _native.check(self._L.pgx_similarity(self._h, int(bool(weighted)), int(row_begin), row_end, _ptr(inter), _ptr(ln)))
+        fn = self._L.pgx_similarity_upper if upper else self._L.pgx_similarity
+        _native.check(fn(self._h, int(bool(weighted)), int(row_begin), row_end, _ptr(inter), _ptr(ln)))
         return inter, ln
 
     # -- reference-shaped convenience --------------------------------------------------------------

@@ -1015,7 +1015,22 @@ int pgx_permuted_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders
     return gm_growth(a, n_orders, orders, n_thresholds, cov_abs, quorum_thr, weighted, curves);
 }
 
+namespace {
+int similarity_rows(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint64_t *inter,
+                    uint64_t *len);
+}
+
 int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint64_t *inter, uint64_t *len) {
+    return similarity_rows(a, weighted, row_begin, row_end, 0u, inter, len);
+}
+
+int pgx_similarity_upper(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint64_t *inter, uint64_t *len) {
+    return similarity_rows(a, weighted, row_begin, row_end, row_begin, inter, len);
+}
+
+namespace {
+int similarity_rows(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint64_t *inter,
+                    uint64_t *len) {
     int rc = check_handle(a);
     if (rc) return rc;
     if (row_begin > row_end || row_end > a->G) return fail(PGX_ERR_INVALID, "bad row range");
@@ -1047,6 +1062,7 @@ int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row
         p.G = G;
         p.row_begin = row_begin;
         p.row_end = row_end;
+        p.col_begin = col_begin;
         p.inter = a->d_scratch;
         const char *env = getenv("PGX_SIM");  // "plain": one POPC per item word and pair; default: carry-save pairs of words
         p.csa = (!use_planes && !(env && !strcmp(env, "plain"))) ? 1u : 0u;
@@ -1067,6 +1083,7 @@ int pgx_similarity(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row
     if (len) std::memcpy(len, a->h_pinned + inter_words, (size_t)G * 8u);
     return PGX_OK;
 }
+}  // namespace
 
 int pgx_fused_pass_async(pgx_abacus *a, int want_hist_count, int want_hist_weight, uint32_t n_thresholds,
                          const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted, uint64_t *d_out) {

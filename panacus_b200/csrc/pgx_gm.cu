@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
         bx = by + lin;
     }
     const uint32_t x0 = p.row_begin + by * kSimTile;  // output rows
-    const uint32_t y0 = bx * kSimTile;                // output columns
+    const uint32_t y0 = p.col_begin + bx * kSimTile;  // output columns (col_begin > 0: upper-triangle sharding)
     const uint64_t k_begin = (uint64_t)blockIdx.z * words_per_split;
     uint64_t k_end = k_begin + words_per_split;
     if (k_end > p.n_words) k_end = p.n_words;
@@ -631,7 +631,8 @@ int launch_gm_growth(const GmGrowthParams &p, int /*sm_count*/, cudaStream_t str
 int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream) {
     const uint32_t rows = p.row_end - p.row_begin;
     if (rows == 0) return PGX_OK;
-    const uint32_t ty = (rows + kSimTile - 1) / kSimTile, tx = (p.G + kSimTile - 1) / kSimTile;
+    if (p.col_begin >= p.G) return PGX_OK;
+    const uint32_t ty = (rows + kSimTile - 1) / kSimTile, tx = (p.G - p.col_begin + kSimTile - 1) / kSimTile;
     // split the item-word range so that the grid fills the GPU a few times over
     uint64_t splits = ((uint64_t)sm_count * 8u + (uint64_t)tx * ty - 1) / ((uint64_t)tx * ty);
     const uint64_t max_splits = (p.n_words + kSimKW - 1) / kSimKW;
@@ -643,7 +644,7 @@ int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream
     splits = (p.n_words + wps - 1) / wps;
     dim3 grid(tx, ty, (unsigned)splits);
     GmSimParams q = p;
-    q.triangular = (p.row_begin == 0 && p.row_end == p.G && tx == ty && tx > 1u) ? 1u : 0u;
+    q.triangular = (p.row_begin == 0 && p.row_end == p.G && p.col_begin == 0 && tx == ty && tx > 1u) ? 1u : 0u;
     if (q.triangular) grid = dim3(tx * (tx + 1u) / 2u, 1u, (unsigned)splits);
     if (p.planes) {
         if (p.n_planes > 32u) return fail(PGX_ERR_INVALID, "n_planes > 32");

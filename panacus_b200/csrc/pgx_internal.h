@@ -141,6 +141,7 @@ struct GmSimParams {
     uint32_t n_planes;
     uint32_t G;
     uint32_t row_begin, row_end;
+    uint32_t col_begin;      // only columns >= col_begin are computed (the rest of `inter` stays zero)
     uint32_t triangular;     // set by the launcher: full square, compute upper tiles only and mirror
     uint32_t csa;            // unweighted: carry-save variant (one POPC per two item words and pair)
     uint64_t *inter;         // device (row_end-row_begin) x G, zeroed by the launcher

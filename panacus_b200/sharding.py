@@ -5,8 +5,9 @@ Two sharding schemes, both exact because every partial re
 
   * item ranges  -- hist / ordered growth: rank r scans items [lo_r, hi_r); one all-reduce (sum) of the
                     KB-sized fused result vector is the path's only exchange step.
-  * work items   -- permuted growth: order p goes to rank p % world; similarity: a block of group rows per
-                    rank.  The bitmap is replicated; results are all-gathered.
+  * work items   -- permuted growth: order p goes to rank p % world; similarity: two folded blocks of group rows
+                    per rank, each computed from its diagonal rightwards (an equal share of the upper triangle;
+                    the matrix is symmetric).  The bitmap is replicated; results are all-gathered.
 
 u64 vectors travel as int64 (same bits; two's-complement wrap-around sums are identical).
 """
@@ -46,6 +47,15 @@ def row_block(n_groups: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(n_groups, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def folded_row_blocks(n_groups: int, rank: int, world: int):
+    """Upper-triangle sharding of the similarity matrix: the rows are cut into 2 * world equal blocks and rank r takes
+    blocks r and 2 * world - 1 - r.  A block is computed for the columns >= its first row, so block b costs about
+    rows x (G - start_b) and every rank's pair of blocks adds up to the same share."""
+    nb = 2 * world
+    bounds = [k * n_groups // nb for k in range(nb + 1)]
+    return [(bounds[b], bounds[b + 1]) for b in (rank, nb - 1 - rank)]
 
 
 def _dist():
@@ -138,12 +148,29 @@ def sharded_permuted_growth(abacus, orders: np.ndarray, cov_abs, quorum_thr=None
     return out
 
 
-def sharded_similarity(abacus, weighted=False, device=None, group=None):
-    """Every rank holds the whole bitmap and computes a block of rows; -> (inter [G, G], len [G]) on every rank."""
+def sharded_similarity(abacus, weighted=False, device=None, group=None, triangle=True):
+    """Every rank holds the whole bitmap; -> (inter [G, G], len [G]) on every rank.
+    triangle=True: two folded row blocks per rank, each from its diagonal rightwards (DeviceAbacus.similarity(upper=True)),
+    all-gathered and mirrored -- half the pair work of whole rows.  triangle=False: one block of whole rows per rank."""
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     G = abacus.n_groups
-    lo, hi = row_block(G, rank, world)
-    inter, ln = abacus.similarity(weighted=weighted, row_begin=lo, row_end=hi)
-    counts = [row_block(G, r, world)[1] - row_block(G, r, world)[0] for r in range(world)]
-    return allgather_rows(inter, counts, device=device, group=group), ln
+    if not triangle:
+        lo, hi = row_block(G, rank, world)
+        inter, ln = abacus.similarity(weighted=weighted, row_begin=lo, row_end=hi)
+        counts = [row_block(G, r, world)[1] - row_block(G, r, world)[0] for r in range(world)]
+        return allgather_rows(inter, counts, device=device, group=group), ln
+    parts, ln = [], None
+    for lo, hi in folded_row_blocks(G, rank, world):
+        part, ln = abacus.similarity(weighted=weighted, row_begin=lo, row_end=hi, upper=True)
+        parts.append(part)
+    local = np.concatenate(parts, axis=0)
+    counts = [sum(hi - lo for lo, hi in folded_row_blocks(G, r, world)) for r in range(world)]
+    gathered = allgather_rows(local, counts, device=device, group=group)
+    upper = np.zeros((G, G), dtype=np.uint64)
+    off = 0
+    for r in range(world):
+        for lo, hi in folded_row_blocks(G, r, world):
+            upper[lo:hi] = gathered[off: off + hi - lo]
+            off += hi - lo
+    return np.triu(upper) + np.triu(upper, 1).T, ln

@@ -49,6 +49,7 @@ def test_errors_are_status_codes_not_crashes():
     assert L.pgx_hist(None, None, None, None) == -1
     assert L.pgx_ordered_growth(None, 0, None, None, None, 0, None) == -1
     assert L.pgx_similarity(None, 0, 0, 0, None, None) == -1
+    assert L.pgx_similarity_upper(None, 0, 0, 0, None, None) == -1
     L.pgx_abacus_destroy(None)  # no-op
 
 

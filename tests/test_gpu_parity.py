@@ -304,6 +304,12 @@ def test_similarity(N, G, variant, monkeypatch):
             # f32 Jaccard exactly as similarity.rs:153-163
             table = inter.astype(np.float32) / (ln[:, None] + ln[None, :] - inter).astype(np.float32)
             assert np.array_equal(table, table_o)
+            # upper-triangle sharding: a block from its diagonal rightwards, the columns left of it stay zero
+            for lo_u, hi_u in ((0, G), (G // 3, max(G // 3 + 1, 2 * G // 3)), (G - 1, G), (G // 2, G // 2)):
+                up, ln_u = a.similarity(weighted=weighted, row_begin=lo_u, row_end=hi_u, upper=True)
+                want_u = inter_o[lo_u:hi_u].copy()
+                want_u[:, :lo_u] = 0
+                assert np.array_equal(up, want_u) and np.array_equal(ln_u, len_o), (lo_u, hi_u)
             # row-block sharding (what each GPU computes in the 8-GPU configuration)
             lo, hi = G // 3, max(G // 3 + 1, 2 * G // 3)
             part, ln2 = a.similarity(weighted=weighted, row_begin=lo, row_end=hi)

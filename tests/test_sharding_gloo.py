@@ -48,10 +48,13 @@ class NumpyAbacus:
         return np.stack([np.stack([self._curve(self.bits[:, o], cov_abs[t], thr[t], weighted) for t in range(T)])
                          for o in orders]) if len(orders) else np.zeros((0, T, G), dtype=np.uint64)
 
-    def similarity(self, weighted=False, row_begin=0, row_end=None):
+    def similarity(self, weighted=False, row_begin=0, row_end=None, upper=False):
         w = self.w if weighted else np.ones_like(self.w)
         inter = (self.bits.T @ (self.bits * w[:, None])).astype(np.uint64)
-        return inter[row_begin:row_end], np.diag(inter).copy()
+        part = inter[row_begin:row_end].copy()
+        if upper:
+            part[:, :row_begin] = 0  # pgx_similarity_upper: columns left of the block's first row are not computed
+        return part, np.diag(inter).copy()
 
 
 def _free_port():
@@ -91,10 +94,13 @@ def _worker(rank, world, port, ret):
         orders = synth.random_orders(5, G, seed=9)
         pg = sharding.sharded_permuted_growth(full, orders, cov, thr, weighted=False)
         assert np.array_equal(pg, full.permuted_growth(orders, cov, thr, weighted=False))
-        # --- similarity row blocks + all-gather
-        inter, ln = sharding.sharded_similarity(full, weighted=True)
+        # --- similarity: folded upper-triangle blocks (default) and whole-row blocks, + all-gather
         inter0, ln0 = full.similarity(weighted=True)
-        assert np.array_equal(inter, inter0) and np.array_equal(ln, ln0)
+        for triangle in (True, False):
+            inter, ln = sharding.sharded_similarity(full, weighted=True, triangle=triangle)
+            assert np.array_equal(inter, inter0) and np.array_equal(ln, ln0), triangle
+        blocks = [b for r in range(world) for b in sharding.folded_row_blocks(G, r, world)]
+        assert sorted(blocks) == [(k * G // (2 * world), (k + 1) * G // (2 * world)) for k in range(2 * world)]
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
