@@ -160,17 +160,26 @@ def sharded_similarity(abacus, weighted=False, device=None, group=None, triangle
         inter, ln = abacus.similarity(weighted=weighted, row_begin=lo, row_end=hi)
         counts = [row_block(G, r, world)[1] - row_block(G, r, world)[0] for r in range(world)]
         return allgather_rows(inter, counts, device=device, group=group), ln
+    import torch
     parts, ln = [], None
     for lo, hi in folded_row_blocks(G, rank, world):
         part, ln = abacus.similarity(weighted=weighted, row_begin=lo, row_end=hi, upper=True)
         parts.append(part)
-    local = np.concatenate(parts, axis=0)
     counts = [sum(hi - lo for lo, hi in folded_row_blocks(G, r, world)) for r in range(world)]
-    gathered = allgather_rows(local, counts, device=device, group=group)
-    upper = np.zeros((G, G), dtype=np.uint64)
-    off = 0
+    maxc = max(counts)
+    pad = np.zeros((maxc, G), dtype=np.uint64)
+    local = np.concatenate(parts, axis=0)
+    pad[: local.shape[0]] = local
+    t = _to_tensor(pad, device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    # assemble and mirror where the gathered blocks live (the GPU under NCCL): the G x G matrix is touched by a few
+    # tensor ops instead of numpy passes over 8 MB per step, then copied to the host once
+    upper = torch.zeros((G, G), dtype=torch.int64, device=t.device)
     for r in range(world):
+        off = 0
         for lo, hi in folded_row_blocks(G, r, world):
-            upper[lo:hi] = gathered[off: off + hi - lo]
+            upper[lo:hi] = outs[r][off: off + hi - lo]
             off += hi - lo
-    return np.triu(upper) + np.triu(upper, 1).T, ln
+    full = torch.triu(upper) + torch.triu(upper, 1).T
+    return full.cpu().numpy().view(np.uint64), ln
