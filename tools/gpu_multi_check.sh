@@ -1,5 +1,6 @@
 #!/bin/bash
-# last 2-GPU call: similarity tests on one GPU, sharded parity and sharded timings with upper-triangle sharding
+# 2-GPU call (gpurun --gpus 2 --timeout 100 -- 'bash tools/gpu_multi_check.sh'): similarity tests on one GPU, sharded
+# parity (tools/check_multigpu.py) and the sharded config 3 / 4 timings (tools/bench_sharded.py)
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out

@@ -1,6 +1,6 @@
 #!/bin/bash
-# One gpurun call: GPU parity suite, old-vs-new kernel comparison, the bench line, smoke, secondary timings and an
-# ncu launch list.  Everything lands in gpurun_out/ (merged back by gpurun).  The steps share one deadline
+# One gpurun call (gpurun --timeout 780 -- 'BUDGET_S=640 bash tools/gpu_round_check.sh'): GPU parity suite, old-vs-new
+# kernel comparison, the bench line, smoke, secondary timings, ncu --set full of the secondary kernels, the c2 bench line.  Everything lands in gpurun_out/ (merged back by gpurun).  The steps share one deadline
 # (BUDGET_S seconds from the start, default 600) so that the call ends on its own, most important step first.
 set -u
 cd "$(dirname "$0")/.."
@@ -27,5 +27,6 @@ tail -c 400 gpurun_out/bench_target.json
 step smoke 90 bash -c 'python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1'
 tail -1 gpurun_out/smoke.log
 step aux 200 bash -c 'python tools/bench_aux.py > gpurun_out/bench_aux.txt 2> gpurun_out/bench_aux.err'
-step ncu 150 bash -c 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_gm\|k_scan\|k_transpose -c 80 --csv --log-file gpurun_out/launches_variants.csv python tools/bench_variants.py --quick > gpurun_out/ncu_variants.log 2>&1'
+step ncu_full 200 bash -c 'ncu --set full --clock-control none --import-source on -k regex:k_gm_quorum\|k_gm_similarity\|k_gm_union -c 8 -f -o gpurun_out/r1_secondary python tools/ncu_targets.py > gpurun_out/ncu_full.log 2>&1'
+step bench_c2 120 bash -c 'python bench.py --workload c2 --steps 50 --warmup 5 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err'
 echo "total $(( $(date +%s) - START )) s"
