@@ -3,12 +3,15 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <fstream>
 #include <regex>
 #include <set>
 #include <sstream>
+#include <mutex>
 #include <string_view>
+#include <thread>
 
 #include "panacus_host.hpp"
 
@@ -20,6 +23,24 @@ constexpr uint64_t kUsizeMax = ~0ull;
 
 // whole file into memory (transparently gunzips, like io.rs:23-33)
 std::string slurp(const std::string &path) {
+    {  // plain (not gzip) files: one read into the buffer instead of zlib's pass-through copies
+        std::ifstream in(path, std::ios::binary);
+        if (!in) throw Error("cannot open " + path);
+        unsigned char magic[2] = {0, 0};
+        in.read(reinterpret_cast<char *>(magic), 2);
+        if (!(in.gcount() == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
+            in.clear();
+            in.seekg(0, std::ios::end);
+            const std::streamoff size = in.tellg();
+            if (size >= 0) {
+                std::string data((size_t)size, '\0');
+                in.seekg(0);
+                in.read(data.data(), size);
+                if (in.gcount() != size) throw Error("read error in " + path);
+                return data;
+            }
+        }
+    }
     gzFile f = gzopen(path.c_str(), "rb");
     if (!f) throw Error("cannot open " + path);
     std::string data;
@@ -299,53 +320,198 @@ uint64_t GraphStorage::edge_key(uint32_t u, bool fu, uint32_t v, bool fv) {
     return ((uint64_t)((u << 1) | (fu ? 1u : 0u)) << 32) | (uint64_t)((v << 1) | (fv ? 1u : 0u));
 }
 
+namespace {
+
+// Segment name -> item id (1-based, S-line order).  Real pangenome GFAs (pggb, minigraph-cactus) name their segments
+// with decimal integers: then the lookup is a direct table indexed by the value, filled and read without hashing
+// (one hash probe per path step is what dominated the parse: ~260 ns per step in a 1M-entry map).  Any other naming
+// scheme falls back to a hash map keyed by views into the file buffer.
+struct NodeIndex {
+    bool numeric = false;
+    std::vector<uint32_t> num2id;                             // numeric: value -> id, 0 = absent
+    std::unordered_map<std::string_view, uint32_t> name2id;  // otherwise
+
+    // canonical decimal (no sign, no leading zero, <= 18 digits) -> value
+    static bool parse_canonical(const char *b, const char *e, uint64_t &v) {
+        const size_t n = (size_t)(e - b);
+        if (n == 0 || n > 18 || (n > 1 && *b == '0')) return false;
+        uint64_t x = 0;
+        for (const char *p = b; p < e; ++p) {
+            const unsigned d = (unsigned)(*p - '0');
+            if (d > 9u) return false;
+            x = x * 10u + d;
+        }
+        v = x;
+        return true;
+    }
+
+    void build(const std::vector<std::string_view> &names) {
+        uint64_t mx = 0;
+        numeric = !names.empty();
+        for (auto &nm : names) {
+            uint64_t v;
+            if (!parse_canonical(nm.data(), nm.data() + nm.size(), v)) {
+                numeric = false;
+                break;
+            }
+            mx = std::max(mx, v);
+        }
+        if (numeric && mx > 8ull * names.size() + (1ull << 20)) numeric = false;  // sparse numbering: the table would be mostly holes
+        if (numeric) {
+            num2id.assign(mx + 1, 0u);
+            for (size_t i = 0; i < names.size(); ++i) {
+                uint64_t v = 0;
+                parse_canonical(names[i].data(), names[i].data() + names[i].size(), v);
+                if (num2id[v]) throw Error("Segment with ID " + std::string(names[i]) + " occurs multiple times in GFA");
+                num2id[v] = (uint32_t)i + 1u;
+            }
+        } else {
+            name2id.reserve(names.size() * 2);
+            for (size_t i = 0; i < names.size(); ++i)
+                if (!name2id.emplace(names[i], (uint32_t)i + 1u).second)
+                    throw Error("Segment with ID " + std::string(names[i]) + " occurs multiple times in GFA");
+        }
+    }
+
+    uint32_t find(const char *b, const char *e) const {  // 0 = unknown
+        if (numeric) {
+            uint64_t v;
+            return (parse_canonical(b, e, v) && v < num2id.size()) ? num2id[v] : 0u;
+        }
+        auto it = name2id.find(std::string_view(b, (size_t)(e - b)));
+        return it == name2id.end() ? 0u : it->second;
+    }
+
+    uint32_t get(const char *b, const char *e) const {
+        const uint32_t id = find(b, e);
+        if (!id) throw Error("unknown node " + std::string(b, (size_t)(e - b)));
+        return id;
+    }
+};
+
+// steps of a P line's segment list "12+,13-,..." (util.rs:1093-1142)
+void parse_path_steps(const NodeIndex &idx, const char *b, const char *e, std::vector<Step> &steps) {
+    steps.reserve((size_t)std::count(b, e, ',') + 1);
+    const char *s = b;
+    while (s < e) {
+        if (idx.numeric) {  // digits, then the orientation; anything else is reported by the generic branch below
+            uint64_t v = 0;
+            const char *q = s;
+            while (q < e && (unsigned)(*q - '0') <= 9u && q - s < 18) v = v * 10u + (unsigned)(*q++ - '0');
+            if (q > s && q < e && (*q == '+' || *q == '-') && !(q - s > 1 && *s == '0') && (q + 1 == e || q[1] == ',')) {
+                const uint32_t id = v < idx.num2id.size() ? idx.num2id[v] : 0u;
+                if (!id) throw Error("unknown node " + std::string(s, (size_t)(q - s)));
+                steps.push_back({id, *q == '+'});
+                s = q + 2;
+                continue;
+            }
+        }
+        const void *t = memchr(s, ',', (size_t)(e - s));
+        const char *te = t ? (const char *)t : e;
+        if (te > s) steps.push_back({idx.get(s, te - 1), te[-1] == '+'});
+        s = te + 1;
+    }
+}
+
+// steps of a W line's walk ">12<13..." (util.rs:916-931)
+void parse_walk_steps(const NodeIndex &idx, const char *b, const char *e, std::vector<Step> &steps) {
+    const char *s = b;
+    while (s < e) {
+        const bool fwd = *s == '>';
+        const char *q = s + 1;
+        while (q < e && *q != '>' && *q != '<') ++q;
+        if (q > s + 1) steps.push_back({idx.get(s + 1, q), fwd});
+        s = q;
+    }
+}
+
+int g_host_threads = 0;  // 0 = hardware concurrency
+
+// fn(k) for k in [0, n) on `nthreads` threads, work handed out through an atomic counter (the units differ a lot in
+// size); the first exception stops the hand-out and is rethrown on the caller's thread
+template <typename F>
+void parallel_for(size_t n, unsigned nthreads, F fn) {
+    nthreads = std::max(1u, std::min<unsigned>({nthreads, 32u, (unsigned)std::max<size_t>(n, 1)}));
+    if (nthreads == 1) {
+        for (size_t k = 0; k < n; ++k) fn(k);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::mutex err_mu;
+    std::string err;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= n) return;
+                try {
+                    fn(k);
+                } catch (const std::exception &e) {
+                    std::lock_guard<std::mutex> lock(err_mu);
+                    if (err.empty()) err = e.what();
+                    next.store(n);
+                    return;
+                }
+            }
+        });
+    for (auto &th : pool) th.join();
+    if (!err.empty()) throw Error(err);
+}
+
+// -t N is taken literally; the default is one thread per core for inputs worth the thread start-up
+unsigned host_threads(bool big_input) {
+    return g_host_threads > 0 ? (unsigned)g_host_threads : (big_input ? std::max(1u, std::thread::hardware_concurrency()) : 1u);
+}
+
+}  // namespace
+
+void set_host_threads(int n) { g_host_threads = n > 0 ? n : 0; }
+
 GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bool with_names) {
     GraphStorage g;
-    // segment name -> id; keys are views into the file buffer (no allocation per lookup), local to the parse
-    std::unordered_map<std::string_view, uint32_t> node2id;
     g.node_lens.push_back(0);
     g.has_edges = with_edges;
     const std::string data = slurp(path);
+    const char *base = data.data();
     std::vector<std::pair<size_t, size_t>> lines;  // [begin, end) without the newline
     for (size_t i = 0; i < data.size();) {
-        size_t j = data.find('\n', i);
-        if (j == std::string::npos) j = data.size();
+        const void *nl = memchr(base + i, '\n', data.size() - i);
+        const size_t j = nl ? (size_t)((const char *)nl - base) : data.size();
         if (j > i) lines.emplace_back(i, j);
         i = j + 1;
     }
     auto field = [&](size_t b, size_t e, int k, size_t &fb, size_t &fe) -> bool {  // k-th TAB separated field
         size_t s = b;
         for (int c = 0; c < k; ++c) {
-            const void *t = memchr(data.data() + s, '\t', e - s);
+            const void *t = memchr(base + s, '\t', e - s);
             if (!t) return false;
-            s = (size_t)((const char *)t - data.data()) + 1;
+            s = (size_t)((const char *)t - base) + 1;
         }
-        const void *t = memchr(data.data() + s, '\t', e - s);
+        const void *t = memchr(base + s, '\t', e - s);
         fb = s;
-        fe = t ? (size_t)((const char *)t - data.data()) : e;
+        fe = t ? (size_t)((const char *)t - base) : e;
         while (fe > fb && data[fe - 1] == '\r') --fe;
         return true;
     };
-    // pass 1: segments and path names (graph.rs:308-375)
-    for (auto &ln : lines) {
+    // pass 1: segments and path names (graph.rs:308-375); ids follow the S-line order
+    std::vector<std::string_view> names;
+    std::vector<size_t> path_lines;  // indices into `lines` of the P / W lines, file order
+    for (size_t li = 0; li < lines.size(); ++li) {
+        const auto &ln = lines[li];
         const char tag = data[ln.first];
         size_t fb, fe;
         if (tag == 'S') {
             if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed S line");
-            const std::string_view name(data.data() + fb, fe - fb);
-            if (!node2id.emplace(name, (uint32_t)node2id.size() + 1).second)
-                throw Error("Segment with ID " + std::string(name) + " occurs multiple times in GFA");
+            names.emplace_back(base + fb, fe - fb);
             size_t sb, se;
             uint32_t len = 0;
             if (field(ln.first, ln.second, 2, sb, se)) len = (uint32_t)(se - sb);
             g.node_lens.push_back(len);
-            if (with_names) {
-                if (g.node_names.empty()) g.node_names.emplace_back();
-                g.node_names.emplace_back(name);
-            }
         } else if (tag == 'P') {
             if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed P line");
             g.path_segments.push_back(PathSegment::from_str(data.substr(fb, fe - fb)));
+            path_lines.push_back(li);
         } else if (tag == 'W') {
             std::string f[6];
             for (int k = 1; k <= 5; ++k) {
@@ -359,14 +525,17 @@ GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bo
             if (f[4] != "*") p.start = std::stoull(f[4]);
             if (f[5] != "*") p.end = std::stoull(f[5]);
             g.path_segments.push_back(p);
+            path_lines.push_back(li);
         }
     }
-    auto node_id = [&](size_t b, size_t e) -> uint32_t {
-        auto it = node2id.find(std::string_view(data.data() + b, e - b));
-        if (it == node2id.end()) throw Error("unknown node " + data.substr(b, e - b));
-        return it->second;
-    };
-    if (node2id.size() >= (1u << 31)) throw Error("more than 2^31 segments are not supported");
+    if (names.size() >= (1u << 31)) throw Error("more than 2^31 segments are not supported");
+    NodeIndex idx;
+    idx.build(names);
+    if (with_names) {
+        g.node_names.reserve(names.size() + 1);
+        g.node_names.emplace_back();
+        for (auto &nm : names) g.node_names.emplace_back(nm);
+    }
     // pass 1b: links (graph.rs:276-306)
     if (with_edges) {
         for (auto &ln : lines) {
@@ -375,39 +544,25 @@ GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bo
             if (!field(ln.first, ln.second, 1, b1, e1) || !field(ln.first, ln.second, 2, b2, e2) ||
                 !field(ln.first, ln.second, 3, b3, e3) || !field(ln.first, ln.second, 4, b4, e4))
                 throw Error("malformed L line");
-            const uint64_t e = canonical_edge(node_id(b1, e1), data[b2] == '+', node_id(b3, e3), data[b4] == '+');
+            const uint64_t e = canonical_edge(idx.get(base + b1, base + e1), data[b2] == '+', idx.get(base + b3, base + e3), data[b4] == '+');
             g.edge2id.emplace(e, (uint32_t)g.edge2id.size() + 1);  // no-op if the edge is already known
         }
     }
-    // pass 2: steps
-    for (auto &ln : lines) {
-        const char tag = data[ln.first];
+    // pass 2: steps.  Every P / W line is independent and the index is read-only: the lines are handed out to a few
+    // threads through an atomic counter (the lines of a pangenome differ a lot in length).
+    g.path_steps.resize(path_lines.size());
+    auto parse_line = [&](size_t k) {
+        const auto &ln = lines[path_lines[k]];
         size_t fb, fe;
-        if (tag == 'P') {
+        if (data[ln.first] == 'P') {
             if (!field(ln.first, ln.second, 2, fb, fe)) throw Error("malformed P line");
-            std::vector<Step> steps;
-            size_t s = fb;
-            while (s < fe) {
-                const void *t = memchr(data.data() + s, ',', fe - s);
-                const size_t e = t ? (size_t)((const char *)t - data.data()) : fe;
-                if (e > s) steps.push_back({node_id(s, e - 1), data[e - 1] == '+'});
-                s = e + 1;
-            }
-            g.path_steps.push_back(std::move(steps));
-        } else if (tag == 'W') {
+            parse_path_steps(idx, base + fb, base + fe, g.path_steps[k]);
+        } else {
             if (!field(ln.first, ln.second, 6, fb, fe)) throw Error("malformed W line");
-            std::vector<Step> steps;
-            size_t s = fb;
-            while (s < fe) {
-                const bool fwd = data[s] == '>';
-                size_t e = s + 1;
-                while (e < fe && data[e] != '>' && data[e] != '<') ++e;
-                if (e > s + 1) steps.push_back({node_id(s + 1, e), fwd});
-                s = e;
-            }
-            g.path_steps.push_back(std::move(steps));
+            parse_walk_steps(idx, base + fb, base + fe, g.path_steps[k]);
         }
-    }
+    };
+    parallel_for(path_lines.size(), host_threads(data.size() >= (8u << 20)), parse_line);
     return g;
 }
 
@@ -681,6 +836,40 @@ ItemTables build_item_tables(const GraphStorage &g, const GraphMask &mask, Count
     if (mask.include_coords) include_map = build_subpath_map(*mask.include_coords);
     if (mask.exclude_coords) exclude_map = build_subpath_map(*mask.exclude_coords);
     const Intervals complete = {{0, kUsizeMax}}, none = {};
+    size_t total_steps = 0;
+    for (auto &v : g.path_steps) total_steps += v.size();
+    if (!mask.include_coords && !mask.exclude_coords) {
+        // no subset / exclude list: every path contributes all of its items and nothing is shared between paths, so
+        // the paths are translated in parallel (edge counting does one hash lookup per step) and concatenated
+        const size_t P = g.path_segments.size();
+        const unsigned nt = host_threads(total_steps >= (1u << 20));
+        std::vector<std::vector<uint64_t>> per(edge ? P : 0);
+        t.id_prefsum.assign(P + 1, 0);
+        if (edge) {
+            parallel_for(P, nt, [&](size_t pi) {
+                const auto c = g.path_segments[pi].coords();
+                per[pi].reserve(g.path_steps[pi].size());
+                update_tables_edgecount(g, g.path_steps[pi], complete, none, c ? c->first : 0, per[pi], nullptr);
+            });
+            for (size_t pi = 0; pi < P; ++pi) t.id_prefsum[pi + 1] = t.id_prefsum[pi] + per[pi].size();
+        } else {
+            for (size_t pi = 0; pi < P; ++pi) t.id_prefsum[pi + 1] = t.id_prefsum[pi] + g.path_steps[pi].size();
+        }
+        t.items.resize(t.id_prefsum[P]);
+        parallel_for(P, nt, [&](size_t pi) {
+            uint64_t *dst = t.items.data() + t.id_prefsum[pi];
+            if (edge) {
+                std::copy(per[pi].begin(), per[pi].end(), dst);
+                std::vector<uint64_t>().swap(per[pi]);
+            } else {
+                const std::vector<Step> &steps = g.path_steps[pi];
+                for (size_t k = 0; k < steps.size(); ++k) dst[k] = steps[k].node;
+            }
+        });
+        return t;
+    }
+    t.items.reserve(total_steps);
+    t.id_prefsum.reserve(g.path_segments.size() + 1);
     t.id_prefsum.push_back(0);
     for (size_t pi = 0; pi < g.path_segments.size(); ++pi) {
         const PathSegment &seg = g.path_segments[pi];

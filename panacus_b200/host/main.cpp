@@ -3,6 +3,7 @@
 // (src/commands/{hist,growth,histgrowth,ordered_histgrowth,similarity}.rs).  Counting runs on the GPU
 // through libpanacus_b200.so; parsing, grouping, thresholds, closed-form growth and TSV stay here.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -34,7 +35,7 @@ const std::map<char, std::string> kShort = {{'s', "subset"},  {'e', "exclude"}, 
                                              {'S', "groupby-sample"}, {'c', "count"}, {'l', "coverage"}, {'q', "quorum"},
                                              {'a', "hist"},    {'O', "order"},    {'m', "method"},  {'t', "threads"},
                                              {'v', "verbose"}};
-const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json"};
+const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json", "names"};
 
 Args parse_args(int argc, char **argv) {
     Args a;
@@ -422,6 +423,37 @@ int cmd_table(const Args &a, const std::string &cmdline, bool with_order, std::o
     return 0;
 }
 
+// `panacus debug-parse <gfa> [-c count] [grouping / subset / exclude flags]`: wall time of the host front-end stages
+// (GFA parse, grouping / ordering, ItemTable) without touching the device -- SURVEY 8f-2 is host work here.
+int cmd_debug_parse(const Args &a, std::ostream &os) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    if (count == CountType::All) throw Error("debug-parse takes one count type");
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto t0, auto t1) { return std::chrono::duration<double, std::milli>(t1 - t0).count(); };
+    const auto t0 = now();
+    Args b = a;
+    GraphStorage g = GraphStorage::from_gfa(a.positional.at(0), count == CountType::Edge, a.has("names"));
+    const auto t1 = now();
+    GraphMaskParameters p;
+    p.groupby = a.get("groupby");
+    p.groupby_sample = a.has("groupby-sample");
+    p.groupby_haplotype = !p.groupby_sample && a.has("groupby-haplotype");
+    if (p.groupby_sample || p.groupby_haplotype) p.groupby.clear();
+    p.positive_list = a.get("subset");
+    p.negative_list = a.get("exclude");
+    const GraphMask mask = GraphMask::from_graph(g, p);
+    const auto order = mask.get_path_order(g.path_segments);
+    const auto t2 = now();
+    const ItemTables t = build_item_tables(g, mask, count);
+    const auto t3 = now();
+    uint64_t steps = 0;
+    for (auto &v : g.path_steps) steps += v.size();
+    os << "nodes\t" << g.node_count() << "\nedges\t" << g.edge_count() << "\npaths\t" << g.path_segments.size() << "\nsteps\t" << steps
+       << "\ngroups\t" << count_groups(order) << "\nitems\t" << t.items.size() << "\nparse_ms\t" << ms(t0, t1) << "\nmask_ms\t"
+       << ms(t1, t2) << "\nitem_table_ms\t" << ms(t2, t3) << "\n";
+    return 0;
+}
+
 // `panacus debug-table-tsv <gfa> --csr FILE [table flags]`: the to_tsv WRITER alone, fed with r / c / v read from a
 // text file (three lines of TAB separated integers) instead of the device -- a test hook like debug-tables, so that the
 // CPU test-suite can check the writer against the oracle's restatement without a GPU.  Nothing is counted here.
@@ -710,6 +742,7 @@ int dispatch(int argc, char **argv, std::ostream &os) {
         return 2;
     }
     const std::string cmdline = argv_joined(argc, argv);
+    if (a.has("threads")) set_host_threads(std::atoi(a.get("threads").c_str()));
     if (a.sub == "hist") return cmd_hist(a, cmdline, os);
     if (a.sub == "growth") return cmd_growth(a, cmdline, false, os);
     if (a.sub == "histgrowth") return cmd_growth(a, cmdline, true, os);
@@ -718,6 +751,7 @@ int dispatch(int argc, char **argv, std::ostream &os) {
     if (a.sub == "table") return cmd_table(a, cmdline, true, os);
     if (a.sub == "coverage-line") return cmd_coverage_line(a, cmdline, os);
     if (a.sub == "debug-table-tsv") return cmd_debug_table_tsv(a, os);
+    if (a.sub == "debug-parse") return cmd_debug_parse(a, os);
     if (a.sub == "debug-tables") return cmd_debug_tables(a, os);
     if (a.sub == "report") return cmd_report(a, os);
     usage();

@@ -67,6 +67,9 @@ struct Step {
     bool forward;
 };
 
+// worker threads of the host front end (GFA step parsing); 0 = hardware concurrency.  The CLI's -t / --threads.
+void set_host_threads(int n);
+
 struct GraphStorage {  // graph.rs:150-375
     std::vector<uint32_t> node_lens;  // [0] = 0; node ids are 1..=node_count() in S-line order (graph.rs:323-340)
     std::vector<PathSegment> path_segments;

@@ -149,3 +149,70 @@ def test_table_writer_matches_oracle(gfa, tmp_path):
                 else:
                     assert p.returncode == 0, p.stderr
                     assert p.stdout == want, (gfa, flags, count, total)
+
+
+# ---- GFA parser variants: numeric segment names (direct table), other names (hash map), walks, gzip, threads ---------
+
+def _write_gfa(path, names, paths, walks=(), links=()):
+    with open(path, "w") as f:
+        f.write("H\tVN:Z:1.1\n")
+        for i, nm in enumerate(names):
+            f.write(f"S\t{nm}\t{'ACGT'[i % 4] * (1 + i % 5)}\n")
+        for u, ou, v, ov in links:
+            f.write(f"L\t{u}\t{ou}\t{v}\t{ov}\t0M\n")
+        for pname, steps in paths:
+            f.write(f"P\t{pname}\t" + ",".join(f"{n}{o}" for n, o in steps) + "\t*\n")
+        for (sample, hap, seq), steps in walks:
+            f.write(f"W\t{sample}\t{hap}\t{seq}\t0\t100\t" + "".join((">" if o == "+" else "<") + n for n, o in steps) + "\n")
+
+
+@pytest.mark.parametrize("naming", ["dense", "sparse", "leading_zero", "alpha"])
+@pytest.mark.parametrize("threads", ["1", "3"])
+def test_parser_naming_schemes(naming, threads, tmp_path):
+    rng = np.random.default_rng(len(naming))
+    n = 300
+    if naming == "dense":
+        names = [str(i) for i in rng.permutation(np.arange(1, n + 1))]          # direct table, ids != values
+    elif naming == "sparse":
+        names = [str(int(v)) for v in rng.choice(10 ** 12, n, replace=False)]    # too sparse for a table -> hash map
+    elif naming == "leading_zero":
+        names = [f"{i:05d}" for i in range(1, n + 1)]                            # not canonical decimals -> hash map
+    else:
+        names = [f"s{i}" for i in range(n)]
+    def steps(k):
+        return [(names[int(j)], "+-"[int(o)]) for j, o in zip(rng.integers(0, n, k), rng.integers(0, 2, k))]
+    paths = [(f"smp{p // 2}#{p % 2 + 1}#ctg{p}", steps(int(rng.integers(1, 400)))) for p in range(7)]
+    walks = [((f"w{p}", "1", f"chr{p}"), steps(int(rng.integers(1, 200)))) for p in range(3)]
+    gfa = str(tmp_path / "g.gfa")
+    _write_gfa(gfa, names, paths, walks)
+    check(gfa, "node", ["-t", threads], {})
+    check(gfa, "bp", ["-S", "-t", threads], {"groupby_sample": True})
+    # the same file gzip-compressed
+    import gzip, shutil
+    with open(gfa, "rb") as fi, gzip.open(gfa + ".gz", "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    check(gfa + ".gz", "node", ["-t", threads], {})
+
+
+def test_parser_errors(tmp_path):
+    gfa = str(tmp_path / "bad.gfa")
+    _write_gfa(gfa, ["1", "2", "3"], [("a#1#x", [("1", "+"), ("9", "-")])])
+    r = subprocess.run([BIN, "debug-tables", gfa], capture_output=True, text=True)
+    assert r.returncode != 0 and "unknown node 9" in r.stderr
+    _write_gfa(gfa, ["1", "2", "7"], [("a#1#x", [("1", "+"), ("07", "-")])])  # "07" is not the segment "7"
+    r = subprocess.run([BIN, "debug-tables", gfa], capture_output=True, text=True)
+    assert r.returncode != 0 and "unknown node 07" in r.stderr
+    _write_gfa(gfa, ["1", "2", "2"], [("a#1#x", [("1", "+")])])
+    r = subprocess.run([BIN, "debug-tables", gfa], capture_output=True, text=True)
+    assert r.returncode != 0 and "occurs multiple times" in r.stderr
+    _write_gfa(gfa, ["s1", "s2"], [("a#1#x", [("s1", "+"), ("s3", "-")])])
+    r = subprocess.run([BIN, "debug-tables", gfa, "-t", "2"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unknown node s3" in r.stderr
+
+
+@pytest.mark.parametrize("count", ["node", "bp", "edge"])
+def test_threaded_front_end_matches_oracle(count):
+    """-t N: P / W lines parsed and (without subset / exclude lists) translated to item ids on N threads"""
+    check(B("chrM_test.gfa"), count, ["-t", "4"], {})
+    check(B("chrM_test.gfa"), count, ["-t", "4", "-S"], {"groupby_sample": True})
+    check(B("chrM_test.gfa"), count, ["-t", "4", "-e", B("exclusion.bed3")], {"exclude": B("exclusion.bed3")})
