@@ -810,9 +810,8 @@ void update_tables_edgecount(const GraphStorage &g, const std::vector<Step> &ste
         while (i < include.size() && include[i].second <= p) ++i;
         while (j < exclude.size() && exclude[j].second <= p) ++j;
         const uint64_t l = g.node_lens[s2.node];
-        auto it = g.edge2id.find(canonical_edge(s1.node, s1.forward, s2.node, s2.forward));
-        if (it == g.edge2id.end()) throw Error("path uses an edge that has no L line");
-        const uint64_t eid = it->second;
+        const uint64_t eid = g.edge2id.find(canonical_edge(s1.node, s1.forward, s2.node, s2.forward));
+        if (!eid) throw Error("path uses an edge that has no L line");
         if (i < include.size() && include[i].first < p + l) items.push_back(eid);
         if (exclude_table && j < exclude.size() && exclude[j].first < p + l)
             exclude_table->activate(eid);

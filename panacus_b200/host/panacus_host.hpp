@@ -70,12 +70,61 @@ struct Step {
 // worker threads of the host front end (GFA step parsing); 0 = hardware concurrency.  The CLI's -t / --threads.
 void set_host_threads(int n);
 
+// canonical edge key -> edge id: open addressing with linear probing (one cache line per lookup instead of the node
+// chasing of std::unordered_map; one lookup per path step when edges are counted).  Keys are never 0 (ids are 1-based).
+class EdgeMap {
+  public:
+    // inserts (key, value) unless the key is present; returns the stored value
+    uint32_t emplace(uint64_t key, uint32_t value) {
+        if ((size_ + 1) * 10 > keys_.size() * 7) grow();
+        size_t i = slot(key);
+        while (keys_[i] != 0 && keys_[i] != key) i = (i + 1) & (keys_.size() - 1);
+        if (keys_[i] == 0) {
+            keys_[i] = key;
+            vals_[i] = value;
+            ++size_;
+        }
+        return vals_[i];
+    }
+    uint32_t find(uint64_t key) const {  // 0 = absent
+        if (keys_.empty()) return 0;
+        size_t i = slot(key);
+        while (keys_[i] != 0 && keys_[i] != key) i = (i + 1) & (keys_.size() - 1);
+        return keys_[i] == key ? vals_[i] : 0u;
+    }
+    size_t size() const { return size_; }
+    template <typename F>
+    void for_each(F f) const {
+        for (size_t i = 0; i < keys_.size(); ++i)
+            if (keys_[i]) f(keys_[i], vals_[i]);
+    }
+
+  private:
+    // locality-preserving: the slot follows the first node of the edge, so the edges a path walks one after the other
+    // (node ids largely follow path order in pangenome graphs) sit in neighbouring cache lines; collisions are probed
+    size_t slot(uint64_t key) const { return (size_t)((key >> 32) * 2u) & (keys_.size() - 1); }
+    void grow() {
+        std::vector<uint64_t> ok;
+        std::vector<uint32_t> ov;
+        ok.swap(keys_);
+        ov.swap(vals_);
+        keys_.assign(ok.empty() ? 1024 : ok.size() * 2, 0);
+        vals_.assign(keys_.size(), 0);
+        size_ = 0;
+        for (size_t i = 0; i < ok.size(); ++i)
+            if (ok[i]) emplace(ok[i], ov[i]);
+    }
+    std::vector<uint64_t> keys_;
+    std::vector<uint32_t> vals_;
+    size_t size_ = 0;
+};
+
 struct GraphStorage {  // graph.rs:150-375
     std::vector<uint32_t> node_lens;  // [0] = 0; node ids are 1..=node_count() in S-line order (graph.rs:323-340)
     std::vector<PathSegment> path_segments;
     std::vector<std::vector<Step>> path_steps;  // steps of every P / W line, file order
     // canonical edge (graph.rs:142-148) packed as ((u << 1 | fwd_u) << 32) | (v << 1 | fwd_v) -> id (1-based)
-    std::unordered_map<uint64_t, uint32_t> edge2id;
+    EdgeMap edge2id;
     bool has_edges = false;
     // segment names by id ([0] = ""), kept only when asked for (the `table` writer, abacus.rs:1067-1072)
     std::vector<std::string> node_names;

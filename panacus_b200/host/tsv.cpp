@@ -124,7 +124,7 @@ std::string abacus_by_group_to_tsv(const GraphStorage &g, CountType count, bool 
     if (count != CountType::Edge) throw Error("inadmissible count type");
     if (!g.has_edges) return out;  // abacus.rs:1121: no edge2id, nothing is written
     std::vector<uint64_t> id2edge(g.edge_count() + 1, 0);
-    for (auto &kv : g.edge2id) id2edge[kv.second] = kv.first;
+    g.edge2id.for_each([&](uint64_t key, uint32_t id) { id2edge[id] = key; });
     header("edge");
     for (uint64_t i = 1; i + 1 < r.size(); ++i) {
         const uint64_t start = r[i], end = r[i + 1];
