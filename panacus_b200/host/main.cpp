@@ -320,8 +320,12 @@ std::vector<size_t> cluster_leaf_order(const std::vector<std::vector<float>> &ta
     std::vector<std::vector<double>> D(n, std::vector<double>(n, 0.0));
     for (size_t i = 0; i < n; ++i)
         for (size_t j = i + 1; j < n; ++j) {
-            float s = 0.f;  // euclidean distance between rows, f32 like similarity.rs:238-244
-            for (size_t k = 0; k < n; ++k) s += std::pow(table[i][k] - table[j][k], 2.0f);
+            float s = 0.f;  // euclidean distance between rows, f32 like similarity.rs:238-244 (`powf(2.0)`, which LLVM
+                            // turns into a multiplication: x * x is the correctly rounded square either way)
+            for (size_t k = 0; k < n; ++k) {
+                const float d = table[i][k] - table[j][k];
+                s += d * d;
+            }
             const float d = std::sqrt(s);
             D[i][j] = D[j][i] = squared ? (double)d * d : (double)d;
         }
