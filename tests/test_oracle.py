@@ -201,3 +201,45 @@ def test_tsv_shapes_from_survey_appendix_a():
     assert po.ordered_growth_table("node", names, [curve], cov, quo) == (
         "panacus\tordered-growth\ncount\tnode\ncoverage\t1\nquorum\t0\n"
         "y#1\t2\ny#2\t5\ny#3\t8\ny#4\t9\ny#5\t10\nx\t10\n")
+
+
+# ---- AbacusByGroup::to_tsv restatement (abacus.rs:1056-1178): no golden in the reference, so the oracle's writer is
+# checked against an independent formulation -- the table recomputed straight from the GFA's P lines ----------------
+
+@pytest.mark.parametrize("gfa,kw", [("t_groups.gfa", {}), ("chrM_test.gfa", {"groupby_sample": True}), ("cdbg.gfa", {})])
+def test_table_writer_equals_direct_count(gfa, kw):
+    path = os.path.join(GOLDEN, gfa)
+    g = go.parse_gfa(path)
+    mask = go.make_mask(g, **kw)
+    op, og, names = go.path_order_arrays(mask, g)
+    id2name = {v: k.decode() for k, v in g.node2id.items()}
+    for count in ("node", "bp"):
+        t = go.item_tables(g, mask, count)
+        r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        # occurrences of every node in every group, counted directly from the path steps
+        occ = np.zeros((g.node_count + 1, len(names)), dtype=np.int64)
+        for pid, grp in zip(op, og):
+            for node, _ in g.path_steps[int(pid)]:
+                occ[node, int(grp)] += 1
+        lines = ["node\t" + "\t".join(names)]
+        totals = ["node\ttotal"]
+        for i in range(1, g.node_count + 1):
+            w = g.node_lens[i] if count == "bp" else 1
+            lines.append(id2name[i] + "".join(f"\t{int(x) * w}" for x in occ[i]))
+            totals.append(f"{id2name[i]}\t{int((occ[i] > 0).sum())}")
+        assert go.abacus_by_group_to_tsv(g, count, False, names, r, c, v, t.uncovered) == "\n".join(lines) + "\n"
+        assert go.abacus_by_group_to_tsv(g, count, True, names, r, c, v, t.uncovered) == "\n".join(totals) + "\n"
+
+
+def test_table_known_answer_t_groups():
+    g = go.parse_gfa(os.path.join(GOLDEN, "t_groups.gfa"))
+    mask = go.make_mask(g)
+    op, og, names = go.path_order_arrays(mask, g)
+    t = go.item_tables(g, mask, "bp")
+    r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+    rows = go.abacus_by_group_to_tsv(g, "bp", False, names, r, c, v, t.uncovered).split("\n")
+    assert rows[0] == "node\ty#1\ty#2\ty#3\ty#4\ty#5\tx"
+    assert rows[1] == "1\t8\t0\t0\t0\t0\t8"        # segment 1 (8 bp) is on y#1 and x
+    assert rows[9] == "9\t0\t0\t19\t0\t0\t19"      # segment 9 (19 bp) is on y#3 and x
+    assert rows[2] == "2\t0\t0\t0\t0\t0\t0"        # segment 2 is on no path
+    assert po.coverage_line_table([("node", [5, 0, 10, 0, 0, 0, 0])]).split("\n")[4:7] == ["1\t0", "2\t10", "3\t0"]
