@@ -43,7 +43,9 @@ typedef enum {
     PGX_ERR_CUDA = -2,        /* CUDA runtime error (message in pgx_last_error) */
     PGX_ERR_NOMEM = -3,       /* host or device allocation failed */
     PGX_ERR_UNSUPPORTED = -4, /* shape outside what the kernels support */
-    PGX_ERR_STATE = -5        /* call order violated (e.g. no bitmap uploaded yet) */
+    PGX_ERR_STATE = -5,       /* call order violated (e.g. no bitmap uploaded yet) */
+    PGX_ERR_EXCHANGE = -6,    /* multi-GPU exchange failed: a peer never arrived (watchdog) or a collective call failed */
+    PGX_ERR_NCCL = -7         /* NCCL could not be loaded or returned an error (message in pgx_last_error) */
 } pgx_status;
 
 typedef struct pgx_abacus pgx_abacus;
@@ -86,6 +88,10 @@ int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, u
 int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
                      uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude);
 int pgx_abacus_clear(pgx_abacus *a);
+/* Device-to-device copy of an item range (bitmap rows + weights when the source has them): items
+ * src_first_item .. src_first_item + dst.n_items - 1 of `src` become items 1 .. dst.n_items of `dst` (same n_groups; the
+ * handles may live on different GPUs: NVLink peer copy).  Cuts an abacus built once into per-GPU item-range shards. */
+int pgx_abacus_copy_rows(pgx_abacus *dst, pgx_abacus *src, uint64_t src_first_item);
 /* AbacusByGroup's CSR {r, c, v} (abacus.rs:790-799) as built by compute_row_storage_space (abacus.rs:859-899) and
  * compute_column_values (abacus.rs:901-986, report_values = true, src/graph_broker.rs:382), derived on the device:
  *   r[0 .. n_items+1]  row offsets (n_items + 2 entries, r[0] = r[1] = 0: item 0 is the empty dummy row); from the
@@ -181,6 +187,57 @@ int pgx_fused_pass_async(pgx_abacus *a, int want_hist_count, int want_hist_weigh
 int pgx_exchange_export(pgx_abacus *a, void *handle_out);
 int pgx_exchange_connect(pgx_abacus *a, uint32_t rank, uint32_t world, const void *all_handles);
 int pgx_exchange_disconnect(pgx_abacus *a);
+/* The synchronous fused passes return PGX_ERR_EXCHANGE themselves when the in-kernel watchdog (10 s) saw a peer
+ * missing.  After pgx_fused_pass_async call this once the work is due: it synchronises the handle's stream and
+ * reports (and clears) the watchdog flag; the device result of a flagged pass is a partial sum and must be dropped. */
+int pgx_exchange_status(pgx_abacus *a);
+
+/* multi-GPU: NCCL communicator + sharded entry points --------------------------------------------------------
+ * One pgx_comm per GPU (one process per GPU, or one thread per GPU in a single process).  NCCL is loaded at run time
+ * (dlopen of libnccl.so.2: the copy PyTorch already loaded when inside a torch process); without it these calls return
+ * PGX_ERR_NCCL and everything single-GPU keeps working.  All *_sharded calls and pgx_abacus_broadcast are COLLECTIVE:
+ * every rank of the communicator calls them with the same arguments (its own handle), in the same order; the work is
+ * enqueued on the handle's stream and the result arrives on every rank.
+ *   pgx_comm_unique_id   rank 0 obtains an id (ncclGetUniqueId) and hands it to the other ranks by any transport
+ *   pgx_comm_create      ncclCommInitRank on `device`
+ *   pgx_comm_create_all  single-process variant (ncclCommInitAll): out[i] drives devices[i]; use one host thread per
+ *                        communicator for the collective calls */
+#define PGX_COMM_ID_BYTES 128
+typedef struct pgx_comm pgx_comm;
+int pgx_comm_unique_id(void *id_out /* PGX_COMM_ID_BYTES */);
+int pgx_comm_create(pgx_comm **out, int device, uint32_t rank, uint32_t world, const void *unique_id);
+int pgx_comm_create_all(pgx_comm **out /* n */, uint32_t n, const int *devices);
+void pgx_comm_destroy(pgx_comm *c);
+int pgx_comm_info(const pgx_comm *c, uint32_t *rank, uint32_t *world, int *device);
+/* Replicates rank `root`'s device bitmap (and weights when with_weights != 0) into every rank's handle over NVLink
+ * (ncclBroadcast) -- one H2D upload per node instead of one per GPU.  All handles must have the same shape. */
+int pgx_abacus_broadcast(pgx_abacus *a, pgx_comm *c, uint32_t root, int with_weights);
+/* pgx_exchange_export + all-gather of the handles over the communicator + pgx_exchange_connect (multi-process only:
+ * CUDA IPC handles cannot be opened in the process that exported them). */
+int pgx_exchange_connect_comm(pgx_abacus *a, pgx_comm *c);
+/* Item-range sharding (each rank's handle holds the rows of its own item range): pgx_hist_ordered_growth followed by
+ * the path's one exchange, an ncclAllReduce (u64 sum) of the KB-sized result vector; results of the whole graph on
+ * every rank.  The NCCL twin of the in-kernel exchange above (which must not be connected at the same time). */
+int pgx_hist_ordered_growth_sharded(pgx_abacus *a, pgx_comm *c, uint64_t *hist_count, uint64_t *hist_weight,
+                                    uint32_t n_thresholds, const uint32_t *cov_abs, const uint32_t *quorum_thr,
+                                    int weighted, uint64_t *curve);
+/* Work-item sharding (every rank's handle holds the WHOLE bitmap):
+ *   pgx_permuted_growth_sharded  order p is computed by rank p % world; the curves stay on the device, are
+ *                                all-gathered (ncclAllGather) and copied to the host once; `curves` as in
+ *                                pgx_permuted_growth, complete on every rank.  The reference's parallel axis on this
+ *                                path is the threshold pairs only (src/analyses/ordered_histgrowth.rs:174-188).
+ *   pgx_similarity_sharded       the upper triangle of the intersection matrix is cut into 2 * world tile-aligned row
+ *                                blocks (pgx_similarity_shard_bounds), rank r computes blocks r and 2 * world - 1 - r from
+ *                                their diagonal rightwards (equal pair work) plus the len entries of its rows; all-gather,
+ *                                assembly and mirroring on the device, one copy to the host: inter (G x G) and len (G)
+ *                                complete on every rank.  Similarity::set_table (src/analyses/similarity.rs:119-163)
+ *                                is serial in the reference. */
+int pgx_permuted_growth_sharded(pgx_abacus *a, pgx_comm *c, uint32_t n_orders, const uint32_t *orders,
+                                uint32_t n_thresholds, const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted,
+                                uint64_t *curves);
+int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *inter, uint64_t *len);
+/* Host-only: the 2 * world + 1 row-block boundaries pgx_similarity_sharded uses (no device, no NCCL needed). */
+int pgx_similarity_shard_bounds(uint32_t n_groups, uint32_t world, uint32_t *bounds);
 
 /* Number of kernel launches issued through this handle so far (for bench accounting). */
 uint64_t pgx_launch_count(const pgx_abacus *a);

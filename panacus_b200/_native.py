@@ -17,12 +17,16 @@ EXPORTS = [
     "pgx_version", "pgx_last_error", "pgx_device_count", "pgx_row_words",
     "pgx_abacus_create", "pgx_abacus_destroy", "pgx_abacus_set_stream", "pgx_abacus_shape",
     "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_build", "pgx_abacus_clear",
-    "pgx_abacus_download", "pgx_abacus_csr_rows", "pgx_abacus_csr_fill", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
+    "pgx_abacus_download", "pgx_abacus_copy_rows", "pgx_abacus_csr_rows", "pgx_abacus_csr_fill", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
     "pgx_permuted_growth", "pgx_similarity", "pgx_similarity_upper", "pgx_fused_out_words", "pgx_fused_pass_async",
     "pgx_launch_count", "pgx_last_launch_info",
-    "pgx_exchange_export", "pgx_exchange_connect", "pgx_exchange_disconnect",
+    "pgx_exchange_export", "pgx_exchange_connect", "pgx_exchange_disconnect", "pgx_exchange_status",
+    "pgx_comm_unique_id", "pgx_comm_create", "pgx_comm_create_all", "pgx_comm_destroy", "pgx_comm_info",
+    "pgx_abacus_broadcast", "pgx_exchange_connect_comm", "pgx_hist_ordered_growth_sharded",
+    "pgx_permuted_growth_sharded", "pgx_similarity_sharded", "pgx_similarity_shard_bounds",
 ]
 EXCHANGE_HANDLE_BYTES = 64
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -68,6 +72,8 @@ def lib() -> C.CDLL:
     L.pgx_abacus_build.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]
     L.pgx_abacus_clear.restype = C.c_int
     L.pgx_abacus_clear.argtypes = [vp]
+    L.pgx_abacus_copy_rows.restype = C.c_int
+    L.pgx_abacus_copy_rows.argtypes = [vp, vp, C.c_uint64]
     L.pgx_abacus_download.restype = C.c_int
     L.pgx_abacus_download.argtypes = [vp, vp, C.c_uint32]
     L.pgx_abacus_csr_rows.restype = C.c_int
@@ -96,6 +102,30 @@ def lib() -> C.CDLL:
     L.pgx_exchange_connect.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
     L.pgx_exchange_disconnect.restype = C.c_int
     L.pgx_exchange_disconnect.argtypes = [vp]
+    L.pgx_exchange_status.restype = C.c_int
+    L.pgx_exchange_status.argtypes = [vp]
+    L.pgx_comm_unique_id.restype = C.c_int
+    L.pgx_comm_unique_id.argtypes = [vp]
+    L.pgx_comm_create.restype = C.c_int
+    L.pgx_comm_create.argtypes = [C.POINTER(vp), C.c_int, C.c_uint32, C.c_uint32, vp]
+    L.pgx_comm_create_all.restype = C.c_int
+    L.pgx_comm_create_all.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(C.c_int)]
+    L.pgx_comm_destroy.restype = None
+    L.pgx_comm_destroy.argtypes = [vp]
+    L.pgx_comm_info.restype = C.c_int
+    L.pgx_comm_info.argtypes = [vp, u32p, u32p, C.POINTER(C.c_int)]
+    L.pgx_abacus_broadcast.restype = C.c_int
+    L.pgx_abacus_broadcast.argtypes = [vp, vp, C.c_uint32, C.c_int]
+    L.pgx_exchange_connect_comm.restype = C.c_int
+    L.pgx_exchange_connect_comm.argtypes = [vp, vp]
+    L.pgx_hist_ordered_growth_sharded.restype = C.c_int
+    L.pgx_hist_ordered_growth_sharded.argtypes = [vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_int, vp]
+    L.pgx_permuted_growth_sharded.restype = C.c_int
+    L.pgx_permuted_growth_sharded.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.c_int, vp]
+    L.pgx_similarity_sharded.restype = C.c_int
+    L.pgx_similarity_sharded.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.pgx_similarity_shard_bounds.restype = C.c_int
+    L.pgx_similarity_shard_bounds.argtypes = [C.c_uint32, C.c_uint32, u32p]
     L.pgx_launch_count.restype = C.c_uint64
     L.pgx_launch_count.argtypes = [vp]
     L.pgx_last_launch_info.restype = C.c_int

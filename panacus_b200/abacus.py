@@ -93,6 +93,69 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class Comm:
+    """One rank's NCCL communicator behind the C ABI (pgx_comm_*): one per GPU, one process (or thread) per GPU."""
+
+    def __init__(self, handle, rank: int, world: int, device: int):
+        self._L = _native.lib()
+        self._h, self.rank, self.world, self.device = handle, int(rank), int(world), int(device)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(_native.COMM_ID_BYTES)
+        _native.check(_native.lib().pgx_comm_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def create(device: int, rank: int, world: int, unique_id: bytes) -> "Comm":
+        if len(unique_id) != _native.COMM_ID_BYTES:
+            raise ValueError("unique_id must be PGX_COMM_ID_BYTES long")
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, len(unique_id))
+        _native.check(_native.lib().pgx_comm_create(C.byref(h), int(device), int(rank), int(world), buf))
+        return Comm(h, rank, world, device)
+
+    @staticmethod
+    def from_torch_distributed(device: int, group=None) -> "Comm":
+        """Rank 0 draws the NCCL id, torch.distributed carries it to the other ranks (any backend)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        raw = bytearray(Comm.unique_id() if rank == 0 else bytes(_native.COMM_ID_BYTES))
+        t = torch.frombuffer(raw, dtype=torch.uint8).clone()
+        if dist.get_backend(group) == "nccl":
+            t = t.to(torch.device("cuda", device))
+        dist.broadcast(t, src=0, group=group)
+        return Comm.create(device, rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    @staticmethod
+    def create_all(devices: Sequence[int]):
+        """Single-process variant (ncclCommInitAll): one Comm per device, to be driven from one thread each."""
+        n = len(devices)
+        hs = (C.c_void_p * n)()
+        devs = (C.c_int * n)(*[int(d) for d in devices])
+        _native.check(_native.lib().pgx_comm_create_all(hs, n, devs))
+        return [Comm(C.c_void_p(hs[i]), i, n, int(devices[i])) for i in range(n)]
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.pgx_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def similarity_shard_bounds(n_groups: int, world: int) -> np.ndarray:
+    """Row-block boundaries (2 * world + 1) of pgx_similarity_sharded; rank r owns blocks r and 2 * world - 1 - r."""
+    out = np.zeros(2 * world + 1, dtype=np.uint32)
+    _native.check(_native.lib().pgx_similarity_shard_bounds(int(n_groups), int(world), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return out
+
+
 class DeviceAbacus:
     """GPU-resident item x group incidence bitmap (+ bp weights) and the hot-path queries on it."""
 
@@ -169,6 +232,10 @@ class DeviceAbacus:
             raise ValueError("exclude must have n_items + 1 entries")
         _native.check(self._L.pgx_abacus_build(self._h, _ptr(items), items.size, _ptr(id_prefsum), path_group.size,
                                                _ptr(path_group), _ptr(ex)))
+
+    def copy_rows_from(self, src: "DeviceAbacus", src_first_item: int):
+        """Items src_first_item .. of `src` (possibly on another GPU) become this handle's items 1 .. n_items."""
+        _native.check(self._L.pgx_abacus_copy_rows(self._h, src._h, int(src_first_item)))
 
     def download(self) -> np.ndarray:
         out = np.zeros((self.n_items + 1, self.row_words), dtype=np.uint64)
@@ -279,6 +346,49 @@ class DeviceAbacus:
         cov, thr = self._cutoffs(cov_abs, quorum_thr, self.n_groups)
         _native.check(self._L.pgx_fused_pass_async(self._h, int(bool(hist_count)), int(bool(hist_weight)), cov.size,
                                                    _ptr(cov), _ptr(thr), int(bool(weighted)), C.c_void_p(d_out_ptr)))
+
+    # -- sharded over an NCCL communicator (collective: every rank calls with its own handle) ------------------
+    def broadcast(self, comm: "Comm", root: int = 0, with_weights: bool = False):
+        _native.check(self._L.pgx_abacus_broadcast(self._h, comm._h, int(root), int(bool(with_weights))))
+
+    def hist_ordered_growth_sharded(self, comm: "Comm", cov_abs, quorum_thr=None, weighted=False, hist_count=True,
+                                    hist_weight=False):
+        """Item-range shards + ncclAllReduce: -> (hist_count | None, hist_weight | None, curve u64[T, G]) of the whole graph."""
+        G = self.n_groups
+        cov, thr = self._cutoffs(cov_abs, quorum_thr, G)
+        hc = np.zeros(G + 1, dtype=np.uint64) if hist_count else None
+        hw = np.zeros(G + 1, dtype=np.uint64) if hist_weight else None
+        curve = np.zeros((cov.size, G), dtype=np.uint64)
+        _native.check(self._L.pgx_hist_ordered_growth_sharded(self._h, comm._h, _ptr(hc), _ptr(hw), cov.size, _ptr(cov),
+                                                              _ptr(thr), int(bool(weighted)), _ptr(curve)))
+        return hc, hw, curve
+
+    def permuted_growth_sharded(self, comm: "Comm", orders: np.ndarray, cov_abs, quorum_thr=None, weighted=False,
+                                out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Order p on rank p % world, ncclAllGather of the device-resident curves -> u64 [P, T, G] on every rank."""
+        G = self.n_groups
+        orders = np.ascontiguousarray(orders, dtype=np.uint32)
+        if orders.ndim != 2 or orders.shape[1] != G:
+            raise ValueError("orders must be [P, n_groups]")
+        cov, thr = self._cutoffs(cov_abs, quorum_thr, G)
+        curves = out if out is not None else np.zeros((orders.shape[0], cov.size, G), dtype=np.uint64)
+        _native.check(self._L.pgx_permuted_growth_sharded(self._h, comm._h, orders.shape[0], _ptr(orders), cov.size,
+                                                          _ptr(cov), _ptr(thr), int(bool(weighted)), _ptr(curves)))
+        return curves
+
+    def similarity_sharded(self, comm: "Comm", weighted: bool = False, out_inter: Optional[np.ndarray] = None):
+        """Upper-triangle row blocks per rank, ncclAllGather, device-side assembly -> (inter u64[G, G], len u64[G])."""
+        G = self.n_groups
+        inter = out_inter if out_inter is not None else np.zeros((G, G), dtype=np.uint64)
+        ln = np.zeros(G, dtype=np.uint64)
+        _native.check(self._L.pgx_similarity_sharded(self._h, comm._h, int(bool(weighted)), _ptr(inter), _ptr(ln)))
+        return inter, ln
+
+    def exchange_connect_comm(self, comm: "Comm"):
+        _native.check(self._L.pgx_exchange_connect_comm(self._h, comm._h))
+
+    def exchange_status(self):
+        _native.check(self._L.pgx_exchange_status(self._h))
 
     # -- fused multi-GPU exchange (item-range sharding) ----------------------------------------------
     def exchange_export(self) -> bytes:

@@ -7,8 +7,7 @@
 #include <string>
 #include <vector>
 
-#include "pgx_common.cuh"
-#include "pgx_internal.h"
+#include "pgx_handle.h"
 
 namespace pgx {
 
@@ -24,80 +23,7 @@ int fail(int code, const std::string &msg) {
 
 using namespace pgx;
 
-struct pgx_abacus {
-    int device = 0;
-    int sm_count = 148;
-    uint64_t n_items = 0, n_rows = 0;
-    uint32_t G = 0, W = 0, Wp = 0;
-
-    uint64_t *d_bitmap = nullptr;
-    bool own_bitmap = false;
-    uint32_t *d_weight = nullptr;  // nullptr = unit weights
-    bool own_weight = false;
-    uint32_t max_weight = 1;
-    bool max_weight_known = true;
-
-    uint32_t *d_countable = nullptr;  // N+1, lazily allocated
-    uint64_t *d_hist_tmp = nullptr;   // histogram by-product of the countable pass
-    bool countable_valid = false;
-
-    uint64_t *d_gm = nullptr;  // group-major copy, lazily built
-    uint64_t gm_stride = 0;
-    bool gm_valid = false;
-    // weighted similarity: a second group-major copy with the items sorted by weight (descending), so that
-    // most 64-item words carry a single weight (one popcount pass) and high weight planes are empty
-    uint64_t *d_gm_w = nullptr;
-    uint32_t *d_perm = nullptr, *d_sorted_w = nullptr;
-    uint64_t *d_planes = nullptr, *d_uniform_w = nullptr;
-    uint32_t *d_plane_mask = nullptr;
-    uint32_t n_planes = 0;
-    bool planes_valid = false;
-
-    uint64_t *d_csr_r = nullptr;  // AbacusByGroup::r (N + 2 row offsets), lazily derived from the bitmap
-    bool csr_valid = false;
-
-    uint64_t *d_acc = nullptr;  // self-cleaning global accumulators of k_scan
-    size_t acc_words = 0;
-    unsigned int *d_ticket = nullptr;
-    unsigned int *d_err = nullptr;
-
-    uint32_t *d_thr = nullptr;  // quorum thresholds of the current call
-    size_t thr_cap = 0;
-    std::vector<uint32_t> thr_cache;
-    uint32_t *d_order = nullptr;
-    size_t order_cap = 0;
-    uint32_t *d_identity = nullptr;  // 0..G-1, for general-quorum growth in group order on the group-major copy
-    uint64_t *d_scratch = nullptr;  // generic device result buffer
-    size_t scratch_cap = 0;
-
-    uint64_t *h_pinned = nullptr;
-    size_t pinned_words = 0;
-
-    // fused NVLink exchange (item-range sharding)
-    unsigned char *d_xchg = nullptr;  // [2 parities][kMaxRanks][acc_words][2] u64 packets {epoch:32 | half:32}
-    void *peer_base[kMaxRanks] = {};
-    Exchange x = {};
-    uint32_t epoch = 0;
-
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    uint64_t launches = 0;
-    std::string last_launch;
-};
-
-namespace {
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        cudaGetDevice(&cur);
-        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-    }
-};
+namespace pgx {
 
 int ensure_pinned(pgx_abacus *a, size_t words) {
     if (a->pinned_words >= words) return PGX_OK;
@@ -109,14 +35,21 @@ int ensure_pinned(pgx_abacus *a, size_t words) {
     return PGX_OK;
 }
 
-template <typename T>
-int ensure_dev(T **ptr, size_t *cap, size_t count) {
-    if (*cap >= count && *ptr) return PGX_OK;
-    if (*ptr) cudaFree(*ptr);
-    *ptr = nullptr;
-    *cap = 0;
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(ptr), std::max<size_t>(count, 1) * sizeof(T)));
-    *cap = count;
+int copy_to_host(pgx_abacus *a, uint64_t *dst, const uint64_t *d_src, size_t words) {
+    if (words == 0) return PGX_OK;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {  // the caller handed us page-locked memory: DMA straight into it
+        PGX_CUDA(cudaMemcpyAsync(dst, d_src, words * 8u, cudaMemcpyDeviceToHost, a->stream));
+        PGX_CUDA(cudaStreamSynchronize(a->stream));
+        return PGX_OK;
+    }
+    const int rc = ensure_pinned(a, words);
+    if (rc) return rc;
+    PGX_CUDA(cudaMemcpyAsync(a->h_pinned, d_src, words * 8u, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    std::memcpy(dst, a->h_pinned, words * 8u);
     return PGX_OK;
 }
 
@@ -130,6 +63,20 @@ void invalidate_derived(pgx_abacus *a) {
 int check_handle(const pgx_abacus *a) {
     if (!a) return fail(PGX_ERR_INVALID, "null handle");
     if (!a->d_bitmap) return fail(PGX_ERR_STATE, "abacus has no bitmap");
+    return PGX_OK;
+}
+
+// After a fused pass with the multi-GPU exchange connected and the stream synchronised: did the in-kernel watchdog
+// fire (a peer never delivered its partial sums)?  The result buffer then holds a partial sum and must not be used.
+int check_exchange(pgx_abacus *a) {
+    if (a->x.world <= 1u) return PGX_OK;
+    unsigned int err = 0;
+    PGX_CUDA(cudaMemcpyAsync(&err, a->d_err + 1, 4, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if (err) {
+        PGX_CUDA(cudaMemsetAsync(a->d_err + 1, 0, 4, a->stream));
+        return fail(PGX_ERR_EXCHANGE, "exchange timeout: a peer rank never delivered its partial sums (result discarded)");
+    }
     return PGX_OK;
 }
 
@@ -159,10 +106,6 @@ int validate_thresholds(const pgx_abacus *a, uint32_t T, const uint32_t *cov) {
     return PGX_OK;
 }
 
-int ensure_countable(pgx_abacus *a);
-int ensure_gm(pgx_abacus *a);
-int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders, const std::vector<uint32_t> &ts,
-                     const uint32_t *cov, const uint32_t *thr, int weighted, uint64_t *d_out_base, uint64_t out_order_stride);
 
 // General-quorum thresholds in group order can run on either layout: k_scan<quorum> (node-major, one
 // thread per item, divergent) or k_gm_growth on the group-major copy (bit-sliced over 64 items per
@@ -325,6 +268,8 @@ int ensure_planes(pgx_abacus *a) {
         a->planes_valid = true;
         return PGX_OK;
     }
+    if (a->n_rows > 0x7FFFFFFFull)  // cub::DeviceRadixSort is called with an int item count
+        return fail(PGX_ERR_UNSUPPORTED, "weight-sorted copy (bp-weighted similarity / permuted growth) needs n_items < 2^31 - 1");
     if (!a->max_weight_known) {
         PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
         k_max_u32<<<296, 256, 0, a->stream>>>(a->d_weight + 1, a->n_items, a->d_err);
@@ -533,9 +478,10 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
     return PGX_OK;
 }
 
-// growth under explicit host orders on the group-major copy -> curves (host)
-int gm_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t T, const uint32_t *cov,
-              const uint32_t *thr, int weighted, uint64_t *curves /*host*/) {
+// Growth under explicit host orders on the group-major copy: uploads the orders, runs the kernels and leaves the
+// CURVES (prefix-summed on the device) of order o, threshold t at d_out + (o * T + t) * G.  No synchronisation.
+int gm_growth_device(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t T, const uint32_t *cov,
+                     const uint32_t *thr, int weighted, uint64_t *d_out) {
     const uint32_t G = a->G;
     int rc = validate_thresholds(a, T, cov);
     if (rc) return rc;
@@ -549,29 +495,84 @@ int gm_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t
     if ((rc = ensure_gm(a))) return rc;
     if ((rc = ensure_dev(&a->d_order, &a->order_cap, (size_t)n_orders * G))) return rc;
     PGX_CUDA(cudaMemcpyAsync(a->d_order, orders, (size_t)n_orders * G * 4u, cudaMemcpyHostToDevice, a->stream));
-    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));  // `orders` is the caller's buffer
 
     const size_t out_words = (size_t)n_orders * T * G;
-    if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, out_words))) return rc;
-    if ((rc = ensure_pinned(a, out_words))) return rc;
-    PGX_CUDA(cudaMemsetAsync(a->d_scratch, 0, out_words * 8u, a->stream));
+    PGX_CUDA(cudaMemsetAsync(d_out, 0, out_words * 8u, a->stream));
     std::vector<uint32_t> ts(T);
     for (uint32_t t = 0; t < T; ++t) ts[t] = t;
-    if ((rc = gm_growth_launch(a, n_orders, a->d_order, ts, cov, thr, weighted, a->d_scratch, (uint64_t)T * G))) return rc;
-    PGX_CUDA(cudaMemcpyAsync(a->h_pinned, a->d_scratch, out_words * 8u, cudaMemcpyDeviceToHost, a->stream));
-    PGX_CUDA(cudaStreamSynchronize(a->stream));
-    // first differences -> curves (wrapping u64 prefix sums)
-    for (size_t c = 0; c < (size_t)n_orders * T; ++c) {
-        uint64_t run = 0;
-        for (uint32_t j = 0; j < G; ++j) {
-            run += a->h_pinned[c * G + j];
-            curves[c * G + j] = run;
-        }
-    }
+    if ((rc = gm_growth_launch(a, n_orders, a->d_order, ts, cov, thr, weighted, d_out, (uint64_t)T * G))) return rc;
+    // first differences -> curves (wrapping u64 prefix sums) where they are
+    if ((rc = launch_prefix_curves(d_out, (uint64_t)n_orders * T, G, a->stream))) return rc;
+    a->launches++;
     return PGX_OK;
 }
 
-}  // namespace
+// ... -> curves in host memory
+int gm_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t T, const uint32_t *cov,
+              const uint32_t *thr, int weighted, uint64_t *curves /*host*/) {
+    const size_t out_words = (size_t)n_orders * T * a->G;
+    if (out_words == 0) return validate_thresholds(a, T, cov);
+    int rc = ensure_dev(&a->d_scratch, &a->scratch_cap, out_words);
+    if (rc) return rc;
+    if ((rc = gm_growth_device(a, n_orders, orders, T, cov, thr, weighted, a->d_scratch))) return rc;
+    return copy_to_host(a, curves, a->d_scratch, out_words);
+}
+
+// Integer part of Similarity::set_table for the group rows [row_begin, row_end) x the columns >= col_begin, into the
+// zeroed device buffer d_inter ((row_end - row_begin) x G).  No synchronisation.
+int sim_rows_device(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint64_t *d_inter,
+                    bool upper_only) {
+    int rc;
+    const bool use_planes = weighted && a->d_weight;
+    if (use_planes) {
+        if ((rc = ensure_planes(a))) return rc;  // weight-sorted group-major copy + planes
+    } else if ((rc = ensure_gm(a))) {
+        return rc;
+    }
+    if (row_end == row_begin) return PGX_OK;
+    GmSimParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.gm = use_planes ? a->d_gm_w : a->d_gm;
+    p.gm_stride = a->gm_stride;
+    p.n_words = (a->n_rows + 63u) / 64u;
+    p.planes = use_planes ? a->d_planes : nullptr;
+    p.uniform_w = use_planes ? a->d_uniform_w : nullptr;
+    p.plane_mask = use_planes ? a->d_plane_mask : nullptr;
+    p.n_planes = use_planes ? a->n_planes : 0;
+    p.G = a->G;
+    p.row_begin = row_begin;
+    p.row_end = row_end;
+    p.col_begin = col_begin;
+    p.inter = d_inter;
+    p.upper_only = upper_only ? 1u : 0u;
+    const char *env = getenv("PGX_SIM");  // "plain": one POPC per item word and pair; default: carry-save pairs of words
+    p.csa = (!use_planes && !(env && !strcmp(env, "plain"))) ? 1u : 0u;
+    if ((rc = launch_gm_similarity(p, a->sm_count, a->stream))) return rc;
+    a->launches++;
+    a->last_launch = use_planes ? "k_gm_similarity<weighted>" : p.csa ? "k_gm_similarity<csa>" : "k_gm_similarity<plain>";
+    return PGX_OK;
+}
+
+// len[g] = sum of w over the items of group g, for the groups [g_begin, g_end) -> d_len[0 .. g_end - g_begin)
+int sim_len_device(pgx_abacus *a, int weighted, uint32_t g_begin, uint32_t g_end, uint64_t *d_len) {
+    int rc;
+    const bool use_planes = weighted && a->d_weight;
+    if (use_planes) {
+        if ((rc = ensure_planes(a))) return rc;
+    } else if ((rc = ensure_gm(a))) {
+        return rc;
+    }
+    if (g_end == g_begin) return PGX_OK;
+    const uint64_t *gm = (use_planes ? a->d_gm_w : a->d_gm) + (uint64_t)g_begin * a->gm_stride;
+    if ((rc = launch_gm_rowsum(gm, a->gm_stride, (a->n_rows + 63u) / 64u, use_planes ? a->d_planes : nullptr,
+                               use_planes ? a->n_planes : 0, use_planes ? a->d_uniform_w : nullptr, g_end - g_begin, d_len, a->stream)))
+        return rc;
+    a->launches++;
+    return PGX_OK;
+}
+
+}  // namespace pgx
 
 extern "C" {
 
@@ -629,10 +630,10 @@ int pgx_abacus_create(pgx_abacus **out, int device, uint64_t n_items, uint32_t n
     if ((e = cudaMemsetAsync(a->d_bitmap, 0, bm_bytes, a->stream)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&a->d_acc), a->acc_words * 8u)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&a->d_ticket), 4)) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_err), 4)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_err), 8)) != cudaSuccess ||
         (e = cudaMemsetAsync(a->d_acc, 0, a->acc_words * 8u, a->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(a->d_ticket, 0, 4, a->stream)) != cudaSuccess ||
-        (e = cudaMemsetAsync(a->d_err, 0, 4, a->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(a->d_err, 0, 8, a->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(a->stream)) != cudaSuccess)
         return bail(fail(PGX_ERR_CUDA, std::string("abacus setup: ") + cudaGetErrorString(e)));
     *out = a;
@@ -736,6 +737,40 @@ int pgx_abacus_adopt_device(pgx_abacus *a, uint64_t *d_bitmap, uint32_t *d_weigh
     a->max_weight_known = d_weight == nullptr;
     a->max_weight = 1;
     invalidate_derived(a);
+    return PGX_OK;
+}
+
+int pgx_abacus_copy_rows(pgx_abacus *dst, pgx_abacus *src, uint64_t src_first_item) {
+    int rc = check_handle(dst);
+    if (rc || (rc = check_handle(src))) return rc;
+    if (dst == src) return fail(PGX_ERR_INVALID, "source and destination are the same handle");
+    if (dst->G != src->G) return fail(PGX_ERR_INVALID, "handles differ in n_groups");
+    if (src_first_item == 0 || src_first_item + dst->n_items > src->n_items + 1u)
+        return fail(PGX_ERR_INVALID, "item range outside the source abacus");
+    {
+        DeviceGuard g(src->device);
+        PGX_CUDA(cudaStreamSynchronize(src->stream));  // the source rows must be complete
+    }
+    DeviceGuard guard(dst->device);
+    const size_t row_bytes = (size_t)dst->Wp * 8u;
+    // rows 1..n of dst <- rows first..first+n-1 of src; row 0 stays the (zero) dummy item
+    PGX_CUDA(cudaMemcpyPeerAsync(dst->d_bitmap + dst->Wp, dst->device, src->d_bitmap + src_first_item * src->Wp, src->device,
+                                 dst->n_items * row_bytes, dst->stream));
+    PGX_CUDA(cudaMemsetAsync(dst->d_bitmap, 0, row_bytes, dst->stream));
+    if (src->d_weight) {
+        if (!dst->own_weight || !dst->d_weight) {
+            dst->d_weight = nullptr;
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&dst->d_weight), dst->n_rows * 4u));
+            dst->own_weight = true;
+        }
+        PGX_CUDA(cudaMemcpyPeerAsync(dst->d_weight + 1, dst->device, src->d_weight + src_first_item, src->device,
+                                     dst->n_items * 4u, dst->stream));
+        PGX_CUDA(cudaMemsetAsync(dst->d_weight, 0, 4u, dst->stream));
+        dst->max_weight = src->max_weight;
+        dst->max_weight_known = src->max_weight_known;
+    }
+    PGX_CUDA(cudaStreamSynchronize(dst->stream));
+    invalidate_derived(dst);
     return PGX_OK;
 }
 
@@ -959,6 +994,7 @@ int pgx_hist_ordered_growth(pgx_abacus *a, uint64_t *hist_count, uint64_t *hist_
     if (rc) return rc;
     PGX_CUDA(cudaMemcpyAsync(a->h_pinned, a->d_scratch, words * 8u, cudaMemcpyDeviceToHost, a->stream));
     PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if ((rc = check_exchange(a))) return rc;
     if (hist_count) std::memcpy(hist_count, a->h_pinned, (size_t)G1 * 8u);
     if (hist_weight) std::memcpy(hist_weight, a->h_pinned + G1, (size_t)G1 * 8u);
     for (uint32_t t = 0; t < n_thresholds; ++t) {
@@ -991,6 +1027,7 @@ int pgx_hist(pgx_abacus *a, uint64_t *hist_count, uint64_t *hist_weight, uint32_
         a->countable_valid = true;
     }
     PGX_CUDA(cudaStreamSynchronize(a->stream));
+    if ((rc = check_exchange(a))) return rc;
     if (hist_count) std::memcpy(hist_count, a->h_pinned, (size_t)G1 * 8u);
     if (hist_weight) std::memcpy(hist_weight, a->h_pinned + G1, (size_t)G1 * 8u);
     return PGX_OK;
@@ -1036,51 +1073,15 @@ int similarity_rows(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t ro
     if (row_begin > row_end || row_end > a->G) return fail(PGX_ERR_INVALID, "bad row range");
     DeviceGuard guard(a->device);
     const uint32_t G = a->G;
-    const bool use_planes = weighted && a->d_weight;
-    if (use_planes) {
-        if ((rc = ensure_planes(a))) return rc;  // weight-sorted group-major copy + planes
-    } else if ((rc = ensure_gm(a))) {
-        return rc;
-    }
-    const uint32_t rows = row_end - row_begin;
+    const uint32_t rows = inter ? row_end - row_begin : 0u;
     const size_t inter_words = (size_t)rows * G;
     const size_t words = inter_words + G;
     if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, words))) return rc;
-    if ((rc = ensure_pinned(a, words))) return rc;
     PGX_CUDA(cudaMemsetAsync(a->d_scratch, 0, words * 8u, a->stream));
-    const uint64_t n_words = (a->n_rows + 63u) / 64u;
-    if (rows && inter) {
-        GmSimParams p;
-        std::memset(&p, 0, sizeof(p));
-        p.gm = use_planes ? a->d_gm_w : a->d_gm;
-        p.gm_stride = a->gm_stride;
-        p.n_words = n_words;
-        p.planes = use_planes ? a->d_planes : nullptr;
-        p.uniform_w = use_planes ? a->d_uniform_w : nullptr;
-        p.plane_mask = use_planes ? a->d_plane_mask : nullptr;
-        p.n_planes = use_planes ? a->n_planes : 0;
-        p.G = G;
-        p.row_begin = row_begin;
-        p.row_end = row_end;
-        p.col_begin = col_begin;
-        p.inter = a->d_scratch;
-        const char *env = getenv("PGX_SIM");  // "plain": one POPC per item word and pair; default: carry-save pairs of words
-        p.csa = (!use_planes && !(env && !strcmp(env, "plain"))) ? 1u : 0u;
-        if ((rc = launch_gm_similarity(p, a->sm_count, a->stream))) return rc;
-        a->launches++;
-        a->last_launch = use_planes ? "k_gm_similarity<weighted>" : p.csa ? "k_gm_similarity<csa>" : "k_gm_similarity<plain>";
-    }
-    if (len) {
-        if ((rc = launch_gm_rowsum(use_planes ? a->d_gm_w : a->d_gm, a->gm_stride, n_words, use_planes ? a->d_planes : nullptr,
-                                   use_planes ? a->n_planes : 0, use_planes ? a->d_uniform_w : nullptr, G,
-                                   a->d_scratch + inter_words, a->stream)))
-            return rc;
-        a->launches++;
-    }
-    PGX_CUDA(cudaMemcpyAsync(a->h_pinned, a->d_scratch, words * 8u, cudaMemcpyDeviceToHost, a->stream));
-    PGX_CUDA(cudaStreamSynchronize(a->stream));
-    if (rows && inter) std::memcpy(inter, a->h_pinned, inter_words * 8u);
-    if (len) std::memcpy(len, a->h_pinned + inter_words, (size_t)G * 8u);
+    if (rows && (rc = sim_rows_device(a, weighted, row_begin, row_end, col_begin, a->d_scratch, false))) return rc;
+    if (len && (rc = sim_len_device(a, weighted, 0, G, a->d_scratch + inter_words))) return rc;
+    if (rows && (rc = copy_to_host(a, inter, a->d_scratch, inter_words))) return rc;
+    if (len && (rc = copy_to_host(a, len, a->d_scratch + inter_words, G))) return rc;
     return PGX_OK;
 }
 }  // namespace
@@ -1122,7 +1123,7 @@ int pgx_exchange_connect(pgx_abacus *a, uint32_t rank, uint32_t world, const voi
     x.world = world;
     x.rank = rank;
     x.stride = (uint32_t)a->acc_words;
-    x.err = a->d_err;
+    x.err = a->d_err + 1;
     for (uint32_t r = 0; r < world; ++r) {
         unsigned char *base = nullptr;
         if (r == rank) {
@@ -1157,6 +1158,13 @@ int pgx_exchange_disconnect(pgx_abacus *a) {
     a->x = Exchange{};
     cudaGetLastError();
     return PGX_OK;
+}
+
+int pgx_exchange_status(pgx_abacus *a) {
+    if (!a) return fail(PGX_ERR_INVALID, "null handle");
+    DeviceGuard guard(a->device);
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    return check_exchange(a);
 }
 
 uint64_t pgx_launch_count(const pgx_abacus *a) { return a ? a->launches : 0; }

@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
     }
     const uint32_t x0 = p.row_begin + by * kSimTile;  // output rows
     const uint32_t y0 = p.col_begin + bx * kSimTile;  // output columns (col_begin > 0: upper-triangle sharding)
+    if (p.upper_only && y0 + kSimTile <= x0) return;  // tile strictly below the diagonal: its mirror image is computed instead
     const uint64_t k_begin = (uint64_t)blockIdx.z * words_per_split;
     uint64_t k_end = k_begin + words_per_split;
     if (k_end > p.n_words) k_end = p.n_words;
@@ -444,6 +445,54 @@ __global__ void __launch_bounds__(256) k_gm_similarity(const __grid_constant__ G
 __global__ void __launch_bounds__(256) k_sim_mirror(uint64_t *inter, uint32_t G) {
     const uint32_t x = blockIdx.y * 16u + (threadIdx.x >> 4), y = blockIdx.x * 16u + (threadIdx.x & 15u);
     if (x < G && y < G && y / kSimTile < x / kSimTile) inter[(uint64_t)x * G + y] = inter[(uint64_t)y * G + x];
+}
+
+// Full G x G intersection matrix (+ len) from the all-gathered upper-triangle row blocks of a sharded run: element
+// (x, y) lives in the block that owns row min(x, y), at column max(x, y) (the matrix is symmetric and every block was
+// computed from its diagonal rightwards).
+__global__ void __launch_bounds__(256) k_sim_assemble(const SimAssembleParams p) {
+    const uint64_t e = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    const uint64_t GG = (uint64_t)p.G * p.G;
+    if (e >= GG + p.G) return;
+    uint32_t r, c;
+    if (e < GG) {
+        const uint32_t x = (uint32_t)(e / p.G), y = (uint32_t)(e - (uint64_t)x * p.G);
+        r = min(x, y);
+        c = max(x, y);
+    } else {
+        r = c = (uint32_t)(e - GG);
+    }
+    uint32_t b = 0;
+    while (b + 1u < p.n_blocks && r >= p.bounds[b + 1u]) ++b;
+    const uint32_t rank = b < p.world ? b : p.n_blocks - 1u - b;
+    // rows of the rank's first block (block `rank`) precede those of its second (block n_blocks - 1 - rank)
+    const uint32_t local = (b < p.world ? 0u : p.bounds[rank + 1u] - p.bounds[rank]) + (r - p.bounds[b]);
+    const uint64_t *src = p.gathered + (uint64_t)rank * p.rank_stride;
+    if (e < GG)
+        p.inter[e] = src[(uint64_t)local * p.G + c];
+    else
+        p.len[r] = src[(uint64_t)p.max_rows * p.G + local];
+}
+
+// first differences -> curves in place (wrapping u64 prefix sums); one warp per curve of G entries
+__global__ void __launch_bounds__(256) k_prefix_curves(uint64_t *d, uint64_t n_curves, uint32_t G) {
+    const uint64_t curve = ((uint64_t)blockIdx.x * 256u + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (curve >= n_curves) return;
+    uint64_t *row = d + curve * G;
+    unsigned long long carry = 0;
+    for (uint32_t j0 = 0; j0 < G; j0 += 32u) {
+        const uint32_t j = j0 + lane;
+        unsigned long long v = j < G ? row[j] : 0ull;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if ((int)lane >= o) v += u;
+        }
+        v += carry;
+        if (j < G) row[j] = v;
+        carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
 }
 
 // ---- per-group totals: len[g] = sum_i w_i [g in i] (similarity.rs:133-137) -------------------------
@@ -665,6 +714,20 @@ int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream
 int launch_gm_rowsum(const uint64_t *gm, uint64_t gm_stride, uint64_t n_words, const uint64_t *planes,
                      uint32_t n_planes, const uint64_t *uniform_w, uint32_t G, uint64_t *len, cudaStream_t stream) {
     k_gm_rowsum<<<G, 256, 0, stream>>>(gm, gm_stride, n_words, planes, n_planes, uniform_w, len);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+int launch_sim_assemble(const SimAssembleParams &p, cudaStream_t stream) {
+    const uint64_t n = (uint64_t)p.G * p.G + p.G;
+    k_sim_assemble<<<(unsigned)((n + 255u) / 256u), 256, 0, stream>>>(p);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+int launch_prefix_curves(uint64_t *d, uint64_t n_curves, uint32_t G, cudaStream_t stream) {
+    if (n_curves == 0 || G == 0) return PGX_OK;
+    k_prefix_curves<<<(unsigned)((n_curves * 32u + 255u) / 256u), 256, 0, stream>>>(d, n_curves, G);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }

@@ -144,9 +144,22 @@ struct GmSimParams {
     uint32_t col_begin;      // only columns >= col_begin are computed (the rest of `inter` stays zero)
     uint32_t triangular;     // set by the launcher: full square, compute upper tiles only and mirror
     uint32_t csa;            // unweighted: carry-save variant (one POPC per two item words and pair)
+    uint32_t upper_only;     // skip tiles strictly below the diagonal (sharded runs read only (x, y) with y >= x)
     uint64_t *inter;         // device (row_end-row_begin) x G, zeroed by the launcher
 };
 int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream);
+// sharded similarity: all-gathered upper-triangle row blocks -> full matrix + len (pgx_comm.cu)
+struct SimAssembleParams {
+    const uint64_t *gathered;  // [world][rank_stride]: per rank max_rows x G intersections, then max_rows len entries
+    uint64_t rank_stride;      // max_rows * (G + 1)
+    uint64_t *inter;           // G x G
+    uint64_t *len;             // G
+    uint32_t G, world, n_blocks, max_rows;
+    uint32_t bounds[2 * kMaxRanks + 1];  // row-block boundaries (n_blocks + 1 entries)
+};
+int launch_sim_assemble(const SimAssembleParams &p, cudaStream_t stream);
+// first differences -> curves, in place: n_curves rows of G u64
+int launch_prefix_curves(uint64_t *d, uint64_t n_curves, uint32_t G, cudaStream_t stream);
 int launch_gm_rowsum(const uint64_t *gm, uint64_t gm_stride, uint64_t n_words, const uint64_t *planes,
                      uint32_t n_planes, const uint64_t *uniform_w, uint32_t G, uint64_t *len, cudaStream_t stream);
 int launch_weight_planes(const uint32_t *weight, uint64_t n_rows, uint64_t *planes, uint64_t gm_stride,

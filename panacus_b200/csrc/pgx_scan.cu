@@ -417,7 +417,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                     // push my partial result into slot [par][rank] of every rank (NVLink peer stores).  Each u64 travels
                     // as two 8-byte packets {epoch : 32 | half : 32}: an aligned 8-byte store is atomic, so the
                     // receiver needs no separate flag, fence or barrier (the idea of NCCL's LL protocol)
-                    const size_t off = ((size_t)(par * kMaxRanks + p.x.rank) * p.x.stride + oi) * 2u;
+                    // slots are indexed by the launch-local accumulator index i (< acc_words = the slot stride for any
+                    // number of thresholds in the call), not by the caller's fused-layout index oi
+                    const size_t off = ((size_t)(par * kMaxRanks + p.x.rank) * p.x.stride + i) * 2u;
                     const uint64_t tag = (uint64_t)p.x.epoch << 32;
                     const uint64_t lo = tag | (v[u] & 0xFFFFFFFFull), hi = tag | (v[u] >> 32);
                     for (uint32_t r = 0; r < p.x.world; ++r) {
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                     for (uint32_t r = 0; r < (uint32_t)kMaxRanks; ++r) {
                         a[r] = b[r] = (uint64_t)p.x.epoch << 32;
                         if (r < p.x.world) {
-                            const uint64_t *q = mine + ((size_t)r * p.x.stride + oi) * 2u;
+                            const uint64_t *q = mine + ((size_t)r * p.x.stride + i) * 2u;
                             asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a[r]), "=l"(b[r]) : "l"(q) : "memory");
                         }
                     }

@@ -35,7 +35,7 @@ const std::map<char, std::string> kShort = {{'s', "subset"},  {'e', "exclude"}, 
                                              {'S', "groupby-sample"}, {'c', "count"}, {'l', "coverage"}, {'q', "quorum"},
                                              {'a', "hist"},    {'O', "order"},    {'m', "method"},  {'t', "threads"},
                                              {'v', "verbose"}};
-const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json", "names"};
+const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json", "names", "no-cluster"};
 
 Args parse_args(int argc, char **argv) {
     Args a;
@@ -135,6 +135,32 @@ uint32_t count_groups(const std::vector<std::pair<uint64_t, std::string>> &po) {
     return n;
 }
 
+// --gpus N (default 1): GPUs of this node the counting is sharded over (one host thread + one NCCL communicator each)
+uint32_t n_gpus(const Args &a) {
+    if (!a.has("gpus")) return 1;
+    const int n = std::atoi(a.get("gpus").c_str());
+    if (n < 1 || n > 8) throw Error("--gpus must be in 1..8");
+    if (n > 1 && n > device_count()) throw Error("--gpus " + std::to_string(n) + ": only " + std::to_string(device_count()) + " CUDA devices visible");
+    return (uint32_t)n;
+}
+
+std::vector<std::unique_ptr<DeviceComm>> make_comms(uint32_t n) {
+    std::vector<int> devs(n);
+    for (uint32_t r = 0; r < n; ++r) devs[r] = (int)r;
+    return DeviceComm::create_all(devs);
+}
+
+// Item-range shards of `full` (which lives on GPU 0), one per GPU, cut on the device (NVLink peer copies)
+std::vector<std::unique_ptr<DeviceAbacus>> shard_items(DeviceAbacus &full, uint32_t n) {
+    std::vector<std::unique_ptr<DeviceAbacus>> shards;
+    for (uint32_t r = 0; r < n; ++r) {
+        const auto range = item_range(full.n_items(), r, n);
+        shards.push_back(std::make_unique<DeviceAbacus>(range.second - range.first, full.n_groups(), (int)r));
+        if (range.second > range.first) shards.back()->copy_rows_from(full, range.first);
+    }
+    return shards;
+}
+
 // One counted abacus on the device plus the host-side facts the analyses need around it; built from a GFA
 // (Run) or read back from a packed-abacus cache file.
 struct Counted {
@@ -210,8 +236,16 @@ Hist device_hist(const Source &src, CountType c, const Args &a) {
     Counted k = get_counted(src, c, a);
     Hist h;
     h.count = c;
-    if (c == CountType::Bp) {
-        k.ab->set_weights(k.weights);
+    const uint32_t gpus = n_gpus(a);
+    const bool bp = c == CountType::Bp;
+    if (bp) k.ab->set_weights(k.weights);
+    if (gpus > 1 && k.uncovered.empty()) {  // item ranges per GPU, ncclAllReduce of the per-shard histograms
+        auto shards = shard_items(*k.ab, gpus);
+        auto comms = make_comms(gpus);
+        std::vector<std::vector<uint64_t>> part(gpus);
+        run_on_devices(gpus, [&](uint32_t r) { shards[r]->hist_sharded(*comms[r], bp ? nullptr : &part[r], bp ? &part[r] : nullptr); });
+        h.coverage = part[0];
+    } else if (bp) {  // (with uncovered bps the patch below needs the per-item coverage: one GPU)
         std::vector<uint32_t> countable;
         k.ab->hist(nullptr, &h.coverage, k.uncovered.empty() ? nullptr : &countable);
         for (auto &kv : k.uncovered) {  // abacus.rs:779-785
@@ -292,7 +326,17 @@ int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
         for (auto &kv : k.uncovered) w[kv.first] = kv.second > w[kv.first] ? 0u : w[kv.first] - (uint32_t)kv.second;
         k.ab->set_weights(w);
     }
-    std::vector<std::vector<double>> cols = k.ab->calc_growth(aux, count == CountType::Bp);
+    std::vector<std::vector<double>> cols;
+    const uint32_t gpus = n_gpus(a);
+    if (gpus > 1) {  // item ranges per GPU; the path's one exchange is an ncclAllReduce of the KB-sized result vector
+        auto shards = shard_items(*k.ab, gpus);
+        auto comms = make_comms(gpus);
+        std::vector<std::vector<std::vector<double>>> part(gpus);
+        run_on_devices(gpus, [&](uint32_t r) { part[r] = shards[r]->calc_growth_sharded(*comms[r], aux, count == CountType::Bp); });
+        cols = part[0];
+    } else {
+        cols = k.ab->calc_growth(aux, count == CountType::Bp);
+    }
     for (auto &c : cols) c.insert(c.begin(), std::nan(""));  // io.rs:580-583
     std::vector<std::vector<std::string>> headers = {{"panacus", "count", "coverage", "quorum"}};
     for (size_t k = 0; k < aux.coverage.size(); ++k)
@@ -378,7 +422,23 @@ int cmd_similarity(const Args &a, const std::string &cmdline, std::ostream &os) 
     const std::vector<std::string> &groups = k.groups;
     if (count == CountType::Bp) k.ab->set_weights(k.weights);  // no uncovered_bps correction here (similarity.rs:130-150)
     std::vector<uint64_t> inter, len;
-    k.ab->similarity(count == CountType::Bp, inter, len);
+    const uint32_t gpus = n_gpus(a);
+    if (gpus > 1) {  // bitmap replicated over NVLink, upper-triangle row blocks per GPU, ncclAllGather
+        const bool bp = count == CountType::Bp;
+        std::vector<std::unique_ptr<DeviceAbacus>> rep(gpus);
+        for (uint32_t r = 1; r < gpus; ++r) rep[r] = std::make_unique<DeviceAbacus>(k.ab->n_items(), k.ab->n_groups(), (int)r);
+        auto comms = make_comms(gpus);
+        std::vector<std::vector<uint64_t>> pi(gpus), pl(gpus);
+        run_on_devices(gpus, [&](uint32_t r) {
+            DeviceAbacus &ab = r == 0 ? *k.ab : *rep[r];
+            ab.broadcast(*comms[r], 0, bp);
+            ab.similarity_sharded(*comms[r], bp, pi[r], pl[r]);
+        });
+        inter.swap(pi[0]);
+        len.swap(pl[0]);
+    } else {
+        k.ab->similarity(count == CountType::Bp, inter, len);
+    }
     const size_t G = groups.size();
     std::vector<std::vector<float>> table(G, std::vector<float>(G));
     for (size_t i = 0; i < G; ++i)
@@ -736,6 +796,7 @@ void usage() {
                  "  -s, --subset FILE   -e, --exclude FILE   -g, --groupby FILE   -H, --groupby-haplotype   -S, --groupby-sample\n"
                  "  -c, --count node|bp|edge|all   -l, --coverage LIST   -q, --quorum LIST   -a, --hist   -O, --order FILE\n"
                  "  -m, --method single|complete|average|weighted|ward|centroid|median (similarity)   -t, --threads N\n"
+                 "  --gpus N   shard the counting over N GPUs of this node (hist / ordered-histgrowth: item ranges; similarity: row blocks)\n"
                  "  --save-abacus PREFIX   write PREFIX.<count>.pabm (packed abacus); a .pabm file is accepted in place of the GFA\n";
 }
 

@@ -8,7 +8,9 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <map>
+#include <memory>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -187,6 +189,30 @@ std::string abacus_by_group_to_tsv(const GraphStorage &g, CountType count, bool 
 std::vector<Hist> parse_hists(const std::string &path, std::vector<std::string> &comments);
 
 // ---- device side (RAII over include/panacus_b200.h) ----------------------------------------------------------
+int device_count();  // pgx_device_count
+
+// One GPU's NCCL communicator (pgx_comm); create_all = the single-process form, one communicator per device, each to be
+// driven from its own host thread (run_on_devices).
+class DeviceComm {
+  public:
+    static std::vector<std::unique_ptr<DeviceComm>> create_all(const std::vector<int> &devices);
+    ~DeviceComm();
+    DeviceComm(const DeviceComm &) = delete;
+    DeviceComm &operator=(const DeviceComm &) = delete;
+    void *handle() const { return h_; }
+    uint32_t rank() const { return rank_; }
+    uint32_t world() const { return world_; }
+
+  private:
+    DeviceComm(void *h, uint32_t rank, uint32_t world) : h_(h), rank_(rank), world_(world) {}
+    void *h_;
+    uint32_t rank_, world_;
+};
+// fn(r) on one host thread per rank (collective calls of rank r); the first exception is rethrown after all joined
+void run_on_devices(uint32_t n, const std::function<void(uint32_t)> &fn);
+// items [lo, hi) (ids from 1) of rank r when n_items are cut into `world` item ranges
+std::pair<uint64_t, uint64_t> item_range(uint64_t n_items, uint32_t rank, uint32_t world);
+
 class DeviceAbacus {
   public:
     DeviceAbacus(uint64_t n_items, uint32_t n_groups, int device = 0);
@@ -205,6 +231,15 @@ class DeviceAbacus {
     // AbacusByGroup::calc_growth for all threshold pairs (abacus.rs:989-1032); f64 like the reference
     std::vector<std::vector<double>> calc_growth(const ThresholdContainer &aux, bool weighted);
     void similarity(bool weighted, std::vector<uint64_t> &inter, std::vector<uint64_t> &len);
+    // ---- multi-GPU (collective: every rank's thread calls with its own abacus and communicator) ----
+    // this abacus <- items first_item .. first_item + n_items() - 1 of `src` (device-to-device, any two GPUs)
+    void copy_rows_from(DeviceAbacus &src, uint64_t first_item);
+    void broadcast(DeviceComm &comm, uint32_t root, bool with_weights);  // replicate root's bitmap (+ weights) over NVLink
+    // item-range shards + ncclAllReduce: results of the whole graph on every rank
+    std::vector<std::vector<double>> calc_growth_sharded(DeviceComm &comm, const ThresholdContainer &aux, bool weighted);
+    void hist_sharded(DeviceComm &comm, std::vector<uint64_t> *count, std::vector<uint64_t> *weight);
+    // replicated bitmap, upper-triangle row blocks per rank + ncclAllGather
+    void similarity_sharded(DeviceComm &comm, bool weighted, std::vector<uint64_t> &inter, std::vector<uint64_t> &len);
     // AbacusByGroup {r, c, v} (abacus.rs:790-799) of the abacus built from `t` under `path_order`; want_v = false skips
     // the occurrence counts (the --total table never reads them, abacus.rs:1093-1096)
     void csr(const ItemTables &t, const std::vector<std::pair<uint64_t, std::string>> &path_order, std::vector<uint64_t> &r,

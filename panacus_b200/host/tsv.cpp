@@ -265,17 +265,23 @@ AbacusFile AbacusFile::load(const std::string &path) {
     f.n_items = get<uint64_t>(i);
     const uint32_t G = get<uint32_t>(i);
     const uint64_t n_unc = get<uint64_t>(i);
-    if (G == 0 || f.n_items >= (1ull << 32)) throw Error("bad shape in " + path);
+    if (!i || G == 0 || G > (1u << 20) || f.n_items >= (1ull << 32) - 2 || n_unc > f.n_items)
+        throw Error("bad shape in " + path);
     for (uint32_t g = 0; g < G; ++g) {
         const uint32_t len = get<uint32_t>(i);
+        if (!i || len > (1u << 16)) throw Error("bad group name in " + path);  // never trust a length from the file
         std::string name(len, '\0');
         i.read(name.data(), len);
+        if (!i) throw Error("truncated abacus cache file " + path);
         f.groups.push_back(std::move(name));
     }
     f.weights.resize(f.n_items + 1);
     i.read(reinterpret_cast<char *>(f.weights.data()), (std::streamsize)(f.weights.size() * 4));
+    if (!i) throw Error("truncated abacus cache file " + path);
     for (uint64_t k = 0; k < n_unc; ++k) {
         const uint64_t id = get<uint64_t>(i), v = get<uint64_t>(i);
+        // the ids index per-item arrays later (hist patch, weight correction): they must name an item of this table
+        if (!i || id == 0 || id > f.n_items) throw Error("bad uncovered-bps entry in " + path);
         f.uncovered[id] = v;
     }
     f.bitmap.resize((size_t)(f.n_items + 1) * ((G + 63u) / 64u));

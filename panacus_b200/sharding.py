@@ -50,11 +50,13 @@ def row_block(n_groups: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def folded_row_blocks(n_groups: int, rank: int, world: int):
-    """Upper-triangle sharding of the similarity matrix: the rows are cut into 2 * world equal blocks and rank r takes
-    blocks r and 2 * world - 1 - r.  A block is computed for the columns >= its first row, so block b costs about
-    rows x (G - start_b) and every rank's pair of blocks adds up to the same share."""
+    """Upper-triangle sharding of the similarity matrix: the rows are cut into 2 * world tile-aligned blocks and rank r
+    takes blocks r and 2 * world - 1 - r.  A block is computed for the columns >= its first row, so block b costs about
+    rows x (G - start_b) and every rank's pair of blocks adds up to the same share.  The boundaries are the ones
+    pgx_similarity_sharded uses (pgx_similarity_shard_bounds, host-only)."""
+    from .abacus import similarity_shard_bounds
     nb = 2 * world
-    bounds = [k * n_groups // nb for k in range(nb + 1)]
+    bounds = [int(b) for b in similarity_shard_bounds(n_groups, world)]
     return [(bounds[b], bounds[b + 1]) for b in (rank, nb - 1 - rank)]
 
 
@@ -114,9 +116,13 @@ def connect_fused_exchange(abacus, group=None):
 # ---- sharded queries (abacus = anything with DeviceAbacus' methods) -----------------------------------------
 
 def sharded_hist_ordered_growth(abacus, cov_abs, quorum_thr=None, weighted=False, hist_weight=False, device=None,
-                                group=None):
+                                group=None, comm=None):
     """Each rank's `abacus` holds its item range.  -> (hist_count, hist_weight | None, curves[T, G]) of the whole
-    graph on every rank.  The sum is taken on the curves' first differences == on the curves themselves (linear)."""
+    graph on every rank.  The sum is taken on the curves' first differences == on the curves themselves (linear).
+    comm (panacus_b200.Comm): the product path -- pgx_hist_ordered_growth_sharded, ncclAllReduce behind the C ABI."""
+    if comm is not None:
+        return abacus.hist_ordered_growth_sharded(comm, cov_abs, quorum_thr, weighted=weighted, hist_count=True,
+                                                  hist_weight=hist_weight)
     hc, hw, cv = abacus.hist_ordered_growth(cov_abs, quorum_thr, weighted=weighted, hist_count=True,
                                             hist_weight=hist_weight)
     G = hc.shape[0] - 1
@@ -127,8 +133,11 @@ def sharded_hist_ordered_growth(abacus, cov_abs, quorum_thr=None, weighted=False
 
 
 def sharded_permuted_growth(abacus, orders: np.ndarray, cov_abs, quorum_thr=None, weighted=False, device=None,
-                            group=None) -> np.ndarray:
-    """Every rank holds the whole bitmap; order p is computed by rank p % world; -> curves [P, T, G] on every rank."""
+                            group=None, comm=None) -> np.ndarray:
+    """Every rank holds the whole bitmap; order p is computed by rank p % world; -> curves [P, T, G] on every rank.
+    comm (panacus_b200.Comm): the product path -- pgx_permuted_growth_sharded (device-resident curves, ncclAllGather)."""
+    if comm is not None:
+        return abacus.permuted_growth_sharded(comm, orders, cov_abs, quorum_thr, weighted=weighted)
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     P = orders.shape[0]
@@ -148,10 +157,14 @@ def sharded_permuted_growth(abacus, orders: np.ndarray, cov_abs, quorum_thr=None
     return out
 
 
-def sharded_similarity(abacus, weighted=False, device=None, group=None, triangle=True):
+def sharded_similarity(abacus, weighted=False, device=None, group=None, triangle=True, comm=None):
     """Every rank holds the whole bitmap; -> (inter [G, G], len [G]) on every rank.
     triangle=True: two folded row blocks per rank, each from its diagonal rightwards (DeviceAbacus.similarity(upper=True)),
-    all-gathered and mirrored -- half the pair work of whole rows.  triangle=False: one block of whole rows per rank."""
+    all-gathered and mirrored -- half the pair work of whole rows.  triangle=False: one block of whole rows per rank.
+    comm (panacus_b200.Comm): the product path -- pgx_similarity_sharded (ncclAllGather + device-side assembly); the
+    torch.distributed path below is the same partition with host-side plumbing, kept for the CPU (gloo) tests."""
+    if comm is not None:
+        return abacus.similarity_sharded(comm, weighted=weighted)
     dist = _dist()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     G = abacus.n_groups

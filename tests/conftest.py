@@ -20,6 +20,36 @@ def pytest_configure(config):
         __graft_entry__.build()
 
 
+def _cuda_devices() -> int:
+    """Number of usable CUDA devices as the product library sees them (0 when the driver / library is unusable)."""
+    try:
+        import ctypes as C
+
+        from panacus_b200 import _native
+        n = C.c_int(0)
+        return n.value if _native.lib().pgx_device_count(C.byref(n)) == 0 else 0
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    # plain `pytest tests` on a machine without a GPU: skip (not fail) everything marked gpu; tests that need
+    # two devices carry @pytest.mark.gpu too and additionally check the count themselves
+    if not any("gpu" in item.keywords for item in items):
+        return
+    if _cuda_devices() > 0:
+        return
+    skip = pytest.mark.skip(reason="no usable CUDA device (pgx_device_count)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def n_cuda_devices():
+    return _cuda_devices()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

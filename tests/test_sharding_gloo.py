@@ -99,8 +99,12 @@ def _worker(rank, world, port, ret):
         for triangle in (True, False):
             inter, ln = sharding.sharded_similarity(full, weighted=True, triangle=triangle)
             assert np.array_equal(inter, inter0) and np.array_equal(ln, ln0), triangle
-        blocks = [b for r in range(world) for b in sharding.folded_row_blocks(G, r, world)]
-        assert sorted(blocks) == [(k * G // (2 * world), (k + 1) * G // (2 * world)) for k in range(2 * world)]
+        # a wider table: several 64-row tiles per block boundary
+        bits2, _, weight2 = synth.numpy_table(301, 333, seed=5)
+        wide = NumpyAbacus(bits2, weight2)
+        inter1, ln1 = wide.similarity(weighted=False)
+        inter, ln = sharding.sharded_similarity(wide, weighted=False, triangle=True)
+        assert np.array_equal(inter, inter1) and np.array_equal(ln, ln1)
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -113,6 +117,26 @@ def test_sharding_over_gloo(world):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {r: "ok" for r in range(world)}
+
+
+def test_similarity_shard_bounds():
+    """pgx_similarity_shard_bounds (host-only entry point of the C ABI): the 2 * world row blocks of the sharded
+    similarity cover the rows once, are 64-row tile aligned, and every rank's folded pair carries the same share of the
+    upper triangle's tile work when the tiles divide evenly."""
+    from panacus_b200 import similarity_shard_bounds
+    for G, world in [(1024, 8), (1024, 2), (1024, 1), (512, 4), (100, 4), (44, 8), (1, 1), (65, 2), (1000, 3), (4096, 8)]:
+        b = [int(x) for x in similarity_shard_bounds(G, world)]
+        assert len(b) == 2 * world + 1 and b[0] == 0 and b[-1] == G
+        assert all(b[k] <= b[k + 1] for k in range(2 * world))
+        assert all(x % 64 == 0 for x in b[:-1])
+        blocks = [blk for r in range(world) for blk in sharding.folded_row_blocks(G, r, world)]
+        rows = sorted(x for lo, hi in blocks for x in range(lo, hi))
+        assert rows == list(range(G))
+        tiles = (G + 63) // 64
+        if tiles % (2 * world) == 0:  # even split: equal tile work per rank (rows x columns right of the block start)
+            work = [sum(((hi - lo) // 64) * (tiles - lo // 64) for lo, hi in sharding.folded_row_blocks(G, r, world))
+                    for r in range(world)]
+            assert len(set(work)) == 1, (G, world, work)
 
 
 def test_partitions_cover_everything_once():
