@@ -87,6 +87,19 @@ int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, u
  * (abacus.rs:859-986). */
 int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
                      uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude);
+/* Same with the ids narrowed to u32 (always possible: n_items < 2^32; for the Rust side a one-line change of
+ * `ItemIdSize`, src/util.rs:15): half the bytes over PCIe.
+ * Both builds stream the table in 16 Mi-step chunks through two device staging buffers, the upload of chunk k + 1
+ * overlapping the scatter kernel of chunk k.  If `items` is page-locked host memory (pgx_host_alloc, cudaHostAlloc,
+ * cudaHostRegister) it is read by DMA where it lies; pageable memory is staged through pinned buffers of the handle,
+ * u64 ids being narrowed to u32 by host threads on the way.  The bits are ORed into the bitmap (pgx_abacus_clear
+ * first to rebuild from scratch). */
+int pgx_abacus_build_u32(pgx_abacus *a, const uint32_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
+                         uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude);
+/* Page-locked host memory for tables and result buffers handed to this library (cudaHostAlloc, portable): uploads from
+ * it and downloads into it are single DMA transfers.  Every entry point also accepts ordinary (pageable) memory. */
+int pgx_host_alloc(void **out, size_t bytes);
+void pgx_host_free(void *p);
 int pgx_abacus_clear(pgx_abacus *a);
 /* Device-to-device copy of an item range (bitmap rows + weights when the source has them): items
  * src_first_item .. src_first_item + dst.n_items - 1 of `src` become items 1 .. dst.n_items of `dst` (same n_groups; the
@@ -238,6 +251,12 @@ int pgx_permuted_growth_sharded(pgx_abacus *a, pgx_comm *c, uint32_t n_orders, c
 int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *inter, uint64_t *len);
 /* Host-only: the 2 * world + 1 row-block boundaries pgx_similarity_sharded uses (no device, no NCCL needed). */
 int pgx_similarity_shard_bounds(uint32_t n_groups, uint32_t world, uint32_t *bounds);
+
+/* Kernel timing for measurements: while enabled, every hot-path kernel section a call launches (k_scan, the group-major
+ * growth kernels, k_gm_similarity) is bracketed by CUDA events on the handle's stream.  pgx_kernel_time_ms waits for
+ * them, returns the summed device time of the sections recorded since the last query and forgets them. */
+int pgx_abacus_set_timing(pgx_abacus *a, int enable);
+int pgx_kernel_time_ms(pgx_abacus *a, float *total_ms, uint32_t *n_sections);
 
 /* Number of kernel launches issued through this handle so far (for bench accounting). */
 uint64_t pgx_launch_count(const pgx_abacus *a);

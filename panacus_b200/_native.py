@@ -16,10 +16,10 @@ LIB_PATH = os.path.join(_HERE, "libpanacus_b200.so")
 EXPORTS = [
     "pgx_version", "pgx_last_error", "pgx_device_count", "pgx_row_words",
     "pgx_abacus_create", "pgx_abacus_destroy", "pgx_abacus_set_stream", "pgx_abacus_shape",
-    "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_build", "pgx_abacus_clear",
+    "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_build", "pgx_abacus_build_u32", "pgx_host_alloc", "pgx_host_free", "pgx_abacus_clear",
     "pgx_abacus_download", "pgx_abacus_copy_rows", "pgx_abacus_csr_rows", "pgx_abacus_csr_fill", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
     "pgx_permuted_growth", "pgx_similarity", "pgx_similarity_upper", "pgx_fused_out_words", "pgx_fused_pass_async",
-    "pgx_launch_count", "pgx_last_launch_info",
+    "pgx_launch_count", "pgx_last_launch_info", "pgx_abacus_set_timing", "pgx_kernel_time_ms",
     "pgx_exchange_export", "pgx_exchange_connect", "pgx_exchange_disconnect", "pgx_exchange_status",
     "pgx_comm_unique_id", "pgx_comm_create", "pgx_comm_create_all", "pgx_comm_destroy", "pgx_comm_info",
     "pgx_abacus_broadcast", "pgx_exchange_connect_comm", "pgx_hist_ordered_growth_sharded",
@@ -70,6 +70,12 @@ def lib() -> C.CDLL:
     L.pgx_abacus_scatter.argtypes = [vp, vp, C.c_uint64, C.c_uint32, vp]
     L.pgx_abacus_build.restype = C.c_int
     L.pgx_abacus_build.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]
+    L.pgx_abacus_build_u32.restype = C.c_int
+    L.pgx_abacus_build_u32.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]
+    L.pgx_host_alloc.restype = C.c_int
+    L.pgx_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.pgx_host_free.restype = None
+    L.pgx_host_free.argtypes = [vp]
     L.pgx_abacus_clear.restype = C.c_int
     L.pgx_abacus_clear.argtypes = [vp]
     L.pgx_abacus_copy_rows.restype = C.c_int
@@ -126,6 +132,10 @@ def lib() -> C.CDLL:
     L.pgx_similarity_sharded.argtypes = [vp, vp, C.c_int, vp, vp]
     L.pgx_similarity_shard_bounds.restype = C.c_int
     L.pgx_similarity_shard_bounds.argtypes = [C.c_uint32, C.c_uint32, u32p]
+    L.pgx_abacus_set_timing.restype = C.c_int
+    L.pgx_abacus_set_timing.argtypes = [vp, C.c_int]
+    L.pgx_kernel_time_ms.restype = C.c_int
+    L.pgx_kernel_time_ms.argtypes = [vp, C.POINTER(C.c_float), u32p]
     L.pgx_launch_count.restype = C.c_uint64
     L.pgx_launch_count.argtypes = [vp]
     L.pgx_last_launch_info.restype = C.c_int

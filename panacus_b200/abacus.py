@@ -93,6 +93,35 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class _PinnedBlock:
+    """Owner of one pgx_host_alloc block; the numpy views made from it keep it alive."""
+
+    def __init__(self, nbytes: int):
+        self._L = _native.lib()
+        self.ptr = C.c_void_p()
+        _native.check(self._L.pgx_host_alloc(C.byref(self.ptr), int(nbytes)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._L.pgx_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array in page-locked host memory (pgx_host_alloc): uploads from / downloads into it are single DMA copies."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    block = _PinnedBlock(max(n * dtype.itemsize, 1))
+    buf = (C.c_ubyte * block.nbytes).from_address(block.ptr.value)
+    buf._pinned_block = block  # ctypes array -> numpy base chain keeps the block alive
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+    return arr.reshape(shape)
+
+
 class Comm:
     """One rank's NCCL communicator behind the C ABI (pgx_comm_*): one per GPU, one process (or thread) per GPU."""
 
@@ -221,8 +250,16 @@ class DeviceAbacus:
         _native.check(self._L.pgx_abacus_scatter(self._h, _ptr(items), items.size, int(group_id), _ptr(ex)))
 
     def build(self, items: np.ndarray, id_prefsum: np.ndarray, path_group: np.ndarray, exclude: Optional[np.ndarray] = None):
-        """Whole ItemTable -> bitmap in one call; path_group[p] = group id of path p, or -1 if not counted."""
-        items = np.ascontiguousarray(items, dtype=np.uint64)
+        """Whole ItemTable -> bitmap in one call; path_group[p] = group id of path p, or -1 if not counted.
+        items: u64 (the reference's ItemIdSize) or u32 (half the PCIe bytes); page-locked arrays (pinned_empty) are
+        read by DMA in place."""
+        items = np.asarray(items)
+        fn = self._L.pgx_abacus_build
+        if items.dtype == np.uint32:
+            fn = self._L.pgx_abacus_build_u32
+            items = np.ascontiguousarray(items)
+        else:
+            items = np.ascontiguousarray(items, dtype=np.uint64)
         id_prefsum = np.ascontiguousarray(id_prefsum, dtype=np.uint64)
         path_group = np.ascontiguousarray(path_group, dtype=np.int64)
         if path_group.size + 1 != id_prefsum.size:
@@ -230,8 +267,7 @@ class DeviceAbacus:
         ex = None if exclude is None else np.ascontiguousarray(exclude, dtype=np.uint8)
         if ex is not None and ex.shape != (self.n_items + 1,):
             raise ValueError("exclude must have n_items + 1 entries")
-        _native.check(self._L.pgx_abacus_build(self._h, _ptr(items), items.size, _ptr(id_prefsum), path_group.size,
-                                               _ptr(path_group), _ptr(ex)))
+        _native.check(fn(self._h, _ptr(items), items.size, _ptr(id_prefsum), path_group.size, _ptr(path_group), _ptr(ex)))
 
     def copy_rows_from(self, src: "DeviceAbacus", src_first_item: int):
         """Items src_first_item .. of `src` (possibly on another GPU) become this handle's items 1 .. n_items."""
@@ -307,24 +343,31 @@ class DeviceAbacus:
                                                       int(bool(weighted)), _ptr(curve)))
         return hc, hw, curve
 
-    def permuted_growth(self, orders: np.ndarray, cov_abs, quorum_thr=None, weighted: bool = False) -> np.ndarray:
-        """orders: u32 [P, G], each row a permutation of the groups -> u64 [P, T, G]"""
+    def permuted_growth(self, orders: np.ndarray, cov_abs, quorum_thr=None, weighted: bool = False,
+                        out: Optional[np.ndarray] = None) -> np.ndarray:
+        """orders: u32 [P, G], each row a permutation of the groups -> u64 [P, T, G] (written into `out` when given, e.g. a
+        pinned_empty array: the result is then copied by DMA straight into it)"""
         G = self.n_groups
         orders = np.ascontiguousarray(orders, dtype=np.uint32)
         if orders.ndim != 2 or orders.shape[1] != G:
             raise ValueError("orders must be [P, n_groups]")
         cov, thr = self._cutoffs(cov_abs, quorum_thr, G)
-        curves = np.zeros((orders.shape[0], cov.size, G), dtype=np.uint64)
+        curves = out if out is not None else np.zeros((orders.shape[0], cov.size, G), dtype=np.uint64)
+        if curves.shape != (orders.shape[0], cov.size, G) or curves.dtype != np.uint64 or not curves.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous u64 [P, T, G] array")
         _native.check(self._L.pgx_permuted_growth(self._h, orders.shape[0], _ptr(orders), cov.size, _ptr(cov), _ptr(thr),
                                                   int(bool(weighted)), _ptr(curves)))
         return curves
 
-    def similarity(self, weighted: bool = False, row_begin: int = 0, row_end: Optional[int] = None, upper: bool = False):
+    def similarity(self, weighted: bool = False, row_begin: int = 0, row_end: Optional[int] = None, upper: bool = False,
+                   out_inter: Optional[np.ndarray] = None):
         """-> (inter u64[rows, G], len u64[G]); integer part of Similarity::set_table.  upper: only the columns
         >= row_begin are computed (the others are zero): the matrix is symmetric (pgx_similarity_upper)."""
         G = self.n_groups
         row_end = G if row_end is None else int(row_end)
-        inter = np.zeros((max(row_end - row_begin, 0), G), dtype=np.uint64)
+        inter = out_inter if out_inter is not None else np.zeros((max(row_end - row_begin, 0), G), dtype=np.uint64)
+        if inter.shape != (max(row_end - row_begin, 0), G) or inter.dtype != np.uint64 or not inter.flags.c_contiguous:
+            raise ValueError("out_inter must be a C-contiguous u64 [rows, G] array")
         ln = np.zeros(G, dtype=np.uint64)
         fn = self._L.pgx_similarity_upper if upper else self._L.pgx_similarity
         _native.check(fn(self._h, int(bool(weighted)), int(row_begin), row_end, _ptr(inter), _ptr(ln)))
@@ -404,6 +447,16 @@ class DeviceAbacus:
 
     def exchange_disconnect(self):
         _native.check(self._L.pgx_exchange_disconnect(self._h))
+
+    def set_timing(self, enable: bool = True):
+        """Bracket the hot-path kernels of every call with CUDA events on the handle's stream (for measurements)."""
+        _native.check(self._L.pgx_abacus_set_timing(self._h, int(bool(enable))))
+
+    def kernel_time_ms(self):
+        """-> (summed device time in ms, number of kernel sections) recorded since the last query."""
+        ms, n = C.c_float(0), C.c_uint32(0)
+        _native.check(self._L.pgx_kernel_time_ms(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     @property
     def launch_count(self) -> int:

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pgx_handle.h"
@@ -24,6 +25,24 @@ int fail(int code, const std::string &msg) {
 using namespace pgx;
 
 namespace pgx {
+
+KernelTimer::KernelTimer(pgx_abacus *h) : a(h) {
+    if (!a->timing) return;
+    if (a->ev_used == a->ev_pool.size()) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        a->ev_pool.emplace_back(e0, e1);
+    }
+    auto &pr = a->ev_pool[a->ev_used++];
+    cudaEventRecord(pr.first, a->stream);
+    stop = pr.second;
+}
+KernelTimer::~KernelTimer() {
+    if (stop) cudaEventRecord(stop, a->stream);
+}
 
 int ensure_pinned(pgx_abacus *a, size_t words) {
     if (a->pinned_words >= words) return PGX_OK;
@@ -159,7 +178,11 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
         p.thr = a->d_thr;
     }
     if (a->x.world > 1u) p.x.epoch = ++a->epoch;  // collective sequence number (never 0)
-    const int rc = launch_scan(p, quorum, grid, a->stream);
+    int rc;
+    {
+        KernelTimer kt(a);
+        rc = launch_scan(p, quorum, grid, a->stream);
+    }
     if (rc) return rc;
     a->launches++;
     char buf[256];
@@ -419,6 +442,7 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
     base.out_order_stride = out_order_stride;
     base.col_fastest = gm_grid_col_fastest() ? 1u : 0u;
     auto run = [&](GmGrowthParams &p) -> int {
+        KernelTimer kt(a);
         const uint32_t kBatch = 4096;  // orders per launch
         for (uint32_t o0 = 0; o0 < n_orders; o0 += kBatch) {
             p.n_orders = std::min<uint32_t>(kBatch, n_orders - o0);
@@ -548,7 +572,11 @@ int sim_rows_device(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t ro
     p.upper_only = upper_only ? 1u : 0u;
     const char *env = getenv("PGX_SIM");  // "plain": one POPC per item word and pair; default: carry-save pairs of words
     p.csa = (!use_planes && !(env && !strcmp(env, "plain"))) ? 1u : 0u;
-    if ((rc = launch_gm_similarity(p, a->sm_count, a->stream))) return rc;
+    {
+        KernelTimer kt(a);
+        rc = launch_gm_similarity(p, a->sm_count, a->stream);
+    }
+    if (rc) return rc;
     a->launches++;
     a->last_launch = use_planes ? "k_gm_similarity<weighted>" : p.csa ? "k_gm_similarity<csa>" : "k_gm_similarity<plain>";
     return PGX_OK;
@@ -666,6 +694,20 @@ void pgx_abacus_destroy(pgx_abacus *a) {
     cudaFree(a->d_identity);
     cudaFree(a->d_scratch);
     if (a->h_pinned) cudaFreeHost(a->h_pinned);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(a->d_stage[b]);
+        if (a->h_stage[b]) cudaFreeHost(a->h_stage[b]);
+        if (a->ev_ready[b]) cudaEventDestroy(a->ev_ready[b]);
+        if (a->ev_free[b]) cudaEventDestroy(a->ev_free[b]);
+    }
+    cudaFree(a->d_prefsum);
+    cudaFree(a->d_path_group);
+    cudaFree(a->d_exclude);
+    for (auto &pr : a->ev_pool) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    if (a->copy_stream) cudaStreamDestroy(a->copy_stream);
     if (a->own_stream) cudaStreamDestroy(a->own_stream);
     cudaGetLastError();
     delete a;
@@ -823,8 +865,68 @@ int pgx_abacus_scatter(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, u
     return PGX_OK;
 }
 
-int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
-                     uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude) {
+namespace {
+
+bool is_pinned_host(const void *p) {
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, p) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    return pinned;
+}
+
+// dst[i] = (u32)src[i] on up to 8 host threads (memory bound: 8 B read + 4 B written per step)
+void narrow_ids(uint32_t *dst, const uint64_t *src, size_t n) {
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min(8u, nt));
+    if (n < (1u << 16)) nt = 1;
+    auto work = [=](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) dst[i] = (uint32_t)src[i];
+    };
+    if (nt == 1) return work(0, n);
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+        if (lo < hi) th.emplace_back(work, lo, hi);
+    }
+    for (auto &x : th) x.join();
+}
+
+int ensure_build_pipeline(pgx_abacus *a, size_t stage_bytes, bool need_host_stage) {
+    if (!a->copy_stream) {
+        PGX_CUDA(cudaStreamCreateWithFlags(&a->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            PGX_CUDA(cudaEventCreateWithFlags(&a->ev_ready[b], cudaEventDisableTiming));
+            PGX_CUDA(cudaEventCreateWithFlags(&a->ev_free[b], cudaEventDisableTiming));
+        }
+    }
+    if (a->d_stage_bytes < stage_bytes) {
+        for (int b = 0; b < 2; ++b) {
+            cudaFree(a->d_stage[b]);
+            a->d_stage[b] = nullptr;
+        }
+        a->d_stage_bytes = 0;
+        for (int b = 0; b < 2; ++b) PGX_CUDA(cudaMalloc(&a->d_stage[b], stage_bytes));
+        a->d_stage_bytes = stage_bytes;
+    }
+    if (need_host_stage && a->h_stage_bytes < stage_bytes) {
+        for (int b = 0; b < 2; ++b) {
+            if (a->h_stage[b]) cudaFreeHost(a->h_stage[b]);
+            a->h_stage[b] = nullptr;
+        }
+        a->h_stage_bytes = 0;
+        for (int b = 0; b < 2; ++b) PGX_CUDA(cudaMallocHost(&a->h_stage[b], stage_bytes));
+        a->h_stage_bytes = stage_bytes;
+    }
+    return PGX_OK;
+}
+
+// ItemTable -> bitmap.  The table is streamed in chunks through two device staging buffers: the copy stream uploads chunk
+// k + 1 while k_build scatters chunk k.  A page-locked caller buffer is read by DMA where it lies (u32 ids: 4 bytes per
+// step over PCIe, u64: 8); a pageable one goes through two pinned host buffers, and its u64 ids (always < 2^32: n_items is)
+// are narrowed to u32 on the way by host threads, which halves the PCIe bytes.
+int build_pipeline(pgx_abacus *a, const void *items, int id_bytes, uint64_t n_steps, const uint64_t *id_prefsum, uint64_t n_paths,
+                   const int64_t *path_group, const uint8_t *exclude) {
     int rc = check_handle(a);
     if (rc) return rc;
     if (!id_prefsum || !path_group || (n_steps && !items)) return fail(PGX_ERR_INVALID, "null table pointer");
@@ -833,37 +935,44 @@ int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, con
     for (uint64_t p = 0; p < n_paths; ++p)
         if (id_prefsum[p] > id_prefsum[p + 1]) return fail(PGX_ERR_INVALID, "id_prefsum is not monotone");
     DeviceGuard guard(a->device);
-    // device staging, freed on every exit path
-    struct Staging {
-        uint64_t *items = nullptr, *prefsum = nullptr;
-        int64_t *group = nullptr;
-        uint8_t *ex = nullptr;
-        ~Staging() {
-            cudaFree(items);
-            cudaFree(prefsum);
-            cudaFree(group);
-            cudaFree(ex);
-        }
-    } st;
-    const uint64_t kChunk = 1ull << 25;  // 32 Mi steps = 256 MB per staging copy
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.prefsum), (n_paths + 1) * 8u));
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.group), n_paths * 8u));
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.items), std::max<uint64_t>(std::min(kChunk, n_steps), 1) * 8u));
-    PGX_CUDA(cudaMemcpyAsync(st.prefsum, id_prefsum, (n_paths + 1) * 8u, cudaMemcpyHostToDevice, a->stream));
-    PGX_CUDA(cudaMemcpyAsync(st.group, path_group, n_paths * 8u, cudaMemcpyHostToDevice, a->stream));
+    const bool pinned = n_steps == 0 || is_pinned_host(items);
+    const int wire_bytes = pinned ? id_bytes : 4;  // pageable tables are narrowed while they are staged
+    const uint64_t kChunk = 1ull << 24;            // 16 Mi steps per chunk: 64 MB of u32 ids, ~1.2 ms of PCIe time
+    const uint64_t chunk = std::max<uint64_t>(std::min(kChunk, n_steps), 1);
+    if ((rc = ensure_build_pipeline(a, chunk * (size_t)wire_bytes, !pinned))) return rc;
+    if ((rc = ensure_dev(&a->d_prefsum, &a->prefsum_cap, n_paths + 1))) return rc;
+    if ((rc = ensure_dev(&a->d_path_group, &a->path_group_cap, n_paths))) return rc;
+    PGX_CUDA(cudaMemcpyAsync(a->d_prefsum, id_prefsum, (n_paths + 1) * 8u, cudaMemcpyHostToDevice, a->stream));
+    PGX_CUDA(cudaMemcpyAsync(a->d_path_group, path_group, n_paths * 8u, cudaMemcpyHostToDevice, a->stream));
+    const uint8_t *d_ex = nullptr;
     if (exclude) {
-        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&st.ex), a->n_rows));
-        PGX_CUDA(cudaMemcpyAsync(st.ex, exclude, a->n_rows, cudaMemcpyHostToDevice, a->stream));
+        if ((rc = ensure_dev(&a->d_exclude, &a->exclude_cap, a->n_rows))) return rc;
+        PGX_CUDA(cudaMemcpyAsync(a->d_exclude, exclude, a->n_rows, cudaMemcpyHostToDevice, a->stream));
+        d_ex = a->d_exclude;
     }
     invalidate_derived(a);
-    for (uint64_t s0 = 0; s0 < n_steps; s0 += kChunk) {
-        const uint64_t n = std::min<uint64_t>(kChunk, n_steps - s0);
-        PGX_CUDA(cudaMemcpyAsync(st.items, items + s0, n * 8u, cudaMemcpyHostToDevice, a->stream));
-        if ((rc = launch_build(a->d_bitmap, a->Wp, a->n_rows, a->G, st.items, s0, n, st.prefsum, n_paths, st.group, st.ex,
-                               a->d_err, a->stream)))
+    uint64_t k = 0;
+    for (uint64_t s0 = 0; s0 < n_steps; s0 += chunk, ++k) {
+        const uint64_t n = std::min<uint64_t>(chunk, n_steps - s0);
+        const int b = (int)(k & 1u);
+        const void *src = static_cast<const unsigned char *>(items) + s0 * (size_t)id_bytes;
+        if (!pinned) {
+            PGX_CUDA(cudaEventSynchronize(a->ev_ready[b]));  // the upload that last read h_stage[b] is done
+            if (id_bytes == 8)
+                narrow_ids(static_cast<uint32_t *>(a->h_stage[b]), static_cast<const uint64_t *>(src), n);
+            else
+                std::memcpy(a->h_stage[b], src, n * 4u);
+            src = a->h_stage[b];
+        }
+        PGX_CUDA(cudaStreamWaitEvent(a->copy_stream, a->ev_free[b], 0));  // k_build is done with d_stage[b]
+        PGX_CUDA(cudaMemcpyAsync(a->d_stage[b], src, n * (size_t)wire_bytes, cudaMemcpyHostToDevice, a->copy_stream));
+        PGX_CUDA(cudaEventRecord(a->ev_ready[b], a->copy_stream));
+        PGX_CUDA(cudaStreamWaitEvent(a->stream, a->ev_ready[b], 0));
+        if ((rc = launch_build(a->d_bitmap, a->Wp, a->n_rows, a->G, a->d_stage[b], wire_bytes, s0, n, a->d_prefsum, n_paths,
+                               a->d_path_group, d_ex, a->d_err, a->stream)))
             return rc;
+        PGX_CUDA(cudaEventRecord(a->ev_free[b], a->stream));
         a->launches++;
-        PGX_CUDA(cudaStreamSynchronize(a->stream));  // the staging buffer is reused by the next chunk
     }
     unsigned int err = 0;
     PGX_CUDA(cudaMemcpyAsync(&err, a->d_err, 4, cudaMemcpyDeviceToHost, a->stream));
@@ -872,8 +981,39 @@ int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, con
         PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
         return fail(PGX_ERR_INVALID, (err & 1u) ? "item id out of range 1..=n_items in the ItemTable" : "path_group entry >= n_groups");
     }
-    a->last_launch = "k_build";
+    char buf[160];
+    snprintf(buf, sizeof buf, "k_build<u%d> chunks=%llu source=%s", wire_bytes * 8, (unsigned long long)k,
+             pinned ? "pinned (direct DMA)" : "pageable (staged, narrowed to u32)");
+    a->last_launch = buf;
     return PGX_OK;
+}
+
+}  // namespace
+
+int pgx_abacus_build(pgx_abacus *a, const uint64_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
+                     uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude) {
+    return build_pipeline(a, items, 8, n_steps, id_prefsum, n_paths, path_group, exclude);
+}
+
+int pgx_abacus_build_u32(pgx_abacus *a, const uint32_t *items, uint64_t n_steps, const uint64_t *id_prefsum,
+                         uint64_t n_paths, const int64_t *path_group, const uint8_t *exclude) {
+    return build_pipeline(a, items, 4, n_steps, id_prefsum, n_paths, path_group, exclude);
+}
+
+int pgx_host_alloc(void **out, size_t bytes) {
+    if (!out) return fail(PGX_ERR_INVALID, "null pointer");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PGX_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    }
+    return PGX_OK;
+}
+
+void pgx_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+    cudaGetLastError();
 }
 
 int pgx_abacus_csr_rows(pgx_abacus *a, uint64_t *r, uint64_t *nnz) {
@@ -1165,6 +1305,29 @@ int pgx_exchange_status(pgx_abacus *a) {
     DeviceGuard guard(a->device);
     PGX_CUDA(cudaStreamSynchronize(a->stream));
     return check_exchange(a);
+}
+
+int pgx_abacus_set_timing(pgx_abacus *a, int enable) {
+    if (!a) return fail(PGX_ERR_INVALID, "null handle");
+    a->timing = enable != 0;
+    a->ev_used = 0;
+    return PGX_OK;
+}
+
+int pgx_kernel_time_ms(pgx_abacus *a, float *total_ms, uint32_t *n_sections) {
+    if (!a || !total_ms) return fail(PGX_ERR_INVALID, "bad arguments");
+    DeviceGuard guard(a->device);
+    float sum = 0.f;
+    for (size_t i = 0; i < a->ev_used; ++i) {
+        float ms = 0.f;
+        PGX_CUDA(cudaEventSynchronize(a->ev_pool[i].second));
+        PGX_CUDA(cudaEventElapsedTime(&ms, a->ev_pool[i].first, a->ev_pool[i].second));
+        sum += ms;
+    }
+    *total_ms = sum;
+    if (n_sections) *n_sections = (uint32_t)a->ev_used;
+    a->ev_used = 0;
+    return PGX_OK;
 }
 
 uint64_t pgx_launch_count(const pgx_abacus *a) { return a ? a->launches : 0; }

@@ -590,36 +590,70 @@ __global__ void __launch_bounds__(256) k_scatter(uint64_t *bitmap, uint32_t Wp, 
     }
 }
 
-// whole-ItemTable build: items[] holds steps [step0, step0 + n_steps) of the table
+// whole-ItemTable build: items[] holds steps [step0, step0 + n_steps) of the table (ids as u32 or as the reference's
+// u64 ItemIdSize).  A thread's steps ascend, so the path that owns a step is found by one binary search for the
+// thread's first step and a forward walk of the cursor afterwards (paths are long runs of steps); the ids of four
+// iterations are loaded before the first is processed so that the scattered atomics overlap the streaming loads.
+__device__ __forceinline__ uint64_t owner_path(const uint64_t *__restrict__ prefsum, uint64_t n_paths, uint64_t s) {
+    uint64_t lo = 0, hi = n_paths;  // largest p with prefsum[p] <= s (empty paths share a boundary; the search lands on the owner)
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(prefsum + mid) <= s) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <typename IdT>
 __global__ void __launch_bounds__(256) k_build(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, uint32_t G,
-                                               const uint64_t *__restrict__ items, uint64_t step0, uint64_t n_steps,
+                                               const IdT *__restrict__ items, uint64_t step0, uint64_t n_steps,
                                                const uint64_t *__restrict__ prefsum, uint64_t n_paths,
                                                const int64_t *__restrict__ path_group,
                                                const uint8_t *__restrict__ exclude, unsigned int *err) {
+    constexpr int kUnroll = 4;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_steps; k += stride) {
-        const uint64_t s = step0 + k;
-        // largest p with prefsum[p] <= s (empty paths share a boundary; the search lands on the owner)
-        uint64_t lo = 0, hi = n_paths;
-        while (hi - lo > 1) {
-            const uint64_t mid = (lo + hi) >> 1;
-            if (__ldg(prefsum + mid) <= s) lo = mid; else hi = mid;
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_steps) return;
+    uint64_t p = owner_path(prefsum, n_paths, step0 + k);
+    uint64_t p_end = __ldg(prefsum + p + 1);
+    long long grp = __ldg(path_group + p);
+    for (; k < n_steps; k += kUnroll * stride) {
+        uint64_t id[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint64_t ku = k + (uint64_t)u * stride;
+            id[u] = ku < n_steps ? (uint64_t)__ldg(items + ku) : 0ull;
         }
-        const long long grp = __ldg(path_group + lo);
-        if (grp < 0) continue;
-        if ((unsigned long long)grp >= G) {
-            atomicOr(err, 4u);
-            continue;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint64_t ku = k + (uint64_t)u * stride;
+            if (ku >= n_steps) break;
+            const uint64_t s = step0 + ku;
+            if (s >= p_end) {  // next path(s): walk a few boundaries, search when the stride skipped many short paths
+                int tries = 0;
+                do {
+                    ++p;
+                    p_end = __ldg(prefsum + p + 1);
+                } while (s >= p_end && ++tries < 8);
+                if (s >= p_end) {
+                    p = owner_path(prefsum, n_paths, s);
+                    p_end = __ldg(prefsum + p + 1);
+                }
+                grp = __ldg(path_group + p);
+            }
+            if (grp < 0) continue;
+            if ((unsigned long long)grp >= G) {
+                atomicOr(err, 4u);
+                continue;
+            }
+            if (id[u] == 0 || id[u] >= n_rows) {
+                atomicOr(err, 1u);
+                continue;
+            }
+            if (exclude && __ldg(exclude + id[u])) continue;
+            unsigned long long *word = reinterpret_cast<unsigned long long *>(bitmap + id[u] * Wp + ((uint32_t)grp >> 6));
+            const unsigned long long bit = 1ull << ((uint32_t)grp & 63u);
+            if (!(*word & bit)) atomicOr(word, bit);  // repeated visits of a group count once (abacus.rs:736-741)
         }
-        const uint64_t id = __ldg(items + k);
-        if (id == 0 || id >= n_rows) {
-            atomicOr(err, 1u);
-            continue;
-        }
-        if (exclude && __ldg(exclude + id)) continue;
-        unsigned long long *word = reinterpret_cast<unsigned long long *>(bitmap + id * Wp + ((uint32_t)grp >> 6));
-        const unsigned long long bit = 1ull << ((uint32_t)grp & 63u);
-        if (!(*word & bit)) atomicOr(word, bit);
     }
 }
 
@@ -771,14 +805,18 @@ int sort_items_by_weight(const uint32_t *weight, uint64_t n_rows, uint32_t *perm
     return PGX_OK;
 }
 
-int launch_build(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, uint32_t G, const uint64_t *d_items, uint64_t step0,
+int launch_build(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, uint32_t G, const void *d_items, int id_bytes, uint64_t step0,
                  uint64_t n_steps, const uint64_t *d_prefsum, uint64_t n_paths, const int64_t *d_path_group,
                  const uint8_t *d_exclude, unsigned int *d_err, cudaStream_t stream) {
     if (n_steps == 0) return PGX_OK;
     uint64_t blocks = (n_steps + 255u) / 256u;
     if (blocks > 148u * 16u) blocks = 148u * 16u;
-    k_build<<<(unsigned)blocks, 256, 0, stream>>>(bitmap, Wp, n_rows, G, d_items, step0, n_steps, d_prefsum, n_paths,
-                                                  d_path_group, d_exclude, d_err);
+    if (id_bytes == 4)
+        k_build<uint32_t><<<(unsigned)blocks, 256, 0, stream>>>(bitmap, Wp, n_rows, G, static_cast<const uint32_t *>(d_items), step0,
+                                                                n_steps, d_prefsum, n_paths, d_path_group, d_exclude, d_err);
+    else
+        k_build<uint64_t><<<(unsigned)blocks, 256, 0, stream>>>(bitmap, Wp, n_rows, G, static_cast<const uint64_t *>(d_items), step0,
+                                                                n_steps, d_prefsum, n_paths, d_path_group, d_exclude, d_err);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "pgx_common.cuh"
@@ -58,11 +59,31 @@ struct pgx_abacus {
     uint64_t *h_pinned = nullptr;
     size_t pinned_words = 0;
 
+    // ItemTable -> bitmap build pipeline: two device staging buffers filled by a copy stream while k_build consumes
+    // the other one; two pinned host buffers when the caller's table is pageable (narrowed to u32 on the way)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {}, ev_free[2] = {};
+    void *d_stage[2] = {};
+    size_t d_stage_bytes = 0;
+    void *h_stage[2] = {};
+    size_t h_stage_bytes = 0;
+    uint64_t *d_prefsum = nullptr;
+    size_t prefsum_cap = 0;
+    int64_t *d_path_group = nullptr;
+    size_t path_group_cap = 0;
+    uint8_t *d_exclude = nullptr;
+    size_t exclude_cap = 0;
+
     // fused NVLink exchange (item-range sharding)
     unsigned char *d_xchg = nullptr;  // [2 parities][kMaxRanks][acc_words][2] u64 packets {epoch:32 | half:32}
     void *peer_base[pgx::kMaxRanks] = {};
     pgx::Exchange x = {};
     uint32_t epoch = 0;
+
+    // optional kernel timing (pgx_abacus_set_timing): CUDA events around the hot-path kernels of a call, on the handle's stream
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;  // created on demand, reused
+    size_t ev_used = 0;
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint64_t launches = 0;
@@ -95,6 +116,13 @@ int ensure_dev(T **ptr, size_t *cap, size_t count) {
     return PGX_OK;
 }
 
+// RAII bracket of CUDA events around the hot kernels of a call (no-op unless timing is enabled on the handle)
+struct KernelTimer {
+    pgx_abacus *a;
+    cudaEvent_t stop = nullptr;
+    explicit KernelTimer(pgx_abacus *h);
+    ~KernelTimer();
+};
 int ensure_pinned(pgx_abacus *a, size_t words);
 void invalidate_derived(pgx_abacus *a);
 int check_handle(const pgx_abacus *a);

@@ -170,7 +170,8 @@ int launch_scatter(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, const uint64_
                    uint32_t group_id, const uint8_t *d_exclude, unsigned int *d_err, cudaStream_t stream);
 
 // whole-ItemTable build: step s belongs to path p with prefsum[p] <= s < prefsum[p+1]
-int launch_build(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, uint32_t G, const uint64_t *d_items, uint64_t step0,
+// (d_items: ids as u32 (id_bytes = 4) or u64 (8))
+int launch_build(uint64_t *bitmap, uint32_t Wp, uint64_t n_rows, uint32_t G, const void *d_items, int id_bytes, uint64_t step0,
                  uint64_t n_steps, const uint64_t *d_prefsum, uint64_t n_paths, const int64_t *d_path_group,
                  const uint8_t *d_exclude, unsigned int *d_err, cudaStream_t stream);
 

@@ -369,6 +369,129 @@ def test_whole_table_build_matches_reference_incidence():
             a.build(np.array([1, 2], dtype=np.uint64), np.array([0, 1], dtype=np.uint64), np.array([0], dtype=np.int64))
 
 
+def test_build_u32_pinned_and_chunked_pipeline():
+    """pgx_abacus_build / pgx_abacus_build_u32 from pageable and page-locked tables, over more than one 16 Mi-step chunk
+    (double-buffered upload overlapping k_build): all four give the bitmap the reference's per-path loops define."""
+    rng = np.random.default_rng(11)
+    N, P, G = 300_000, 70, 70
+    lens = rng.integers(100_000, 400_000, P)
+    lens[[5, 6, 40]] = 0
+    lens[9] = 17_000_000  # one path longer than a chunk: its steps straddle the staging buffers
+    items = rng.integers(1, N + 1, int(lens.sum())).astype(np.uint64)
+    prefsum = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    path_group = rng.permutation(P).astype(np.int64) % G
+    path_group[3] = -1
+    exclude = (rng.random(N + 1) < 0.05).astype(np.uint8)
+    want = np.zeros((N + 1, G), dtype=np.uint8)
+    for p in range(P):
+        if path_group[p] >= 0:
+            ids = items[int(prefsum[p]):int(prefsum[p + 1])].astype(np.int64)
+            want[ids[exclude[ids] == 0], path_group[p]] = 1
+    want = pb.pack_bits(want)
+    items32 = items.astype(np.uint32)
+    pin64 = pb.pinned_empty(items.size, np.uint64)
+    pin64[:] = items
+    pin32 = pb.pinned_empty(items.size, np.uint32)
+    pin32[:] = items32
+    with pb.DeviceAbacus(N, G) as a:
+        for src in (items, items32, pin64, pin32):
+            a.clear()
+            a.build(src, prefsum, path_group, exclude)
+            assert np.array_equal(a.download(), want), (src.dtype, a.last_launch_info())
+        assert "pinned" in a.last_launch_info() and "u32" in a.last_launch_info()
+        a.build(items, prefsum, path_group, exclude)  # ORs into the existing bits: idempotent
+        assert np.array_equal(a.download(), want)
+        bad = items32.copy()
+        bad[-1] = N + 1
+        with pytest.raises(pb.PgxError):
+            a.build(bad, prefsum, path_group)
+
+
+def test_copy_rows_and_results_into_pinned_memory():
+    N, G = 50_000, 130
+    bits, bitmap, weight = synth.numpy_table(N, G, seed=21)
+    cov, thr = cutoffs(G, [(1, 0.0), (2, 0.5)])
+    with pb.DeviceAbacus(N, G) as full:
+        full.upload(bitmap, weight)
+        lo, n = 12_345, 20_000
+        with pb.DeviceAbacus(n, G) as part:
+            part.copy_rows_from(full, lo)
+            got = part.download()
+            assert np.array_equal(got[1:], bitmap[lo:lo + n, :got.shape[1]]) and not got[0].any()
+            _, hw, _ = part.hist(count=False, weight=True)
+            assert int(hw.sum()) == int(weight[lo:lo + n].sum())
+            with pytest.raises(pb.PgxError):
+                part.copy_rows_from(full, N - n + 2)
+        orders = synth.random_orders(3, G, seed=4)
+        want = full.permuted_growth(orders, cov, thr)
+        out = pb.pinned_empty(want.shape, np.uint64)
+        assert full.permuted_growth(orders, cov, thr, out=out) is out and np.array_equal(out, want)
+        inter, ln = full.similarity()
+        outi = pb.pinned_empty((G, G), np.uint64)
+        i2, l2 = full.similarity(out_inter=outi)
+        assert i2 is outi and np.array_equal(outi, inter) and np.array_equal(l2, ln)
+        # kernel timing: events around the hot kernels of a call
+        full.set_timing(True)
+        full.kernel_time_ms()
+        full.similarity()
+        ms, sections = full.kernel_time_ms()
+        assert sections == 1 and ms > 0
+        full.hist_ordered_growth(cov, None)
+        ms, sections = full.kernel_time_ms()
+        assert sections >= 1 and ms > 0
+        full.set_timing(False)
+        full.hist()
+        assert full.kernel_time_ms() == (0.0, 0)
+
+
+def test_config2_full_against_oracle():
+    """BASELINE.json configs[1] in full: 1M items x 256 groups, count = node, hist + ordered growth for the three
+    threshold pairs, every value against the C oracle (ItemTable -> coverage -> CSR -> calc_growth)."""
+    import torch
+    N, G = 1_000_000, 256
+    bitmap, weight = synth.torch_table(N, G, seed=synth.SEED_BASE + 2)
+    host = bitmap.cpu().numpy().view(np.uint64)
+    wh = weight.cpu().numpy().view(np.uint32)
+    pairs = [(1, 0.0), (2, 0.5), (4, 0.9)]
+    exp = oracle_all(host, G, wh, pairs)
+    cov, thr = cutoffs(G, pairs)
+    with pb.DeviceAbacus(N, G) as a:
+        a.adopt_device(bitmap.data_ptr(), weight.data_ptr(), keepalive=(bitmap, weight))
+        hc, hw, cv = a.hist_ordered_growth(cov, thr, weighted=False, hist_count=True, hist_weight=True)
+        assert np.array_equal(hc, exp["hist"]) and np.array_equal(hw, exp["hist_bp"])
+        cvw = a.ordered_growth(cov, thr, weighted=True)
+        for t, (c, q) in enumerate(pairs):
+            assert np.array_equal(cv[t].astype(np.float64), exp[("node", c, q)]), (c, q)
+            assert np.array_equal(cvw[t].astype(np.float64), exp[("bp", c, q)]), (c, q)
+    del torch
+
+
+def test_config3_shape_random_orders_against_oracle():
+    """BASELINE.json configs[2]'s shape (512 groups, pairs (1,0) (2,0.5) (4,0.9)) on a 200k-item slice of the bench table:
+    growth under 3 random group orders against the C oracle run on the abacus rebuilt under each order (what the
+    reference does for `--order`, abacus.rs:324-326)."""
+    N, G = 200_000, 512
+    bitmap, weight = synth.torch_table(N, G, seed=synth.SEED_BASE + 3)
+    host = bitmap.cpu().numpy().view(np.uint64)
+    wh = weight.cpu().numpy().view(np.uint32)
+    pairs = [(1, 0.0), (2, 0.5), (4, 0.9)]
+    cov, thr = cutoffs(G, pairs)
+    orders = synth.random_orders(3, G, seed=synth.SEED_BASE + 3)
+    bits = np.unpackbits(host.view(np.uint8).reshape(N + 1, -1), axis=1, bitorder="little")[:, :G]
+    with pb.DeviceAbacus(N, G) as a:
+        a.adopt_device(bitmap.data_ptr(), weight.data_ptr(), keepalive=(bitmap, weight))
+        pg = a.permuted_growth(orders, cov, thr, weighted=False)
+        pgw = a.permuted_growth(orders[:1], cov, thr, weighted=True)
+    for p in range(3):
+        items, prefsum, op, og = po.bitmap_to_item_table(pb.pack_bits(bits[:, orders[p]]), G)
+        r, c, _ = po.csr_build(N, items, prefsum, op, og)
+        for t, (cv, q) in enumerate(pairs):
+            assert np.array_equal(pg[p, t].astype(np.float64), po.calc_growth(r, c, G, po.absolute(cv), po.relative(q))), (p, cv, q)
+            if p == 0:
+                want = po.calc_growth(r, c, G, po.absolute(cv), po.relative(q), count_bp=True, node_lens=wh)
+                assert np.array_equal(pgw[0, t].astype(np.float64), want), ("bp", cv, q)
+
+
 def test_csr_build_matches_reference_r_c_v():
     """AbacusByGroup {r, c, v}: device CSR (bitmap popcounts + scan, bit positions, one atomic per step) against the
     reference's two cursor passes (abacus.rs:859-986) restated in oracle/."""
