@@ -467,6 +467,7 @@ unsigned host_threads(bool big_input) {
 }  // namespace
 
 void set_host_threads(int n) { g_host_threads = n > 0 ? n : 0; }
+unsigned host_thread_budget() { return host_threads(true); }
 
 GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bool with_names) {
     GraphStorage g;

@@ -542,6 +542,26 @@ int cmd_debug_table_tsv(const Args &a, std::ostream &os) {
     return 0;
 }
 
+// `panacus debug-growth <hist.tsv> -l .. -q ..`: the closed-form growth values of every hist column as C hex floats
+// (%a: every bit of the f64), one line per threshold pair -- a test hook: the TSV prints floor(), which would hide a
+// last-bit difference between the threaded host code and the oracle's statement-by-statement port.
+int cmd_debug_growth(const Args &a, std::ostream &os) {
+    const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
+    std::vector<std::string> comments;
+    const std::vector<Hist> hists = parse_hists(a.positional.at(0), comments);
+    char buf[64];
+    for (auto &h : hists)
+        for (auto &g : h.calc_all_growths(aux)) {
+            os << to_string(h.count);
+            for (size_t k = 1; k < g.size(); ++k) {
+                snprintf(buf, sizeof buf, "\t%a", g[k]);
+                os << buf;
+            }
+            os << "\n";
+        }
+    return 0;
+}
+
 // CoverageLine (analyses/coverage_line.rs:23-57): the run's histograms without row 0, index starting at 1
 int cmd_coverage_line(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
@@ -817,6 +837,7 @@ int dispatch(int argc, char **argv, std::ostream &os) {
     if (a.sub == "coverage-line") return cmd_coverage_line(a, cmdline, os);
     if (a.sub == "debug-table-tsv") return cmd_debug_table_tsv(a, os);
     if (a.sub == "debug-parse") return cmd_debug_parse(a, os);
+    if (a.sub == "debug-growth") return cmd_debug_growth(a, os);
     if (a.sub == "debug-tables") return cmd_debug_tables(a, os);
     if (a.sub == "report") return cmd_report(a, os);
     usage();

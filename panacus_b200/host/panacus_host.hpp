@@ -71,6 +71,7 @@ struct Step {
 
 // worker threads of the host front end (GFA step parsing); 0 = hardware concurrency.  The CLI's -t / --threads.
 void set_host_threads(int n);
+unsigned host_thread_budget();  // -t N, or one per core
 
 // canonical edge key -> edge id: open addressing with linear probing (one cache line per lookup instead of the node
 // chasing of std::unordered_map; one lookup per path step when edges are counted).  Keys are never 0 (ids are 1-based).
@@ -172,6 +173,7 @@ struct Hist {
     std::vector<uint64_t> coverage;
     std::vector<double> calc_growth(const Threshold &t_coverage, const Threshold &t_quorum) const;  // hist.rs:51-66
     std::vector<std::vector<double>> calc_all_growths(const ThresholdContainer &aux) const;         // hist.rs:69-87
+    unsigned growth_threads_ = 1;  // threads one quorum pair may use (set by calc_all_growths from the -t budget)
 };
 double choose(uint64_t n, uint64_t k);  // hist.rs:21-36
 

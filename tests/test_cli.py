@@ -86,6 +86,34 @@ def test_growth_from_hist_tsv_matches_oracle_table():
     assert body(out) == po.growth_table([("node", [5, 0, 10, 0, 0, 0, 0])], cov, quo, add_hist=True)
 
 
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+def test_closed_form_growth_bits_match_oracle_for_any_thread_count(tmp_path, threads):
+    """The host's closed-form growth (threads over coverage classes, log2 table) against the oracle's
+    statement-by-statement port of hist.rs:51-187: every f64 bit (the TSV only shows floor()), for union, core and
+    quorum pairs, on random hists with empty bins and on the reference's own KAT hists (hist.rs:352-398)."""
+    rng = np.random.default_rng(12)
+    hists = [[0, 5, 3, 2], [0, 5, 3, 2, 3, 5, 0, 4, 2, 1]]
+    for n in (7, 45, 130):
+        h = rng.integers(0, 10**6, n + 1)
+        h[rng.random(n + 1) < 0.2] = 0
+        h[0] = 0
+        hists.append([int(x) for x in h])
+    pairs = [("1", "0"), ("2", "0"), ("1", "1"), ("1", "0.5"), ("2", "0.9"), ("1", "0.1"), ("3", "0.33")]
+    cov_s, quo_s = ",".join(c for c, _ in pairs), ",".join(q for _, q in pairs)
+    cov, quo = po.parse_thresholds(quo_s, cov_s)
+    for k, h in enumerate(hists):
+        f = tmp_path / f"h{k}.tsv"
+        f.write_text("panacus\thist\ncount\tnode\n\t\n\t\n" + "".join(f"{i}\t{v}\n" for i, v in enumerate(h)))
+        out = run_cli("debug-growth", str(f), "-l", cov_s, "-q", quo_s, "-t", threads).stdout.strip().split("\n")
+        assert len(out) == len(pairs)
+        for t, line in enumerate(out):
+            got = [float.fromhex(x) for x in line.split("\t")[1:]]
+            want = po.hist_calc_growth(np.array(h, dtype=np.uint64), cov[t], quo[t])
+            assert len(got) == len(want) - 1 or len(got) == len(want)
+            want = [float(x) for x in (want[1:] if len(want) == len(got) + 1 else want)]
+            assert [x.hex() for x in got] == [x.hex() for x in want], (k, pairs[t], threads)
+
+
 def test_cli_errors():
     r = run_cli("growth", os.path.join(GOLDEN, "t_groups.hist.tsv"), "-q", "1.5", expect_ok=False)
     assert r.returncode != 0 and "within [0,1]" in r.stderr
