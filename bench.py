@@ -503,10 +503,11 @@ def run_ordered(args):
                       "api": "pgx_abacus_upload(packed host bitmap, pinned) + pgx_hist_ordered_growth"}
         del host, host_np
         # (b) ItemTable seam (what the CPU reference arm is timed on, abacus.rs:539-586, 859-1032)
-        steps_total = int((np.arange(G + 1, dtype=np.float64) * hc[: G + 1]).sum()) if world == 1 else None
-        need = (int(N) * G // 2) * 4  # generous estimate of the pinned table (u32 per step, density <= 0.5)
+        hc_local = a.hist()[0] if world == 1 else None
+        steps_total = int((np.arange(G + 1, dtype=np.float64) * hc_local).sum()) if world == 1 else None
+        need = steps_total * 4 if steps_total else (int(N) * G // 2) * 4  # the pinned table: u32 per step
         avail = host_mem_available()
-        if avail and avail < 3 * need * (world if world > 1 else 1):
+        if avail and avail < 1.5 * need * world:  # every rank of this node pins its own table
             e2e = {"skipped": f"host memory: {avail >> 30} GiB available, ItemTable needs ~{need >> 30} GiB pinned per rank"}
         else:
             items, prefsum, path_group = gpu_item_table(c, bitmap, N, G)
