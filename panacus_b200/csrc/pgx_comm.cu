@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -61,6 +62,8 @@ bool sym(void *lib, const char *name, F &fn, std::string &err) {
 const Nccl *nccl() {
     std::call_once(g_nccl_once, [] {
         Nccl &n = g_nccl;
+        // NCCL_DEBUG output goes to stdout by default; results (TSV) own stdout, so send the log to stderr unless the user chose a file
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
         const char *env = getenv("PGX_NCCL_LIB");  // explicit path override
         const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
         for (const char *name : names) {

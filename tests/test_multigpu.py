@@ -90,8 +90,9 @@ def test_one_thread_per_gpu_in_one_process(n_cuda_devices):
 
 
 def _body(text):
+    """from the table's first row on (comment lines carry argv; NCCL may log its version when NCCL_DEBUG is set)"""
     lines = text.splitlines()
-    k = next(i for i, l in enumerate(lines) if not l.startswith("#"))
+    k = next(i for i, l in enumerate(lines) if l.startswith("panacus\t") or l.startswith("group\t"))
     return "\n".join(lines[k:])
 
 
