@@ -185,9 +185,13 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
     }
     if (rc) return rc;
     a->launches++;
-    char buf[256];
-    snprintf(buf, sizeof buf, "k_scan<%s> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u",
-             quorum ? "quorum" : "fast", grid, kScanThreads, p.L.total, p.tile_items, p.stages, p.n_tiles, p.T);
+    char buf[320];
+    if (p.flags & kPrivate)
+        snprintf(buf, sizeof buf, "k_scan_priv<u%u> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u classes=%u bins=%u",
+                 p.L.priv_cw * 8u, grid, kScanThreads, p.L.total, p.tile_items, p.stages, p.n_tiles, p.T, p.n_classes, p.L.priv_bins);
+    else
+        snprintf(buf, sizeof buf, "k_scan<%s%s> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u", quorum ? "quorum" : "fast",
+                 (p.flags & kJoint) ? ",joint" : "", grid, kScanThreads, p.L.total, p.tile_items, p.stages, p.n_tiles, p.T);
     a->last_launch = buf;
     *n_done = n;
     return PGX_OK;
@@ -284,7 +288,23 @@ __global__ void k_max_u32(const uint32_t *w, uint64_t n, unsigned int *out) {
     if ((threadIdx.x & 31u) == 0) atomicMax(out, m);
 }
 
+// largest weight of the table (one reduction kernel when the weights were adopted on the device)
+int ensure_max_weight(pgx_abacus *a) {
+    if (a->max_weight_known || !a->d_weight) return PGX_OK;
+    PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
+    k_max_u32<<<296, 256, 0, a->stream>>>(a->d_weight + 1, a->n_items, a->d_err);
+    PGX_CUDA(cudaGetLastError());
+    unsigned int m = 0;
+    PGX_CUDA(cudaMemcpyAsync(&m, a->d_err, 4, cudaMemcpyDeviceToHost, a->stream));
+    PGX_CUDA(cudaStreamSynchronize(a->stream));
+    PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
+    a->max_weight = m;
+    a->max_weight_known = true;
+    return PGX_OK;
+}
+
 int ensure_planes(pgx_abacus *a) {
+    int rc_mw;
     if (a->planes_valid) return PGX_OK;
     if (!a->d_weight) {
         a->n_planes = 0;
@@ -293,17 +313,7 @@ int ensure_planes(pgx_abacus *a) {
     }
     if (a->n_rows > 0x7FFFFFFFull)  // cub::DeviceRadixSort is called with an int item count
         return fail(PGX_ERR_UNSUPPORTED, "weight-sorted copy (bp-weighted similarity / permuted growth) needs n_items < 2^31 - 1");
-    if (!a->max_weight_known) {
-        PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
-        k_max_u32<<<296, 256, 0, a->stream>>>(a->d_weight + 1, a->n_items, a->d_err);
-        PGX_CUDA(cudaGetLastError());
-        unsigned int m = 0;
-        PGX_CUDA(cudaMemcpyAsync(&m, a->d_err, 4, cudaMemcpyDeviceToHost, a->stream));
-        PGX_CUDA(cudaStreamSynchronize(a->stream));
-        PGX_CUDA(cudaMemsetAsync(a->d_err, 0, 4, a->stream));
-        a->max_weight = m;
-        a->max_weight_known = true;
-    }
+    if ((rc_mw = ensure_max_weight(a))) return rc_mw;
     uint32_t np = 0;
     while (np < 32u && (a->max_weight >> np)) ++np;
     a->gm_stride = gm_stride_words(a->n_rows);

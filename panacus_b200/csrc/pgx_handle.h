@@ -133,6 +133,7 @@ int is_permutation(const uint32_t *order, uint32_t G);
 int ensure_countable(pgx_abacus *a);
 int ensure_gm(pgx_abacus *a);
 int ensure_planes(pgx_abacus *a);
+int ensure_max_weight(pgx_abacus *a);
 // fused node-major pass -> device buffer in the fused layout (see pgx_fused_pass_async)
 int fused_pass(pgx_abacus *a, bool want_cnt, bool want_w, uint32_t T, const uint32_t *cov, const uint32_t *thr, int weighted,
                uint32_t *d_countable, uint64_t *d_out);

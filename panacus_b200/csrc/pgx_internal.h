@@ -22,6 +22,7 @@ enum ScanFlags : uint32_t {
     kHistWeight = 2u,  // accumulate hist_weight
     kWeighted = 4u,    // growth deltas sum weight[i] instead of 1
     kJoint = 8u,       // small G: one joint (coverage, first group) histogram, marginalised in the epilogue
+    kPrivate = 16u,    // lane-private narrow counters (plain LDS / STS; a shared atomic only when one wraps), folded after the last tile
 };
 
 // Byte offsets into the dynamic shared memory of k_scan (identical on host and device).
@@ -37,6 +38,12 @@ struct ScanLayout {
     uint32_t off_joint_cnt;  // u32[(G+1)*G] joint histogram of counts      (kJoint)
     uint32_t off_joint_wlo;  // u32[(G+1)*G] joint histogram of weights, low  (kJoint, weights in use)
     uint32_t off_joint_whi;  //                                       high
+    uint32_t off_cls_lo;     // u32[D*G] per coverage class (kPrivate): items whose coverage reaches exactly d thresholds, by first group
+    uint32_t off_cls_hi;     //          high words (weights)
+    uint32_t off_cbase;      // u32[G+1]: coverage -> first bin of the item's coverage class, ~0 = not counted (kPrivate)
+    uint32_t off_carry;      // u32[priv_bins]: what wrapped out of the narrow lane-private counters
+    uint32_t off_priv;       // lane-private counters: priv_bins rows of 256 counters of priv_cw bytes (kPrivate)
+    uint32_t priv_bins, priv_cw, priv_hist_bins;
     uint32_t off_stage0;     // first pipeline stage (128-byte aligned)
     uint32_t stage_stride;   // bytes per stage
     uint32_t off_stage_w;    // offset of the weight tile inside a stage
@@ -69,6 +76,9 @@ struct ScanParams {
     uint32_t cov[kMaxThresholds];
     uint32_t slot[kMaxThresholds];  // threshold k's deltas go to out[2(G+1) + slot[k]*G ...]
     uint32_t flags;
+    // kPrivate: the D distinct coverage cutoffs (ascending); an item of coverage c is in class #{d : c >= cls_thr[d]};
+    // threshold t's curve sums the classes >= cls_rank[t] (1-based)
+    uint32_t n_classes, cls_thr[kMaxThresholds], cls_rank[kMaxThresholds];
     uint32_t tile_items;     // rows per pipeline stage (multiple of 4)
     uint32_t stages;
     uint32_t n_tiles;

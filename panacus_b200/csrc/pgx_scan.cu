@@ -12,6 +12,7 @@
 //                   them into `out` and re-zeroes accumulators + ticket (self-cleaning, one launch)
 //
 // Integer-only, HBM-bandwidth-bound: algorithmic bytes per item = W*8 (+4 weighted).
+#include <algorithm>
 #include <cstdlib>
 
 #include "pgx_common.cuh"
@@ -152,9 +153,8 @@ struct GlobalRowReader {
 // popcount and "first non-empty chunk" are order independent, so the rotation costs nothing; the
 // first set bit is extracted once, after the loop, from the first non-empty chunk.
 template <int C_T, bool MASK>
-__device__ __forceinline__ void item_fast_smem(const ScanParams &p, const SmemAcc &s, uint64_t item, uint32_t wgt,
-                                               uint32_t row_addr, uint32_t li, uint32_t C_rt, uint32_t rot_shift,
-                                               uint32_t rot_mask) {
+__device__ __forceinline__ void row_cov_first(const ScanParams &p, uint32_t row_addr, uint32_t li, uint32_t C_rt,
+                                              uint32_t rot_shift, uint32_t rot_mask, uint32_t &cov_out, uint32_t &first_out) {
     constexpr bool kXor = C_T > 0 && (C_T & (C_T - 1)) == 0;
     const uint32_t C = C_T > 0 ? (uint32_t)C_T : C_rt;
     const uint32_t r = (li >> rot_shift) & rot_mask;
@@ -187,6 +187,16 @@ __device__ __forceinline__ void item_fast_smem(const ScanParams &p, const SmemAc
         }
         first = firstc * 128u + (x ? first_bit(x) : 64u + first_bit(y));
     }
+    cov_out = cov;
+    first_out = first;
+}
+
+template <int C_T, bool MASK>
+__device__ __forceinline__ void item_fast_smem(const ScanParams &p, const SmemAcc &s, uint64_t item, uint32_t wgt,
+                                               uint32_t row_addr, uint32_t li, uint32_t C_rt, uint32_t rot_shift,
+                                               uint32_t rot_mask) {
+    uint32_t cov, first;
+    row_cov_first<C_T, MASK>(p, row_addr, li, C_rt, rot_shift, rot_mask, cov, first);
     account_fast(p, s, item, cov, first, wgt);
 }
 
@@ -196,127 +206,9 @@ uint32_t env_u32(const char *name) {
     return v ? (uint32_t)strtoul(v, nullptr, 10) : 0u;
 }
 
-template <bool QUORUM, int C_T, bool MASK>
-__global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant__ ScanParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t warp = tid >> 5, lane = tid & 31u;
-    const uint32_t S = p.stages;
-    const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
-    const uint32_t stage0 = smem_u32(smem + p.L.off_stage0);
-    const uint32_t rowbytes = p.Wp * 8u;
-
-    SmemAcc s;
-    s.hist_cnt = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_cnt);
-    s.hist_wlo = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_wlo);
-    s.hist_whi = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_whi);
-    s.delta_lo = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_lo);
-    s.delta_hi = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_hi);
-    uint32_t *s_thr = reinterpret_cast<uint32_t *>(smem + p.L.off_thr);
-    s.thr = s_thr;
-    s.joint_cnt = reinterpret_cast<uint32_t *>(smem + p.L.off_joint_cnt);
-    s.joint_wlo = reinterpret_cast<uint32_t *>(smem + p.L.off_joint_wlo);
-    s.joint_whi = reinterpret_cast<uint32_t *>(smem + p.L.off_joint_whi);
-
-    {
-        uint32_t *acc32 = reinterpret_cast<uint32_t *>(smem + p.L.off_acc);
-        for (uint32_t i = tid; i < p.L.acc_words; i += kScanThreads) acc32[i] = 0u;
-        if (QUORUM)
-            for (uint32_t i = tid; i < p.T * p.G; i += kScanThreads) s_thr[i] = p.thr[i];
-    }
-    if (tid == 0) {
-        for (uint32_t i = 0; i < S; ++i) {
-            mbar_init(full0 + 8u * i, 1u);
-            mbar_init(empty0 + 8u * i, (uint32_t)kConsumerWarps);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    const uint32_t last_tile = p.n_tiles - 1u;
-    // rows of the last tile (may be partial); every other tile is full
-    const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
-
-    if (warp == (uint32_t)kConsumerWarps) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
-            uint32_t st = 0, ph = 0;
-            bool ring_full = false;  // true once every stage has been used at least once
-            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
-                const uint64_t row0 = (uint64_t)tile * p.tile_items;
-                const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
-                const uint32_t trows = rows & ~3u;  // TMA needs 16-byte multiples; <=3 tail rows read directly
-                const uint32_t full = full0 + 8u * st;
-                if (trows) {
-                    const uint32_t bytes_b = trows * rowbytes;
-                    const uint32_t bytes_w = p.weight ? trows * 4u : 0u;
-                    const uint32_t dst = stage0 + st * p.L.stage_stride;
-                    mbar_arrive_expect_tx(full, bytes_b + bytes_w);
-                    tma_bulk_g2s(dst, p.bitmap + row0 * p.Wp, bytes_b, full, pol);
-                    if (bytes_w) tma_bulk_g2s(dst + p.L.off_stage_w, p.weight + row0, bytes_w, full, pol);
-                } else {
-                    mbar_arrive(full);
-                }
-                if (++st == S) {
-                    st = 0;
-                    ph ^= 1u;
-                    ring_full = true;
-                }
-            }
-        }
-    } else {
-        // ===== consumers: one thread per item =====
-        const uint32_t C_rt = p.Wp >> 1;
-        uint32_t a = 0;
-        while (a < 3 && C_rt && !((C_rt >> a) & 1u)) ++a;  // a' = min(ctz(C), 3)
-        const uint32_t rot_shift = 3u - a, rot_mask = (1u << a) - 1u;
-        uint32_t st = 0, ph = 0;
-        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const uint64_t row0 = (uint64_t)tile * p.tile_items;
-            const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
-            const uint32_t trows = rows & ~3u;
-            const uint32_t base = stage0 + st * p.L.stage_stride;
-            const uint32_t wbase = base + p.L.off_stage_w;
-            mbar_wait(full0 + 8u * st, ph);
-            for (uint32_t li = tid; li < rows; li += kConsumerThreads) {
-                const uint64_t item = row0 + li;
-                if (item == 0) {  // the reference's dummy item (abacus.rs:551, 1000-1002)
-                    if (p.countable) p.countable[0] = 0xFFFFFFFFu;
-                    continue;
-                }
-                if (li < trows) {
-                    uint32_t wgt = 1u;
-                    if (p.weight) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wgt) : "r"(wbase + li * 4u));
-                    const uint32_t row_addr = base + li * rowbytes;
-                    if (QUORUM) {
-                        item_quorum_natural(p, s, item, wgt, SmemRowReader{row_addr});
-                    } else if (C_T < 0) {  // 8-byte rows (G <= 64)
-                        const uint64_t x = lds_u64(row_addr) & p.last_mask0;
-                        account_fast(p, s, item, __popcll(x), x ? first_bit(x) : 0xFFFFFFFFu, wgt);
-                    } else {
-                        item_fast_smem<C_T, MASK>(p, s, item, wgt, row_addr, li, C_rt, rot_shift, rot_mask);
-                    }
-                } else {  // <= 3 tail rows of the last tile, straight from global memory
-                    const uint32_t wgt = p.weight ? __ldg(p.weight + item) : 1u;
-                    GlobalRowReader rd{p.bitmap + item * p.Wp};
-                    if (QUORUM)
-                        item_quorum_natural(p, s, item, wgt, rd);
-                    else
-                        item_fast_natural(p, s, item, wgt, rd);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8u * st);
-            if (++st == S) {
-                st = 0;
-                ph ^= 1u;
-            }
-        }
-    }
-    __syncthreads();
-
+// Per-CTA accumulators -> global u64 accumulators -> (last CTA) the caller's result vector, or the multi-GPU exchange.
+// Shared by k_scan and k_scan_priv; expects every thread of the CTA, after a __syncthreads().
+__device__ __forceinline__ void scan_epilogue(const ScanParams &p, const SmemAcc &s, const uint32_t tid) {
     // ===== epilogue: per-CTA accumulators -> global u64 accumulators =====
     const uint32_t G1 = p.G + 1u;
     if (p.flags & kJoint) {  // marginalise the joint histogram into hist[] and the curves' first differences
@@ -473,6 +365,373 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
     }
 }
 
+template <bool QUORUM, int C_T, bool MASK>
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    const uint32_t S = p.stages;
+    const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
+    const uint32_t stage0 = smem_u32(smem + p.L.off_stage0);
+    const uint32_t rowbytes = p.Wp * 8u;
+
+    SmemAcc s;
+    s.hist_cnt = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_cnt);
+    s.hist_wlo = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_wlo);
+    s.hist_whi = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_whi);
+    s.delta_lo = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_lo);
+    s.delta_hi = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_hi);
+    uint32_t *s_thr = reinterpret_cast<uint32_t *>(smem + p.L.off_thr);
+    s.thr = s_thr;
+    s.joint_cnt = reinterpret_cast<uint32_t *>(smem + p.L.off_joint_cnt);
+    s.joint_wlo = reinterpret_cast<uint32_t *>(smem + p.L.off_joint_wlo);
+    s.joint_whi = reinterpret_cast<uint32_t *>(smem + p.L.off_joint_whi);
+
+    {
+        uint32_t *acc32 = reinterpret_cast<uint32_t *>(smem + p.L.off_acc);
+        for (uint32_t i = tid; i < p.L.acc_words; i += kScanThreads) acc32[i] = 0u;
+        if (QUORUM)
+            for (uint32_t i = tid; i < p.T * p.G; i += kScanThreads) s_thr[i] = p.thr[i];
+    }
+    if (tid == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(full0 + 8u * i, 1u);
+            mbar_init(empty0 + 8u * i, (uint32_t)kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint32_t last_tile = p.n_tiles - 1u;
+    // rows of the last tile (may be partial); every other tile is full
+    const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
+
+    if (warp == (uint32_t)kConsumerWarps) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            uint32_t st = 0, ph = 0;
+            bool ring_full = false;  // true once every stage has been used at least once
+            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
+                const uint64_t row0 = (uint64_t)tile * p.tile_items;
+                const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
+                const uint32_t trows = rows & ~3u;  // TMA needs 16-byte multiples; <=3 tail rows read directly
+                const uint32_t full = full0 + 8u * st;
+                if (trows) {
+                    const uint32_t bytes_b = trows * rowbytes;
+                    const uint32_t bytes_w = p.weight ? trows * 4u : 0u;
+                    const uint32_t dst = stage0 + st * p.L.stage_stride;
+                    mbar_arrive_expect_tx(full, bytes_b + bytes_w);
+                    tma_bulk_g2s(dst, p.bitmap + row0 * p.Wp, bytes_b, full, pol);
+                    if (bytes_w) tma_bulk_g2s(dst + p.L.off_stage_w, p.weight + row0, bytes_w, full, pol);
+                } else {
+                    mbar_arrive(full);
+                }
+                if (++st == S) {
+                    st = 0;
+                    ph ^= 1u;
+                    ring_full = true;
+                }
+            }
+        }
+    } else {
+        // ===== consumers: one thread per item =====
+        const uint32_t C_rt = p.Wp >> 1;
+        uint32_t a = 0;
+        while (a < 3 && C_rt && !((C_rt >> a) & 1u)) ++a;  // a' = min(ctz(C), 3)
+        const uint32_t rot_shift = 3u - a, rot_mask = (1u << a) - 1u;
+        uint32_t st = 0, ph = 0;
+        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const uint64_t row0 = (uint64_t)tile * p.tile_items;
+            const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
+            const uint32_t trows = rows & ~3u;
+            const uint32_t base = stage0 + st * p.L.stage_stride;
+            const uint32_t wbase = base + p.L.off_stage_w;
+            mbar_wait(full0 + 8u * st, ph);
+            for (uint32_t li = tid; li < rows; li += kConsumerThreads) {
+                const uint64_t item = row0 + li;
+                if (item == 0) {  // the reference's dummy item (abacus.rs:551, 1000-1002)
+                    if (p.countable) p.countable[0] = 0xFFFFFFFFu;
+                    continue;
+                }
+                if (li < trows) {
+                    uint32_t wgt = 1u;
+                    if (p.weight) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wgt) : "r"(wbase + li * 4u));
+                    const uint32_t row_addr = base + li * rowbytes;
+                    if (QUORUM) {
+                        item_quorum_natural(p, s, item, wgt, SmemRowReader{row_addr});
+                    } else if (C_T < 0) {  // 8-byte rows (G <= 64)
+                        const uint64_t x = lds_u64(row_addr) & p.last_mask0;
+                        account_fast(p, s, item, __popcll(x), x ? first_bit(x) : 0xFFFFFFFFu, wgt);
+                    } else {
+                        item_fast_smem<C_T, MASK>(p, s, item, wgt, row_addr, li, C_rt, rot_shift, rot_mask);
+                    }
+                } else {  // <= 3 tail rows of the last tile, straight from global memory
+                    const uint32_t wgt = p.weight ? __ldg(p.weight + item) : 1u;
+                    GlobalRowReader rd{p.bitmap + item * p.Wp};
+                    if (QUORUM)
+                        item_quorum_natural(p, s, item, wgt, rd);
+                    else
+                        item_fast_natural(p, s, item, wgt, rd);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8u * st);
+            if (++st == S) {
+                st = 0;
+                ph ^= 1u;
+            }
+        }
+    }
+    __syncthreads();
+
+    scan_epilogue(p, s, tid);
+}
+
+// ---- lane-private counters (kPrivate) ---------------------------------------------------------------
+// Shared atomics cost ~2 cycles per lane on this part (and serialise on equal addresses, which a U-shaped coverage
+// histogram produces all the time), plain shared loads / stores 1/32: below ~300 groups the atomics, not HBM, bound
+// k_scan.  Here every consumer thread owns one narrow counter per bin: row `bin` of the private region holds the 256
+// threads' counters (u8 for counts, u16 for bp sums), laid out so that the 32 lanes of a warp always hit 32 different
+// banks whatever bins they address.  An item costs two plain read-modify-writes (its coverage bin; its (coverage class,
+// first group) bin -- one bin for ANY number of q = 0 thresholds: a class is "how many of the distinct coverage cutoffs
+// the item reaches").  A counter that wraps (once per 256 items of a thread and bin; for bp sums whenever 64 Ki bp have
+// piled up, plus the bits of a weight above 2^16) carries into a per-CTA u32 word with a shared atomic -- rare.  After
+// the last tile each bin is folded by one thread (128-bit loads, DP4A byte sums): low parts + (carries << 8 or 16).
+template <int CW>
+__device__ __forceinline__ uint32_t priv_thread_off(uint32_t tid) {
+    const uint32_t w = tid >> 5, l = tid & 31u;
+    constexpr uint32_t kPerWord = 4u / CW;  // threads sharing one 32-bit word: warps w, w + 1, ... of the same 128-byte segment
+    return (w / kPerWord) * 128u + l * 4u + (w % kPerWord) * CW;
+}
+
+template <int CW>
+__device__ __forceinline__ uint32_t priv_ld(uint32_t addr) {
+    uint32_t v;
+    if (CW == 1)
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    else
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int CW>
+__device__ __forceinline__ void priv_st(uint32_t addr, uint32_t v) {  // stores the low CW bytes
+    if (CW == 1)
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+    else
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// fold the lane-private rows (+ carries) into the CTA accumulators: every thread of the CTA, after a __syncthreads()
+template <int CW, bool WEIGHTED>
+__device__ __forceinline__ void priv_fold(const ScanParams &p, const SmemAcc &s, uint32_t *cls_lo, uint32_t *cls_hi,
+                                          const uint32_t *carry, uint32_t priv_base, uint32_t tid) {
+    constexpr uint32_t kRow = 256u * CW, kChunks = kRow / 16u, kBits = 8u * CW;
+    for (uint32_t bin = tid; bin < p.L.priv_bins; bin += kScanThreads) {
+        const uint32_t row = priv_base + bin * kRow;
+        uint32_t sum32 = 0;  // 256 x (2^16 - 1) < 2^24
+#pragma unroll 4
+        for (uint32_t k = 0; k < kChunks; ++k) {
+            const uint32_t a = row + ((k + bin) & (kChunks - 1u)) * 16u;  // rotated: the lanes of a quarter-warp hit different banks
+            uint32_t x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(a));
+            if (CW == 1) {
+                sum32 = __dp4a(x0, 0x01010101u, sum32);
+                sum32 = __dp4a(x1, 0x01010101u, sum32);
+                sum32 = __dp4a(x2, 0x01010101u, sum32);
+                sum32 = __dp4a(x3, 0x01010101u, sum32);
+            } else {
+                sum32 += (x0 & 0xFFFFu) + (x0 >> 16) + (x1 & 0xFFFFu) + (x1 >> 16) + (x2 & 0xFFFFu) + (x2 >> 16) + (x3 & 0xFFFFu) + (x3 >> 16);
+            }
+        }
+        const uint64_t sum = (uint64_t)sum32 + ((uint64_t)carry[bin] << kBits);
+        uint32_t *lo, *hi;
+        uint32_t idx;
+        if (bin < p.L.priv_hist_bins) {
+            lo = WEIGHTED ? s.hist_wlo : s.hist_cnt;
+            hi = s.hist_whi;
+            idx = bin;
+        } else {
+            lo = cls_lo;
+            hi = cls_hi;
+            idx = bin - p.L.priv_hist_bins;
+        }
+        lo[idx] = (uint32_t)sum;
+        if (WEIGHTED) hi[idx] = (uint32_t)(sum >> 32);
+    }
+}
+
+template <int CW, bool WEIGHTED, int C_T>
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    const uint32_t S = p.stages;
+    const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
+    const uint32_t stage0 = smem_u32(smem + p.L.off_stage0);
+    const uint32_t rowbytes = p.Wp * 8u;
+
+    SmemAcc s;
+    s.hist_cnt = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_cnt);
+    s.hist_wlo = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_wlo);
+    s.hist_whi = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_whi);
+    s.delta_lo = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_lo);
+    s.delta_hi = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_hi);
+    s.thr = nullptr;
+    s.joint_cnt = s.joint_wlo = s.joint_whi = nullptr;
+    uint32_t *cls_lo = reinterpret_cast<uint32_t *>(smem + p.L.off_cls_lo);
+    uint32_t *cls_hi = reinterpret_cast<uint32_t *>(smem + p.L.off_cls_hi);
+    uint32_t *carry = reinterpret_cast<uint32_t *>(smem + p.L.off_carry);
+    uint32_t *s_cbase = reinterpret_cast<uint32_t *>(smem + p.L.off_cbase);  // coverage -> first bin of its class (or ~0)
+    const uint32_t priv_base = smem_u32(smem + p.L.off_priv);
+
+    {  // accumulators and the private region (contiguous) start at zero
+        uint4 *z = reinterpret_cast<uint4 *>(smem + p.L.off_acc);
+        const uint32_t n16 = (p.L.off_cbase - p.L.off_acc + 15u) / 16u;
+        for (uint32_t i = tid; i < n16; i += kScanThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t c = tid; c <= p.G; c += kScanThreads) {
+            uint32_t cls = 0;
+            for (uint32_t d = 0; d < p.n_classes; ++d) cls += c >= p.cls_thr[d] ? 1u : 0u;
+            s_cbase[c] = (cls && c) ? p.L.priv_hist_bins + (cls - 1u) * p.G : 0xFFFFFFFFu;
+        }
+    }
+    if (tid == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(full0 + 8u * i, 1u);
+            mbar_init(empty0 + 8u * i, (uint32_t)kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint32_t last_tile = p.n_tiles - 1u;
+    const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
+
+    if (warp == (uint32_t)kConsumerWarps) {
+        // ===== TMA producer (same ring as k_scan) =====
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            uint32_t st = 0, ph = 0;
+            bool ring_full = false;
+            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
+                const uint64_t row0 = (uint64_t)tile * p.tile_items;
+                const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
+                const uint32_t trows = rows & ~3u;
+                const uint32_t full = full0 + 8u * st;
+                if (trows) {
+                    const uint32_t bytes_b = trows * rowbytes;
+                    const uint32_t bytes_w = p.weight ? trows * 4u : 0u;
+                    const uint32_t dst = stage0 + st * p.L.stage_stride;
+                    mbar_arrive_expect_tx(full, bytes_b + bytes_w);
+                    tma_bulk_g2s(dst, p.bitmap + row0 * p.Wp, bytes_b, full, pol);
+                    if (bytes_w) tma_bulk_g2s(dst + p.L.off_stage_w, p.weight + row0, bytes_w, full, pol);
+                } else {
+                    mbar_arrive(full);
+                }
+                if (++st == S) {
+                    st = 0;
+                    ph ^= 1u;
+                    ring_full = true;
+                }
+            }
+        }
+    } else {
+        // ===== consumers: two items per thread and step, lane-private counters =====
+        const uint32_t C_rt = p.Wp >> 1;
+        uint32_t a = 0;
+        while (a < 3 && C_rt && !((C_rt >> a) & 1u)) ++a;
+        const uint32_t rot_shift = 3u - a, rot_mask = (1u << a) - 1u;
+        const uint32_t my = priv_base + priv_thread_off<CW>(tid);
+        uint32_t st = 0, ph = 0;
+        constexpr uint32_t kRow = 256u * CW;
+        const bool has_hist = p.L.priv_hist_bins != 0u, has_cls = p.n_classes != 0u;
+        // (coverage, first group, weight) of one item -> its two lane-private counters
+        auto account = [&](bool valid, uint32_t cov, uint32_t first, uint32_t wgt) {
+            const uint32_t inc = valid ? (WEIGHTED ? wgt : 1u) : 0u;
+            // class bin: s_cbase[cov] = first bin of the item's coverage class, or ~0 when it reaches no cutoff
+            const uint32_t cb = has_cls ? s_cbase[cov] : 0xFFFFFFFFu;
+            const bool counted = cb != 0xFFFFFFFFu;
+            const uint32_t cbin = counted ? cb + first : 0u;
+            const uint32_t ha = my + cov * kRow, ca = my + cbin * kRow;
+            // the two loads are in flight together (disjoint regions); the narrow counters keep the low bits, and whatever
+            // wraps out of them (rarely) is added to the bin's u32 carry word of the CTA -- one branch for both
+            constexpr uint32_t kBits = 8u * CW, kMask = (1u << kBits) - 1u;
+            const uint32_t cinc = counted ? inc : 0u;
+            uint32_t hv = 0, cv = 0;
+            if (has_hist) hv = priv_ld<CW>(ha);
+            if (has_cls) cv = priv_ld<CW>(ca);
+            const uint32_t nh = hv + (WEIGHTED ? (inc & kMask) : inc), nc = cv + (WEIGHTED ? (cinc & kMask) : cinc);
+            if (has_hist) priv_st<CW>(ha, nh);
+            if (has_cls) priv_st<CW>(ca, nc);
+            if (((nh | nc) >> kBits) | (WEIGHTED ? (inc >> kBits) : 0u)) {
+                const uint32_t ch = (nh >> kBits) + (WEIGHTED ? (inc >> kBits) : 0u), cc = (nc >> kBits) + (WEIGHTED ? (cinc >> kBits) : 0u);
+                if (has_hist && ch) atomicAdd(carry + cov, ch);
+                if (has_cls && cc) atomicAdd(carry + cbin, cc);
+            }
+        };
+        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const uint64_t row0 = (uint64_t)tile * p.tile_items;
+            const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
+            const uint32_t trows = rows & ~3u;
+            const uint32_t base = stage0 + st * p.L.stage_stride;
+            const uint32_t wbase = base + p.L.off_stage_w;
+            mbar_wait(full0 + 8u * st, ph);
+#pragma unroll 2
+            for (uint32_t li = tid; li < trows; li += kConsumerThreads) {
+                uint32_t cov, first, wgt = 1u;
+                if (WEIGHTED) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wgt) : "r"(wbase + li * 4u));
+                const uint32_t row_addr = base + li * rowbytes;
+                if (C_T < 0) {  // 8-byte rows (G <= 64): 2 POPC for the coverage, 1 for the first group (trailing zeros)
+                    const uint64_t x = lds_u64(row_addr) & p.last_mask0;
+                    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+                    cov = __popc(lo) + __popc(hi);
+                    const uint32_t sel = lo ? lo : hi;
+                    first = (lo ? 0u : 32u) + __popc((sel - 1u) & ~sel);
+                } else {
+                    row_cov_first<C_T, true>(p, row_addr, li, C_rt, rot_shift, rot_mask, cov, first);
+                }
+                const bool valid = (tile | li) != 0u;  // item 0: the reference's dummy item, never counted
+                if (p.countable) p.countable[row0 + li] = valid ? cov : 0xFFFFFFFFu;
+                account(valid, cov, first, wgt);
+            }
+            if (tid < rows - trows) {  // <= 3 tail rows of the last tile, straight from global memory
+                const uint64_t item = row0 + trows + tid;
+                const uint32_t wgt = WEIGHTED ? __ldg(p.weight + item) : 1u;
+                uint32_t cov = 0, first = 0xFFFFFFFFu;
+                for (uint32_t w = 0; w < p.W; ++w) {
+                    const uint64_t x = __ldg(p.bitmap + item * p.Wp + w) & word_mask(p, w);
+                    cov += __popcll(x);
+                    if (x && first == 0xFFFFFFFFu) first = w * 64u + first_bit(x);
+                }
+                if (p.countable) p.countable[item] = item ? cov : 0xFFFFFFFFu;
+                account(item != 0, cov, first, wgt);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8u * st);
+            if (++st == S) {
+                st = 0;
+                ph ^= 1u;
+            }
+        }
+    }
+    __syncthreads();
+    priv_fold<CW, WEIGHTED>(p, s, cls_lo, cls_hi, carry, priv_base, tid);
+    __syncthreads();
+    // classes -> first differences of every threshold's curve: threshold t counts the classes >= cls_rank[t]
+    for (uint32_t i = tid; i < p.T * p.G; i += kScanThreads) {
+        const uint32_t t = i / p.G, f = i - t * p.G;
+        uint64_t v = 0;
+        for (uint32_t k = p.cls_rank[t] - 1u; k < p.n_classes; ++k)
+            v += WEIGHTED ? (((uint64_t)cls_hi[k * p.G + f] << 32) | cls_lo[k * p.G + f]) : (uint64_t)cls_lo[k * p.G + f];
+        s.delta_lo[i] = (uint32_t)v;
+        if (WEIGHTED) s.delta_hi[i] = (uint32_t)(v >> 32);
+    }
+    __syncthreads();
+    scan_epilogue(p, s, tid);
+}
+
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; }
 
 template <bool QUORUM, int C_T, bool MASK>
@@ -507,9 +766,68 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     off += TG * 4u;
     L.off_delta_hi = off;
     off += (p.flags & kWeighted) ? TG * 4u : 0u;
+    // lane-private counters (no shared atomics) when the private region fits next to a pipeline: G <~ 300 for counts
+    L.off_cls_lo = L.off_cls_hi = L.off_carry = L.off_priv = L.off_cbase = off;
+    L.priv_bins = L.priv_cw = L.priv_hist_bins = 0;
+    p.n_classes = 0;
+    bool priv = false;
+    uint32_t priv_tile = 0;
+    if (!quorum && env_u32("PGX_SCAN_PRIV") != 2u) {
+        const bool count_mode = !(p.flags & (kWeighted | kHistWeight));
+        const bool weight_mode = !(p.flags & kHistCount) && ((p.flags & kWeighted) || p.T == 0) &&
+                                 (p.flags & (kHistWeight | kWeighted)) && p.weight != nullptr;
+        if (count_mode || weight_mode) {
+            // distinct coverage cutoffs, ascending; threshold t sums the classes >= its rank
+            uint32_t D = 0;
+            for (uint32_t t = 0; t < p.T; ++t) {
+                bool seen = false;
+                for (uint32_t d = 0; d < D; ++d) seen |= p.cls_thr[d] == p.cov[t];
+                if (!seen) p.cls_thr[D++] = p.cov[t];
+            }
+            for (uint32_t i = 1; i < D; ++i)
+                for (uint32_t j = i; j > 0 && p.cls_thr[j - 1] > p.cls_thr[j]; --j) {
+                    const uint32_t tmp = p.cls_thr[j];
+                    p.cls_thr[j] = p.cls_thr[j - 1];
+                    p.cls_thr[j - 1] = tmp;
+                }
+            for (uint32_t t = 0; t < p.T; ++t)
+                for (uint32_t d = 0; d < D; ++d)
+                    if (p.cls_thr[d] == p.cov[t]) p.cls_rank[t] = d + 1u;
+            const uint32_t cw = count_mode ? 1u : 2u;
+            const uint32_t hist_bins = (count_mode ? (p.flags & kHistCount) : (p.flags & kHistWeight)) ? G1 : 0u;
+            const uint64_t bins = std::max<uint64_t>(1u, (uint64_t)hist_bins + (uint64_t)D * p.G);
+            uint32_t tile;
+            if (rowbytes <= 8u) tile = 3072u;
+            else if (rowbytes <= 16u) tile = 2048u;
+            else if (rowbytes <= 32u) tile = 1024u;
+            else tile = std::max(512u, 32768u / rowbytes / 512u * 512u);
+            if (const uint32_t t_env = env_u32("PGX_SCAN_TILE")) tile = std::max(512u, t_env / 512u * 512u);
+            const uint32_t stage = align_up(tile * rowbytes, 128u) + (p.weight ? align_up(tile * 4u, 128u) : 0u);
+            const uint64_t need = (uint64_t)off + (uint64_t)D * p.G * 4u * (count_mode ? 1u : 2u) + 16u + bins * (256u * cw + 4u) + G1 * 4u + 128u + 2ull * stage;
+            if (need <= 232448u && rowbytes <= 64u) {
+                priv = true;
+                priv_tile = tile;
+                p.flags |= kPrivate;
+                p.n_classes = D;
+                L.off_cls_lo = off;
+                off += D * p.G * 4u;
+                L.off_cls_hi = off;
+                off += count_mode ? 0u : D * p.G * 4u;
+                L.off_carry = off;
+                off += (uint32_t)bins * 4u;
+                off = align_up(off, 16u);
+                L.off_priv = off;
+                L.priv_bins = (uint32_t)bins;
+                L.priv_cw = cw;
+                L.priv_hist_bins = hist_bins;
+                off += (uint32_t)bins * 256u * cw;
+                L.off_cbase = off;  // (thr region below keeps it out of the zeroed accumulator words: see acc_words / off_thr)
+            }
+        }
+    }
     // small G: joint (coverage, first group) histogram -- one atomic per item instead of 1 + T
     L.off_joint_cnt = L.off_joint_wlo = L.off_joint_whi = off;
-    if (!quorum && env_u32("PGX_SCAN_JOINT") != 2u) {
+    if (!priv && !quorum && env_u32("PGX_SCAN_JOINT") != 2u) {
         const bool use_cnt = (p.flags & kHistCount) || !(p.flags & kWeighted);
         const bool use_w = (p.flags & (kHistWeight | kWeighted)) != 0;
         const uint32_t one = G1 * p.G * 4u, bytes = one * ((use_cnt ? 1u : 0u) + (use_w ? 2u : 0u));
@@ -526,6 +844,7 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     L.acc_words = (off - L.off_acc) / 4u;
     L.off_thr = off;
     off += quorum ? TG * 4u : 0u;
+    off += priv ? G1 * 4u : 0u;  // the coverage -> class-bin table of k_scan_priv (at off_cbase == off_thr)
     off = align_up(off, 128u);
     L.off_stage0 = off;
 
@@ -533,7 +852,11 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     // (tools/sweep_scan.py, profiles/r1_sweep_*.txt).  The quorum kernel keeps one item per thread.
     uint32_t tile, want_ctas, want_stages;
     const bool heavy = quorum || (p.flags & (kHistWeight | kWeighted)) != 0;  // more atomics per item
-    if (rowbytes >= 256u) {
+    if (priv) {
+        tile = priv_tile;
+        want_stages = 4;
+        want_ctas = (off + 3u * (align_up(tile * rowbytes, 128u) + (p.weight ? align_up(tile * 4u, 128u) : 0u)) <= 232448u / 2u - 1024u) ? 2u : 1u;
+    } else if (rowbytes >= 256u) {
         tile = 256u, want_ctas = 1, want_stages = 3;
         // wide rows: fewer rows per stage; shrink further while accumulators + two stages do not fit
         const uint32_t wbytes = p.weight ? 4u : 0u;
@@ -549,7 +872,7 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
         if (tile > 3072u) tile = 3072u;
         want_ctas = 2, want_stages = 3;
     }
-    if (const uint32_t t_env = env_u32("PGX_SCAN_TILE")) tile = (t_env + 3u) & ~3u;
+    if (const uint32_t t_env = env_u32("PGX_SCAN_TILE")) tile = priv ? tile : ((t_env + 3u) & ~3u);
     p.tile_items = tile;
     L.off_stage_w = align_up(tile * rowbytes, 128u);
     L.stage_stride = L.off_stage_w + (p.weight ? align_up(tile * 4u, 128u) : 0u);
@@ -575,6 +898,8 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     p.n_tiles = (uint32_t)n_tiles;
     const uint64_t max_grid = (uint64_t)sm_count * ctas;
     *grid_out = (int)(n_tiles < max_grid ? n_tiles : max_grid);
+    if (const uint32_t g_env = env_u32("PGX_SCAN_GRID"))  // test hook: few CTAs walk many tiles each (ring wrap-around, counter folds)
+        *grid_out = (int)std::min<uint64_t>(g_env, n_tiles);
 
     // masks for the two words of a row's last 16-byte chunk
     const uint64_t lastmask = (p.G & 63u) ? ((1ull << (p.G & 63u)) - 1ull) : ~0ull;
@@ -597,7 +922,27 @@ int launch_fast(const ScanParams &p, int grid, cudaStream_t stream) {
     return mask ? launch_one<false, C_T, true>(p, grid, stream) : launch_one<false, C_T, false>(p, grid, stream);
 }
 
+template <int CW, bool WEIGHTED, int C_T>
+int launch_priv_one(const ScanParams &p, int grid, cudaStream_t stream) {
+    auto kern = k_scan_priv<CW, WEIGHTED, C_T>;
+    PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.L.total));
+    kern<<<grid, kScanThreads, p.L.total, stream>>>(p);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+template <int CW, bool WEIGHTED>
+int launch_priv(const ScanParams &p, int grid, cudaStream_t stream) {
+    if (p.Wp == 1u) return launch_priv_one<CW, WEIGHTED, -1>(p, grid, stream);
+    switch (p.Wp >> 1) {
+        case 1: return launch_priv_one<CW, WEIGHTED, 1>(p, grid, stream);
+        case 2: return launch_priv_one<CW, WEIGHTED, 2>(p, grid, stream);
+        default: return launch_priv_one<CW, WEIGHTED, 0>(p, grid, stream);
+    }
+}
+
 int launch_scan(const ScanParams &p, bool quorum, int grid, cudaStream_t stream) {
+    if (p.flags & kPrivate) return p.L.priv_cw == 1u ? launch_priv<1, false>(p, grid, stream) : launch_priv<2, true>(p, grid, stream);
     if (quorum) return launch_one<true, 0, true>(p, grid, stream);
     if (p.Wp == 1u) return launch_one<false, -1, true>(p, grid, stream);
     switch (p.Wp >> 1) {

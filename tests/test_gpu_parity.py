@@ -170,6 +170,48 @@ def test_random_tables(N, G):
     check_table(bitmap, G, weights)
 
 
+@pytest.mark.parametrize("N,G", [(300_000, 44), (150_000, 64), (120_000, 100), (100_000, 130), (90_000, 256), (40_000, 300), (777, 7)])
+def test_lane_private_counter_kernel(N, G, monkeypatch):
+    """k_scan_priv (lane-private counters instead of shared atomics, G <~ 300) against the oracle and against the
+    atomics kernel: count and bp modes, several q = 0 thresholds with repeated coverage cutoffs (classes), per-item
+    coverage output, and -- with the grid capped to 3 CTAs -- many tiles per CTA, so that the narrow counters wrap and
+    carry many times and the ring wraps around."""
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=N + G)
+    pairs = [(1, 0.0), (3, 0.0), (2, 0.0), (3, 0.0), (G, 0.0), (G + 1, 0.0)]
+    exp = oracle_all(bitmap, G, weights, pairs)
+    cov = [c for c, _ in pairs]
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        for grid in ("3", None):
+            if grid:
+                monkeypatch.setenv("PGX_SCAN_GRID", grid)
+            else:
+                monkeypatch.delenv("PGX_SCAN_GRID", raising=False)
+            for priv in (True, False):
+                if priv:
+                    monkeypatch.delenv("PGX_SCAN_PRIV", raising=False)
+                else:
+                    monkeypatch.setenv("PGX_SCAN_PRIV", "2")
+                hc, _, ct = a.hist(count=True, weight=False, countable=True)
+                assert ("k_scan_priv<u8>" in a.last_launch_info()) == priv, a.last_launch_info()
+                assert np.array_equal(hc, exp["hist"]) and np.array_equal(ct, exp["countable"])
+                _, hw, _ = a.hist(count=False, weight=True)
+                assert ("k_scan_priv<u16>" in a.last_launch_info()) == priv, a.last_launch_info()
+                assert np.array_equal(hw, exp["hist_bp"])
+                h2, _, cv = a.hist_ordered_growth(cov, None, weighted=False, hist_count=True, hist_weight=False)
+                assert priv or "k_scan_priv" not in a.last_launch_info()
+                assert not (priv and G <= 64) or "k_scan_priv<u8>" in a.last_launch_info(), a.last_launch_info()
+                _, w2, cvw = a.hist_ordered_growth(cov, None, weighted=True, hist_count=False, hist_weight=True)
+                assert np.array_equal(h2, exp["hist"]) and np.array_equal(w2, exp["hist_bp"])
+                for t, (c, q) in enumerate(pairs):
+                    assert np.array_equal(cv[t].astype(np.float64), exp[("node", c, q)]), (grid, priv, c)
+                    assert np.array_equal(cvw[t].astype(np.float64), exp[("bp", c, q)]), (grid, priv, c)
+                one = a.ordered_growth([2], None, weighted=False)  # growth only: no histogram bins at all
+                assert np.array_equal(one[0].astype(np.float64), exp[("node", 2, 0.0)])
+                if priv and G <= 256:
+                    assert "k_scan_priv<u8>" in a.last_launch_info(), a.last_launch_info()
+
+
 def test_dense_and_sparse_variants():
     for variant in ("dense", "sparse"):
         bits, bitmap, weights = synth.numpy_table(3000, 200, seed=5, variant=variant)
