@@ -148,7 +148,7 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
     for (;;) {
         std::memset(&p, 0, sizeof(p));
         p.bitmap = a->d_bitmap;
-        p.weight = a->d_weight;
+        p.weight = (flags & (kWeighted | kHistWeight)) ? a->d_weight : nullptr;  // count modes never stage the weights
         p.acc = a->d_acc;
         p.ticket = a->d_ticket;
         p.out = d_out;

@@ -268,9 +268,9 @@ __device__ __forceinline__ void scan_epilogue(const ScanParams &p, const SmemAcc
 
     // ===== last CTA: snapshot + re-zero (threadfence reduction pattern) =====
     __shared__ uint32_t s_is_last;
-    __threadfence();
     __syncthreads();
     if (tid == 0) {
+        __threadfence();  // (after the barrier: cumulative over the CTA's RED.ADDs, the grid-sync pattern of cooperative groups)
         const unsigned int t = atomicAdd(p.ticket, 1u);
         s_is_last = (t == gridDim.x - 1u) ? 1u : 0u;
     }
@@ -646,31 +646,32 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
         const uint32_t my = priv_base + priv_thread_off<CW>(tid);
         uint32_t st = 0, ph = 0;
         constexpr uint32_t kRow = 256u * CW;
+        constexpr uint32_t kBits = 8u * CW, kMask = (1u << kBits) - 1u;
         const bool has_hist = p.L.priv_hist_bins != 0u, has_cls = p.n_classes != 0u;
-        // (coverage, first group, weight) of one item -> its two lane-private counters
-        auto account = [&](bool valid, uint32_t cov, uint32_t first, uint32_t wgt) {
+        // One item's two read-modify-writes on the thread's own counters.  The two loads are in flight together (disjoint
+        // regions); the narrow counters keep the low bits, and whatever wraps out of them (rarely) is added to the bin's
+        // u32 carry word of the CTA -- one branch for both.  cb = s_cbase[cov]: first bin of the item's coverage class.
+        auto account = [&](bool valid, uint32_t cov, uint32_t first, uint32_t wgt, uint32_t cb) {
             const uint32_t inc = valid ? (WEIGHTED ? wgt : 1u) : 0u;
-            // class bin: s_cbase[cov] = first bin of the item's coverage class, or ~0 when it reaches no cutoff
-            const uint32_t cb = has_cls ? s_cbase[cov] : 0xFFFFFFFFu;
             const bool counted = cb != 0xFFFFFFFFu;
             const uint32_t cbin = counted ? cb + first : 0u;
             const uint32_t ha = my + cov * kRow, ca = my + cbin * kRow;
-            // the two loads are in flight together (disjoint regions); the narrow counters keep the low bits, and whatever
-            // wraps out of them (rarely) is added to the bin's u32 carry word of the CTA -- one branch for both
-            constexpr uint32_t kBits = 8u * CW, kMask = (1u << kBits) - 1u;
             const uint32_t cinc = counted ? inc : 0u;
             uint32_t hv = 0, cv = 0;
             if (has_hist) hv = priv_ld<CW>(ha);
             if (has_cls) cv = priv_ld<CW>(ca);
             const uint32_t nh = hv + (WEIGHTED ? (inc & kMask) : inc), nc = cv + (WEIGHTED ? (cinc & kMask) : cinc);
             if (has_hist) priv_st<CW>(ha, nh);
-            if (has_cls) priv_st<CW>(ca, nc);
+            if (has_cls && counted) priv_st<CW>(ca, nc);  // (an uncounted item's class address is a dummy: row 0)
             if (((nh | nc) >> kBits) | (WEIGHTED ? (inc >> kBits) : 0u)) {
                 const uint32_t ch = (nh >> kBits) + (WEIGHTED ? (inc >> kBits) : 0u), cc = (nc >> kBits) + (WEIGHTED ? (cinc >> kBits) : 0u);
                 if (has_hist && ch) atomicAdd(carry + cov, ch);
                 if (has_cls && cc) atomicAdd(carry + cbin, cc);
             }
         };
+        // items per thread and step: their row loads, popcounts and class look-ups are independent and overlap; only the
+        // counter updates run one item after the other (two items of a thread may share a bin)
+        constexpr int K = (C_T < 0 || C_T == 1) ? 4 : 2;
         for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const uint64_t row0 = (uint64_t)tile * p.tile_items;
             const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
@@ -678,23 +679,37 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const uint32_t wbase = base + p.L.off_stage_w;
             mbar_wait(full0 + 8u * st, ph);
-#pragma unroll 2
-            for (uint32_t li = tid; li < trows; li += kConsumerThreads) {
-                uint32_t cov, first, wgt = 1u;
-                if (WEIGHTED) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wgt) : "r"(wbase + li * 4u));
-                const uint32_t row_addr = base + li * rowbytes;
-                if (C_T < 0) {  // 8-byte rows (G <= 64): 2 POPC for the coverage, 1 for the first group (trailing zeros)
-                    const uint64_t x = lds_u64(row_addr) & p.last_mask0;
-                    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-                    cov = __popc(lo) + __popc(hi);
-                    const uint32_t sel = lo ? lo : hi;
-                    first = (lo ? 0u : 32u) + __popc((sel - 1u) & ~sel);
-                } else {
-                    row_cov_first<C_T, true>(p, row_addr, li, C_rt, rot_shift, rot_mask, cov, first);
+            for (uint32_t li0 = tid; li0 < trows; li0 += K * kConsumerThreads) {
+                uint32_t cov[K], first[K], wgt[K], cb[K];
+                bool valid[K];
+                uint64_t x[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t lk = li0 + (uint32_t)k * kConsumerThreads;
+                    valid[k] = lk < trows && (tile | lk) != 0u;  // item 0: the reference's dummy item, never counted
+                    const uint32_t li = lk < trows ? lk : li0;     // out-of-tile slots re-read a valid row and add nothing
+                    wgt[k] = 1u;
+                    if (WEIGHTED) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wgt[k]) : "r"(wbase + li * 4u));
+                    if (C_T < 0) x[k] = lds_u64(base + li * rowbytes);
                 }
-                const bool valid = (tile | li) != 0u;  // item 0: the reference's dummy item, never counted
-                if (p.countable) p.countable[row0 + li] = valid ? cov : 0xFFFFFFFFu;
-                account(valid, cov, first, wgt);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t lk = li0 + (uint32_t)k * kConsumerThreads;
+                    const uint32_t li = lk < trows ? lk : li0;
+                    if (C_T < 0) {  // 8-byte rows (G <= 64): 2 POPC for the coverage, 1 for the first group (trailing zeros)
+                        const uint64_t xm = x[k] & p.last_mask0;
+                        const uint32_t lo = (uint32_t)xm, hi = (uint32_t)(xm >> 32);
+                        cov[k] = __popc(lo) + __popc(hi);
+                        const uint32_t sel = lo ? lo : hi;
+                        first[k] = (lo ? 0u : 32u) + __popc((sel - 1u) & ~sel);
+                    } else {
+                        row_cov_first<C_T, true>(p, base + li * rowbytes, li, C_rt, rot_shift, rot_mask, cov[k], first[k]);
+                    }
+                    cb[k] = has_cls ? s_cbase[cov[k]] : 0xFFFFFFFFu;
+                    if (p.countable && lk < trows) p.countable[row0 + lk] = (tile | lk) != 0u ? cov[k] : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) account(valid[k], cov[k], first[k], wgt[k], cb[k]);
             }
             if (tid < rows - trows) {  // <= 3 tail rows of the last tile, straight from global memory
                 const uint64_t item = row0 + trows + tid;
@@ -706,7 +721,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
                     if (x && first == 0xFFFFFFFFu) first = w * 64u + first_bit(x);
                 }
                 if (p.countable) p.countable[item] = item ? cov : 0xFFFFFFFFu;
-                account(item != 0, cov, first, wgt);
+                account(item != 0, cov, first, wgt, has_cls ? s_cbase[cov] : 0xFFFFFFFFu);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8u * st);
@@ -803,8 +818,18 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
             else tile = std::max(512u, 32768u / rowbytes / 512u * 512u);
             if (const uint32_t t_env = env_u32("PGX_SCAN_TILE")) tile = std::max(512u, t_env / 512u * 512u);
             const uint32_t stage = align_up(tile * rowbytes, 128u) + (p.weight ? align_up(tile * 4u, 128u) : 0u);
-            const uint64_t need = (uint64_t)off + (uint64_t)D * p.G * 4u * (count_mode ? 1u : 2u) + 16u + bins * (256u * cw + 4u) + G1 * 4u + 128u + 2ull * stage;
-            if (need <= 232448u && rowbytes <= 64u) {
+            // measured (profiles/r2_scan_shapes_*.txt): the private counters only pay with two CTAs per SM -- with one
+            // (8 consumer warps) the dependent shared-memory round trips of the updates are not hidden and the atomics
+            // kernel (16 warps, fire-and-forget ATOMS) is faster; so: eligible iff 3 stages of some tile fit in half an SM
+            const uint64_t fixed = (uint64_t)off + (uint64_t)D * p.G * 4u * (count_mode ? 1u : 2u) + 16u + bins * (256u * cw + 4u) + G1 * 4u + 128u;
+            const uint32_t min_tile = rowbytes <= 16u ? 1024u : 512u;
+            bool two_ctas = false;
+            for (uint32_t t = tile; t >= min_tile && !two_ctas; t >>= 1) {
+                const uint64_t st_bytes = align_up(t * rowbytes, 128u) + (p.weight ? align_up(t * 4u, 128u) : 0u);
+                two_ctas = fixed + 3u * st_bytes <= 232448u / 2u - 1024u;
+            }
+            (void)stage;
+            if ((two_ctas || env_u32("PGX_SCAN_PRIV") == 1u) && fixed + 2ull * stage <= 232448u && rowbytes <= 64u) {
                 priv = true;
                 priv_tile = tile;
                 p.flags |= kPrivate;
@@ -853,9 +878,21 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     uint32_t tile, want_ctas, want_stages;
     const bool heavy = quorum || (p.flags & (kHistWeight | kWeighted)) != 0;  // more atomics per item
     if (priv) {
+        // two CTAs per SM (16 consumer warps hide the shared-memory latencies of the counter updates) whenever three
+        // stages of some tile size fit next to the private region in half an SM's shared memory; else one CTA, deep ring
         tile = priv_tile;
         want_stages = 4;
-        want_ctas = (off + 3u * (align_up(tile * rowbytes, 128u) + (p.weight ? align_up(tile * 4u, 128u) : 0u)) <= 232448u / 2u - 1024u) ? 2u : 1u;
+        want_ctas = 1;
+        const uint32_t min_tile = rowbytes <= 16u ? 1024u : 512u;  // a thread takes 4 (narrow rows) or 2 items per step
+        for (uint32_t t = priv_tile; t >= min_tile; t >>= 1) {
+            const uint32_t stage = align_up(t * rowbytes, 128u) + (p.weight ? align_up(t * 4u, 128u) : 0u);
+            if (off + 3u * stage <= 232448u / 2u - 1024u) {
+                tile = t;
+                want_ctas = 2;
+                want_stages = 3;
+                break;
+            }
+        }
     } else if (rowbytes >= 256u) {
         tile = 256u, want_ctas = 1, want_stages = 3;
         // wide rows: fewer rows per stage; shrink further while accumulators + two stages do not fit

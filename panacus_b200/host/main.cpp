@@ -35,7 +35,7 @@ const std::map<char, std::string> kShort = {{'s', "subset"},  {'e', "exclude"}, 
                                              {'S', "groupby-sample"}, {'c', "count"}, {'l', "coverage"}, {'q', "quorum"},
                                              {'a', "hist"},    {'O', "order"},    {'m', "method"},  {'t', "threads"},
                                              {'v', "verbose"}};
-const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json", "names", "no-cluster"};
+const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json", "names", "no-cluster", "timing"};
 
 Args parse_args(int argc, char **argv) {
     Args a;
@@ -96,6 +96,35 @@ std::string argv_joined(int argc, char **argv) {
     return s;
 }
 
+// --timing: wall time of the phases of a run, one JSON object on stderr at exit (stdout carries the table)
+struct PhaseTimer {
+    bool on = false;
+    std::vector<std::pair<std::string, double>> ms;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const std::string &name) {
+        const auto t1 = std::chrono::steady_clock::now();
+        const double d = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+        for (auto &kv : ms)
+            if (kv.first == name) {
+                kv.second += d;
+                return;
+            }
+        ms.emplace_back(name, d);
+    }
+    void report() const {
+        if (!on) return;
+        double total = 0;
+        std::cerr << "{\"phases_ms\": {";
+        for (size_t i = 0; i < ms.size(); ++i) {
+            std::cerr << (i ? ", " : "") << "\"" << ms[i].first << "\": " << ms[i].second;
+            total += ms[i].second;
+        }
+        std::cerr << "}, \"total_ms\": " << total << "}\n";
+    }
+};
+PhaseTimer g_phase;
+
 struct Run {
     GraphStorage graph;
     GraphMask mask;
@@ -106,7 +135,9 @@ Run load(const Args &a, const std::vector<CountType> &counts, bool with_order, b
     bool edges = false;
     for (auto c : counts) edges = edges || c == CountType::Edge;
     Run r;
+    g_phase.lap("other");
     r.graph = GraphStorage::from_gfa(a.positional.at(0), edges, with_names);
+    g_phase.lap("gfa_parse");
     GraphMaskParameters p;
     p.groupby = a.get("groupby");
     p.groupby_sample = a.has("groupby-sample");  // commands/hist.rs:44-50: -S wins over -H, both over -g
@@ -117,6 +148,7 @@ Run load(const Args &a, const std::vector<CountType> &counts, bool with_order, b
     if (with_order && a.has("order")) p.order = a.get("order");
     r.mask = GraphMask::from_graph(r.graph, p);
     r.path_order = r.mask.get_path_order(r.graph.path_segments);
+    g_phase.lap("grouping_order");
     return r;
 }
 
@@ -210,11 +242,15 @@ Counted get_counted(const Source &src, CountType c, const Args &a) {
         return k;
     }
     const Run &r = src.run;
+    g_phase.lap("other");
     ItemTables t = build_item_tables(r.graph, r.mask, c);
+    g_phase.lap("item_table");
     const uint32_t G = count_groups(r.path_order);
     if (G == 0) throw Error("no path left to count (check --subset / --exclude)");
     k.ab = std::make_unique<DeviceAbacus>(t.n_items, G);
+    g_phase.lap("device_init");
     k.ab->build(t, r.path_order, k.groups);
+    g_phase.lap("h2d_build");
     k.weights = c == CountType::Edge ? std::vector<uint32_t>(t.n_items + 1, 1u) : r.graph.node_lens;
     if (c == CountType::Edge) k.weights[0] = 0;
     k.uncovered = std::move(t.uncovered_bps);
@@ -234,6 +270,9 @@ Counted get_counted(const Source &src, CountType c, const Args &a) {
 // Hist::from_abacus (graph_broker/hist.rs:39-49): coverage histogram of one count type
 Hist device_hist(const Source &src, CountType c, const Args &a) {
     Counted k = get_counted(src, c, a);
+    struct Lap {
+        ~Lap() { g_phase.lap("kernels"); }
+    } lap;
     Hist h;
     h.count = c;
     const uint32_t gpus = n_gpus(a);
@@ -284,12 +323,16 @@ std::string growth_table(const std::vector<Hist> &hists, const ThresholdContaine
             cols.push_back(as_f64(h.coverage));
             headers.push_back({"hist", to_string(h.count), "", ""});
         }
+    g_phase.lap("other");
     for (auto &h : hists) {
         for (auto &g : h.calc_all_growths(aux)) cols.push_back(g);
+        g_phase.lap("closed_form_growth");
         for (size_t k = 0; k < aux.coverage.size(); ++k)
             headers.push_back({"growth", to_string(h.count), aux.coverage[k].get_string(), aux.quorum[k].get_string()});
     }
-    return write_table(headers, cols);
+    std::string out = write_table(headers, cols);
+    g_phase.lap("tsv");
+    return out;
 }
 
 int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth, std::ostream &os) {
@@ -327,6 +370,7 @@ int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
         k.ab->set_weights(w);
     }
     std::vector<std::vector<double>> cols;
+    g_phase.lap("other");
     const uint32_t gpus = n_gpus(a);
     if (gpus > 1) {  // item ranges per GPU; the path's one exchange is an ncclAllReduce of the KB-sized result vector
         auto shards = shard_items(*k.ab, gpus);
@@ -337,6 +381,7 @@ int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
     } else {
         cols = k.ab->calc_growth(aux, count == CountType::Bp);
     }
+    g_phase.lap("kernels");
     for (auto &c : cols) c.insert(c.begin(), std::nan(""));  // io.rs:580-583
     std::vector<std::vector<std::string>> headers = {{"panacus", "count", "coverage", "quorum"}};
     for (size_t k = 0; k < aux.coverage.size(); ++k)
@@ -559,6 +604,66 @@ int cmd_debug_growth(const Args &a, std::ostream &os) {
             }
             os << "\n";
         }
+    return 0;
+}
+
+// `panacus debug-synth-gfa <out.gfa> --nodes N [--samples 44 --haps 2 --contigs 22 --seed S --mean-len L --hist-file FILE]`:
+// writes a pangenome-shaped GFA (synth.cpp).  FILE: two lines of samples + 1 numbers, the node and the bp coverage
+// histogram to imitate (second line optional).
+int cmd_debug_synth_gfa(const Args &a, std::ostream &os) {
+    const uint64_t nodes = std::strtoull(a.get("nodes", "100000").c_str(), nullptr, 10);
+    const uint32_t samples = (uint32_t)std::atoi(a.get("samples", "44").c_str());
+    const uint32_t haps = (uint32_t)std::atoi(a.get("haps", "2").c_str());
+    const uint32_t contigs = (uint32_t)std::atoi(a.get("contigs", "22").c_str());
+    std::vector<double> node_hist, bp_hist;
+    if (a.has("hist-file")) {  // (--hist is the -a flag of the growth subcommands)
+        std::ifstream in(a.get("hist-file"));
+        if (!in) throw Error("cannot open " + a.get("hist-file"));
+        std::string line;
+        for (int k = 0; k < 2 && std::getline(in, line); ++k) {
+            std::stringstream ss(line);
+            double x;
+            while (ss >> x) (k ? bp_hist : node_hist).push_back(x);
+        }
+    } else {  // U shape: many private nodes, a long flat shell, a core peak
+        node_hist.assign(samples + 1u, 1.0);
+        node_hist[0] = 0.3;
+        node_hist[1] = 0.25 * samples;
+        if (samples >= 2) node_hist[2] = 0.12 * samples;
+        node_hist[samples] = 0.2 * samples;
+    }
+    const uint64_t steps = synth_gfa(a.positional.at(0), nodes, samples, haps, contigs, node_hist, bp_hist,
+                                     std::atof(a.get("mean-len", "100").c_str()), std::strtoull(a.get("seed", "22").c_str(), nullptr, 10));
+    os << "nodes\t" << nodes << "\nsamples\t" << samples << "\npaths\t<= " << (uint64_t)samples * haps * contigs << "\nsteps\t" << steps << "\n";
+    return 0;
+}
+
+// `panacus debug-dump-tables <gfa> --out PREFIX [-c count] [grouping flags]`: what the host front end hands to the device as
+// raw little-endian files -- PREFIX.items.u64, PREFIX.prefsum.u64, PREFIX.path_group.i64, PREFIX.node_lens.u32 -- plus the
+// group names on stdout.  Feeds the CPU oracle with the same tables at sizes where the text form of debug-tables is too big.
+int cmd_debug_dump_tables(const Args &a, std::ostream &os) {
+    const CountType count = count_type_from_str(a.get("count", "node"));
+    if (count == CountType::All) throw Error("debug-dump-tables takes one count type");
+    const Run r = load(a, {count}, true);
+    const ItemTables t = build_item_tables(r.graph, r.mask, count);
+    std::vector<std::string> groups;
+    std::vector<int64_t> path_group(t.id_prefsum.size() - 1, -1);
+    for (auto &po : r.path_order) {
+        if (groups.empty() || groups.back() != po.second) groups.push_back(po.second);
+        path_group[po.first] = (int64_t)groups.size() - 1;
+    }
+    auto dump = [&](const std::string &suffix, const void *p, size_t bytes) {
+        std::ofstream o(a.get("out") + suffix, std::ios::binary);
+        if (!o) throw Error("cannot write " + a.get("out") + suffix);
+        o.write(static_cast<const char *>(p), (std::streamsize)bytes);
+    };
+    dump(".items.u64", t.items.data(), t.items.size() * 8);
+    dump(".prefsum.u64", t.id_prefsum.data(), t.id_prefsum.size() * 8);
+    dump(".path_group.i64", path_group.data(), path_group.size() * 8);
+    dump(".node_lens.u32", r.graph.node_lens.data(), r.graph.node_lens.size() * 4);
+    os << "n_items\t" << t.n_items << "\nsteps\t" << t.items.size() << "\ngroups";
+    for (auto &g : groups) os << "\t" << g;
+    os << "\n";
     return 0;
 }
 
@@ -828,6 +933,13 @@ int dispatch(int argc, char **argv, std::ostream &os) {
     }
     const std::string cmdline = argv_joined(argc, argv);
     if (a.has("threads")) set_host_threads(std::atoi(a.get("threads").c_str()));
+    g_phase.on = a.has("timing");
+    struct Report {
+        ~Report() {
+            g_phase.lap("other");
+            g_phase.report();
+        }
+    } report;
     if (a.sub == "hist") return cmd_hist(a, cmdline, os);
     if (a.sub == "growth") return cmd_growth(a, cmdline, false, os);
     if (a.sub == "histgrowth") return cmd_growth(a, cmdline, true, os);
@@ -838,6 +950,8 @@ int dispatch(int argc, char **argv, std::ostream &os) {
     if (a.sub == "debug-table-tsv") return cmd_debug_table_tsv(a, os);
     if (a.sub == "debug-parse") return cmd_debug_parse(a, os);
     if (a.sub == "debug-growth") return cmd_debug_growth(a, os);
+    if (a.sub == "debug-synth-gfa") return cmd_debug_synth_gfa(a, os);
+    if (a.sub == "debug-dump-tables") return cmd_debug_dump_tables(a, os);
     if (a.sub == "debug-tables") return cmd_debug_tables(a, os);
     if (a.sub == "report") return cmd_report(a, os);
     usage();

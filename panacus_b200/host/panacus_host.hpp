@@ -255,6 +255,11 @@ class DeviceAbacus {
     uint32_t n_groups_;
 };
 
+// ---- measurement helpers (not part of the reference CLI) ----------------------------------------------------------
+// pangenome-shaped GFA text for a given coverage histogram (synth.cpp); returns the number of path steps written
+uint64_t synth_gfa(const std::string &path, uint64_t n_nodes, uint32_t samples, uint32_t haps, uint32_t contigs,
+                   const std::vector<double> &node_hist, const std::vector<double> &bp_hist, double mean_len, uint64_t seed);
+
 // ---- packed-abacus cache file (".pabm"): skip GFA parsing on repeated runs (the analogue of the
 // reference's hist-TSV reuse, io.rs:244-290) -----------------------------------------------------------------------
 struct AbacusFile {

@@ -1,0 +1,175 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs[4] stand-in: `panacus histgrowth -c bp -S -q 0,0.5,1 -l 0,1,2` on a generated chr22-shaped GFA.
+
+The HPRC v1.0 pggb chr22 graph (402 MB gz, test/README.md:11-16 of the reference) is not available offline, so the input
+is generated (`panacus debug-synth-gfa`, panacus_b200/host/synth.cpp) with the statistics the reference documents for
+it (docs/chr22.hprc-v1.0-pggb.histgrowth.html:267-269, committed as tests/golden/chr22_histgrowth.json): 3,759,736
+segments, 44 sample groups (2 haplotypes x 22 contigs each = 1,936 P lines), node coverage drawn from the documented
+node histogram, node lengths from the documented bp / node ratio per coverage class.  The reference's only published
+timing is for this command with count = node: "~17 s" (test/integrated_test.R:107-108).
+
+ours       wall clock of the CLI, end to end, plus its --timing phase breakdown
+reference  CPU port at the same seams: the same C++ front end (parse / grouping / ItemTable -- the reference's own
+           five-pass parser is Rust and cannot be built here) + the oracle's C restatement of coverage -> bp histogram
+           -> closed-form growth for the three pairs, one thread (the reference's parallel axis there is the pairs).
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "panacus_b200", "bin", "panacus")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "chr22_histgrowth.json")
+CLI_ARGS = ["-c", "bp", "-S", "-q", "0,0.5,1", "-l", "0,1,2"]
+
+
+def make_gfa(path: str, n_nodes: int, seed: int = 22) -> dict:
+    d = json.load(open(GOLDEN))
+    node_hist, bp_hist = d["hist"]["node"]["values"], d["hist"]["bp"]["values"]
+    with tempfile.NamedTemporaryFile("w", suffix=".hist", delete=False) as f:
+        f.write(" ".join(str(v) for v in node_hist) + "\n" + " ".join(str(v) for v in bp_hist) + "\n")
+        hist_file = f.name
+    t0 = time.perf_counter()
+    r = subprocess.run([BIN, "debug-synth-gfa", path, "--nodes", str(n_nodes), "--samples", str(len(node_hist) - 1),
+                        "--haps", "2", "--contigs", "22", "--seed", str(seed), "--hist-file", hist_file],
+                       capture_output=True, text=True)
+    os.unlink(hist_file)
+    if r.returncode != 0:
+        raise SystemExit("debug-synth-gfa failed: " + r.stderr)
+    info = dict(line.split("\t", 1) for line in r.stdout.strip().split("\n"))
+    return {"gfa_bytes": os.path.getsize(path), "steps": int(info["steps"]), "gen_s": time.perf_counter() - t0}
+
+
+def run_cli(gfa: str, threads: int, gpus: int = 1):
+    cmd = [BIN, "histgrowth", gfa] + CLI_ARGS + ["-t", str(threads), "--timing"] + (["--gpus", str(gpus)] if gpus > 1 else [])
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise SystemExit("panacus histgrowth failed: " + r.stderr[-2000:])
+    phases = {}
+    for line in r.stderr.splitlines():
+        if line.startswith('{"phases_ms"'):
+            phases = json.loads(line)
+    return wall, phases, r.stdout
+
+
+def cpu_port(gfa: str, threads: int, workdir: str):
+    """front end (shared C++) + the oracle's coverage / bp histogram / closed-form growth on the dumped ItemTable"""
+    from oracle import oracle as po
+    prefix = os.path.join(workdir, "c5_tables")
+    t0 = time.perf_counter()
+    r = subprocess.run([BIN, "debug-dump-tables", gfa, "--out", prefix, "-c", "bp", "-S", "-t", str(threads)], capture_output=True, text=True)
+    front_s = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise SystemExit("debug-dump-tables failed: " + r.stderr[-2000:])
+    info = dict(line.split("\t", 1) for line in r.stdout.strip().split("\n"))
+    groups = info["groups"].split("\t")
+    G, n_items = len(groups), int(info["n_items"])
+    items = np.fromfile(prefix + ".items.u64", dtype=np.uint64)
+    prefsum = np.fromfile(prefix + ".prefsum.u64", dtype=np.uint64)
+    path_group = np.fromfile(prefix + ".path_group.i64", dtype=np.int64)
+    node_lens = np.fromfile(prefix + ".node_lens.u32", dtype=np.uint32)
+    for suf in (".items.u64", ".prefsum.u64", ".path_group.i64", ".node_lens.u32"):
+        os.unlink(prefix + suf)
+    # counting order: the paths of a group are contiguous (abacus.rs:310-347); path_group is already the group id
+    order_path = np.array([p for p in np.argsort(path_group, kind="stable") if path_group[p] >= 0], dtype=np.uint64)
+    order_group = path_group[order_path.astype(np.int64)].astype(np.uint64)
+    t1 = time.perf_counter()
+    countable = po.abacus_by_total(n_items, items, prefsum, order_path, order_group)
+    hist = po.construct_hist_bps(countable, node_lens, G)
+    t2 = time.perf_counter()
+    cov, quo = po.parse_thresholds("0,0.5,1", "0,1,2")
+    growths = [po.hist_calc_growth(hist, c, q) for c, q in zip(cov, quo)]
+    t3 = time.perf_counter()
+    table = po.growth_table([("bp", hist)], cov, quo)
+    return {"front_end_s": front_s, "coverage_hist_s": t2 - t1, "closed_form_s": t3 - t2, "total_s": front_s + (t3 - t1),
+            "n_items": n_items, "n_groups": G, "steps": int(items.size), "table": table, "growths": growths}
+
+
+def body(text):
+    return "\n".join(l for l in text.split("\n") if not l.startswith("#")).strip() + "\n"
+
+
+def bench(args, reference, metric, unit, config):
+    n_nodes = args.items or 3_759_736
+    threads = os.cpu_count() or 8
+    workdir = tempfile.mkdtemp(prefix="pgx_c5_")
+    gfa = os.path.join(workdir, "chr22_shape.gfa")
+    gen = make_gfa(gfa, n_nodes)
+    G = 44
+    cells = float(n_nodes) * G
+    steps = max(1, min(args.steps, 3))
+    try:
+        if reference:
+            r = cpu_port(gfa, threads, workdir)
+            value = cells / r["total_s"]
+            sample = (f"the whole generated graph ({n_nodes} segments, {r['steps']} path steps, {gen['gfa_bytes'] >> 20} MiB of GFA): "
+                      f"front end {r['front_end_s']:.2f}s (the same C++ parser as the GPU arm, {threads} threads; the reference's "
+                      f"five-pass Rust parser cannot be built here) + coverage / bp histogram {r['coverage_hist_s']:.2f}s + closed-form "
+                      f"growth {r['closed_form_s']:.3f}s (oracle/ C restatement, 1 thread)")
+            line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": r["total_s"] * 1e3, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+                    "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": "port", "sample": sample},
+                    "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            print(json.dumps(line))
+            return 0
+        run_cli(gfa, threads)  # warm-up: page cache, CUDA context creation cost is part of every real run and stays in
+        walls, phases = [], None
+        for _ in range(steps):
+            wall, phases, out = run_cli(gfa, threads)
+            walls.append(wall)
+        wall = float(np.median(walls))
+        # the CPU port on the same file: same table (from the `panacus` header row on), and its time beside ours
+        cpu = None
+        if not args.no_cpu:
+            r = cpu_port(gfa, threads, workdir)
+            same = body(out) == body(r["table"])
+            if not same:
+                raise SystemExit("c5: the CLI table differs from the CPU oracle's table")
+            cpu = {"value": cells / r["total_s"], "unit": unit, "cores": 1, "kind": "port",
+                   "sample": f"same file: front end {r['front_end_s']:.2f}s (shared C++ parser, {threads} threads) + coverage / bp hist "
+                             f"{r['coverage_hist_s']:.2f}s + closed-form growth {r['closed_form_s']:.3f}s (oracle C, 1 thread)",
+                   "table_identical_to_cli": same}
+        value = cells / wall
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": steps, "warmup": 1, "ms_per_step": wall * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": config, "phases_ms": phases.get("phases_ms") if phases else None,
+                "input": {"gfa_bytes": gen["gfa_bytes"], "segments": n_nodes, "path_steps": gen["steps"], "p_lines": "<= 1936",
+                          "generated_in_s": round(gen["gen_s"], 1)},
+                "context": "the reference's only published wall time: ~17 s for this command with count = node on the real chr22 graph "
+                           "(test/integrated_test.R:107-108), hardware unstated",
+                "roofline": None, "cpu_baseline": cpu,
+                "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": int(gen["steps"] * 4), "d2h_bytes_per_step": 45 * 8,
+                        "note": "the CLI is end to end by construction: GFA text on disk -> TSV on stdout, process start to exit"},
+                "gpu_launches": 1, "clocks": None, "threads": threads}
+        print(json.dumps(line))
+        return 0
+    finally:
+        try:
+            os.unlink(gfa)
+            os.rmdir(workdir)
+        except OSError:
+            pass
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, ROOT)
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--items", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reference", action="store_true")
+    a = ap.parse_args()
+    sys.exit(bench(a, a.reference, "ordered-histgrowth item x group cells per second", "cells/s", {"workload": "c5 (stand-alone run)"}))
