@@ -125,6 +125,36 @@ def test_chrM_against_reference_goldens(count):
         assert list(curves[0]) == [89, 106, 140, 154]
 
 
+def test_ordered_growth_against_independent_witness():
+    """The CUDA path against tests/golden/ordered_growth_witness.json (brute force over the GFA's P lines, independent
+    of the oracle): node-major and group-major kernels, every grouping / count type / threshold pair of the witness."""
+    d = json.load(open(os.path.join(GOLDEN, "ordered_growth_witness.json")))
+    pairs = [tuple(p) for p in d["pairs"]]
+    for case in d["cases"]:
+        g, t, op, og, names, bits, weights = fixture_bitmap(case["gfa"], case["count"], groupby_sample=case["grouping"] == "sample",
+                                                            groupby_haplotype=case["grouping"] == "haplotype")
+        assert list(names) == case["groups"]
+        if t.n_items == 0:
+            continue
+        G = len(names)
+        cov, thr = cutoffs(G, pairs)
+        with pb.DeviceAbacus(t.n_items, G) as a:
+            path_group = np.full(len(t.id_prefsum) - 1, -1, dtype=np.int64)
+            path_group[op.astype(np.int64)] = og.astype(np.int64)
+            a.build(t.items, t.id_prefsum, path_group, t.exclude)  # from the ItemTable, like the CLI
+            a.upload(None, weights)
+            for path in ("scan", "gm"):
+                os.environ["PGX_QUORUM_PATH"] = path
+                try:
+                    cv = a.ordered_growth(cov, thr, weighted=(case["count"] == "bp"))
+                finally:
+                    os.environ.pop("PGX_QUORUM_PATH", None)
+                assert [[int(x) for x in row] for row in cv] == case["curves"], (case["gfa"], case["grouping"], case["count"], path)
+            ident = np.arange(G, dtype=np.uint32)[None, :]
+            pg = a.permuted_growth(ident, cov, thr, weighted=(case["count"] == "bp"))
+            assert [[int(x) for x in row] for row in pg[0]] == case["curves"]
+
+
 @pytest.mark.parametrize("gfa", ["t_groups.gfa", "cdbg.gfa"])
 def test_small_fixtures(gfa):
     for count in ("node", "bp", "edge"):

@@ -243,3 +243,29 @@ def test_table_known_answer_t_groups():
     assert rows[9] == "9\t0\t0\t19\t0\t0\t19"      # segment 9 (19 bp) is on y#3 and x
     assert rows[2] == "2\t0\t0\t0\t0\t0\t0"        # segment 2 is on no path
     assert po.coverage_line_table([("node", [5, 0, 10, 0, 0, 0, 0])]).split("\n")[4:7] == ["1\t0", "2\t10", "3\t0"]
+
+
+def test_ordered_growth_against_independent_witness():
+    """The reference holds no golden vector for AbacusByGroup::calc_growth.  tests/golden/ordered_growth_witness.json is a
+    brute-force evaluation of abacus.rs:1003-1010 straight from the P lines of the fixture GFAs
+    (tests/golden/make_ordered_growth_witness.py: pure Python, no ItemTable, no CSR, nothing imported from oracle/); the
+    oracle's chain GFA parser -> ItemTable -> CSR -> calc_growth must give the same curves for every grouping, count
+    type and threshold pair."""
+    import json
+    from oracle import gfa_oracle as go
+    d = json.load(open(os.path.join(GOLDEN, "ordered_growth_witness.json")))
+    pairs = [tuple(p) for p in d["pairs"]]
+    for case in d["cases"]:
+        g = go.parse_gfa(os.path.join(GOLDEN, case["gfa"]))
+        mask = go.make_mask(g, groupby_sample=case["grouping"] == "sample", groupby_haplotype=case["grouping"] == "haplotype")
+        t = go.item_tables(g, mask, case["count"])
+        op, og, names = go.path_order_arrays(mask, g)
+        assert list(names) == case["groups"], (case["gfa"], case["grouping"])
+        if t.n_items == 0:
+            assert all(not any(cv) for cv in case["curves"])
+            continue
+        r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        for (cov, q), want in zip(pairs, case["curves"]):
+            got = po.calc_growth(r, c, len(names), po.absolute(cov), po.relative(q), count_bp=(case["count"] == "bp"),
+                                 node_lens=g.node_lens)
+            assert [int(x) for x in got] == want, (case["gfa"], case["grouping"], case["count"], cov, q)
