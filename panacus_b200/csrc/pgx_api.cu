@@ -273,7 +273,11 @@ int ensure_gm(pgx_abacus *a) {
     if (a->gm_valid) return PGX_OK;
     a->gm_stride = gm_stride_words(a->n_rows);
     if (!a->d_gm) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_gm), (size_t)a->G * a->gm_stride * 8u));
-    int rc = launch_transpose(a->d_bitmap, a->n_rows, a->G, a->Wp, a->d_gm, a->gm_stride, nullptr, a->stream);
+    int rc;
+    {
+        KernelTimer kt(a);
+        rc = launch_transpose(a->d_bitmap, a->n_rows, a->G, a->Wp, a->d_gm, a->gm_stride, nullptr, a->stream);
+    }
     if (rc) return rc;
     a->launches++;
     a->gm_valid = true;
