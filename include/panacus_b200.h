@@ -54,6 +54,10 @@ typedef struct pgx_abacus pgx_abacus;
 const char *pgx_version(void);
 const char *pgx_last_error(void);
 int pgx_device_count(int *n);
+/* Creates the CUDA context of `device` (what the first pgx_abacus_create would otherwise pay, ~1-2 s in a cold
+ * process).  Thread safe and idempotent: a host program calls it from a side thread at start-up so that context
+ * creation overlaps its own input parsing. */
+int pgx_device_warmup(int device);
 /* u64 words per bitmap row for n_groups groups (see layout above). */
 uint32_t pgx_row_words(uint32_t n_groups);
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpanacus_b200.so")
 
 # every symbol include/panacus_b200.h declares (tests check that the .so exports all of them)
 EXPORTS = [
-    "pgx_version", "pgx_last_error", "pgx_device_count", "pgx_row_words",
+    "pgx_version", "pgx_last_error", "pgx_device_count", "pgx_device_warmup", "pgx_row_words",
     "pgx_abacus_create", "pgx_abacus_destroy", "pgx_abacus_set_stream", "pgx_abacus_shape",
     "pgx_abacus_upload", "pgx_abacus_adopt_device", "pgx_abacus_scatter", "pgx_abacus_build", "pgx_abacus_build_u32", "pgx_host_alloc", "pgx_host_free", "pgx_abacus_clear",
     "pgx_abacus_download", "pgx_abacus_copy_rows", "pgx_abacus_csr_rows", "pgx_abacus_csr_fill", "pgx_hist", "pgx_ordered_growth", "pgx_hist_ordered_growth",
@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
     L.pgx_last_error.argtypes = []
     L.pgx_device_count.restype = C.c_int
     L.pgx_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.pgx_device_warmup.restype = C.c_int
+    L.pgx_device_warmup.argtypes = [C.c_int]
     L.pgx_row_words.restype = C.c_uint32
     L.pgx_row_words.argtypes = [C.c_uint32]
     L.pgx_abacus_create.restype = C.c_int

@@ -628,6 +628,15 @@ int pgx_device_count(int *n) {
     return PGX_OK;
 }
 
+int pgx_device_warmup(int device) {
+    int ndev = 0;
+    PGX_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PGX_ERR_INVALID, "no such CUDA device");
+    DeviceGuard guard(device);
+    PGX_CUDA(cudaFree(nullptr));  // creates the primary context (seconds on a cold process); idempotent
+    return PGX_OK;
+}
+
 uint32_t pgx_row_words(uint32_t n_groups) {
     const uint32_t w = (n_groups + 63u) / 64u;
     return w <= 1u ? 1u : (w + 1u) / 2u * 2u;

@@ -24,17 +24,19 @@ uint64_t gm_stride_words(uint64_t n_rows) {
 namespace {
 
 // ---- transpose -----------------------------------------------------------------------------------
-// A CTA turns 1024 items x WC word-columns (WC x 64 groups) of the node-major bitmap into WC x 64 group rows x 128
-// bytes: (A) coalesced 128-bit loads into a padded shared-memory tile; (B) every warp transposes 32-item x 64-group
-// blocks across its lanes -- two 32 x 32 bit transposes of 5 butterfly stages each, one SHFL + one PRMT (byte stages)
-// or one SHF + one LOP3 (bit stages) per stage with per-lane constants hoisted -- into a second tile; (C) every group
-// row leaves as one full 128-byte line (the first version wrote 32-byte pieces and spent ~6 ALU operations per stage:
-// 1.04 ms for 10M x 1024, 37 % of the HBM roofline of read + write).
-constexpr int kTrItems = 1024;
-constexpr int kTrThreads = 256;
+// A CTA stages 256 items x COLS word-columns of the node-major bitmap in shared memory with coalesced
+// 128-bit loads (row pitch padded by one word: the column reads below are then conflict free for 64-bit
+// accesses); warp w then turns word-column w into 64 group rows x 8 u32 (32 contiguous bytes per row =
+// one full sector per store).  The 32x32 bit blocks are transposed across the lanes of a warp with the
+// 5-stage butterfly: per stage one SHFL and one PRMT (the byte-granular stages) or one SHF + one LOP3 (the
+// bit stages), all per-lane constants hoisted -- the first version spent ~6 ALU operations per stage and
+// was ALU-pipe bound (1.04 ms for 10M x 1024; a variant with 1024-item tiles and full 128-byte output
+// lines but 8 warps per CTA was slower still, 1.19 ms: occupancy, not the write granularity, is what
+// counts here -- profiles/r2_transpose_*.jsonl).
+constexpr int kTrItems = 256;
 
 struct TrLane {  // per-lane constants of the butterfly
-    uint32_t sel16, sel8;      // PRMT selectors of the 16- and 8-bit stages
+    uint32_t sel16, sel8;          // PRMT selectors of the 16- and 8-bit stages
     uint32_t keep4, keep2, keep1;  // bits that stay in place in the 4-, 2-, 1-bit stages
     uint32_t rot4, rot2, rot1;     // left-rotation of the partner's word
 };
@@ -70,61 +72,64 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, const TrLane &t) {
     return x;
 }
 
-template <int WC>
-__global__ void __launch_bounds__(kTrThreads) k_transpose(const uint64_t *__restrict__ bitmap, uint64_t n_rows, uint32_t G,
-                                                          uint32_t W, uint32_t Wp, uint32_t *__restrict__ gm32,
-                                                          uint64_t gm_stride32, const uint32_t *__restrict__ perm) {
+template <int COLS>
+__global__ void __launch_bounds__(COLS * 32) k_transpose(const uint64_t *__restrict__ bitmap, uint64_t n_rows, uint32_t G,
+                                                         uint32_t W, uint32_t Wp, uint32_t *__restrict__ gm32,
+                                                         uint64_t gm_stride32, const uint32_t *__restrict__ perm) {
     // perm != nullptr: bit position i of the output rows holds item perm[i] (weight-sorted copy for similarity)
-    constexpr int kPitch = WC > 1 ? WC + 1 : 1;  // u64 words per staged row: odd pitch -> conflict-free 64-bit column reads
-    constexpr int kOutPitch = 33;                // u32 words per staged output row
-    extern __shared__ __align__(16) unsigned char tr_smem[];
-    uint64_t *tin = reinterpret_cast<uint64_t *>(tr_smem);
-    uint32_t *tout = reinterpret_cast<uint32_t *>(tr_smem + (size_t)kTrItems * kPitch * 8u);
+    constexpr int kPitch = COLS + 1, kThreads = COLS * 32;
+    __shared__ uint64_t tile[kTrItems * kPitch];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t item0 = (uint64_t)blockIdx.x * kTrItems;
-    const uint32_t wc0 = blockIdx.y * WC;
-    // (A) stage the tile
-    if (WC > 1) {
-        constexpr uint32_t kChunks = WC / 2;  // 16-byte chunks per row
-        for (uint32_t e = tid; e < kTrItems * kChunks; e += kTrThreads) {
-            const uint32_t r = e / kChunks, c = e - r * kChunks;
+    const uint32_t wc0 = blockIdx.y * COLS;
+    const uint32_t ncols = min((uint32_t)COLS, Wp - wc0);  // word-columns staged by this CTA (Wp is even or 1)
+    if (ncols >= 2u && !(ncols & 1u)) {
+        const uint32_t chunks = ncols >> 1;  // 16-byte chunks per row
+        for (uint32_t e = tid; e < kTrItems * chunks; e += kThreads) {
+            const uint32_t r = e / chunks, c = e - r * chunks;
             uint64_t item = item0 + r;
             if (perm && item < n_rows) item = __ldg(perm + item);
             uint64_t x0 = 0, x1 = 0;
-            if (item != 0 && item < n_rows && wc0 + 2u * c < Wp) {  // (Wp is even here: a 16-byte chunk never straddles the row end)
+            if (item != 0 && item < n_rows) {
                 const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(bitmap + item * Wp + wc0) + c);
                 x0 = v.x;
                 x1 = v.y;
             }
-            tin[r * kPitch + 2u * c] = x0;
-            tin[r * kPitch + 2u * c + 1u] = x1;
+            tile[r * kPitch + 2u * c] = x0;
+            tile[r * kPitch + 2u * c + 1u] = x1;
         }
     } else {
-        for (uint32_t r = tid; r < kTrItems; r += kTrThreads) {
+        for (uint32_t e = tid; e < kTrItems * ncols; e += kThreads) {
+            const uint32_t r = e / ncols, c = e - r * ncols;
             uint64_t item = item0 + r;
             if (perm && item < n_rows) item = __ldg(perm + item);
-            tin[r] = (item != 0 && item < n_rows && wc0 < Wp) ? __ldg(bitmap + item * Wp + wc0) : 0ull;
+            tile[r * kPitch + c] = (item != 0 && item < n_rows) ? __ldg(bitmap + item * Wp + wc0 + c) : 0ull;
         }
     }
     __syncthreads();
-    // (B) 32 x 64 blocks: lane = item of the block on the way in, group of the block on the way out
+    const uint32_t wc = wc0 + warp;  // word column of the node-major row handled by this warp
+    if (warp >= ncols || wc >= W) return;
     const TrLane tl = tr_lane(lane);
-    for (uint32_t u = warp; u < (kTrItems / 32u) * WC; u += kTrThreads / 32u) {
-        const uint32_t ib = u / WC, c = u - ib * WC;
-        const uint64_t x = tin[(ib * 32u + lane) * kPitch + c];
-        const uint32_t lo = transpose32((uint32_t)x, tl), hi = transpose32((uint32_t)(x >> 32), tl);
-        tout[(c * 64u + lane) * kOutPitch + ib] = lo;
-        tout[(c * 64u + 32u + lane) * kOutPitch + ib] = hi;
+    uint32_t keep0[8], keep1[8];
+#pragma unroll
+    for (int ib = 0; ib < 8; ++ib) {
+        const uint64_t x = tile[(ib * 32 + lane) * kPitch + warp];
+        keep0[ib] = transpose32((uint32_t)x, tl);
+        keep1[ib] = transpose32((uint32_t)(x >> 32), tl);
     }
-    __syncthreads();
-    // (C) one 128-byte line per group row
+    // lane b owns groups wc*64 + b and wc*64 + 32 + b; 8 u32 = items item0 .. item0+255
     const uint64_t col32 = item0 / 32u;
-    for (uint32_t gl = warp; gl < WC * 64u; gl += kTrThreads / 32u) {
-        const uint32_t g = wc0 * 64u + gl;
-        if (g >= G) break;
-        gm32[(uint64_t)g * gm_stride32 + col32 + lane] = tout[gl * kOutPitch + lane];
+    const uint32_t g0 = wc * 64u + lane, g1 = g0 + 32u;
+    if (g0 < G) {
+        uint4 *dst = reinterpret_cast<uint4 *>(gm32 + (uint64_t)g0 * gm_stride32 + col32);
+        dst[0] = make_uint4(keep0[0], keep0[1], keep0[2], keep0[3]);
+        dst[1] = make_uint4(keep0[4], keep0[5], keep0[6], keep0[7]);
     }
-    (void)W;
+    if (g1 < G) {
+        uint4 *dst = reinterpret_cast<uint4 *>(gm32 + (uint64_t)g1 * gm_stride32 + col32);
+        dst[0] = make_uint4(keep1[0], keep1[1], keep1[2], keep1[3]);
+        dst[1] = make_uint4(keep1[4], keep1[5], keep1[6], keep1[7]);
+    }
 }
 
 // ---- group-major growth -----------------------------------------------------------------------
@@ -706,26 +711,18 @@ size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general, bool direc
     return (((size_t)(G + thr_words) * 4u + 15u) & ~(size_t)15u) + (direct_out ? 0u : (size_t)T * G * 8u);
 }
 
-template <int WC>
-int launch_transpose_wc(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t W, uint32_t Wp, uint64_t *gm, uint64_t gm_stride,
-                        const uint32_t *perm, cudaStream_t stream) {
-    constexpr int kPitch = WC > 1 ? WC + 1 : 1;
-    const size_t smem = (size_t)kTrItems * kPitch * 8u + (size_t)WC * 64u * 33u * 4u;
-    auto kern = k_transpose<WC>;
-    PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned gx = (unsigned)(gm_stride * 64u / kTrItems);  // gm_stride is a multiple of 16 words = 1024 items
-    kern<<<dim3(gx, (Wp + WC - 1u) / WC), kTrThreads, smem, stream>>>(bitmap, n_rows, G, W, Wp, reinterpret_cast<uint32_t *>(gm),
-                                                                        gm_stride * 2u, perm);
-    PGX_CUDA(cudaGetLastError());
-    return PGX_OK;
-}
-
 int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
                      uint64_t gm_stride, const uint32_t *perm, cudaStream_t stream) {
     const uint32_t W = (G + 63u) / 64u;
-    if (Wp >= 4u) return launch_transpose_wc<4>(bitmap, n_rows, G, W, Wp, gm, gm_stride, perm, stream);
-    if (Wp == 2u) return launch_transpose_wc<2>(bitmap, n_rows, G, W, Wp, gm, gm_stride, perm, stream);
-    return launch_transpose_wc<1>(bitmap, n_rows, G, W, Wp, gm, gm_stride, perm, stream);
+    const unsigned gx = (unsigned)(gm_stride * 64u / kTrItems);
+    if (Wp >= 16u)  // 128-byte (or wider) rows: one CTA reads whole lines
+        k_transpose<16><<<dim3(gx, (W + 15u) / 16u), 512, 0, stream>>>(bitmap, n_rows, G, W, Wp,
+                                                                      reinterpret_cast<uint32_t *>(gm), gm_stride * 2u, perm);
+    else
+        k_transpose<8><<<dim3(gx, (W + 7u) / 8u), 256, 0, stream>>>(bitmap, n_rows, G, W, Wp,
+                                                                    reinterpret_cast<uint32_t *>(gm), gm_stride * 2u, perm);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
 }
 
 template <int P, bool GENERAL>

@@ -119,6 +119,11 @@ std::vector<std::vector<double>> DeviceAbacus::calc_growth(const ThresholdContai
     return out;
 }
 
+void device_warmup_async(int n_devices) {
+    // context creation overlaps the GFA parse; errors surface later, at the first real device call
+    for (int d = 0; d < n_devices; ++d) std::thread([d] { pgx_device_warmup(d); }).detach();
+}
+
 int device_count() {
     int n = 0;
     check(pgx_device_count(&n), "pgx_device_count");

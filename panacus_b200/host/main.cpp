@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -940,6 +941,12 @@ int dispatch(int argc, char **argv, std::ostream &os) {
             g_phase.report();
         }
     } report;
+    {  // the subcommands that count on the GPU: start creating the CUDA context(s) now, while the GFA is parsed
+        static const std::set<std::string> kDevice = {"hist", "histgrowth", "ordered-histgrowth", "similarity", "table", "coverage-line", "report"};
+        const bool from_tsv = a.sub == "growth" && ends_with(a.positional.at(0), ".tsv");
+        if ((kDevice.count(a.sub) || (a.sub == "growth" && !from_tsv)) && !a.has("dry-run"))
+            device_warmup_async(a.has("gpus") ? std::max(1, std::atoi(a.get("gpus").c_str())) : 1);
+    }
     if (a.sub == "hist") return cmd_hist(a, cmdline, os);
     if (a.sub == "growth") return cmd_growth(a, cmdline, false, os);
     if (a.sub == "histgrowth") return cmd_growth(a, cmdline, true, os);
@@ -991,11 +998,17 @@ int run_batch(const char *prog, const std::string &file) {
 }  // namespace
 
 int main(int argc, char **argv) {
+    int rc;
     try {
         if (argc == 3 && std::string(argv[1]) == "batch") return run_batch(argv[0], argv[2]);
-        return dispatch(argc, argv, std::cout);
+        rc = dispatch(argc, argv, std::cout);
     } catch (const std::exception &e) {
         std::cerr << "error: " << e.what() << "\n";
-        return 1;
+        std::cerr.flush();
+        std::_Exit(1);  // (a context-creation side thread may still be running: no static teardown under it)
     }
+    // results are out: skip the teardown of the CUDA context and of GB-sized host structures (fractions of a second each)
+    std::cout.flush();
+    std::cerr.flush();
+    std::_Exit(rc);
 }

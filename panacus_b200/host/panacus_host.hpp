@@ -192,6 +192,7 @@ std::vector<Hist> parse_hists(const std::string &path, std::vector<std::string> 
 
 // ---- device side (RAII over include/panacus_b200.h) ----------------------------------------------------------
 int device_count();  // pgx_device_count
+void device_warmup_async(int n_devices);  // CUDA context creation on side threads (overlaps the GFA parse)
 
 // One GPU's NCCL communicator (pgx_comm); create_all = the single-process form, one communicator per device, each to be
 // driven from its own host thread (run_on_devices).

@@ -217,28 +217,32 @@ def test_lane_private_counter_kernel(N, G, monkeypatch):
                 monkeypatch.setenv("PGX_SCAN_GRID", grid)
             else:
                 monkeypatch.delenv("PGX_SCAN_GRID", raising=False)
-            for priv in (True, False):
-                if priv:
+            # "force": lane-private counters whenever they fit in one CTA; "off": the shared-atomics kernel; "auto": the
+            # library's own choice (private counters only where two CTAs per SM fit)
+            for mode in ("force", "off", "auto"):
+                if mode == "auto":
                     monkeypatch.delenv("PGX_SCAN_PRIV", raising=False)
                 else:
-                    monkeypatch.setenv("PGX_SCAN_PRIV", "2")
+                    monkeypatch.setenv("PGX_SCAN_PRIV", "1" if mode == "force" else "2")
                 hc, _, ct = a.hist(count=True, weight=False, countable=True)
-                assert ("k_scan_priv<u8>" in a.last_launch_info()) == priv, a.last_launch_info()
+                if mode != "auto":
+                    assert ("k_scan_priv<u8>" in a.last_launch_info()) == (mode == "force"), a.last_launch_info()
                 assert np.array_equal(hc, exp["hist"]) and np.array_equal(ct, exp["countable"])
                 _, hw, _ = a.hist(count=False, weight=True)
-                assert ("k_scan_priv<u16>" in a.last_launch_info()) == priv, a.last_launch_info()
+                if mode != "auto":
+                    assert ("k_scan_priv<u16>" in a.last_launch_info()) == (mode == "force"), a.last_launch_info()
                 assert np.array_equal(hw, exp["hist_bp"])
                 h2, _, cv = a.hist_ordered_growth(cov, None, weighted=False, hist_count=True, hist_weight=False)
-                assert priv or "k_scan_priv" not in a.last_launch_info()
-                assert not (priv and G <= 64) or "k_scan_priv<u8>" in a.last_launch_info(), a.last_launch_info()
+                assert mode != "off" or "k_scan_priv" not in a.last_launch_info()
+                assert not (mode == "force" and G <= 64) or "k_scan_priv<u8>" in a.last_launch_info(), a.last_launch_info()
                 _, w2, cvw = a.hist_ordered_growth(cov, None, weighted=True, hist_count=False, hist_weight=True)
                 assert np.array_equal(h2, exp["hist"]) and np.array_equal(w2, exp["hist_bp"])
                 for t, (c, q) in enumerate(pairs):
-                    assert np.array_equal(cv[t].astype(np.float64), exp[("node", c, q)]), (grid, priv, c)
-                    assert np.array_equal(cvw[t].astype(np.float64), exp[("bp", c, q)]), (grid, priv, c)
+                    assert np.array_equal(cv[t].astype(np.float64), exp[("node", c, q)]), (grid, mode, c)
+                    assert np.array_equal(cvw[t].astype(np.float64), exp[("bp", c, q)]), (grid, mode, c)
                 one = a.ordered_growth([2], None, weighted=False)  # growth only: no histogram bins at all
                 assert np.array_equal(one[0].astype(np.float64), exp[("node", 2, 0.0)])
-                if priv and G <= 256:
+                if mode == "force" and G <= 256:
                     assert "k_scan_priv<u8>" in a.last_launch_info(), a.last_launch_info()
 
 
