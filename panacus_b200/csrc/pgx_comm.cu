@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -346,6 +347,12 @@ int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *i
     // scratch: [ full matrix + len | gathered: world x per_rank | send: per_rank ]
     if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, full + per_rank * ((size_t)world + 1u)))) return rc;
     uint64_t *d_full = a->d_scratch, *d_all = d_full + full, *d_send = d_all + per_rank * world;
+    // with timing enabled: device time of the phases (compute | all-gather | assembly | copy to the host) in last_launch_info
+    cudaEvent_t ev[5] = {};
+    auto mark = [&](int k) {
+        if (a->timing && cudaEventCreate(&ev[k]) == cudaSuccess) cudaEventRecord(ev[k], a->stream);
+    };
+    mark(0);
     PGX_CUDA(cudaMemsetAsync(d_send, 0, per_rank * 8u, a->stream));
     uint32_t row_off = 0;
     for (uint32_t b : {rank, nb - 1u - rank}) {
@@ -355,7 +362,9 @@ int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *i
         if ((rc = sim_len_device(a, weighted, lo, hi, d_send + (size_t)max_rows * G + row_off))) return rc;
         row_off += hi - lo;
     }
+    mark(1);
     PGX_NCCL(N->AllGather(d_send, d_all, per_rank, ncclUint64, c->comm, a->stream));
+    mark(2);
     ap.gathered = d_all;
     ap.rank_stride = per_rank;
     ap.inter = d_full;
@@ -366,8 +375,21 @@ int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *i
     ap.max_rows = max_rows;
     if ((rc = launch_sim_assemble(ap, a->stream))) return rc;
     a->launches++;
+    mark(3);
     if ((rc = copy_to_host(a, inter, d_full, (size_t)G * G))) return rc;
-    return copy_to_host(a, len, d_full + (size_t)G * G, G);
+    rc = copy_to_host(a, len, d_full + (size_t)G * G, G);
+    mark(4);
+    if (a->timing && ev[0] && ev[1] && ev[2] && ev[3] && ev[4]) {
+        float t[4] = {};
+        cudaEventSynchronize(ev[4]);
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], ev[k], ev[k + 1]);
+        char buf[200];
+        snprintf(buf, sizeof buf, "pgx_similarity_sharded phases ms: compute %.3f | all-gather %.3f | assembly %.3f | to host %.3f", t[0], t[1], t[2], t[3]);
+        a->last_launch = buf;
+    }
+    for (auto e : ev)
+        if (e) cudaEventDestroy(e);
+    return rc;
 }
 
 }  // extern "C"
