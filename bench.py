@@ -641,6 +641,7 @@ def run_sharded(args):
     torch.cuda.synchronize()
     total_ms = max_over_ranks(c, e0.elapsed_time(e1))
     kernel_ms, n_sections = a.kernel_time_ms()
+    launch_info = a.last_launch_info()  # (with timing on, the sharded similarity reports its phase times here)
     a.set_timing(False)
     launches = a.launch_count - launches0
     n_extra = max(1, min(200, int(250.0 / max(total_ms / args.steps, 1e-3))))
@@ -665,7 +666,7 @@ def run_sharded(args):
     achieved = alg_bytes / (kms * 1e-3) / 1e9 if kms > 0 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                 "traffic": None, "peak_source": peak_src, "kernel": kernel_name, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms_mean": kms, "kernel_sections_per_step": n_sections / args.steps, "launch": a.last_launch_info(),
+                "kernel_ms_mean": kms, "kernel_sections_per_step": n_sections / args.steps, "launch": launch_info,
                 "note": ("integer-ALU bound (bit-sliced rank counters), DRAM sees about one pass for all orders of a launch (L2 reuse)"
                          if kind == "permuted" else "POPC / LOP3 issue bound (G^2/2 x N/64 AND+POPC word pairs); the HBM figure is reported "
                                                     "because the contract asks for it")}
