@@ -402,9 +402,15 @@ def run_ordered(args):
     if bitmap_bytes < 256 * 1024 * 1024:  # smaller than 2x L2: flush L2 between steps
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    def flush_l2():
+        # 256 MB write evicts the table from L2; the spin kernel after it (~100 us) keeps the stream busy while the host
+        # enqueues the event and the pass, so that no host-side launch gap lands between the two events of a step
+        flush.fill_(1)
+        torch.cuda._sleep(200_000)
+
     def step():
         if flush is not None:
-            flush.fill_(1)
+            flush_l2()
         a.fused_pass_async(out.data_ptr(), cov, None, weighted=False, hist_count=True, hist_weight=False)
         if nccl_exchange:
             dist.all_reduce(out)  # the path's one exchange: sum of per-shard integer results
@@ -427,7 +433,7 @@ def run_ordered(args):
     e0.record()
     for i in range(args.steps):
         if flush is not None:
-            flush.fill_(1)
+            flush_l2()
         k_ev[i][0].record()
         a.fused_pass_async(out.data_ptr(), cov, None, weighted=False, hist_count=True, hist_weight=False)
         k_ev[i][1].record()

@@ -584,8 +584,23 @@ int sim_rows_device(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t ro
     p.col_begin = col_begin;
     p.inter = d_inter;
     p.upper_only = upper_only ? 1u : 0u;
-    const char *env = getenv("PGX_SIM");  // "plain": one POPC per item word and pair; default: carry-save pairs of words
+    // PGX_SIM: "mma" = tensor cores (tcgen05 kind::i8 on the expanded bits), "csa" = carry-save AND / POPC pairs,
+    // "plain" = one POPC per item word and pair.  Default: mma for unweighted tables with >= 256 groups.
+    const char *env = getenv("PGX_SIM");
+    const bool want_mma = env ? !strcmp(env, "mma") : a->G >= 256u;  // (a 128 x 256 tile is mostly padding below that)
     p.csa = (!use_planes && !(env && !strcmp(env, "plain"))) ? 1u : 0u;
+    if (!use_planes && want_mma) {
+        p.triangular = (row_begin == 0u && row_end == a->G && col_begin == 0u) ? 1u : 0u;
+        {
+            KernelTimer kt(a);
+            rc = launch_sim_mma(p, a->sm_count, a->stream);
+            if (!rc && p.triangular) rc = launch_sim_mirror(d_inter, a->G, a->stream);
+        }
+        if (rc) return rc;
+        a->launches++;
+        a->last_launch = "k_sim_mma (tcgen05.mma kind::i8)";
+        return PGX_OK;
+    }
     {
         KernelTimer kt(a);
         rc = launch_gm_similarity(p, a->sm_count, a->stream);
@@ -1242,9 +1257,15 @@ int similarity_rows(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t ro
     if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, words))) return rc;
     PGX_CUDA(cudaMemsetAsync(a->d_scratch, 0, words * 8u, a->stream));
     if (rows && (rc = sim_rows_device(a, weighted, row_begin, row_end, col_begin, a->d_scratch, false))) return rc;
-    if (len && (rc = sim_len_device(a, weighted, 0, G, a->d_scratch + inter_words))) return rc;
+    // len[g] = the diagonal entry inter[g][g]: the full square carries it, row blocks need the row sums of all G groups
+    const bool full_square = rows == G && row_begin == 0u && col_begin == 0u;
+    if (len && !full_square && (rc = sim_len_device(a, weighted, 0, G, a->d_scratch + inter_words))) return rc;
     if (rows && (rc = copy_to_host(a, inter, a->d_scratch, inter_words))) return rc;
-    if (len && (rc = copy_to_host(a, len, a->d_scratch + inter_words, G))) return rc;
+    if (len && full_square) {
+        for (uint32_t g = 0; g < G; ++g) len[g] = inter[(size_t)g * G + g];
+    } else if (len && (rc = copy_to_host(a, len, a->d_scratch + inter_words, G))) {
+        return rc;
+    }
     return PGX_OK;
 }
 }  // namespace

@@ -342,7 +342,7 @@ int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *i
     uint32_t max_rows = 0;
     for (uint32_t r = 0; r < world; ++r)
         max_rows = std::max(max_rows, (ap.bounds[r + 1] - ap.bounds[r]) + (ap.bounds[nb - r] - ap.bounds[nb - 1u - r]));
-    const size_t per_rank = (size_t)max_rows * (G + 1u);  // intersections of the rank's rows, then their len entries
+    const size_t per_rank = (size_t)max_rows * G;  // intersections of the rank's rows (their diagonal entries are the len values)
     const size_t full = (size_t)G * G + G;
     // scratch: [ full matrix + len | gathered: world x per_rank | send: per_rank ]
     if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, full + per_rank * ((size_t)world + 1u)))) return rc;
@@ -359,7 +359,6 @@ int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *i
         const uint32_t lo = ap.bounds[b], hi = ap.bounds[b + 1u];
         if (hi == lo) continue;
         if ((rc = sim_rows_device(a, weighted, lo, hi, lo, d_send + (size_t)row_off * G, true))) return rc;
-        if ((rc = sim_len_device(a, weighted, lo, hi, d_send + (size_t)max_rows * G + row_off))) return rc;
         row_off += hi - lo;
     }
     mark(1);

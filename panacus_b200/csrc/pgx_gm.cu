@@ -500,10 +500,11 @@ __global__ void __launch_bounds__(256) k_sim_assemble(const SimAssembleParams p)
     // rows of the rank's first block (block `rank`) precede those of its second (block n_blocks - 1 - rank)
     const uint32_t local = (b < p.world ? 0u : p.bounds[rank + 1u] - p.bounds[rank]) + (r - p.bounds[b]);
     const uint64_t *src = p.gathered + (uint64_t)rank * p.rank_stride;
+    // len[g] = sum of w over the items of g = the diagonal entry (an item of g is in g and g): no separate row sums
     if (e < GG)
         p.inter[e] = src[(uint64_t)local * p.G + c];
     else
-        p.len[r] = src[(uint64_t)p.max_rows * p.G + local];
+        p.len[r] = src[(uint64_t)local * p.G + r];
 }
 
 // first differences -> curves in place (wrapping u64 prefix sums); one warp per curve of G entries
@@ -774,6 +775,12 @@ int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream
         k_sim_mirror<<<dim3((p.G + 15u) / 16u, (p.G + 15u) / 16u), 256, 0, stream>>>(p.inter, p.G);
         PGX_CUDA(cudaGetLastError());
     }
+    return PGX_OK;
+}
+
+int launch_sim_mirror(uint64_t *inter, uint32_t G, cudaStream_t stream) {
+    k_sim_mirror<<<dim3((G + 15u) / 16u, (G + 15u) / 16u), 256, 0, stream>>>(inter, G);
+    PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }
 

@@ -158,10 +158,14 @@ struct GmSimParams {
     uint64_t *inter;         // device (row_end-row_begin) x G, zeroed by the launcher
 };
 int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream);
+// the same contract on the tensor cores (pgx_simmma.cu: tcgen05.mma.kind::i8 on the bits expanded to u8), unweighted only;
+// p.triangular must be set by the caller for a full square (then follow with launch_sim_mirror)
+int launch_sim_mma(const GmSimParams &p, int sm_count, cudaStream_t stream);
+int launch_sim_mirror(uint64_t *inter, uint32_t G, cudaStream_t stream);
 // sharded similarity: all-gathered upper-triangle row blocks -> full matrix + len (pgx_comm.cu)
 struct SimAssembleParams {
-    const uint64_t *gathered;  // [world][rank_stride]: per rank max_rows x G intersections, then max_rows len entries
-    uint64_t rank_stride;      // max_rows * (G + 1)
+    const uint64_t *gathered;  // [world][rank_stride]: per rank max_rows x G intersections (len = their diagonal entries)
+    uint64_t rank_stride;      // max_rows * G
     uint64_t *inter;           // G x G
     uint64_t *len;             // G
     uint32_t G, world, n_blocks, max_rows;

@@ -359,6 +359,32 @@ def test_permuted_growth_q0_only(N, G, kernel, monkeypatch):
 
 # ---- similarity -------------------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("N,G", [(3000, 256), (70_000, 300), (100_001, 1024), (5000, 700), (127, 256), (449, 512), (900, 70)])
+def test_similarity_tensor_core_kernel(N, G, monkeypatch):
+    """k_sim_mma (tcgen05.mma.kind::i8 on the bits expanded to u8, s32 accumulators in TMEM) against the oracle's
+    restatement of Similarity::set_table and against the AND / POPC kernel: full square (upper tiles + mirror), row
+    blocks, upper-triangle blocks; ragged shapes (groups and items that do not fill a tile / a stage)."""
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=N * 3 + G)
+    items, prefsum, op, og = po.bitmap_to_item_table(bitmap, G)
+    r, c, _ = po.csr_build(N, items, prefsum, op, og)
+    want, want_len, _ = po.similarity(r, c, G)
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        monkeypatch.setenv("PGX_SIM", "mma")
+        inter, ln = a.similarity()
+        assert "k_sim_mma" in a.last_launch_info()
+        assert np.array_equal(inter, want) and np.array_equal(ln, want_len)
+        lo, hi = min(64, G // 3), min(G, 300)
+        part, ln2 = a.similarity(row_begin=lo, row_end=hi)
+        assert np.array_equal(part, want[lo:hi]) and np.array_equal(ln2, want_len)
+        up, _ = a.similarity(row_begin=lo, row_end=hi, upper=True)
+        for x in range(lo, hi):  # columns >= the row (what a sharded run reads) are computed, columns < row_begin are zero
+            assert np.array_equal(up[x - lo, x:], want[x, x:]) and not up[x - lo, :lo].any()
+        monkeypatch.setenv("PGX_SIM", "csa")
+        inter2, _ = a.similarity()
+        assert np.array_equal(inter2, want)
+
+
 @pytest.mark.parametrize("variant", ["csa", "plain"])
 @pytest.mark.parametrize("N,G", [(10, 2), (500, 64), (3000, 70), (1500, 130), (70000, 40)])
 def test_similarity(N, G, variant, monkeypatch):
