@@ -243,17 +243,18 @@ int pgx_hist_ordered_growth_sharded(pgx_abacus *a, pgx_comm *c, uint64_t *hist_c
  *                                all-gathered (ncclAllGather) and copied to the host once; `curves` as in
  *                                pgx_permuted_growth, complete on every rank.  The reference's parallel axis on this
  *                                path is the threshold pairs only (src/analyses/ordered_histgrowth.rs:174-188).
- *   pgx_similarity_sharded       the upper triangle of the intersection matrix is cut into 2 * world tile-aligned row
- *                                blocks (pgx_similarity_shard_bounds), rank r computes blocks r and 2 * world - 1 - r from
- *                                their diagonal rightwards (equal pair work) plus the len entries of its rows; all-gather,
- *                                assembly and mirroring on the device, one copy to the host: inter (G x G) and len (G)
- *                                complete on every rank.  Similarity::set_table (src/analyses/similarity.rs:119-163)
- *                                is serial in the reference. */
+ *   pgx_similarity_sharded       the sum runs over the items, so the items are split: rank r computes the whole matrix
+ *                                (upper triangle + mirror) over its share of the 64-item words, one ncclAllReduce (u64
+ *                                sum) of the partial matrices, one copy to the host: inter (G x G) and len (G, = the
+ *                                diagonal) complete on every rank.  Similarity::set_table
+ *                                (src/analyses/similarity.rs:119-163) is serial in the reference. */
 int pgx_permuted_growth_sharded(pgx_abacus *a, pgx_comm *c, uint32_t n_orders, const uint32_t *orders,
                                 uint32_t n_thresholds, const uint32_t *cov_abs, const uint32_t *quorum_thr, int weighted,
                                 uint64_t *curves);
 int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *inter, uint64_t *len);
-/* Host-only: the 2 * world + 1 row-block boundaries pgx_similarity_sharded uses (no device, no NCCL needed). */
+/* Host-only helper for callers that shard the similarity matrix by ROWS themselves with pgx_similarity_upper (the
+ * torch.distributed twin in panacus_b200/sharding.py does): 2 * world + 1 tile-aligned boundaries; rank r takes blocks r and
+ * 2 * world - 1 - r, each from its diagonal rightwards -- an equal share of the pair work. */
 int pgx_similarity_shard_bounds(uint32_t n_groups, uint32_t world, uint32_t *bounds);
 
 /* Kernel timing for measurements: while enabled, every hot-path kernel section a call launches (k_scan, the group-major

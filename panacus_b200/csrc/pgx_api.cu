@@ -560,7 +560,7 @@ int gm_growth(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t
 // Integer part of Similarity::set_table for the group rows [row_begin, row_end) x the columns >= col_begin, into the
 // zeroed device buffer d_inter ((row_end - row_begin) x G).  No synchronisation.
 int sim_rows_device(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint64_t *d_inter,
-                    bool upper_only) {
+                    bool upper_only, uint64_t word_begin, uint64_t word_end) {
     int rc;
     const bool use_planes = weighted && a->d_weight;
     if (use_planes) {
@@ -571,12 +571,16 @@ int sim_rows_device(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t ro
     if (row_end == row_begin) return PGX_OK;
     GmSimParams p;
     std::memset(&p, 0, sizeof(p));
-    p.gm = use_planes ? a->d_gm_w : a->d_gm;
+    // items [64 word_begin, 64 word_end) only (a rank's share of a sharded run): every per-word array starts at word_begin
+    const uint64_t all_words = (a->n_rows + 63u) / 64u;
+    if (word_end > all_words) word_end = all_words;
+    if (word_begin >= word_end) return PGX_OK;
+    p.gm = (use_planes ? a->d_gm_w : a->d_gm) + word_begin;
     p.gm_stride = a->gm_stride;
-    p.n_words = (a->n_rows + 63u) / 64u;
-    p.planes = use_planes ? a->d_planes : nullptr;
-    p.uniform_w = use_planes ? a->d_uniform_w : nullptr;
-    p.plane_mask = use_planes ? a->d_plane_mask : nullptr;
+    p.n_words = word_end - word_begin;
+    p.planes = use_planes ? a->d_planes + word_begin : nullptr;
+    p.uniform_w = use_planes ? a->d_uniform_w + word_begin : nullptr;
+    p.plane_mask = use_planes ? a->d_plane_mask + word_begin : nullptr;
     p.n_planes = use_planes ? a->n_planes : 0;
     p.G = a->G;
     p.row_begin = row_begin;
@@ -591,6 +595,7 @@ int sim_rows_device(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t ro
     p.csa = (!use_planes && !(env && !strcmp(env, "plain"))) ? 1u : 0u;
     if (!use_planes && want_mma) {
         p.triangular = (row_begin == 0u && row_end == a->G && col_begin == 0u) ? 1u : 0u;
+        if (const char *dbg = getenv("PGX_SIM_DEBUG")) p.csa = (uint32_t)atoi(dbg);  // timing experiments only (see k_sim_mma)
         {
             KernelTimer kt(a);
             rc = launch_sim_mma(p, a->sm_count, a->stream);
@@ -1256,7 +1261,7 @@ int similarity_rows(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t ro
     const size_t words = inter_words + G;
     if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, words))) return rc;
     PGX_CUDA(cudaMemsetAsync(a->d_scratch, 0, words * 8u, a->stream));
-    if (rows && (rc = sim_rows_device(a, weighted, row_begin, row_end, col_begin, a->d_scratch, false))) return rc;
+    if (rows && (rc = sim_rows_device(a, weighted, row_begin, row_end, col_begin, a->d_scratch, false, 0, ~0ull))) return rc;
     // len[g] = the diagonal entry inter[g][g]: the full square carries it, row blocks need the row sums of all G groups
     const bool full_square = rows == G && row_begin == 0u && col_begin == 0u;
     if (len && !full_square && (rc = sim_len_device(a, weighted, 0, G, a->d_scratch + inter_words))) return rc;

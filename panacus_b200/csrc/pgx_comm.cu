@@ -4,8 +4,8 @@
 //   pgx_permuted_growth_sharded     order p -> rank p % world; curves stay on the device, one ncclAllGather on the
 //                                   handle's stream, one copy to the host.  The reference's only parallel axis here is
 //                                   across threshold pairs (src/analyses/ordered_histgrowth.rs:174-188).
-//   pgx_similarity_sharded          two folded row blocks of the upper triangle per rank (equal pair work), ncclAllGather,
-//                                   assembly + mirroring on the device (k_sim_assemble), one copy to the host.
+//   pgx_similarity_sharded          every rank sums the (mirrored upper-triangular) matrix over its share of the ITEMS,
+//                                   one ncclAllReduce (u64 sum) of the G x G partial matrices, one copy to the host.
 //                                   Similarity::set_table is serial in the reference (src/analyses/similarity.rs:130-150).
 //   pgx_hist_ordered_growth_sharded item-range shards, ncclAllReduce(u64 sum) of the KB-sized fused result vector (the
 //                                   NCCL twin of the in-kernel NVLink exchange of pgx_exchange_connect).
@@ -335,55 +335,40 @@ int pgx_similarity_sharded(pgx_abacus *a, pgx_comm *c, int weighted, uint64_t *i
     const Nccl *N;
     if ((rc = need_nccl(&N))) return rc;
     DeviceGuard guard(a->device);
-    const uint32_t G = a->G, world = c->world, rank = c->rank, nb = 2u * world;
-    SimAssembleParams ap;
-    std::memset(&ap, 0, sizeof(ap));
-    sim_block_bounds(G, world, ap.bounds);
-    uint32_t max_rows = 0;
-    for (uint32_t r = 0; r < world; ++r)
-        max_rows = std::max(max_rows, (ap.bounds[r + 1] - ap.bounds[r]) + (ap.bounds[nb - r] - ap.bounds[nb - 1u - r]));
-    const size_t per_rank = (size_t)max_rows * G;  // intersections of the rank's rows (their diagonal entries are the len values)
-    const size_t full = (size_t)G * G + G;
-    // scratch: [ full matrix + len | gathered: world x per_rank | send: per_rank ]
-    if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, full + per_rank * ((size_t)world + 1u)))) return rc;
-    uint64_t *d_full = a->d_scratch, *d_all = d_full + full, *d_send = d_all + per_rank * world;
-    // with timing enabled: device time of the phases (compute | all-gather | assembly | copy to the host) in last_launch_info
-    cudaEvent_t ev[5] = {};
+    const uint32_t G = a->G, world = c->world, rank = c->rank;
+    // The contraction runs over the items, so the ITEMS are split: rank r sums the whole (upper-triangular, mirrored)
+    // matrix over its share of the 64-item words, then one ncclAllReduce (u64 sum) of the G x G partial matrices.  Any G
+    // and any world size balance perfectly (row blocks -- the first version, kept as pgx_similarity_upper for callers
+    // that shard themselves -- leave the 128 x 256 tensor-core tiles half empty at 8 ranks x 64 rows).
+    const uint64_t n_words = (a->n_rows + 63u) / 64u;
+    uint64_t per = (n_words + world - 1u) / world;
+    per = (per + 1u) & ~1ull;  // even: keeps the 16-byte operand loads of k_sim_mma aligned
+    const uint64_t wb = std::min<uint64_t>((uint64_t)rank * per, n_words), we = std::min<uint64_t>(wb + per, n_words);
+    const size_t full = (size_t)G * G;
+    if ((rc = ensure_dev(&a->d_scratch, &a->scratch_cap, full))) return rc;
+    uint64_t *d_full = a->d_scratch;
+    // with timing enabled: device time of the phases (compute | all-reduce | copy to the host) in last_launch_info
+    cudaEvent_t ev[4] = {};
     auto mark = [&](int k) {
         if (a->timing && cudaEventCreate(&ev[k]) == cudaSuccess) cudaEventRecord(ev[k], a->stream);
     };
     mark(0);
-    PGX_CUDA(cudaMemsetAsync(d_send, 0, per_rank * 8u, a->stream));
-    uint32_t row_off = 0;
-    for (uint32_t b : {rank, nb - 1u - rank}) {
-        const uint32_t lo = ap.bounds[b], hi = ap.bounds[b + 1u];
-        if (hi == lo) continue;
-        if ((rc = sim_rows_device(a, weighted, lo, hi, lo, d_send + (size_t)row_off * G, true))) return rc;
-        row_off += hi - lo;
-    }
+    PGX_CUDA(cudaMemsetAsync(d_full, 0, full * 8u, a->stream));
+    if ((rc = sim_rows_device(a, weighted, 0, G, 0, d_full, false, wb, we))) return rc;
     mark(1);
-    PGX_NCCL(N->AllGather(d_send, d_all, per_rank, ncclUint64, c->comm, a->stream));
+    PGX_NCCL(N->AllReduce(d_full, d_full, full, ncclUint64, ncclSum, c->comm, a->stream));
     mark(2);
-    ap.gathered = d_all;
-    ap.rank_stride = per_rank;
-    ap.inter = d_full;
-    ap.len = d_full + (size_t)G * G;
-    ap.G = G;
-    ap.world = world;
-    ap.n_blocks = nb;
-    ap.max_rows = max_rows;
-    if ((rc = launch_sim_assemble(ap, a->stream))) return rc;
-    a->launches++;
+    rc = copy_to_host(a, inter, d_full, full);
     mark(3);
-    if ((rc = copy_to_host(a, inter, d_full, (size_t)G * G))) return rc;
-    rc = copy_to_host(a, len, d_full + (size_t)G * G, G);
-    mark(4);
-    if (a->timing && ev[0] && ev[1] && ev[2] && ev[3] && ev[4]) {
-        float t[4] = {};
-        cudaEventSynchronize(ev[4]);
-        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], ev[k], ev[k + 1]);
+    if (!rc)
+        for (uint32_t g = 0; g < G; ++g) len[g] = inter[(size_t)g * G + g];  // len[g] = the diagonal entry
+    if (a->timing && ev[0] && ev[1] && ev[2] && ev[3]) {
+        float t[3] = {};
+        cudaEventSynchronize(ev[3]);
+        for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&t[k], ev[k], ev[k + 1]);
         char buf[200];
-        snprintf(buf, sizeof buf, "pgx_similarity_sharded phases ms: compute %.3f | all-gather %.3f | assembly %.3f | to host %.3f", t[0], t[1], t[2], t[3]);
+        snprintf(buf, sizeof buf, "pgx_similarity_sharded phases ms: compute %.3f | all-reduce %.3f | to host %.3f (%s)", t[0], t[1], t[2],
+                 a->last_launch.c_str());
         a->last_launch = buf;
     }
     for (auto e : ev)

@@ -479,34 +479,6 @@ __global__ void __launch_bounds__(256) k_sim_mirror(uint64_t *inter, uint32_t G)
     if (x < G && y < G && y / kSimTile < x / kSimTile) inter[(uint64_t)x * G + y] = inter[(uint64_t)y * G + x];
 }
 
-// Full G x G intersection matrix (+ len) from the all-gathered upper-triangle row blocks of a sharded run: element
-// (x, y) lives in the block that owns row min(x, y), at column max(x, y) (the matrix is symmetric and every block was
-// computed from its diagonal rightwards).
-__global__ void __launch_bounds__(256) k_sim_assemble(const SimAssembleParams p) {
-    const uint64_t e = (uint64_t)blockIdx.x * 256u + threadIdx.x;
-    const uint64_t GG = (uint64_t)p.G * p.G;
-    if (e >= GG + p.G) return;
-    uint32_t r, c;
-    if (e < GG) {
-        const uint32_t x = (uint32_t)(e / p.G), y = (uint32_t)(e - (uint64_t)x * p.G);
-        r = min(x, y);
-        c = max(x, y);
-    } else {
-        r = c = (uint32_t)(e - GG);
-    }
-    uint32_t b = 0;
-    while (b + 1u < p.n_blocks && r >= p.bounds[b + 1u]) ++b;
-    const uint32_t rank = b < p.world ? b : p.n_blocks - 1u - b;
-    // rows of the rank's first block (block `rank`) precede those of its second (block n_blocks - 1 - rank)
-    const uint32_t local = (b < p.world ? 0u : p.bounds[rank + 1u] - p.bounds[rank]) + (r - p.bounds[b]);
-    const uint64_t *src = p.gathered + (uint64_t)rank * p.rank_stride;
-    // len[g] = sum of w over the items of g = the diagonal entry (an item of g is in g and g): no separate row sums
-    if (e < GG)
-        p.inter[e] = src[(uint64_t)local * p.G + c];
-    else
-        p.len[r] = src[(uint64_t)local * p.G + r];
-}
-
 // first differences -> curves in place (wrapping u64 prefix sums); one warp per curve of G entries
 __global__ void __launch_bounds__(256) k_prefix_curves(uint64_t *d, uint64_t n_curves, uint32_t G) {
     const uint64_t curve = ((uint64_t)blockIdx.x * 256u + threadIdx.x) >> 5;
@@ -787,13 +759,6 @@ int launch_sim_mirror(uint64_t *inter, uint32_t G, cudaStream_t stream) {
 int launch_gm_rowsum(const uint64_t *gm, uint64_t gm_stride, uint64_t n_words, const uint64_t *planes,
                      uint32_t n_planes, const uint64_t *uniform_w, uint32_t G, uint64_t *len, cudaStream_t stream) {
     k_gm_rowsum<<<G, 256, 0, stream>>>(gm, gm_stride, n_words, planes, n_planes, uniform_w, len);
-    PGX_CUDA(cudaGetLastError());
-    return PGX_OK;
-}
-
-int launch_sim_assemble(const SimAssembleParams &p, cudaStream_t stream) {
-    const uint64_t n = (uint64_t)p.G * p.G + p.G;
-    k_sim_assemble<<<(unsigned)((n + 255u) / 256u), 256, 0, stream>>>(p);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }

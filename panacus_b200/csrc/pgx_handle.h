@@ -144,8 +144,9 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
 int gm_growth_device(pgx_abacus *a, uint32_t n_orders, const uint32_t *orders, uint32_t T, const uint32_t *cov,
                      const uint32_t *thr, int weighted, uint64_t *d_out);
 // similarity building blocks on device buffers (no sync): rows [row_begin, row_end) x columns >= col_begin; group totals
+// (word_begin / word_end: restrict the sum to the items of these 64-item words; 0 / ~0 = all)
 int sim_rows_device(pgx_abacus *a, int weighted, uint32_t row_begin, uint32_t row_end, uint32_t col_begin, uint64_t *d_inter,
-                    bool upper_only);
+                    bool upper_only, uint64_t word_begin, uint64_t word_end);
 void sim_block_bounds(uint32_t G, uint32_t world, uint32_t *bounds /* 2 * world + 1 */);
 int sim_len_device(pgx_abacus *a, int weighted, uint32_t g_begin, uint32_t g_end, uint64_t *d_len);
 // device -> host copy of `words` u64 on the handle's stream + synchronise: straight into `dst` when it is pinned /

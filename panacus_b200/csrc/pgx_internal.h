@@ -162,16 +162,6 @@ int launch_gm_similarity(const GmSimParams &p, int sm_count, cudaStream_t stream
 // p.triangular must be set by the caller for a full square (then follow with launch_sim_mirror)
 int launch_sim_mma(const GmSimParams &p, int sm_count, cudaStream_t stream);
 int launch_sim_mirror(uint64_t *inter, uint32_t G, cudaStream_t stream);
-// sharded similarity: all-gathered upper-triangle row blocks -> full matrix + len (pgx_comm.cu)
-struct SimAssembleParams {
-    const uint64_t *gathered;  // [world][rank_stride]: per rank max_rows x G intersections (len = their diagonal entries)
-    uint64_t rank_stride;      // max_rows * G
-    uint64_t *inter;           // G x G
-    uint64_t *len;             // G
-    uint32_t G, world, n_blocks, max_rows;
-    uint32_t bounds[2 * kMaxRanks + 1];  // row-block boundaries (n_blocks + 1 entries)
-};
-int launch_sim_assemble(const SimAssembleParams &p, cudaStream_t stream);
 // first differences -> curves, in place: n_curves rows of G u64
 int launch_prefix_curves(uint64_t *d, uint64_t n_curves, uint32_t G, cudaStream_t stream);
 int launch_gm_rowsum(const uint64_t *gm, uint64_t gm_stride, uint64_t n_words, const uint64_t *planes,

@@ -5,10 +5,14 @@
 // 64-item words (k_gm_similarity: 30.7 ms at 10M x 1024, both integer pipes ~75 % busy).  Here the bits of the
 // group-major bitmap are expanded to u8 0/1 operands in shared memory and multiplied with tcgen05.mma.kind::i8
 // (u8 x u8 -> s32, exact): one CTA owns a 128 x 256 tile of the matrix over a range of items,
-//   * 12 expander warps: one thread per operand row (128 A rows + 256 B rows); per stage it turns 128 item bits of its
-//     group (one 16-byte global load, prefetched 3 stages ahead) into eight 16-byte rows of the canonical K-major,
-//     no-swizzle UMMA layout (core matrix = 8 rows x 16 bytes; LBO = 128 B between the two K halves of an MMA, SBO =
-//     256 B between 8-row groups), fences the generic-proxy stores for the async proxy and arrives on full[stage];
+//   * 12 loader warps: one thread per operand row (128 A rows + 256 B rows) streams the row's bits, 16 bytes = 128 items
+//     per stage, global -> registers (4 loads in flight) -> a ring of raw slots in shared memory.  They execute no
+//     fence, so their loads overlap freely;
+//   * 12 expander warps: one thread per operand row turns the 128 bits of its row into 128 bytes of the K-major
+//     SWIZZLE_128B UMMA layout (8-row groups of 1 KB, 16-byte chunks XORed with the row index), fences the
+//     generic-proxy stores for the async proxy and arrives on full[stage].  (In the first version the expanders loaded
+//     their bits themselves: `fence.proxy.async` is a MEMBAR.ALL.CTA in SASS and waited for the prefetches it followed --
+//     one DRAM latency per stage.)
 //   * 1 MMA warp: one elected lane issues four m128 n256 k32 MMAs per stage into a 128-lane x 256-column s32
 //     accumulator in TMEM and commits them to empty[stage];
 //   * epilogue (8 warps): tcgen05.ld 32 lanes x 32 columns at a time -> u64 atomicAdd into the caller's matrix (the item
@@ -27,20 +31,24 @@ namespace {
 constexpr int kMmaM = 128, kMmaN = 256, kMmaK = 32;  // one tcgen05.mma: u8, K = 32 bytes
 constexpr int kStageItems = 128;                      // items per stage = one 16-byte load per operand row
 constexpr int kKBlocks = kStageItems / kMmaK;         // MMAs per stage
-constexpr int kStages = 4;
+constexpr int kStages = 3;
+constexpr int kRawSlots = 8;                          // ring of raw (bit) slots between loaders and expanders
 constexpr int kExpanders = kMmaM + kMmaN;             // one thread per operand row
 constexpr int kMmaWarp = kExpanders / 32;             // warp 12
-constexpr int kSimMmaThreads = kExpanders + 32;
+constexpr int kLoaderWarp0 = kMmaWarp + 1;            // warps 13 .. 24: loaders, one thread per operand row
+constexpr int kSimMmaThreads = 2 * kExpanders + 32;
+constexpr uint32_t kRawBytes = kExpanders * 16u;      // 6 KB per raw slot
 constexpr uint32_t kABytes = kMmaM * kStageItems;     // 16 KB per stage
 constexpr uint32_t kBBytes = kMmaN * kStageItems;     // 32 KB per stage
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr uint32_t kTmemCols = 256;
 constexpr int kPrefetch = 3;                          // global loads in flight per expander thread
 
-// K-major, no swizzle: start address, LBO (K direction), SBO (M / N direction), version 1 (cute/arch/mma_sm100_desc.hpp)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+// K-major SWIZZLE_128B operand (cute/arch/mma_sm100_desc.hpp): rows of 128 bytes, 8-row groups of 1 KB (SBO), the
+// 16-byte chunks of a row XORed with (row % 8); LBO is unused for swizzled K-major layouts (1 by convention); version 1;
+// layout type 2 in bits 61..63.  K advances inside the 128-byte atom by moving the start address (32 bytes per MMA).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 // instruction descriptor of kind::i8: D = s32 (bits 4-5 = 2), A and B unsigned 8 bit (0), both K-major (bits 15, 16 = 0),
@@ -74,7 +82,7 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 
 __global__ void __launch_bounds__(kSimMmaThreads, 1) k_sim_mma(const __grid_constant__ GmSimParams p, uint32_t words_per_split) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long s_bar[2 * kStages + 1];
+    __shared__ __align__(8) unsigned long long s_bar[2 * kStages + 2 * kRawSlots + 1];
     __shared__ uint32_t s_tmem;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const uint32_t x0 = p.row_begin + blockIdx.y * kMmaM;  // output rows of the tile
@@ -87,12 +95,19 @@ __global__ void __launch_bounds__(kSimMmaThreads, 1) k_sim_mma(const __grid_cons
     if (k_begin >= k_end) return;
     const uint32_t n_it = (uint32_t)((k_end - k_begin + 1u) / 2u);  // stages of two words
 
-    const uint32_t stage0 = (smem_u32(smem) + 127u) & ~127u;  // (1 KB of slack is allocated)
-    const uint32_t full0 = smem_u32(s_bar), empty0 = full0 + 8u * kStages, accum_bar = full0 + 16u * kStages;
+    const uint32_t stage0 = (smem_u32(smem) + 1023u) & ~1023u;  // SWIZZLE_128B atoms are 1 KB aligned (2 KB of slack is allocated)
+    const uint32_t raw0 = stage0 + (uint32_t)kStages * kStageBytes;
+    // barriers: full[kStages] | empty[kStages] | raw_full[kRawSlots] | raw_empty[kRawSlots] | accum
+    const uint32_t full0 = smem_u32(s_bar), empty0 = full0 + 8u * kStages, rawfull0 = empty0 + 8u * kStages,
+                   rawempty0 = rawfull0 + 8u * kRawSlots, accum_bar = rawempty0 + 8u * kRawSlots;
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full0 + 8u * s, (uint32_t)kMmaWarp);  // one arrival per expander warp
             mbar_init(empty0 + 8u * s, 1u);                 // tcgen05.commit
+        }
+        for (int s = 0; s < kRawSlots; ++s) {
+            mbar_init(rawfull0 + 8u * s, (uint32_t)kMmaWarp);   // one arrival per loader warp
+            mbar_init(rawempty0 + 8u * s, (uint32_t)kMmaWarp);  // one arrival per expander warp
         }
         mbar_init(accum_bar, 1u);
         mbar_fence_init();
@@ -106,16 +121,13 @@ __global__ void __launch_bounds__(kSimMmaThreads, 1) k_sim_mma(const __grid_cons
     tc_fence_after();
     const uint32_t tmem = s_tmem;
 
-    if (warp < (uint32_t)kMmaWarp) {
-        // ===== expanders: one operand row per thread =====
-        const bool is_a = tid < (uint32_t)kMmaM;
-        const uint32_t r = is_a ? tid : tid - kMmaM;  // row inside the A / B block
-        const uint32_t g = is_a ? x0 + r : y0 + r;
+    if (warp >= (uint32_t)kLoaderWarp0) {
+        // ===== loaders: one operand row per thread, global -> registers -> raw slot =====
+        const uint32_t t = tid - (uint32_t)kLoaderWarp0 * 32u;  // operand row 0 .. 383 (A rows first)
+        const bool is_a = t < (uint32_t)kMmaM;
+        const uint32_t g = is_a ? x0 + t : y0 + (t - kMmaM);
         const bool live = is_a ? g < p.row_end : g < p.G;
         const uint64_t *row = p.gm + (uint64_t)(live ? g : 0u) * p.gm_stride;
-        // byte offset of this row's first 16-byte chunk inside a k-block: 8-row groups of 256 B, rows of 16 B
-        const uint32_t row_off = (is_a ? 0u : kABytes) + (r >> 3) * 256u + (r & 7u) * 16u;
-        const uint32_t kb_stride = is_a ? (uint32_t)(kMmaM * kMmaK) : (uint32_t)(kMmaN * kMmaK);  // 4 KB / 8 KB per k-block
         auto fetch = [&](uint32_t it) -> ulonglong2 {
             const uint64_t w = k_begin + 2ull * it;
             ulonglong2 v = make_ulonglong2(0ull, 0ull);
@@ -128,35 +140,74 @@ __global__ void __launch_bounds__(kSimMmaThreads, 1) k_sim_mma(const __grid_cons
             }
             return v;
         };
-        ulonglong2 ring[kPrefetch];
+        constexpr int kRing = 4;  // loads in flight per thread (kRawSlots is a multiple of it)
+        ulonglong2 ring[kRing];
 #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) ring[u] = fetch((uint32_t)u);
-        uint32_t st = 0, ph = 0;
-        for (uint32_t it0 = 0; it0 < n_it; it0 += kPrefetch) {
+        for (int u = 0; u < kRing; ++u) ring[u] = fetch((uint32_t)u);
+        uint32_t slot = 0, ph = 0;
+        for (uint32_t it0 = 0; it0 < n_it; it0 += kRing) {
 #pragma unroll
-            for (int u = 0; u < kPrefetch; ++u) {
+            for (int u = 0; u < kRing; ++u) {
                 const uint32_t it = it0 + (uint32_t)u;
                 if (it >= n_it) break;
                 const ulonglong2 v = ring[u];
-                ring[u] = fetch(it + kPrefetch);
-                if (it >= (uint32_t)kStages) mbar_wait(empty0 + 8u * st, ph ^ 1u);  // the MMAs that read this stage are done
-                const uint32_t base = stage0 + st * kStageBytes + row_off;
-                const uint32_t w32[4] = {(uint32_t)v.x, (uint32_t)(v.x >> 32), (uint32_t)v.y, (uint32_t)(v.y >> 32)};
-#pragma unroll
-                for (int kb = 0; kb < kKBlocks; ++kb) {  // 32 items = one MMA's K
-                    const uint32_t bits = w32[kb];
-                    const uint32_t a = base + (uint32_t)kb * kb_stride;
-                    sts_v4(a, spread4(bits & 0xFu), spread4((bits >> 4) & 0xFu), spread4((bits >> 8) & 0xFu), spread4((bits >> 12) & 0xFu));
-                    sts_v4(a + 128u, spread4((bits >> 16) & 0xFu), spread4((bits >> 20) & 0xFu), spread4((bits >> 24) & 0xFu),
-                           spread4(bits >> 28));
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+                ring[u] = fetch(it + kRing);
+                if (it >= (uint32_t)kRawSlots) mbar_wait(rawempty0 + 8u * slot, ph ^ 1u);
+                sts_v4(raw0 + slot * kRawBytes + t * 16u, (uint32_t)v.x, (uint32_t)(v.x >> 32), (uint32_t)v.y, (uint32_t)(v.y >> 32));
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full0 + 8u * st);
-                if (++st == (uint32_t)kStages) {
-                    st = 0;
+                if (lane == 0) mbar_arrive(rawfull0 + 8u * slot);
+                if (++slot == (uint32_t)kRawSlots) {
+                    slot = 0;
                     ph ^= 1u;
                 }
+            }
+        }
+    } else if (warp < (uint32_t)kMmaWarp) {
+        // ===== expanders: one operand row per thread, raw bits -> u8 operand rows =====
+        const bool is_a = tid < (uint32_t)kMmaM;
+        const uint32_t r = is_a ? tid : tid - kMmaM;  // row inside the A / B block
+        // the row's 128 bytes inside a stage: 8-row groups of 1 KB; chunk c of the row lives at chunk (c ^ (r % 8))
+        const uint32_t row_off = (is_a ? 0u : kABytes) + (r >> 3) * 1024u + (r & 7u) * 128u;
+        const uint32_t sw = r & 7u;
+        uint32_t st = 0, ph = 0, slot = 0, rph = 0;
+        for (uint32_t it = 0; it < n_it; ++it) {
+            mbar_wait(rawfull0 + 8u * slot, rph);
+            uint32_t w32[4];
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w32[0]), "=r"(w32[1]), "=r"(w32[2]), "=r"(w32[3]) : "r"(raw0 + slot * kRawBytes + tid * 16u));
+            if (it >= (uint32_t)kStages) mbar_wait(empty0 + 8u * st, ph ^ 1u);  // the MMAs that read this stage are done
+            const uint32_t base = stage0 + st * kStageBytes + row_off;
+            if (p.csa == 5u) {  // (timing experiment PGX_SIM_DEBUG=5: the ALU work of the expansion, one store instead of eight)
+                uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int kb = 0; kb < kKBlocks; ++kb) {
+                    const uint32_t bits = w32[kb];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j & 3] ^= spread4((bits >> (4 * j)) & 0xFu) << (j >> 2);
+                }
+                sts_v4(base + (sw << 4), acc[0], acc[1], acc[2], acc[3]);
+            } else if (p.csa != 2u)  // (timing experiment PGX_SIM_DEBUG=2: no expansion, results are wrong)
+#pragma unroll
+                for (int kb = 0; kb < kKBlocks; ++kb) {  // 32 items = one MMA's K = chunks 2 kb, 2 kb + 1
+                    const uint32_t bits = w32[kb];
+                    sts_v4(base + (((uint32_t)(2 * kb) ^ sw) << 4), spread4(bits & 0xFu), spread4((bits >> 4) & 0xFu),
+                           spread4((bits >> 8) & 0xFu), spread4((bits >> 12) & 0xFu));
+                    sts_v4(base + (((uint32_t)(2 * kb + 1) ^ sw) << 4), spread4((bits >> 16) & 0xFu), spread4((bits >> 20) & 0xFu),
+                           spread4((bits >> 24) & 0xFu), spread4(bits >> 28));
+                }
+            if (p.csa != 4u)  // (timing experiment PGX_SIM_DEBUG=4: no proxy fence, results may be wrong)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(rawempty0 + 8u * slot);  // (the raw bits are in registers and used)
+                mbar_arrive(full0 + 8u * st);
+            }
+            if (++st == (uint32_t)kStages) {
+                st = 0;
+                ph ^= 1u;
+            }
+            if (++slot == (uint32_t)kRawSlots) {
+                slot = 0;
+                rph ^= 1u;
             }
         }
     } else {
@@ -167,10 +218,11 @@ __global__ void __launch_bounds__(kSimMmaThreads, 1) k_sim_mma(const __grid_cons
                 mbar_wait(full0 + 8u * st, ph);
                 tc_fence_after();
                 const uint32_t a0 = stage0 + st * kStageBytes, b0 = a0 + kABytes;
+                if (p.csa != 3u || it == 0u)  // (timing experiment PGX_SIM_DEBUG=3: only the first stage's MMAs)
 #pragma unroll
-                for (int kb = 0; kb < kKBlocks; ++kb)
-                    umma_i8(tmem, umma_desc(a0 + (uint32_t)kb * (kMmaM * kMmaK), 128u, 256u),
-                            umma_desc(b0 + (uint32_t)kb * (kMmaN * kMmaK), 128u, 256u), (it | (uint32_t)kb) ? 1u : 0u);
+                    for (int kb = 0; kb < kKBlocks; ++kb)
+                        umma_i8(tmem, umma_desc_sw128(a0 + (uint32_t)kb * kMmaK), umma_desc_sw128(b0 + (uint32_t)kb * kMmaK),
+                                (it | (uint32_t)kb) ? 1u : 0u);
                 umma_commit(empty0 + 8u * st);  // frees the stage when these MMAs have read it
                 if (++st == (uint32_t)kStages) {
                     st = 0;
@@ -241,7 +293,7 @@ int launch_sim_mma(const GmSimParams &p, int sm_count, cudaStream_t stream) {
     uint64_t wps = (p.n_words + splits - 1u) / splits;
     wps = (wps + 1u) & ~1ull;  // whole stages of two words; keeps the 16-byte loads aligned
     splits = (p.n_words + wps - 1u) / wps;
-    const size_t smem = (size_t)kStages * kStageBytes + 1024u;
+    const size_t smem = (size_t)kStages * kStageBytes + (size_t)kRawSlots * kRawBytes + 2048u;
     PGX_CUDA(cudaFuncSetAttribute(k_sim_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_sim_mma<<<dim3(tx, ty, (unsigned)splits), kSimMmaThreads, smem, stream>>>(p, (uint32_t)wps);
     PGX_CUDA(cudaGetLastError());
