@@ -177,7 +177,12 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
         if (rc) return rc;
         p.thr = a->d_thr;
     }
-    if (a->x.world > 1u) p.x.epoch = ++a->epoch;  // collective sequence number (never 0)
+    if (a->x.world > 1u) {
+        p.x.epoch = ++a->epoch;  // collective sequence number (never 0)
+    } else if (!getenv("PGX_SCAN_TICKET")) {  // (PGX_SCAN_TICKET=1: the round-1 ticket + snapshot epilogue, for measurements)
+        if (++a->scan_epoch == 0u) ++a->scan_epoch;
+        p.zero_epoch = a->scan_epoch;
+    }
     int rc;
     {
         KernelTimer kt(a);
@@ -186,7 +191,10 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
     if (rc) return rc;
     a->launches++;
     char buf[320];
-    if (p.flags & kPrivate)
+    if (p.flags & kVertical)
+        snprintf(buf, sizeof buf, "k_scan_vert<hist=%u,D=%u> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u planes=%u",
+                 (p.flags & kHistCount) ? 1u : 0u, p.n_classes, grid, kScanThreads, p.L.total, p.tile_items, p.stages, p.n_tiles, p.T, p.L.vert_planes);
+    else if (p.flags & kPrivate)
         snprintf(buf, sizeof buf, "k_scan_priv<u%u> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u classes=%u bins=%u",
                  p.L.priv_cw * 8u, grid, kScanThreads, p.L.total, p.tile_items, p.stages, p.n_tiles, p.T, p.n_classes, p.L.priv_bins);
     else
@@ -700,10 +708,10 @@ int pgx_abacus_create(pgx_abacus **out, int device, uint64_t n_items, uint32_t n
     a->own_bitmap = true;
     if ((e = cudaMemsetAsync(a->d_bitmap, 0, bm_bytes, a->stream)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&a->d_acc), a->acc_words * 8u)) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_ticket), 4)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_ticket), 8)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&a->d_err), 8)) != cudaSuccess ||
         (e = cudaMemsetAsync(a->d_acc, 0, a->acc_words * 8u, a->stream)) != cudaSuccess ||
-        (e = cudaMemsetAsync(a->d_ticket, 0, 4, a->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(a->d_ticket, 0, 8, a->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(a->d_err, 0, 8, a->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(a->stream)) != cudaSuccess)
         return bail(fail(PGX_ERR_CUDA, std::string("abacus setup: ") + cudaGetErrorString(e)));

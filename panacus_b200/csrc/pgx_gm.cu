@@ -9,6 +9,9 @@
 //                      (integer part of Similarity::set_table, src/analyses/similarity.rs:125-150)
 //   * k_weight_planes  bit-planes of the u32 item weights (bp-weighted intersections)
 //   * k_scatter        ItemTable slice -> bitmap bits (abacus.rs:719-744 de-duplication = idempotent OR)
+#include <cstdlib>
+#include <cstring>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "pgx_common.cuh"
@@ -129,6 +132,121 @@ __global__ void __launch_bounds__(COLS * 32) k_transpose(const uint64_t *__restr
         uint4 *dst = reinterpret_cast<uint4 *>(gm32 + (uint64_t)g1 * gm_stride32 + col32);
         dst[0] = make_uint4(keep1[0], keep1[1], keep1[2], keep1[3]);
         dst[1] = make_uint4(keep1[4], keep1[5], keep1[6], keep1[7]);
+    }
+}
+
+// ---- transpose, second version: 32x32 bit blocks transposed inside one thread ---------------------------------------
+// The shuffle butterfly above is bound by the MIO queue (10 SHFL per 64-bit word next to the tile's STS / LDS).  Here a
+// thread owns one 32x32 block -- 32 items x one 32-bit column of the node-major rows -- reads it from the staged tile
+// with 32 conflict-free LDS.32, transposes it in registers (5 stages x 16 word pairs: 2 PRMT for the 16- and 8-bit
+// stages, 2 SHF + 2 LOP3 for the bit stages = 256 ALU operations, no shuffles) and stores word b straight to group row
+// 32 c + b.  The lanes of a warp own CONSECUTIVE 32-item blocks of the same column, so every warp store writes 128
+// contiguous bytes of one group row (64 for 128-byte-wide tiles, where a warp covers two columns).
+// Tile: 16384 32-bit words = 32 IB items x WC columns, WC = 2^WC_LOG 32-bit columns (8 .. 128 bytes of a row), IB item
+// blocks; 512 threads, one block each.  Lanes 32 rows apart would all hit one bank, so word (R, c) of the tile lives at
+// L ^ s(R / 32) with L = R WC + c: the XOR only permutes the 32 words of a 128-byte line (all of one item block), and
+// the lanes' banks become (const ^ s(ib)) -- all different.
+template <int WC_LOG>
+__global__ void __launch_bounds__(512, 2) k_transpose_reg(const uint64_t *__restrict__ bitmap, uint64_t n_rows, uint32_t G,
+                                                          uint32_t Wp, uint32_t *__restrict__ gm32, uint64_t gm_stride32,
+                                                          const uint32_t *__restrict__ perm) {
+    constexpr uint32_t WC = 1u << WC_LOG;          // 32-bit columns per tile row
+    constexpr uint32_t IB = 512u >> WC_LOG;        // 32-item blocks per tile
+    constexpr uint32_t kRows = IB * 32u;
+    extern __shared__ __align__(16) uint32_t tile[];  // 16384 words
+    const uint32_t tid = threadIdx.x;
+    const uint64_t item0 = (uint64_t)blockIdx.x * kRows;
+    const uint32_t col0 = blockIdx.y * WC;          // first 32-bit column of this tile
+    const uint32_t row_cols = Wp * 2u;              // 32-bit columns per bitmap row
+    auto swz = [](uint32_t ib) -> uint32_t { return IB >= 32u ? (ib & 31u) : ((ib << 1) & 31u); };
+
+    // ---- stage: coalesced 16-byte (8-byte for one-word rows) loads -> swizzled shared-memory tile ----
+    if (WC_LOG >= 2) {
+        constexpr uint32_t CH = WC / 4u;            // 16-byte chunks per tile row
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) {
+            const uint32_t e = tid + k * 512u;
+            const uint32_t R = e / CH, q = e % CH;
+            uint64_t item = item0 + R;
+            if (perm && item < n_rows) item = __ldg(perm + item);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (item != 0 && item < n_rows && col0 + 4u * q < row_cols)
+                v = __ldg(reinterpret_cast<const uint4 *>(bitmap + item * Wp) + (col0 / 4u + q));
+            const uint32_t s = swz(R >> 5);
+            if (s & 1u) {
+                uint32_t t = v.x; v.x = v.y; v.y = t;
+                t = v.z; v.z = v.w; v.w = t;
+            }
+            if (s & 2u) {
+                uint32_t t = v.x; v.x = v.z; v.z = t;
+                t = v.y; v.y = v.w; v.w = t;
+            }
+            *reinterpret_cast<uint4 *>(tile + ((R * WC + 4u * q) ^ (s & 28u))) = v;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < 16u; ++k) {
+            const uint32_t R = tid + k * 512u;     // one 8-byte row per element
+            uint64_t item = item0 + R;
+            if (perm && item < n_rows) item = __ldg(perm + item);
+            uint2 v = make_uint2(0u, 0u);
+            if (item != 0 && item < n_rows) v = __ldg(reinterpret_cast<const uint2 *>(bitmap + item * Wp));
+            const uint32_t s = swz(R >> 5);
+            if (s & 1u) {
+                const uint32_t t = v.x; v.x = v.y; v.y = t;
+            }
+            *reinterpret_cast<uint2 *>(tile + ((R * 2u) ^ (s & 30u))) = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- one 32x32 block per thread ----
+    const uint32_t ib = tid % IB, c = tid / IB;
+    const uint32_t s = swz(ib);
+    uint32_t a[32];
+#pragma unroll
+    for (uint32_t r = 0; r < 32u; ++r) {
+        const uint32_t L = (32u * ib + r) * WC + c;
+        a[r] = tile[L ^ s];
+    }
+    // rows -> columns: swap the off-diagonal blocks of size 16, 8 (byte permutes), 4, 2, 1 (funnel shift + select)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t x = a[k], y = a[k + 16];
+        a[k] = __byte_perm(x, y, 0x5410);
+        a[k + 16] = __byte_perm(x, y, 0x7632);
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k & 8) continue;
+        const uint32_t x = a[k], y = a[k + 8];
+        a[k] = __byte_perm(x, y, 0x6240);
+        a[k + 8] = __byte_perm(x, y, 0x7351);
+    }
+#pragma unroll
+    for (int sh = 4; sh >= 1; sh >>= 1) {
+        const uint32_t m = sh == 4 ? 0x0F0F0F0Fu : (sh == 2 ? 0x33333333u : 0x55555555u);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if (k & sh) continue;
+            const uint32_t x = a[k], y = a[k + sh];
+            asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(a[k]) : "r"(m), "r"(x), "r"(y << sh));       // m ? x : y << sh
+            asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(a[k + sh]) : "r"(m), "r"(x >> sh), "r"(y));  // m ? x >> sh : y
+        }
+    }
+    // a[b]: bit r = item 32 (item block) + r of group 32 (col0 + c) + b
+    const uint64_t ibg = item0 / 32u + ib;
+    const uint32_t g0 = (col0 + c) * 32u;
+    if (ibg < gm_stride32 && g0 < G) {
+        uint32_t *dst = gm32 + (uint64_t)g0 * gm_stride32 + ibg;
+        if (g0 + 32u <= G) {
+#pragma unroll
+            for (uint32_t b = 0; b < 32u; ++b, dst += gm_stride32) *dst = a[b];
+        } else {
+#pragma unroll
+            for (uint32_t b = 0; b < 32u; ++b, dst += gm_stride32)
+                if (g0 + b < G) *dst = a[b];
+        }
     }
 }
 
@@ -687,6 +805,30 @@ size_t gm_growth_smem_bytes(uint32_t G, uint32_t T, bool any_general, bool direc
 int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
                      uint64_t gm_stride, const uint32_t *perm, cudaStream_t stream) {
     const uint32_t W = (G + 63u) / 64u;
+    const char *env = getenv("PGX_TRANSPOSE");
+    if (!(env && !strcmp(env, "shfl"))) {  // default: in-register 32x32 transposes (PGX_TRANSPOSE=shfl: the shuffle butterfly)
+        const uint32_t row_cols = Wp * 2u;
+        uint32_t wl = 1;
+        while (wl < 5u && (1u << wl) < row_cols) ++wl;  // widest tile row that the bitmap row fills: 2, 4, 8, 16 or 32 columns
+        const uint64_t rows_per_tile = (512u >> wl) * 32u;
+        const dim3 grid((unsigned)((gm_stride * 64u + rows_per_tile - 1u) / rows_per_tile), (row_cols + (1u << wl) - 1u) >> wl);
+        uint32_t *gm32 = reinterpret_cast<uint32_t *>(gm);
+        auto go = [&](auto kern) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+            if (e != cudaSuccess) return e;
+            kern<<<grid, 512, 65536, stream>>>(bitmap, n_rows, G, Wp, gm32, gm_stride * 2u, perm);
+            return cudaSuccess;
+        };
+        switch (wl) {
+            case 1: PGX_CUDA(go(k_transpose_reg<1>)); break;
+            case 2: PGX_CUDA(go(k_transpose_reg<2>)); break;
+            case 3: PGX_CUDA(go(k_transpose_reg<3>)); break;
+            case 4: PGX_CUDA(go(k_transpose_reg<4>)); break;
+            default: PGX_CUDA(go(k_transpose_reg<5>)); break;
+        }
+        PGX_CUDA(cudaGetLastError());
+        return PGX_OK;
+    }
     const unsigned gx = (unsigned)(gm_stride * 64u / kTrItems);
     if (Wp >= 16u)  // 128-byte (or wider) rows: one CTA reads whole lines
         k_transpose<16><<<dim3(gx, (W + 15u) / 16u), 512, 0, stream>>>(bitmap, n_rows, G, W, Wp,
@@ -784,7 +926,7 @@ int sort_items_by_weight(const uint32_t *weight, uint64_t n_rows, uint32_t *perm
     uint32_t *keys = nullptr, *vals = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
-    const int n = (int)n_rows;
+    const int64_t n = (int64_t)n_rows;  // CUB takes a 64-bit count: n_rows may exceed 2^31
     auto cleanup = [&]() {
         cudaFree(keys);
         cudaFree(vals);

@@ -44,7 +44,8 @@ struct pgx_abacus {
 
     uint64_t *d_acc = nullptr;  // self-cleaning global accumulators of k_scan
     size_t acc_words = 0;
-    unsigned int *d_ticket = nullptr;
+    unsigned int *d_ticket = nullptr;  // [0] completion ticket of the exchange epilogue, [1] epoch flag of the direct epilogue
+    uint32_t scan_epoch = 0;           // launches of the direct epilogue (value published in d_ticket[1])
     unsigned int *d_err = nullptr;   // [0]: build / scatter / csr input errors, [1]: fused-exchange watchdog (own word: never mixed)
 
     uint32_t *d_thr = nullptr;  // quorum thresholds of the current call

@@ -23,6 +23,7 @@ enum ScanFlags : uint32_t {
     kWeighted = 4u,    // growth deltas sum weight[i] instead of 1
     kJoint = 8u,       // small G: one joint (coverage, first group) histogram, marginalised in the epilogue
     kPrivate = 16u,    // lane-private narrow counters (plain LDS / STS; a shared atomic only when one wraps), folded after the last tile
+    kVertical = 32u,   // G <= 64, counts: bit-sliced vertical counters (carry-save adders over one-hot words), no atomics in the loop
 };
 
 // Byte offsets into the dynamic shared memory of k_scan (identical on host and device).
@@ -44,6 +45,9 @@ struct ScanLayout {
     uint32_t off_carry;      // u32[priv_bins]: what wrapped out of the narrow lane-private counters
     uint32_t off_priv;       // lane-private counters: priv_bins rows of 256 counters of priv_cw bytes (kPrivate)
     uint32_t priv_bins, priv_cw, priv_hist_bins;
+    // kVertical (k_scan_vert): per-thread high bit-planes [counter][plane][thread] u64 at off_priv, the warps' folded
+    // planes at off_carry, per-class totals u32[D][64] at off_cls_lo; everything in [off_acc, vert_end) starts at zero
+    uint32_t vert_planes, vert_counters, vert_end;
     uint32_t off_stage0;     // first pipeline stage (128-byte aligned)
     uint32_t stage_stride;   // bytes per stage
     uint32_t off_stage_w;    // offset of the weight tile inside a stage
@@ -69,7 +73,9 @@ struct ScanParams {
     const uint32_t *thr;     // device T*G quorum thresholds (quorum kernel), else nullptr
     uint64_t *acc;           // global accumulators (zero on entry, zero again on exit)
     uint64_t *out;           // caller's fused-layout result buffer, written by the last CTA
-    unsigned int *ticket;    // CTA completion counter (zero on entry and exit)
+    unsigned int *ticket;    // CTA completion counter (zero on entry and exit); ticket[1]: "out is zeroed" epoch flag
+    uint32_t zero_epoch;     // != 0 (single GPU): CTA 0 zeroes the requested words of `out` and publishes this epoch in
+                             // ticket[1]; every CTA then adds its sums straight into `out` -- no ticket, no snapshot
     uint64_t n_rows;         // N + 1
     uint32_t G, W, Wp;
     uint32_t T;

@@ -14,6 +14,7 @@
 // Integer-only, HBM-bandwidth-bound: algorithmic bytes per item = W*8 (+4 weighted).
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "pgx_common.cuh"
 #include "pgx_internal.h"
@@ -32,6 +33,9 @@ struct SmemAcc {
 };
 
 // ---- q = 0 path: hist bin + first-set-bit delta -------------------------------------------------
+// (Keeping the dominant bins -- coverage 1, first group 0 -- in registers and only the rest on shared atomics was
+// measured SLOWER, 10M x 1024: 0.195 -> 0.225 ms, 10M x 256: 80 -> 96 us, profiles/r2_scan_shapes_v3_regacc.jsonl: the
+// divergent branch costs more than the same-address serialisation it removes.)
 __device__ __forceinline__ void account_fast(const ScanParams &p, const SmemAcc &s, uint64_t item, uint32_t cov,
                                              uint32_t first, uint32_t wgt) {
     if (p.countable) p.countable[item] = cov;
@@ -206,11 +210,38 @@ uint32_t env_u32(const char *name) {
     return v ? (uint32_t)strtoul(v, nullptr, 10) : 0u;
 }
 
+// ---- direct epilogue (single GPU): the CTAs add their sums straight into the caller's result vector ------------------
+// CTA 0 zeroes the requested words of `out` while the first tiles are in flight and publishes the launch's epoch; every
+// CTA's TMA lane, idle once its last copy is issued, waits for that epoch before the CTA-wide barrier that precedes
+// the RED flush.  The kernel's end is the end of the pass: no completion ticket, no fence, no snapshot by a last CTA
+// (three dependent L2 round trips of the round-1 epilogue, ~2-3 us of every launch).
+__device__ __forceinline__ void direct_zero_out(const ScanParams &p, uint32_t tid) {  // CTA 0, all threads, before a __syncthreads()
+    const uint32_t G1 = p.G + 1u;
+    if (p.flags & kHistCount)
+        for (uint32_t i = tid; i < G1; i += kScanThreads) p.out[i] = 0ull;
+    if (p.flags & kHistWeight)
+        for (uint32_t i = tid; i < G1; i += kScanThreads) p.out[G1 + i] = 0ull;
+    for (uint32_t t = 0; t < p.T; ++t)
+        for (uint32_t j = tid; j < p.G; j += kScanThreads) p.out[2u * G1 + p.slot[t] * p.G + j] = 0ull;
+}
+__device__ __forceinline__ void direct_publish(const ScanParams &p) {  // CTA 0, one thread, after that __syncthreads()
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.ticket + 1), "r"(p.zero_epoch) : "memory");
+}
+__device__ __forceinline__ void direct_wait_zeroed(const ScanParams &p) {  // one thread per CTA, before the barrier ahead of the epilogue
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ticket + 1) : "memory");
+    } while (v != p.zero_epoch);
+}
+
 // Per-CTA accumulators -> global u64 accumulators -> (last CTA) the caller's result vector, or the multi-GPU exchange.
 // Shared by k_scan and k_scan_priv; expects every thread of the CTA, after a __syncthreads().
 __device__ __forceinline__ void scan_epilogue(const ScanParams &p, const SmemAcc &s, const uint32_t tid) {
     // ===== epilogue: per-CTA accumulators -> global u64 accumulators =====
     const uint32_t G1 = p.G + 1u;
+    const bool direct = p.zero_epoch != 0u;
+    uint64_t *const dst = direct ? p.out : p.acc;
     if (p.flags & kJoint) {  // marginalise the joint histogram into hist[] and the curves' first differences
         const bool use_cnt = (p.flags & kHistCount) || !(p.flags & kWeighted);
         const bool use_w = (p.flags & (kHistWeight | kWeighted)) != 0;
@@ -249,22 +280,28 @@ __device__ __forceinline__ void scan_epilogue(const ScanParams &p, const SmemAcc
     for (uint32_t i = tid; i < G1; i += kScanThreads) {
         if (p.flags & kHistCount) {
             const uint32_t c = s.hist_cnt[i];
-            if (c) atomicAdd(reinterpret_cast<unsigned long long *>(p.acc + i), (unsigned long long)c);
+            if (c) atomicAdd(reinterpret_cast<unsigned long long *>(dst + i), (unsigned long long)c);
         }
         if (p.flags & kHistWeight) {
             const uint64_t v = ((uint64_t)s.hist_whi[i] << 32) | s.hist_wlo[i];
-            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(p.acc + G1 + i), (unsigned long long)v);
+            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(dst + G1 + i), (unsigned long long)v);
         }
     }
     const uint32_t nd = p.T * p.G;
-    for (uint32_t i = tid; i < nd; i += kScanThreads) {
-        uint64_t v;
-        if (p.flags & kWeighted)
-            v = ((uint64_t)s.delta_hi[i] << 32) | s.delta_lo[i];
-        else
-            v = (uint64_t)(int64_t)(int32_t)s.delta_lo[i];  // signed per-CTA net flip count
-        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(p.acc + 2u * G1 + i), (unsigned long long)v);
+    for (uint32_t t = 0; t < p.T; ++t) {
+        // accumulators: launch-local threshold index; the caller's vector: its fused-layout slot
+        uint64_t *const row = dst + 2u * G1 + (direct ? p.slot[t] : t) * p.G;
+        for (uint32_t j = tid; j < p.G; j += kScanThreads) {
+            const uint32_t i = t * p.G + j;
+            uint64_t v;
+            if (p.flags & kWeighted)
+                v = ((uint64_t)s.delta_hi[i] << 32) | s.delta_lo[i];
+            else
+                v = (uint64_t)(int64_t)(int32_t)s.delta_lo[i];  // signed per-CTA net flip count
+            if (v) atomicAdd(reinterpret_cast<unsigned long long *>(row + j), (unsigned long long)v);
+        }
     }
+    if (direct) return;
 
     // ===== last CTA: snapshot + re-zero (threadfence reduction pattern) =====
     __shared__ uint32_t s_is_last;
@@ -400,7 +437,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         }
         mbar_fence_init();
     }
+    const bool zeroes_out = p.zero_epoch != 0u && blockIdx.x == 0u;
+    if (zeroes_out) direct_zero_out(p, tid);
     __syncthreads();
+    if (zeroes_out && tid == kScanThreads - 1) direct_publish(p);
 
     const uint32_t last_tile = p.n_tiles - 1u;
     // rows of the last tile (may be partial); every other tile is full
@@ -434,6 +474,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
                     ring_full = true;
                 }
             }
+            if (p.zero_epoch) direct_wait_zeroed(p);
         }
     } else {
         // ===== consumers: one thread per item =====
@@ -603,7 +644,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
         }
         mbar_fence_init();
     }
+    const bool zeroes_out = p.zero_epoch != 0u && blockIdx.x == 0u;
+    if (zeroes_out) direct_zero_out(p, tid);
     __syncthreads();
+    if (zeroes_out && tid == kScanThreads - 1) direct_publish(p);
 
     const uint32_t last_tile = p.n_tiles - 1u;
     const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
@@ -636,6 +680,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
                     ring_full = true;
                 }
             }
+            if (p.zero_epoch) direct_wait_zeroed(p);
         }
     } else {
         // ===== consumers: two items per thread and step, lane-private counters =====
@@ -747,6 +792,315 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
     scan_epilogue(p, s, tid);
 }
 
+// ---- bit-sliced vertical counters (kVertical): G <= 64, counting nodes / edges ---------------------------------------
+// An item's row is one 64-bit word x.  Its two facts are turned into ONE-HOT words -- 1 << popc(x) (coverage) and x & -x
+// (first group) -- so a histogram is the column sum of a 64-column bit matrix.  Column sums of words are what carry-save
+// adders do: a thread adds 16 one-hot words with 15 full adders (xor3 / majority = 2 LOP3 per 32-bit half) into the four
+// bit-planes ones / twos / fours / eights it keeps in registers; the "sixteens" word that falls out ripples into P more
+// planes in shared memory (the thread's own words: no conflicts, no atomics), P chosen by the host from the tiles a CTA
+// walks.  ~22 instructions per item for a histogram plus one curve (the lane-private kernel: ~45, the atomics kernel is
+// bound by ATOMS throughput).  After the last tile the threads' counters are added with the same full adders across the
+// warp (shuffles), then across the warps through shared memory, and only then read out bin by bin.
+// One counter for the histogram (HIST), one per distinct coverage cutoff (D <= 3: items with coverage >= cutoff, by
+// first group); C1: the lowest cutoff is 1 (any covered item counts: no mask needed).  Coverage 64 (G = 64) does not fit
+// the one-hot word: those items are counted in a register.
+struct V64 {
+    uint32_t lo, hi;
+};
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// full adder on 64 one-bit columns: (h, l) = a + b + c; l may alias a
+__device__ __forceinline__ void csa(V64 &h, V64 &l, const V64 a, const V64 b, const V64 c) {
+    const V64 hh = {lop3_maj(a.lo, b.lo, c.lo), lop3_maj(a.hi, b.hi, c.hi)};
+    l = {lop3_xor3(a.lo, b.lo, c.lo), lop3_xor3(a.hi, b.hi, c.hi)};
+    h = hh;
+}
+struct VertTree {  // ones, twos, fours, eights of one counter + the pending fours / eights words of the running 16-block
+    V64 p1 = {0, 0}, p2 = {0, 0}, p4 = {0, 0}, p8 = {0, 0}, q4 = {0, 0}, q8 = {0, 0};
+};
+constexpr int kVertK = 16;          // items per thread and step = inputs of one adder tree
+constexpr int kVertMaxPlanes = 12;  // shared-memory planes per counter (sixteens .. ): 16 * 2^12 items per thread
+constexpr int kVertFoldPlanes = 4 + kVertMaxPlanes + 5;  // a warp's total
+
+// four more words of the running 16-block (quarter Q = 0..3 of it); the last quarter returns the sixteens word in s16
+template <int Q>
+__device__ __forceinline__ void vert_feed4(VertTree &t, const V64 v0, const V64 v1, const V64 v2, const V64 v3, V64 &s16) {
+    V64 a2, b2, f4, e8;
+    csa(a2, t.p1, t.p1, v0, v1);
+    csa(b2, t.p1, t.p1, v2, v3);
+    csa(f4, t.p2, t.p2, a2, b2);
+    if (Q == 0 || Q == 2) {
+        t.q4 = f4;
+    } else {
+        csa(e8, t.p4, t.p4, t.q4, f4);
+        if (Q == 1)
+            t.q8 = e8;
+        else
+            csa(s16, t.p8, t.p8, t.q8, e8);
+    }
+}
+// ripple the sixteens word into the thread's shared-memory planes (plane stride: 256 threads x 8 bytes)
+__device__ __forceinline__ void vert_ripple(uint32_t addr, uint32_t n_planes, V64 e) {
+    for (uint32_t k = 0; k < n_planes && (e.lo | e.hi); ++k, addr += 256u * 8u) {
+        uint32_t vlo, vhi;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vlo), "=r"(vhi) : "r"(addr));
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(vlo ^ e.lo), "r"(vhi ^ e.hi) : "memory");
+        e.lo &= vlo;
+        e.hi &= vhi;
+    }
+}
+
+// One step of a consumer thread: 16 rows of the stage at `base` (rows li0 + k * 256) into the trees; s16[c] = the
+// sixteens word of counter c.  SLOW: per-slot validity (item 0, rows past the end of a short tile) and the per-item
+// coverage output; every other tile takes the branch-free path (immediate-offset loads, no predicates).
+template <int HIST, int D, bool C1, bool SLOW>
+__device__ __forceinline__ void vert_step(const ScanParams &p, VertTree (&tree)[HIST + D], V64 (&s16)[HIST + D], uint32_t base,
+                                          uint32_t li0, uint32_t trows, uint32_t tile, uint64_t row0, const uint32_t *cthr,
+                                          uint32_t mask_lo, uint32_t mask_hi) {
+    uint64_t x[kVertK];
+#pragma unroll
+    for (int k = 0; k < kVertK; ++k) {
+        const uint32_t lk = li0 + (uint32_t)k * kConsumerThreads;
+        x[k] = lds_u64(base + ((SLOW && lk >= trows) ? li0 : lk) * 8u);
+    }
+    auto quarter = [&](auto qtag) {
+        constexpr int Q = decltype(qtag)::value;
+        V64 oh[4], fw[D > 0 ? D : 1][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = Q * 4 + j;
+            const uint32_t lk = li0 + (uint32_t)k * kConsumerThreads;
+            uint32_t lo = (uint32_t)x[k] & mask_lo, hi = (uint32_t)(x[k] >> 32) & mask_hi;
+            bool valid = true;
+            if (SLOW) {
+                valid = lk < trows && (tile | lk) != 0u;  // item 0: the reference's dummy item, never counted
+                lo = valid ? lo : 0u;
+                hi = valid ? hi : 0u;
+            }
+            const uint32_t cov = __popc(lo) + __popc(hi);
+            if (SLOW && p.countable && lk < trows) p.countable[row0 + lk] = valid ? cov : 0xFFFFFFFFu;
+            if (HIST) {
+                const uint32_t one = SLOW ? (valid ? 1u : 0u) : 1u;
+                uint32_t olo, ohi;  // 1 << cov in two halves (shl.b32 clamps: shifts >= 32 give 0; coverage 64: see the read-out)
+                asm("shl.b32 %0, %1, %2;" : "=r"(olo) : "r"(one), "r"(cov));
+                asm("shl.b32 %0, %1, %2;" : "=r"(ohi) : "r"(one), "r"(cov - 32u));
+                oh[j] = {olo, ohi};
+            }
+            if (D > 0) {
+                const uint64_t xm = ((uint64_t)hi << 32) | lo;
+                const uint64_t first = xm & (0ull - xm);
+                const uint32_t flo = (uint32_t)first, fhi = (uint32_t)(first >> 32);
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    if (C1 && d == 0) {
+                        fw[d][j] = {flo, fhi};
+                    } else {
+                        const uint32_t m = cov >= cthr[d] ? 0xFFFFFFFFu : 0u;
+                        fw[d][j] = {flo & m, fhi & m};
+                    }
+                }
+            }
+        }
+        if (HIST) vert_feed4<Q>(tree[0], oh[0], oh[1], oh[2], oh[3], s16[0]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) vert_feed4<Q>(tree[HIST + d], fw[d][0], fw[d][1], fw[d][2], fw[d][3], s16[HIST + d]);
+    };
+    quarter(std::integral_constant<int, 0>{});
+    quarter(std::integral_constant<int, 1>{});
+    quarter(std::integral_constant<int, 2>{});
+    quarter(std::integral_constant<int, 3>{});
+}
+
+template <int HIST, int D, bool C1>
+__global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_constant__ ScanParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int C = HIST + D;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    const uint32_t S = p.stages;
+    const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
+    const uint32_t stage0 = smem_u32(smem + p.L.off_stage0);
+    const uint32_t P = p.L.vert_planes;
+
+    SmemAcc s;
+    s.hist_cnt = reinterpret_cast<uint32_t *>(smem + p.L.off_hist_cnt);
+    s.hist_wlo = s.hist_whi = nullptr;
+    s.delta_lo = reinterpret_cast<uint32_t *>(smem + p.L.off_delta_lo);
+    s.delta_hi = nullptr;
+    s.thr = nullptr;
+    s.joint_cnt = s.joint_wlo = s.joint_whi = nullptr;
+    uint32_t *cls_tot = reinterpret_cast<uint32_t *>(smem + p.L.off_cls_lo);  // [D][64]
+    uint64_t *fold = reinterpret_cast<uint64_t *>(smem + p.L.off_carry);      // [warp][C][kVertFoldPlanes]
+    const uint32_t planes0 = smem_u32(smem + p.L.off_priv);                   // [C][P][256] u64
+    __shared__ uint32_t s_missing_word;
+    uint32_t *s_missing = &s_missing_word;
+
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(smem + p.L.off_acc);
+        const uint32_t n16 = (p.L.vert_end - p.L.off_acc) / 16u;
+        for (uint32_t i = tid; i < n16; i += kScanThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        for (uint32_t i = 0; i < S; ++i) {
+            mbar_init(full0 + 8u * i, 1u);
+            mbar_init(empty0 + 8u * i, (uint32_t)kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    const bool zeroes_out = p.zero_epoch != 0u && blockIdx.x == 0u;
+    if (zeroes_out) direct_zero_out(p, tid);
+    __syncthreads();
+    if (zeroes_out && tid == kScanThreads - 1) direct_publish(p);
+
+    const uint32_t last_tile = p.n_tiles - 1u;
+    const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
+
+    if (warp == (uint32_t)kConsumerWarps) {
+        // ===== TMA producer (same ring as k_scan; rows only: counting never stages the weights) =====
+        if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
+            uint32_t st = 0, ph = 0;
+            bool ring_full = false;
+            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
+                const uint64_t row0 = (uint64_t)tile * p.tile_items;
+                const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
+                const uint32_t trows = rows & ~3u;
+                const uint32_t full = full0 + 8u * st;
+                if (trows) {
+                    mbar_arrive_expect_tx(full, trows * 8u);
+                    tma_bulk_g2s(stage0 + st * p.L.stage_stride, p.bitmap + row0, trows * 8u, full, pol);
+                } else {
+                    mbar_arrive(full);
+                }
+                if (++st == S) {
+                    st = 0;
+                    ph ^= 1u;
+                    ring_full = true;
+                }
+            }
+            if (p.zero_epoch) direct_wait_zeroed(p);
+        }
+    } else {
+        // ===== consumers: 16 items per thread and step =====
+        VertTree tree[C];
+        uint32_t seen = 0;  // (thread 0) items fed to the trees: the histogram's bins must add up to it (coverage 64, see below)
+        const uint32_t my_planes = planes0 + tid * 8u;
+        const uint32_t mask_lo = (uint32_t)p.last_mask0, mask_hi = (uint32_t)(p.last_mask0 >> 32);
+        uint32_t cthr[D > 0 ? D : 1];
+#pragma unroll
+        for (int d = 0; d < D; ++d) cthr[d] = p.cls_thr[d];
+        uint32_t st = 0, ph = 0;
+        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const uint64_t row0 = (uint64_t)tile * p.tile_items;
+            const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
+            const uint32_t trows = rows & ~3u;
+            const uint32_t base = stage0 + st * p.L.stage_stride;
+            const bool slow = tile == 0u || trows != p.tile_items || p.countable != nullptr;  // item 0 / a short tile / coverage output
+            mbar_wait(full0 + 8u * st, ph);
+            for (uint32_t li0 = tid; li0 < trows; li0 += kVertK * kConsumerThreads) {
+                V64 s16[C];
+                if (slow)
+                    vert_step<HIST, D, C1, true>(p, tree, s16, base, li0, trows, tile, row0, cthr, mask_lo, mask_hi);
+                else
+                    vert_step<HIST, D, C1, false>(p, tree, s16, base, li0, trows, tile, row0, cthr, mask_lo, mask_hi);
+#pragma unroll
+                for (int c = 0; c < C; ++c) vert_ripple(my_planes + (uint32_t)c * P * 2048u, P, s16[c]);
+            }
+            if (tid == 0) seen += trows - (tile == 0u && trows ? 1u : 0u);  // items this CTA fed to the trees
+            if (tid < rows - trows) {  // <= 3 tail rows of the last tile, straight from global memory, plain shared atomics
+                const uint64_t item = row0 + trows + tid;
+                const uint64_t xm = __ldg(p.bitmap + item) & p.last_mask0;
+                const uint32_t cov = __popcll(xm);
+                if (p.countable) p.countable[item] = item ? cov : 0xFFFFFFFFu;
+                if (item) {
+                    if (HIST) atomicAdd(&s.hist_cnt[cov], 1u);
+                    if (cov)
+                        for (uint32_t t = 0; t < p.T; ++t)
+                            if (cov >= p.cov[t]) atomicAdd(&s.delta_lo[t * p.G + first_bit(xm)], 1u);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8u * st);
+            if (++st == S) {
+                st = 0;
+                ph ^= 1u;
+            }
+        }
+        // ===== fold: add the 32 lanes' counters with full adders (butterfly), lane 0 keeps the warp's planes =====
+        if (HIST && tid == 0) *s_missing = seen;
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            V64 pl[kVertFoldPlanes];
+            VertTree t = tree[0];
+#pragma unroll
+            for (int cc = 1; cc < C; ++cc)
+                if (cc == c) t = tree[cc];
+            pl[0] = t.p1, pl[1] = t.p2, pl[2] = t.p4, pl[3] = t.p8;
+#pragma unroll
+            for (int k = 0; k < kVertMaxPlanes + 5; ++k) {
+                pl[4 + k] = {0u, 0u};
+                if ((uint32_t)k < P) {
+                    const uint32_t a = my_planes + ((uint32_t)c * P + (uint32_t)k) * 2048u;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pl[4 + k].lo), "=r"(pl[4 + k].hi) : "r"(a));
+                }
+            }
+            uint32_t n = 4u + P;  // planes that can be non-zero
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                V64 carry = {0u, 0u};
+#pragma unroll
+                for (int k = 0; k < kVertFoldPlanes; ++k) {
+                    if ((uint32_t)k > n) break;
+                    const V64 o = {__shfl_xor_sync(0xFFFFFFFFu, pl[k].lo, off), __shfl_xor_sync(0xFFFFFFFFu, pl[k].hi, off)};
+                    csa(carry, pl[k], pl[k], o, carry);
+                }
+                ++n;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < kVertFoldPlanes; ++k)
+                    fold[((size_t)warp * C + c) * kVertFoldPlanes + k] = ((uint64_t)pl[k].hi << 32) | pl[k].lo;
+            }
+        }
+    }
+    __syncthreads();
+    // ===== read the bins out: bit b of plane k of every warp's total weighs 2^k =====
+    for (uint32_t i = tid; i < (uint32_t)C * 64u; i += kScanThreads) {
+        const uint32_t c = i >> 6, b = i & 63u;
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < (uint32_t)kConsumerWarps; ++w) {
+            const uint64_t *f = fold + ((size_t)w * C + c) * kVertFoldPlanes;
+            for (uint32_t k = 0; k < 4u + P + 5u; ++k) total += (uint32_t)((f[k] >> b) & 1ull) << k;
+        }
+        if (HIST && c == 0) {
+            if (total) {
+                atomicAdd(&s.hist_cnt[b], total);  // (the tail rows' atomics are in there already; bits above G are never set)
+                atomicSub(s_missing, total);
+            }
+        } else {
+            cls_tot[(c - HIST) * 64u + b] = total;
+        }
+    }
+    __syncthreads();
+    // coverage 64 (G = 64) has no bit in the one-hot word: those items are the ones the 64 bins did not account for
+    if (HIST && tid == 0 && p.G == 64u && *s_missing) s.hist_cnt[64] += *s_missing;
+    for (uint32_t i = tid; i < p.T * p.G; i += kScanThreads) {
+        const uint32_t t = i / p.G, f = i - t * p.G;
+        s.delta_lo[i] += cls_tot[(p.cls_rank[t] - 1u) * 64u + f];
+    }
+    __syncthreads();
+    scan_epilogue(p, s, tid);
+}
+
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1u) / a * a; }
 
 template <bool QUORUM, int C_T, bool MASK>
@@ -785,29 +1139,61 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     L.off_cls_lo = L.off_cls_hi = L.off_carry = L.off_priv = L.off_cbase = off;
     L.priv_bins = L.priv_cw = L.priv_hist_bins = 0;
     p.n_classes = 0;
-    bool priv = false;
+    bool priv = false, vert = false;
     uint32_t priv_tile = 0;
-    if (!quorum && env_u32("PGX_SCAN_PRIV") != 2u) {
+    L.vert_planes = L.vert_counters = L.vert_end = 0;
+    // distinct coverage cutoffs, ascending (k_scan_priv: threshold t sums the classes >= its rank; k_scan_vert: counter
+    // cls_rank[t] - 1 holds the items of coverage >= cutoff)
+    uint32_t D = 0;
+    if (!quorum) {
+        for (uint32_t t = 0; t < p.T; ++t) {
+            bool seen = false;
+            for (uint32_t d = 0; d < D; ++d) seen |= p.cls_thr[d] == p.cov[t];
+            if (!seen) p.cls_thr[D++] = p.cov[t];
+        }
+        for (uint32_t i = 1; i < D; ++i)
+            for (uint32_t j = i; j > 0 && p.cls_thr[j - 1] > p.cls_thr[j]; --j) {
+                const uint32_t tmp = p.cls_thr[j];
+                p.cls_thr[j] = p.cls_thr[j - 1];
+                p.cls_thr[j - 1] = tmp;
+            }
+        for (uint32_t t = 0; t < p.T; ++t)
+            for (uint32_t d = 0; d < D; ++d)
+                if (p.cls_thr[d] == p.cov[t]) p.cls_rank[t] = d + 1u;
+    }
+    // bit-sliced vertical counters: one-word rows (G <= 64), counting (no weights), at most 3 distinct cutoffs
+    // (PGX_SCAN_VERT=2 switches it off; PGX_SCAN_PRIV=1 / 2 ask for the lane-private / the shared-atomics kernel explicitly)
+    if (!quorum && p.Wp == 1u && !(p.flags & (kWeighted | kHistWeight)) && D <= 3u && env_u32("PGX_SCAN_VERT") != 2u &&
+        env_u32("PGX_SCAN_PRIV") == 0u) {
+        const uint32_t C = ((p.flags & kHistCount) ? 1u : 0u) + D;
+        const uint64_t n_tiles = (p.n_rows + 4095u) / 4096u;
+        uint64_t worst_grid = env_u32("PGX_SCAN_GRID") ? env_u32("PGX_SCAN_GRID") : (uint64_t)sm_count;  // fewest CTAs the launch may use
+        if (worst_grid > n_tiles) worst_grid = n_tiles;
+        const uint64_t blocks = worst_grid ? (n_tiles + worst_grid - 1u) / worst_grid : 0u;  // 16-blocks a thread adds up
+        uint32_t P = 1;
+        while (P <= 32u && (blocks >> P)) ++P;  // 2^P > blocks
+        if (C >= 1u && P <= (uint32_t)kVertMaxPlanes) {
+            vert = true;
+            p.flags |= kVertical;
+            p.n_classes = D;
+            off = align_up(off, 16u);
+            L.off_cls_lo = off;
+            off += D * 64u * 4u;
+            L.off_carry = off = align_up(off, 16u);
+            off += (uint32_t)kConsumerWarps * C * (uint32_t)kVertFoldPlanes * 8u;
+            L.off_priv = off = align_up(off, 16u);
+            off += C * P * 2048u;
+            L.vert_planes = P;
+            L.vert_counters = C;
+            L.vert_end = off;
+            L.off_cls_hi = L.off_cbase = off;
+        }
+    }
+    if (!quorum && !vert && env_u32("PGX_SCAN_PRIV") != 2u) {
         const bool count_mode = !(p.flags & (kWeighted | kHistWeight));
         const bool weight_mode = !(p.flags & kHistCount) && ((p.flags & kWeighted) || p.T == 0) &&
                                  (p.flags & (kHistWeight | kWeighted)) && p.weight != nullptr;
         if (count_mode || weight_mode) {
-            // distinct coverage cutoffs, ascending; threshold t sums the classes >= its rank
-            uint32_t D = 0;
-            for (uint32_t t = 0; t < p.T; ++t) {
-                bool seen = false;
-                for (uint32_t d = 0; d < D; ++d) seen |= p.cls_thr[d] == p.cov[t];
-                if (!seen) p.cls_thr[D++] = p.cov[t];
-            }
-            for (uint32_t i = 1; i < D; ++i)
-                for (uint32_t j = i; j > 0 && p.cls_thr[j - 1] > p.cls_thr[j]; --j) {
-                    const uint32_t tmp = p.cls_thr[j];
-                    p.cls_thr[j] = p.cls_thr[j - 1];
-                    p.cls_thr[j - 1] = tmp;
-                }
-            for (uint32_t t = 0; t < p.T; ++t)
-                for (uint32_t d = 0; d < D; ++d)
-                    if (p.cls_thr[d] == p.cov[t]) p.cls_rank[t] = d + 1u;
             const uint32_t cw = count_mode ? 1u : 2u;
             const uint32_t hist_bins = (count_mode ? (p.flags & kHistCount) : (p.flags & kHistWeight)) ? G1 : 0u;
             const uint64_t bins = std::max<uint64_t>(1u, (uint64_t)hist_bins + (uint64_t)D * p.G);
@@ -852,7 +1238,7 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     }
     // small G: joint (coverage, first group) histogram -- one atomic per item instead of 1 + T
     L.off_joint_cnt = L.off_joint_wlo = L.off_joint_whi = off;
-    if (!priv && !quorum && env_u32("PGX_SCAN_JOINT") != 2u) {
+    if (!priv && !vert && !quorum && env_u32("PGX_SCAN_JOINT") != 2u) {
         const bool use_cnt = (p.flags & kHistCount) || !(p.flags & kWeighted);
         const bool use_w = (p.flags & (kHistWeight | kWeighted)) != 0;
         const uint32_t one = G1 * p.G * 4u, bytes = one * ((use_cnt ? 1u : 0u) + (use_w ? 2u : 0u));
@@ -877,7 +1263,10 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     // (tools/sweep_scan.py, profiles/r1_sweep_*.txt).  The quorum kernel keeps one item per thread.
     uint32_t tile, want_ctas, want_stages;
     const bool heavy = quorum || (p.flags & (kHistWeight | kWeighted)) != 0;  // more atomics per item
-    if (priv) {
+    if (vert) {
+        tile = (uint32_t)kVertK * (uint32_t)kConsumerThreads;  // one 16-block per thread and tile
+        want_ctas = 2, want_stages = 3;
+    } else if (priv) {
         // two CTAs per SM (16 consumer warps hide the shared-memory latencies of the counter updates) whenever three
         // stages of some tile size fit next to the private region in half an SM's shared memory; else one CTA, deep ring
         tile = priv_tile;
@@ -909,7 +1298,7 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
         if (tile > 3072u) tile = 3072u;
         want_ctas = 2, want_stages = 3;
     }
-    if (const uint32_t t_env = env_u32("PGX_SCAN_TILE")) tile = priv ? tile : ((t_env + 3u) & ~3u);
+    if (const uint32_t t_env = env_u32("PGX_SCAN_TILE")) tile = (priv || vert) ? tile : ((t_env + 3u) & ~3u);
     p.tile_items = tile;
     L.off_stage_w = align_up(tile * rowbytes, 128u);
     L.stage_stride = L.off_stage_w + (p.weight ? align_up(tile * 4u, 128u) : 0u);
@@ -978,7 +1367,30 @@ int launch_priv(const ScanParams &p, int grid, cudaStream_t stream) {
     }
 }
 
+template <int HIST, int D, bool C1>
+int launch_vert_one(const ScanParams &p, int grid, cudaStream_t stream) {
+    auto kern = k_scan_vert<HIST, D, C1>;
+    PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.L.total));
+    kern<<<grid, kScanThreads, p.L.total, stream>>>(p);
+    PGX_CUDA(cudaGetLastError());
+    return PGX_OK;
+}
+
+template <int HIST>
+int launch_vert(const ScanParams &p, int grid, cudaStream_t stream) {
+    const bool c1 = p.n_classes && p.cls_thr[0] <= 1u;
+    switch (p.n_classes) {
+        case 0:
+            if constexpr (HIST != 0) return launch_vert_one<1, 0, false>(p, grid, stream);
+            return fail(PGX_ERR_INVALID, "k_scan_vert without a counter");
+        case 1: return c1 ? launch_vert_one<HIST, 1, true>(p, grid, stream) : launch_vert_one<HIST, 1, false>(p, grid, stream);
+        case 2: return c1 ? launch_vert_one<HIST, 2, true>(p, grid, stream) : launch_vert_one<HIST, 2, false>(p, grid, stream);
+        default: return c1 ? launch_vert_one<HIST, 3, true>(p, grid, stream) : launch_vert_one<HIST, 3, false>(p, grid, stream);
+    }
+}
+
 int launch_scan(const ScanParams &p, bool quorum, int grid, cudaStream_t stream) {
+    if (p.flags & kVertical) return (p.flags & kHistCount) ? launch_vert<1>(p, grid, stream) : launch_vert<0>(p, grid, stream);
     if (p.flags & kPrivate) return p.L.priv_cw == 1u ? launch_priv<1, false>(p, grid, stream) : launch_priv<2, true>(p, grid, stream);
     if (quorum) return launch_one<true, 0, true>(p, grid, stream);
     if (p.Wp == 1u) return launch_one<false, -1, true>(p, grid, stream);

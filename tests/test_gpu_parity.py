@@ -766,3 +766,66 @@ def test_extreme_shapes(N, G):
             assert not inter.any() and not ln.any()
         return
     check_table(pb.pack_bits(bits), G, weights, pairs=pairs)
+
+
+# ---- bit-sliced vertical counters (k_scan_vert: G <= 64, counting) -------------------------------------------------
+
+@pytest.mark.parametrize("N,G", [(3, 5), (4095, 1), (4096, 7), (4097, 31), (12_289, 32), (50_000, 33), (300_000, 44),
+                                 (100_001, 63), (200_003, 64)])
+def test_vertical_counter_kernel(N, G, monkeypatch):
+    """k_scan_vert (carry-save adders over one-hot words instead of atomics) against the oracle: histogram and / or q = 0
+    curves with 1..3 distinct coverage cutoffs (more fall back to the other kernels), per-item coverage output, item 0,
+    short last tiles, <= 3 tail rows, coverage 64 (G = 64: no bit in the one-hot word), and -- with the grid capped to 2
+    CTAs -- many tiles per CTA, so that the sixteens words ripple through several shared-memory planes."""
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=N * 3 + G)
+    if N >= 8:
+        bits[1] = 0
+        bits[2] = 1
+        bits[5] = 1  # full rows: coverage G
+        bits[6] = 0
+        bits[6, G - 1] = 1
+        bitmap = pb.pack_bits(bits)
+    if G == 64:  # a good share of coverage-64 items
+        bits[N // 2:N // 2 + N // 7] = 1
+        bitmap = pb.pack_bits(bits)
+    cases = [[(1, 0.0)], [(3, 0.0)], [(1, 0.0), (2, 0.0)], [(2, 0.0), (1, 0.0), (2, 0.0), (G, 0.0)], [(G + 1, 0.0), (1, 0.0)]]
+    all_pairs = sorted({pr for cs in cases for pr in cs})
+    exp = oracle_all(bitmap, G, weights, all_pairs)
+    dirty = bitmap.copy()
+    if G < 64:
+        dirty[:, 0] |= np.uint64(((1 << 64) - 1) ^ ((1 << G) - 1))  # garbage above bit G must be ignored
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(dirty, weights)
+        for grid in ("2", None):
+            if grid:
+                monkeypatch.setenv("PGX_SCAN_GRID", grid)
+            else:
+                monkeypatch.delenv("PGX_SCAN_GRID", raising=False)
+            hc, _, ct = a.hist(count=True, weight=False, countable=True)
+            assert "k_scan_vert<hist=1,D=0>" in a.last_launch_info(), a.last_launch_info()
+            assert np.array_equal(hc, exp["hist"]) and np.array_equal(ct, exp["countable"])
+            hc, _, _ = a.hist(count=True, weight=False)
+            assert np.array_equal(hc, exp["hist"])
+            for pairs in cases:
+                cov = [c for c, _ in pairs]
+                D = len(set(cov))
+                h2, _, cv = a.hist_ordered_growth(cov, None, weighted=False, hist_count=True, hist_weight=False)
+                assert f"k_scan_vert<hist=1,D={D}>" in a.last_launch_info(), a.last_launch_info()
+                assert np.array_equal(h2, exp["hist"])
+                only = a.ordered_growth(cov, None, weighted=False)
+                assert f"k_scan_vert<hist=0,D={D}>" in a.last_launch_info(), a.last_launch_info()
+                for t, (c, q) in enumerate(pairs):
+                    assert np.array_equal(cv[t].astype(np.float64), exp[("node", c, q)]), (grid, pairs, c)
+                    assert np.array_equal(only[t].astype(np.float64), exp[("node", c, q)]), (grid, pairs, c)
+            # the weighted modes and more than 3 cutoffs stay on the other kernels
+            _, hw, _ = a.hist(count=False, weight=True)
+            assert "k_scan_vert" not in a.last_launch_info() and np.array_equal(hw, exp["hist_bp"])
+
+
+def test_ticket_epilogue_matches(monkeypatch):
+    """PGX_SCAN_TICKET=1 keeps the round-1 epilogue (global accumulators, completion ticket, snapshot by the last CTA --
+    still what the multi-GPU exchange builds on); the default adds straight into the caller's vector.  Same numbers."""
+    monkeypatch.setenv("PGX_SCAN_TICKET", "1")
+    for N, G in ((1030, 1024), (4099, 512), (5000, 44)):
+        bits, bitmap, weights = synth.numpy_table(N, G, seed=N + 3 * G)
+        check_table(bitmap, G, weights)

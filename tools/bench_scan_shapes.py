@@ -36,11 +36,13 @@ for N, G in shapes:
         T = len(kw["cov"])
         out = torch.zeros(a.fused_out_words(max(T, 1)), dtype=torch.int64, device=dev)
         res = {}
-        for name, env in (("priv", None), ("atomics", "2")):
-            if env:
+        for name, env in (("priv", None), ("atomics", "2"), ("novert", "v")):
+            os.environ.pop("PGX_SCAN_PRIV", None)
+            os.environ.pop("PGX_SCAN_VERT", None)
+            if env == "v":
+                os.environ["PGX_SCAN_VERT"] = "2"  # the library's choice without the vertical-counter kernel
+            elif env:
                 os.environ["PGX_SCAN_PRIV"] = env
-            else:
-                os.environ.pop("PGX_SCAN_PRIV", None)
             ts = []
             for it in range(14):
                 if (N + 1) * Wp * 8 < 256 * 1024 * 1024:
@@ -55,10 +57,11 @@ for N, G in shapes:
                     ts.append(e0.elapsed_time(e1) * 1e3)
             res[name] = (float(np.median(ts)), int(out.cpu().numpy().view(np.uint64).sum() % (1 << 61)), a.last_launch_info())
         os.environ.pop("PGX_SCAN_PRIV", None)
+        os.environ.pop("PGX_SCAN_VERT", None)
         bytes_ = N * ((G + 63) // 64) * 8 + (4 * N if (kw["weighted"] or kw["hist_weight"]) else 0)
         us = res["priv"][0]
-        print(json.dumps({"N": N, "G": G, "mode": mode, "priv_us": round(us, 2), "atomics_us": round(res["atomics"][0], 2),
+        print(json.dumps({"N": N, "G": G, "mode": mode, "priv_us": round(us, 2), "atomics_us": round(res["atomics"][0], 2), "novert_us": round(res["novert"][0], 2),
                           "gbps": round(bytes_ / us / 1e3, 1), "frac_of_hbm": round(bytes_ / us / 1e3 / peak, 3),
-                          "same_result": res["priv"][1] == res["atomics"][1], "launch": res["priv"][2]}), flush=True)
+                          "same_result": res["priv"][1] == res["atomics"][1] == res["novert"][1], "launch": res["priv"][2]}), flush=True)
     a.close()
     del bitmap, weight
