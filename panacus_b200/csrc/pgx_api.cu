@@ -183,10 +183,38 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
         if (++a->scan_epoch == 0u) ++a->scan_epoch;
         p.zero_epoch = a->scan_epoch;
     }
+    uint64_t *d_ts = nullptr;
+    if (getenv("PGX_SCAN_TS")) {  // measurement aid: per-CTA phase time stamps of this launch, summarised on stderr
+        if (cudaMalloc(reinterpret_cast<void **>(&d_ts), (size_t)grid * 64u) == cudaSuccess) {
+            cudaMemsetAsync(d_ts, 0, (size_t)grid * 64u, a->stream);
+            p.dbg_ts = d_ts;
+        }
+    }
     int rc;
     {
         KernelTimer kt(a);
         rc = launch_scan(p, quorum, grid, a->stream);
+    }
+    if (d_ts) {
+        std::vector<uint64_t> ts((size_t)grid * 8u);
+        cudaStreamSynchronize(a->stream);
+        cudaMemcpy(ts.data(), d_ts, ts.size() * 8u, cudaMemcpyDeviceToHost);
+        cudaFree(d_ts);
+        uint64_t t0 = ~0ull;
+        for (int b = 0; b < grid; ++b)
+            if (ts[(size_t)b * 8u]) t0 = std::min(t0, ts[(size_t)b * 8u]);
+        static const char *names[6] = {"cta_start", "init_done", "first_tile", "loop_done", "epilogue_start", "reds_issued"};
+        fprintf(stderr, "PGX_SCAN_TS grid=%d (ns after the first CTA's start: min / median / max over CTAs)", grid);
+        for (int k = 0; k < 6; ++k) {
+            std::vector<uint64_t> v;
+            for (int b = 0; b < grid; ++b)
+                if (ts[(size_t)b * 8u + k]) v.push_back(ts[(size_t)b * 8u + k] - t0);
+            if (v.empty()) continue;
+            std::sort(v.begin(), v.end());
+            fprintf(stderr, " | %s %llu / %llu / %llu", names[k], (unsigned long long)v.front(), (unsigned long long)v[v.size() / 2],
+                    (unsigned long long)v.back());
+        }
+        fprintf(stderr, "\n");
     }
     if (rc) return rc;
     a->launches++;

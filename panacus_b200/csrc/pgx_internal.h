@@ -91,6 +91,7 @@ struct ScanParams {
     uint64_t last_mask0, last_mask1;  // masks of the two words of the last 16-byte chunk of a row
     ScanLayout L;
     Exchange x;              // x.world <= 1: no exchange
+    uint64_t *dbg_ts;        // PGX_SCAN_TS=1: per CTA 8 globaltimer stamps (phase timeline of one launch), else nullptr
 };
 
 struct ScanPlan {

@@ -210,6 +210,15 @@ uint32_t env_u32(const char *name) {
     return v ? (uint32_t)strtoul(v, nullptr, 10) : 0u;
 }
 
+// PGX_SCAN_TS=1: thread-0 time stamps of a CTA's phases (measurement aid, tools/scan_timeline.py)
+__device__ __forceinline__ void ts_mark(const ScanParams &p, uint32_t slot) {
+    if (p.dbg_ts) {
+        uint64_t t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg_ts[(size_t)blockIdx.x * 8u + slot] = t;
+    }
+}
+
 // ---- direct epilogue (single GPU): the CTAs add their sums straight into the caller's result vector ------------------
 // CTA 0 zeroes the requested words of `out` while the first tiles are in flight and publishes the launch's epoch; every
 // CTA's TMA lane, idle once its last copy is issued, waits for that epoch before the CTA-wide barrier that precedes
@@ -242,6 +251,7 @@ __device__ __forceinline__ void scan_epilogue(const ScanParams &p, const SmemAcc
     const uint32_t G1 = p.G + 1u;
     const bool direct = p.zero_epoch != 0u;
     uint64_t *const dst = direct ? p.out : p.acc;
+    if (tid == 0) ts_mark(p, 4);
     if (p.flags & kJoint) {  // marginalise the joint histogram into hist[] and the curves' first differences
         const bool use_cnt = (p.flags & kHistCount) || !(p.flags & kWeighted);
         const bool use_w = (p.flags & (kHistWeight | kWeighted)) != 0;
@@ -301,7 +311,10 @@ __device__ __forceinline__ void scan_epilogue(const ScanParams &p, const SmemAcc
             if (v) atomicAdd(reinterpret_cast<unsigned long long *>(row + j), (unsigned long long)v);
         }
     }
-    if (direct) return;
+    if (direct) {
+        if (tid == 0) ts_mark(p, 5);
+        return;
+    }
 
     // ===== last CTA: snapshot + re-zero (threadfence reduction pattern) =====
     __shared__ uint32_t s_is_last;
@@ -406,6 +419,7 @@ template <bool QUORUM, int C_T, bool MASK>
 __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t tid = threadIdx.x;
+    if (tid == 0) ts_mark(p, 0);
     const uint32_t warp = tid >> 5, lane = tid & 31u;
     const uint32_t S = p.stages;
     const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
@@ -441,6 +455,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
     if (zeroes_out) direct_zero_out(p, tid);
     __syncthreads();
     if (zeroes_out && tid == kScanThreads - 1) direct_publish(p);
+    if (tid == 0) ts_mark(p, 1);
 
     const uint32_t last_tile = p.n_tiles - 1u;
     // rows of the last tile (may be partial); every other tile is full
@@ -490,6 +505,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const uint32_t wbase = base + p.L.off_stage_w;
             mbar_wait(full0 + 8u * st, ph);
+            if (tid == 0 && tile == blockIdx.x) ts_mark(p, 2);
             for (uint32_t li = tid; li < rows; li += kConsumerThreads) {
                 const uint64_t item = row0 + li;
                 if (item == 0) {  // the reference's dummy item (abacus.rs:551, 1000-1002)
@@ -525,6 +541,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
             }
         }
     }
+    if (tid == 0) ts_mark(p, 3);
     __syncthreads();
 
     scan_epilogue(p, s, tid);
@@ -607,6 +624,7 @@ template <int CW, bool WEIGHTED, int C_T>
 __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t tid = threadIdx.x;
+    if (tid == 0) ts_mark(p, 0);
     const uint32_t warp = tid >> 5, lane = tid & 31u;
     const uint32_t S = p.stages;
     const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
@@ -648,6 +666,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
     if (zeroes_out) direct_zero_out(p, tid);
     __syncthreads();
     if (zeroes_out && tid == kScanThreads - 1) direct_publish(p);
+    if (tid == 0) ts_mark(p, 1);
 
     const uint32_t last_tile = p.n_tiles - 1u;
     const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
@@ -724,6 +743,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const uint32_t wbase = base + p.L.off_stage_w;
             mbar_wait(full0 + 8u * st, ph);
+            if (tid == 0 && tile == blockIdx.x) ts_mark(p, 2);
             for (uint32_t li0 = tid; li0 < trows; li0 += K * kConsumerThreads) {
                 uint32_t cov[K], first[K], wgt[K], cb[K];
                 bool valid[K];
@@ -776,6 +796,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
             }
         }
     }
+    if (tid == 0) ts_mark(p, 3);
     __syncthreads();
     priv_fold<CW, WEIGHTED>(p, s, cls_lo, cls_hi, carry, priv_base, tid);
     __syncthreads();
@@ -924,6 +945,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int C = HIST + D;
     const uint32_t tid = threadIdx.x;
+    if (tid == 0) ts_mark(p, 0);
     const uint32_t warp = tid >> 5, lane = tid & 31u;
     const uint32_t S = p.stages;
     const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
@@ -959,6 +981,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
     if (zeroes_out) direct_zero_out(p, tid);
     __syncthreads();
     if (zeroes_out && tid == kScanThreads - 1) direct_publish(p);
+    if (tid == 0) ts_mark(p, 1);
 
     const uint32_t last_tile = p.n_tiles - 1u;
     const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
@@ -1006,6 +1029,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const bool slow = tile == 0u || trows != p.tile_items || p.countable != nullptr;  // item 0 / a short tile / coverage output
             mbar_wait(full0 + 8u * st, ph);
+            if (tid == 0 && tile == blockIdx.x) ts_mark(p, 2);
             for (uint32_t li0 = tid; li0 < trows; li0 += kVertK * kConsumerThreads) {
                 V64 s16[C];
                 if (slow)
@@ -1035,6 +1059,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
                 ph ^= 1u;
             }
         }
+        if (tid == 0) ts_mark(p, 3);
         // ===== fold: add the 32 lanes' counters with full adders (butterfly), lane 0 keeps the warp's planes =====
         if (HIST && tid == 0) *s_missing = seen;
 #pragma unroll 1
@@ -1073,21 +1098,18 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
         }
     }
     __syncthreads();
-    // ===== read the bins out: bit b of plane k of every warp's total weighs 2^k =====
-    for (uint32_t i = tid; i < (uint32_t)C * 64u; i += kScanThreads) {
-        const uint32_t c = i >> 6, b = i & 63u;
+    // ===== read the bins out: bit b of plane k of a warp's total weighs 2^k (one thread per warp, counter and bin) =====
+    for (uint32_t i = tid; i < (uint32_t)(C * 64 * kConsumerWarps); i += kScanThreads) {
+        const uint32_t w = i / (uint32_t)(C * 64), c = (i >> 6) % (uint32_t)C, b = i & 63u;
+        const uint64_t *f = fold + ((size_t)w * C + c) * kVertFoldPlanes;
         uint32_t total = 0;
-        for (uint32_t w = 0; w < (uint32_t)kConsumerWarps; ++w) {
-            const uint64_t *f = fold + ((size_t)w * C + c) * kVertFoldPlanes;
-            for (uint32_t k = 0; k < 4u + P + 5u; ++k) total += (uint32_t)((f[k] >> b) & 1ull) << k;
-        }
+        for (uint32_t k = 0; k < 4u + P + 5u; ++k) total += (uint32_t)((f[k] >> b) & 1ull) << k;
+        if (!total) continue;
         if (HIST && c == 0) {
-            if (total) {
-                atomicAdd(&s.hist_cnt[b], total);  // (the tail rows' atomics are in there already; bits above G are never set)
-                atomicSub(s_missing, total);
-            }
+            atomicAdd(&s.hist_cnt[b], total);  // (the tail rows' atomics are in there already; bits above G are never set)
+            atomicSub(s_missing, total);
         } else {
-            cls_tot[(c - HIST) * 64u + b] = total;
+            atomicAdd(&cls_tot[(c - HIST) * 64u + b], total);
         }
     }
     __syncthreads();

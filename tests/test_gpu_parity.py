@@ -829,3 +829,34 @@ def test_ticket_epilogue_matches(monkeypatch):
     for N, G in ((1030, 1024), (4099, 512), (5000, 44)):
         bits, bitmap, weights = synth.numpy_table(N, G, seed=N + 3 * G)
         check_table(bitmap, G, weights)
+
+
+# ---- node-major -> group-major transpose: both kernels, every tile width ---------------------------------------------
+
+@pytest.mark.parametrize("N,G", [(3000, 20), (40_000, 100), (9000, 200), (33_000, 300), (5000, 700), (20_000, 1024),
+                                 (17_000, 1100), (2500, 2100), (70_000, 64)])
+def test_transpose_kernels(N, G, monkeypatch):
+    """k_transpose_reg (in-register 32x32 transposes, default; tile rows of 2 / 4 / 8 / 16 / 32 32-bit columns, partial last
+    column blocks, ragged item counts) and the shuffle-butterfly kernel (PGX_TRANSPOSE=shfl): the group-major copy is
+    checked through its consumers -- per-group item counts and the union growth under random group orders, which needs
+    every item's bits aligned across all group rows -- against numpy."""
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=5 * N + G)
+    bits[N // 2] = 1
+    bits[N - 1] = 0
+    bits[N - 1, G - 1] = 1
+    bitmap = pb.pack_bits(bits)
+    orders = synth.random_orders(3, G, seed=N + G)
+    want_len = bits[1:].sum(axis=0).astype(np.uint64)
+    want = [np.maximum.accumulate(bits[1:][:, o], axis=1).sum(axis=0).astype(np.uint64) for o in orders]
+    for mode in ("reg", "shfl"):
+        if mode == "shfl":
+            monkeypatch.setenv("PGX_TRANSPOSE", "shfl")
+        else:
+            monkeypatch.delenv("PGX_TRANSPOSE", raising=False)
+        with pb.DeviceAbacus(N, G) as a:
+            a.upload(bitmap, weights)
+            _, ln = a.similarity(row_begin=0, row_end=0)
+            assert np.array_equal(ln, want_len), mode
+            pg = a.permuted_growth(orders, [1], None, weighted=False)
+            for k in range(len(orders)):
+                assert np.array_equal(pg[k, 0].astype(np.uint64), want[k]), (mode, k)
