@@ -75,6 +75,7 @@ int copy_to_host(pgx_abacus *a, uint64_t *dst, const uint64_t *d_src, size_t wor
 void invalidate_derived(pgx_abacus *a) {
     a->countable_valid = false;
     a->gm_valid = false;
+    a->gm_c_valid = false;
     a->planes_valid = false;
     a->csr_valid = false;
 }
@@ -183,6 +184,8 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
         if (++a->scan_epoch == 0u) ++a->scan_epoch;
         p.zero_epoch = a->scan_epoch;
     }
+    p.sched_dynamic = getenv("PGX_SCAN_STATIC") ? 0u : 1u;  // (PGX_SCAN_STATIC=1: round-robin tiles, for measurements)
+    p.sched_parity = a->scan_launches++ & 1u;
     uint64_t *d_ts = nullptr;
     if (getenv("PGX_SCAN_TS")) {  // measurement aid: per-CTA phase time stamps of this launch, summarised on stderr
         if (cudaMalloc(reinterpret_cast<void **>(&d_ts), (size_t)grid * 64u) == cudaSuccess) {
@@ -317,6 +320,29 @@ int ensure_gm(pgx_abacus *a) {
     if (rc) return rc;
     a->launches++;
     a->gm_valid = true;
+    return PGX_OK;
+}
+
+// Coverage-sorted group-major copy (items by descending coverage; bit position i of every row = item d_perm_c[i]).
+int ensure_gm_cov(pgx_abacus *a) {
+    if (a->gm_c_valid) return PGX_OK;
+    int rc = ensure_countable(a);
+    if (rc) return rc;
+    a->gm_stride = gm_stride_words(a->n_rows);
+    if (!a->d_gm_c) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_gm_c), (size_t)a->G * a->gm_stride * 8u));
+    if (!a->d_perm_c) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_perm_c), a->n_rows * 4u));
+    uint32_t *d_keys_out = nullptr;  // the sorted coverages themselves are not needed afterwards
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_keys_out), a->n_rows * 4u));
+    {
+        KernelTimer kt(a);
+        rc = sort_items_by_weight(a->d_countable, a->n_rows, a->d_perm_c, d_keys_out, a->stream);
+        if (!rc) rc = launch_transpose(a->d_bitmap, a->n_rows, a->G, a->Wp, a->d_gm_c, a->gm_stride, a->d_perm_c, a->stream);
+    }
+    cudaStreamSynchronize(a->stream);
+    cudaFree(d_keys_out);
+    if (rc) return rc;
+    a->launches += 2;
+    a->gm_c_valid = true;
     return PGX_OK;
 }
 
@@ -477,14 +503,25 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
     int rc;
     const bool sorted = w && a->d_weight != nullptr;  // weight-sorted item order: uniform-weight columns are the rule
     if (sorted && (rc = ensure_planes(a))) return rc;
+    // counting, general thresholds with coverage cutoffs > 1, several orders: run on the coverage-sorted copy, where whole
+    // warps hold only items below a cutoff and skip that threshold's rank comparison (or the ranks altogether).  One sort +
+    // one permuted transpose per graph, so only when the work is repeated (PGX_GM_COVSORT=0 / 1: never / always).
+    bool cov_sorted = false;
+    if (!w && !gen.empty()) {
+        bool any_cut = false;
+        for (uint32_t t : gen) any_cut |= cov[t] > 1u;
+        const char *cs = getenv("PGX_GM_COVSORT");
+        cov_sorted = any_cut && !(cs && !strcmp(cs, "0")) && (n_orders >= 4u || a->gm_c_valid || (cs && !strcmp(cs, "1")));
+        if (cov_sorted && (rc = ensure_gm_cov(a))) return rc;
+    }
     GmGrowthParams base;
     std::memset(&base, 0, sizeof(base));
-    base.gm = sorted ? a->d_gm_w : a->d_gm;
+    base.gm = sorted ? a->d_gm_w : (cov_sorted ? a->d_gm_c : a->d_gm);
     base.gm_stride = a->gm_stride;
     base.n_words = (a->n_rows + 63u) / 64u;
     base.n_rows = a->n_rows;
     base.weight = sorted ? a->d_sorted_w : nullptr;
-    base.perm = sorted ? a->d_perm : nullptr;
+    base.perm = sorted ? a->d_perm : (cov_sorted ? a->d_perm_c : nullptr);
     base.uniform_w = sorted ? a->d_uniform_w : nullptr;
     base.countable = a->d_countable;
     base.G = G;
@@ -504,10 +541,10 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
         }
         char buf[192];
         if (p.T == 0)
-            snprintf(buf, sizeof buf, "k_gm_union orders=%u T=0 q0=%u%s", n_orders, p.n_fast, sorted ? " weight-sorted" : "");
+            snprintf(buf, sizeof buf, "k_gm_union orders=%u T=0 q0=%u%s", n_orders, p.n_fast, sorted ? " weight-sorted" : (cov_sorted ? " coverage-sorted" : ""));
         else
             snprintf(buf, sizeof buf, "k_gm_quorum<P=%d> orders=%u T=%u q0=%u%s smem=%zu", p.T ? gm_quorum_planes(G) : 0, n_orders,
-                     p.T, p.n_fast, sorted ? " weight-sorted" : "", gm_quorum_smem_bytes(G, p.T, gm_quorum_fast_slots(p.T, p.n_fast), w));
+                     p.T, p.n_fast, sorted ? " weight-sorted" : (cov_sorted ? " coverage-sorted" : ""), gm_quorum_smem_bytes(G, p.T, gm_quorum_fast_slots(p.T, p.n_fast), w));
         a->last_launch = buf;
         return PGX_OK;
     };
@@ -736,10 +773,10 @@ int pgx_abacus_create(pgx_abacus **out, int device, uint64_t n_items, uint32_t n
     a->own_bitmap = true;
     if ((e = cudaMemsetAsync(a->d_bitmap, 0, bm_bytes, a->stream)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&a->d_acc), a->acc_words * 8u)) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_ticket), 8)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&a->d_ticket), 16)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&a->d_err), 8)) != cudaSuccess ||
         (e = cudaMemsetAsync(a->d_acc, 0, a->acc_words * 8u, a->stream)) != cudaSuccess ||
-        (e = cudaMemsetAsync(a->d_ticket, 0, 8, a->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(a->d_ticket, 0, 16, a->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(a->d_err, 0, 8, a->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(a->stream)) != cudaSuccess)
         return bail(fail(PGX_ERR_CUDA, std::string("abacus setup: ") + cudaGetErrorString(e)));
@@ -761,6 +798,8 @@ void pgx_abacus_destroy(pgx_abacus *a) {
     cudaFree(a->d_gm);
     cudaFree(a->d_planes);
     cudaFree(a->d_gm_w);
+    cudaFree(a->d_gm_c);
+    cudaFree(a->d_perm_c);
     cudaFree(a->d_perm);
     cudaFree(a->d_sorted_w);
     cudaFree(a->d_uniform_w);

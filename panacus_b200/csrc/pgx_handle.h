@@ -39,6 +39,12 @@ struct pgx_abacus {
     uint32_t n_planes = 0;
     bool planes_valid = false;
 
+    // general-quorum growth under many orders (counting): a third group-major copy with the items sorted by coverage,
+    // so that whole warps of k_gm_quorum hold only items below a threshold's coverage cutoff and skip its rank logic
+    uint64_t *d_gm_c = nullptr;
+    uint32_t *d_perm_c = nullptr;
+    bool gm_c_valid = false;
+
     uint64_t *d_csr_r = nullptr;  // AbacusByGroup::r (N + 2 row offsets), lazily derived from the bitmap
     bool csr_valid = false;
 
@@ -46,6 +52,7 @@ struct pgx_abacus {
     size_t acc_words = 0;
     unsigned int *d_ticket = nullptr;  // [0] completion ticket of the exchange epilogue, [1] epoch flag of the direct epilogue
     uint32_t scan_epoch = 0;           // launches of the direct epilogue (value published in d_ticket[1])
+    uint32_t scan_launches = 0;        // parity selects the tile counter d_ticket[2 + parity] of a launch
     unsigned int *d_err = nullptr;   // [0]: build / scatter / csr input errors, [1]: fused-exchange watchdog (own word: never mixed)
 
     uint32_t *d_thr = nullptr;  // quorum thresholds of the current call

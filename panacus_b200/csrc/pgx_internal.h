@@ -73,7 +73,8 @@ struct ScanParams {
     const uint32_t *thr;     // device T*G quorum thresholds (quorum kernel), else nullptr
     uint64_t *acc;           // global accumulators (zero on entry, zero again on exit)
     uint64_t *out;           // caller's fused-layout result buffer, written by the last CTA
-    unsigned int *ticket;    // CTA completion counter (zero on entry and exit); ticket[1]: "out is zeroed" epoch flag
+    unsigned int *ticket;    // CTA completion counter (zero on entry and exit); ticket[1]: "out is zeroed" epoch flag;
+                             // ticket[2], ticket[3]: tile counters of even / odd launches
     uint32_t zero_epoch;     // != 0 (single GPU): CTA 0 zeroes the requested words of `out` and publishes this epoch in
                              // ticket[1]; every CTA then adds its sums straight into `out` -- no ticket, no snapshot
     uint64_t n_rows;         // N + 1
@@ -91,6 +92,8 @@ struct ScanParams {
     uint64_t last_mask0, last_mask1;  // masks of the two words of the last 16-byte chunk of a row
     ScanLayout L;
     Exchange x;              // x.world <= 1: no exchange
+    uint32_t sched_dynamic;  // 1: tiles after a CTA's first one come from the global counter ticket[2 + sched_parity]
+    uint32_t sched_parity;   // launch parity: this launch's counter; CTA 0 zeroes the other one for the next launch
     uint64_t *dbg_ts;        // PGX_SCAN_TS=1: per CTA 8 globaltimer stamps (phase timeline of one launch), else nullptr
 };
 

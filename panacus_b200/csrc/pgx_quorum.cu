@@ -69,7 +69,7 @@ __device__ __forceinline__ long long warp_sum_i64(long long v) {
 
 // T general thresholds (cov / slot index 0 .. T-1) and p.n_fast <= NF thresholds with q = 0 (index T .. T+n_fast-1).
 template <int P, int T, int NF, bool WEIGHTED>
-__global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(const __grid_constant__ GmGrowthParams p) {
+__global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : ((T <= 2 && !WEIGHTED && P <= 10) ? 3 : 2)) k_gm_quorum(const __grid_constant__ GmGrowthParams p) {
     static_assert(T >= 1 && T <= (int)kGmQuorumMaxT && NF == 1, "1..4 general thresholds and at most one q = 0 rider");
     constexpr int PP = RankMaskWords<P>::value;
     constexpr int kPrefetch = 4;  // rows in flight per thread (divides 32); a single order streams from DRAM, many orders from L2
@@ -134,6 +134,19 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
         }
     }
 
+    if (!active) {
+#pragma unroll
+        for (int t = 0; t < T + NF; ++t) elo[t] = ehi[t] = 0u;
+    }
+    // warp-uniform: does any of the warp's 2048 items reach threshold t's coverage cutoff?  On the coverage-sorted copy
+    // (p.perm, counting) most warps are all-or-nothing, and a warp without eligible items skips the threshold's rank
+    // comparison -- without any general threshold left, the rank counters themselves.
+    bool act[T], any_act = false;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        act[t] = __any_sync(0xFFFFFFFFu, (elo[t] | ehi[t]) != 0u) != 0;
+        any_act |= act[t];
+    }
     RankColumn<P> R;
     R.clear();
     uint32_t vlo[T], vhi[T];
@@ -148,10 +161,6 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
     // they never count
     const unsigned char *col = reinterpret_cast<const unsigned char *>(p.gm + wsafe);
     auto load_row = [&](uint32_t j) -> uint64_t { return __ldg(reinterpret_cast<const unsigned long long *>(col + s_off[j])); };
-    if (!active) {
-#pragma unroll
-        for (int t = 0; t < T + NF; ++t) elo[t] = ehi[t] = 0u;
-    }
     uint64_t ring[kPrefetch];  // slot u holds row j0 + u; refilled with row j0 + kPrefetch + u as soon as it is consumed
 #pragma unroll
     for (int u = 0; u < kPrefetch; ++u) ring[u] = load_row((uint32_t)u);
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
             const uint64_t rowbits = ring[u];
             ring[u] = load_row(j + kPrefetch);
             const uint32_t blo = (uint32_t)rowbits, bhi = (uint32_t)(rowbits >> 32);
-            R.add(blo, bhi);
+            if (any_act) R.add(blo, bhi);
             if (n_fast != 0u) {  // warp-uniform: an item starts counting at its first group and never stops (q = 0)
                 const uint32_t olo = slo, ohi = shi;
                 slo |= blo;
@@ -205,6 +214,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : 2) k_gm_quorum(cons
             const uint4 *row = reinterpret_cast<const uint4 *>(s_mask + (size_t)j * (T * PP));
 #pragma unroll
             for (int t = 0; t < T; ++t) {
+                if (!act[t]) continue;  // (park[t] stays 0: the warp adds nothing to this curve)
                 uint32_t m[PP];
 #pragma unroll
                 for (int q = 0; q < PP / 4; ++q) {

@@ -210,6 +210,59 @@ uint32_t env_u32(const char *name) {
     return v ? (uint32_t)strtoul(v, nullptr, 10) : 0u;
 }
 
+// ---- tile scheduling + TMA producer (one elected lane per CTA; shared by k_scan, k_scan_priv, k_scan_vert) --------------
+// A CTA's first tile is blockIdx.x; every further one comes from a global counter (p.tile_ctr[parity], requested one tile
+// ahead so that the atomic's round trip hides behind the ring): CTAs whose first bytes arrive late -- the first tiles of
+// a launch take 2 .. 8 us on this part, profiles/r2_scan_timeline_v1.txt -- simply take fewer tiles instead of making
+// the whole grid wait for them.  The tile a stage holds is published in s_tile[stage] before the stage's "full" barrier
+// is armed; index >= n_tiles is the end-of-work marker.  CTA 0 zeroes the OTHER parity's counter for the next launch.
+// max_tiles: most tiles this CTA may take (k_scan_vert's counters have a capacity; the others pass ~0).
+__device__ __forceinline__ void scan_producer(const ScanParams &p, uint32_t full0, uint32_t empty0, uint32_t stage0,
+                                              volatile uint32_t *s_tile, uint32_t max_tiles) {
+    const uint64_t pol = l2_policy_evict_first();
+    const uint32_t S = p.stages, rowbytes = p.Wp * 8u;
+    const uint32_t last_tile = p.n_tiles - 1u;
+    const uint32_t last_rows = (uint32_t)(p.n_rows - (uint64_t)last_tile * p.tile_items);
+    unsigned int *ctr = p.ticket + 2u + (p.sched_parity & 1u);
+    if (blockIdx.x == 0u) p.ticket[2u + ((p.sched_parity & 1u) ^ 1u)] = 0u;
+    const bool dynamic = p.sched_dynamic != 0u;
+    uint32_t st = 0, ph = 0, taken = 0;
+    bool ring_full = false;  // true once every stage has been used at least once
+    uint32_t tile = blockIdx.x;
+    for (;;) {
+        // the tile after this one: requested now, needed one iteration later
+        uint32_t nxt = 0xFFFFFFFFu;
+        ++taken;
+        if (tile < p.n_tiles && taken < max_tiles) nxt = dynamic ? gridDim.x + atomicAdd(ctr, 1u) : tile + gridDim.x;
+        if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
+        s_tile[st] = tile;
+        const uint32_t full = full0 + 8u * st;
+        if (tile >= p.n_tiles) {  // end marker
+            mbar_arrive(full);
+            break;
+        }
+        const uint64_t row0 = (uint64_t)tile * p.tile_items;
+        const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
+        const uint32_t trows = rows & ~3u;  // TMA needs 16-byte multiples; <= 3 tail rows are read directly
+        if (trows) {
+            const uint32_t bytes_b = trows * rowbytes;
+            const uint32_t bytes_w = p.weight ? trows * 4u : 0u;
+            const uint32_t dst = stage0 + st * p.L.stage_stride;
+            mbar_arrive_expect_tx(full, bytes_b + bytes_w);
+            tma_bulk_g2s(dst, p.bitmap + row0 * p.Wp, bytes_b, full, pol);
+            if (bytes_w) tma_bulk_g2s(dst + p.L.off_stage_w, p.weight + row0, bytes_w, full, pol);
+        } else {
+            mbar_arrive(full);
+        }
+        if (++st == S) {
+            st = 0;
+            ph ^= 1u;
+            ring_full = true;
+        }
+        tile = nxt;
+    }
+}
+
 // PGX_SCAN_TS=1: thread-0 time stamps of a CTA's phases (measurement aid, tools/scan_timeline.py)
 __device__ __forceinline__ void ts_mark(const ScanParams &p, uint32_t slot) {
     if (p.dbg_ts) {
@@ -424,6 +477,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
     const uint32_t S = p.stages;
     const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
     const uint32_t stage0 = smem_u32(smem + p.L.off_stage0);
+    __shared__ uint32_t s_tile_words[kMaxStages];  // tile held by each stage (written by the producer lane)
+    volatile uint32_t *s_tile = s_tile_words;
     const uint32_t rowbytes = p.Wp * 8u;
 
     SmemAcc s;
@@ -464,31 +519,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
     if (warp == (uint32_t)kConsumerWarps) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
-            uint32_t st = 0, ph = 0;
-            bool ring_full = false;  // true once every stage has been used at least once
-            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
-                const uint64_t row0 = (uint64_t)tile * p.tile_items;
-                const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
-                const uint32_t trows = rows & ~3u;  // TMA needs 16-byte multiples; <=3 tail rows read directly
-                const uint32_t full = full0 + 8u * st;
-                if (trows) {
-                    const uint32_t bytes_b = trows * rowbytes;
-                    const uint32_t bytes_w = p.weight ? trows * 4u : 0u;
-                    const uint32_t dst = stage0 + st * p.L.stage_stride;
-                    mbar_arrive_expect_tx(full, bytes_b + bytes_w);
-                    tma_bulk_g2s(dst, p.bitmap + row0 * p.Wp, bytes_b, full, pol);
-                    if (bytes_w) tma_bulk_g2s(dst + p.L.off_stage_w, p.weight + row0, bytes_w, full, pol);
-                } else {
-                    mbar_arrive(full);
-                }
-                if (++st == S) {
-                    st = 0;
-                    ph ^= 1u;
-                    ring_full = true;
-                }
-            }
+            scan_producer(p, full0, empty0, stage0, s_tile, p.L.vert_planes ? ((1u << p.L.vert_planes) - 1u) : 0xFFFFFFFFu);
             if (p.zero_epoch) direct_wait_zeroed(p);
         }
     } else {
@@ -498,14 +529,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan(const __grid_constant_
         while (a < 3 && C_rt && !((C_rt >> a) & 1u)) ++a;  // a' = min(ctz(C), 3)
         const uint32_t rot_shift = 3u - a, rot_mask = (1u << a) - 1u;
         uint32_t st = 0, ph = 0;
-        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (bool first_wait = true;; first_wait = false) {
+            mbar_wait(full0 + 8u * st, ph);
+            const uint32_t tile = s_tile[st];
+            if (tile >= p.n_tiles) break;
+            if (tid == 0 && first_wait) ts_mark(p, 2);
             const uint64_t row0 = (uint64_t)tile * p.tile_items;
             const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
             const uint32_t trows = rows & ~3u;
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const uint32_t wbase = base + p.L.off_stage_w;
-            mbar_wait(full0 + 8u * st, ph);
-            if (tid == 0 && tile == blockIdx.x) ts_mark(p, 2);
             for (uint32_t li = tid; li < rows; li += kConsumerThreads) {
                 const uint64_t item = row0 + li;
                 if (item == 0) {  // the reference's dummy item (abacus.rs:551, 1000-1002)
@@ -629,6 +662,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
     const uint32_t S = p.stages;
     const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
     const uint32_t stage0 = smem_u32(smem + p.L.off_stage0);
+    __shared__ uint32_t s_tile_words[kMaxStages];  // tile held by each stage (written by the producer lane)
+    volatile uint32_t *s_tile = s_tile_words;
     const uint32_t rowbytes = p.Wp * 8u;
 
     SmemAcc s;
@@ -674,31 +709,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
     if (warp == (uint32_t)kConsumerWarps) {
         // ===== TMA producer (same ring as k_scan) =====
         if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
-            uint32_t st = 0, ph = 0;
-            bool ring_full = false;
-            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
-                const uint64_t row0 = (uint64_t)tile * p.tile_items;
-                const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
-                const uint32_t trows = rows & ~3u;
-                const uint32_t full = full0 + 8u * st;
-                if (trows) {
-                    const uint32_t bytes_b = trows * rowbytes;
-                    const uint32_t bytes_w = p.weight ? trows * 4u : 0u;
-                    const uint32_t dst = stage0 + st * p.L.stage_stride;
-                    mbar_arrive_expect_tx(full, bytes_b + bytes_w);
-                    tma_bulk_g2s(dst, p.bitmap + row0 * p.Wp, bytes_b, full, pol);
-                    if (bytes_w) tma_bulk_g2s(dst + p.L.off_stage_w, p.weight + row0, bytes_w, full, pol);
-                } else {
-                    mbar_arrive(full);
-                }
-                if (++st == S) {
-                    st = 0;
-                    ph ^= 1u;
-                    ring_full = true;
-                }
-            }
+            scan_producer(p, full0, empty0, stage0, s_tile, p.L.vert_planes ? ((1u << p.L.vert_planes) - 1u) : 0xFFFFFFFFu);
             if (p.zero_epoch) direct_wait_zeroed(p);
         }
     } else {
@@ -736,14 +747,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
         // items per thread and step: their row loads, popcounts and class look-ups are independent and overlap; only the
         // counter updates run one item after the other (two items of a thread may share a bin)
         constexpr int K = (C_T < 0 || C_T == 1) ? 4 : 2;
-        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (bool first_wait = true;; first_wait = false) {
+            mbar_wait(full0 + 8u * st, ph);
+            const uint32_t tile = s_tile[st];
+            if (tile >= p.n_tiles) break;
+            if (tid == 0 && first_wait) ts_mark(p, 2);
             const uint64_t row0 = (uint64_t)tile * p.tile_items;
             const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
             const uint32_t trows = rows & ~3u;
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const uint32_t wbase = base + p.L.off_stage_w;
-            mbar_wait(full0 + 8u * st, ph);
-            if (tid == 0 && tile == blockIdx.x) ts_mark(p, 2);
             for (uint32_t li0 = tid; li0 < trows; li0 += K * kConsumerThreads) {
                 uint32_t cov[K], first[K], wgt[K], cb[K];
                 bool valid[K];
@@ -849,7 +862,7 @@ struct VertTree {  // ones, twos, fours, eights of one counter + the pending fou
 };
 constexpr int kVertK = 16;          // items per thread and step = inputs of one adder tree
 constexpr int kVertMaxPlanes = 12;  // shared-memory planes per counter (sixteens .. ): 16 * 2^12 items per thread
-constexpr int kVertFoldPlanes = 4 + kVertMaxPlanes + 5;  // a warp's total
+constexpr int kVertFoldPlanes = 4 + kVertMaxPlanes + 8;  // a CTA's total: 256 threads = 8 more bits
 
 // four more words of the running 16-block (quarter Q = 0..3 of it); the last quarter returns the sixteens word in s16
 template <int Q>
@@ -950,6 +963,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
     const uint32_t S = p.stages;
     const uint32_t full0 = smem_u32(smem), empty0 = full0 + 8u * kMaxStages;
     const uint32_t stage0 = smem_u32(smem + p.L.off_stage0);
+    __shared__ uint32_t s_tile_words[kMaxStages];  // tile held by each stage (written by the producer lane)
+    volatile uint32_t *s_tile = s_tile_words;
     const uint32_t P = p.L.vert_planes;
 
     SmemAcc s;
@@ -960,7 +975,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
     s.thr = nullptr;
     s.joint_cnt = s.joint_wlo = s.joint_whi = nullptr;
     uint32_t *cls_tot = reinterpret_cast<uint32_t *>(smem + p.L.off_cls_lo);  // [D][64]
-    uint64_t *fold = reinterpret_cast<uint64_t *>(smem + p.L.off_carry);      // [warp][C][kVertFoldPlanes]
+    uint64_t *fold = reinterpret_cast<uint64_t *>(smem + p.L.off_carry);      // [C][kVertFoldPlanes]: the CTA's totals
     const uint32_t planes0 = smem_u32(smem + p.L.off_priv);                   // [C][P][256] u64
     __shared__ uint32_t s_missing_word;
     uint32_t *s_missing = &s_missing_word;
@@ -989,27 +1004,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
     if (warp == (uint32_t)kConsumerWarps) {
         // ===== TMA producer (same ring as k_scan; rows only: counting never stages the weights) =====
         if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
-            uint32_t st = 0, ph = 0;
-            bool ring_full = false;
-            for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                if (ring_full) mbar_wait(empty0 + 8u * st, ph ^ 1u);
-                const uint64_t row0 = (uint64_t)tile * p.tile_items;
-                const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
-                const uint32_t trows = rows & ~3u;
-                const uint32_t full = full0 + 8u * st;
-                if (trows) {
-                    mbar_arrive_expect_tx(full, trows * 8u);
-                    tma_bulk_g2s(stage0 + st * p.L.stage_stride, p.bitmap + row0, trows * 8u, full, pol);
-                } else {
-                    mbar_arrive(full);
-                }
-                if (++st == S) {
-                    st = 0;
-                    ph ^= 1u;
-                    ring_full = true;
-                }
-            }
+            scan_producer(p, full0, empty0, stage0, s_tile, p.L.vert_planes ? ((1u << p.L.vert_planes) - 1u) : 0xFFFFFFFFu);
             if (p.zero_epoch) direct_wait_zeroed(p);
         }
     } else {
@@ -1022,14 +1017,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
 #pragma unroll
         for (int d = 0; d < D; ++d) cthr[d] = p.cls_thr[d];
         uint32_t st = 0, ph = 0;
-        for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (bool first_wait = true;; first_wait = false) {
+            mbar_wait(full0 + 8u * st, ph);
+            const uint32_t tile = s_tile[st];
+            if (tile >= p.n_tiles) break;
+            if (tid == 0 && first_wait) ts_mark(p, 2);
             const uint64_t row0 = (uint64_t)tile * p.tile_items;
             const uint32_t rows = tile == last_tile ? last_rows : p.tile_items;
             const uint32_t trows = rows & ~3u;
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const bool slow = tile == 0u || trows != p.tile_items || p.countable != nullptr;  // item 0 / a short tile / coverage output
-            mbar_wait(full0 + 8u * st, ph);
-            if (tid == 0 && tile == blockIdx.x) ts_mark(p, 2);
             for (uint32_t li0 = tid; li0 < trows; li0 += kVertK * kConsumerThreads) {
                 V64 s16[C];
                 if (slow)
@@ -1037,7 +1034,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
                 else
                     vert_step<HIST, D, C1, false>(p, tree, s16, base, li0, trows, tile, row0, cthr, mask_lo, mask_hi);
 #pragma unroll
-                for (int c = 0; c < C; ++c) vert_ripple(my_planes + (uint32_t)c * P * 2048u, P, s16[c]);
+                for (int c = 0; c < C; ++c) vert_ripple(my_planes + ((uint32_t)c * (P + 4u) + 4u) * 2048u, P, s16[c]);
             }
             if (tid == 0) seen += trows - (tile == 0u && trows ? 1u : 0u);  // items this CTA fed to the trees
             if (tid < rows - trows) {  // <= 3 tail rows of the last tile, straight from global memory, plain shared atomics
@@ -1060,56 +1057,86 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
             }
         }
         if (tid == 0) ts_mark(p, 3);
-        // ===== fold: add the 32 lanes' counters with full adders (butterfly), lane 0 keeps the warp's planes =====
         if (HIST && tid == 0) *s_missing = seen;
-#pragma unroll 1
+        // the trees' register planes join the thread's shared-memory planes (slots 0..3 of each counter) ...
+#pragma unroll
         for (int c = 0; c < C; ++c) {
-            V64 pl[kVertFoldPlanes];
-            VertTree t = tree[0];
-#pragma unroll
-            for (int cc = 1; cc < C; ++cc)
-                if (cc == c) t = tree[cc];
-            pl[0] = t.p1, pl[1] = t.p2, pl[2] = t.p4, pl[3] = t.p8;
-#pragma unroll
-            for (int k = 0; k < kVertMaxPlanes + 5; ++k) {
-                pl[4 + k] = {0u, 0u};
-                if ((uint32_t)k < P) {
-                    const uint32_t a = my_planes + ((uint32_t)c * P + (uint32_t)k) * 2048u;
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pl[4 + k].lo), "=r"(pl[4 + k].hi) : "r"(a));
-                }
-            }
-            uint32_t n = 4u + P;  // planes that can be non-zero
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                V64 carry = {0u, 0u};
-#pragma unroll
-                for (int k = 0; k < kVertFoldPlanes; ++k) {
-                    if ((uint32_t)k > n) break;
-                    const V64 o = {__shfl_xor_sync(0xFFFFFFFFu, pl[k].lo, off), __shfl_xor_sync(0xFFFFFFFFu, pl[k].hi, off)};
-                    csa(carry, pl[k], pl[k], o, carry);
-                }
-                ++n;
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < kVertFoldPlanes; ++k)
-                    fold[((size_t)warp * C + c) * kVertFoldPlanes + k] = ((uint64_t)pl[k].hi << 32) | pl[k].lo;
-            }
+            const uint32_t a = my_planes + (uint32_t)c * (P + 4u) * 2048u;
+            const VertTree &t = tree[c];
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(t.p1.lo), "r"(t.p1.hi) : "memory");
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 2048u), "r"(t.p2.lo), "r"(t.p2.hi) : "memory");
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 4096u), "r"(t.p4.lo), "r"(t.p4.hi) : "memory");
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 6144u), "r"(t.p8.lo), "r"(t.p8.hi) : "memory");
         }
     }
     __syncthreads();
-    // ===== read the bins out: bit b of plane k of a warp's total weighs 2^k (one thread per warp, counter and bin) =====
-    for (uint32_t i = tid; i < (uint32_t)(C * 64 * kConsumerWarps); i += kScanThreads) {
-        const uint32_t w = i / (uint32_t)(C * 64), c = (i >> 6) % (uint32_t)C, b = i & 63u;
-        const uint64_t *f = fold + ((size_t)w * C + c) * kVertFoldPlanes;
+    // ===== fold: warp c adds up counter c =====
+    // Shuffles are the scarce resource here (~0.25 warp-SHFL per clock and SM: a butterfly over all 8 warps of both
+    // resident CTAs cost 5-9 us, profiles/r2_scan_timeline_v2.txt), shared-memory loads are not: lane l first adds the
+    // planes of threads l, l + 32, .. l + 224 (conflict-free LDS.64, ripple-carry full adders), then one butterfly over
+    // the warp's 32 lanes finishes the sum; lane 0 keeps it for the read-out.
+    if (warp < (uint32_t)C) {
+        const uint32_t c = warp;
+        V64 pl[kVertFoldPlanes];
+#pragma unroll
+        for (int k = 0; k < kVertFoldPlanes; ++k) pl[k] = {0u, 0u};
+        // plane-major: the eight threads' words of a plane are loaded together (independent LDS), then added one after
+        // the other, each with its own carry word -- the eight ripple chains run pipelined across the planes instead of
+        // one after the other (this phase is pure latency: one warp per counter)
+        const uint32_t src = planes0 + ((c * (P + 4u)) * 256u + lane) * 8u;
+        V64 carry[kConsumerWarps];
+#pragma unroll
+        for (int j = 0; j < kConsumerWarps; ++j) carry[j] = {0u, 0u};
+#pragma unroll
+        for (int k = 0; k < kVertFoldPlanes; ++k) {
+            if ((uint32_t)k >= P + 4u + 3u) break;  // 8 numbers of P + 4 planes: P + 7 planes
+            V64 o[kConsumerWarps];
+#pragma unroll
+            for (int j = 0; j < kConsumerWarps; ++j) {
+                o[j] = {0u, 0u};
+                if ((uint32_t)k < P + 4u)
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o[j].lo), "=r"(o[j].hi) : "r"(src + (uint32_t)k * 2048u + (uint32_t)j * 256u));
+            }
+#pragma unroll
+            for (int j = 0; j < kConsumerWarps; ++j) csa(carry[j], pl[k], pl[k], o[j], carry[j]);
+        }
+        uint32_t n = 4u + P + 3u;  // planes that can be non-zero
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            V64 carry = {0u, 0u};
+#pragma unroll
+            for (int k0 = 0; k0 < kVertFoldPlanes; k0 += 8) {  // eight planes' shuffles in flight, then their carry chain
+                if ((uint32_t)k0 > n) break;
+                V64 o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    o[k] = {0u, 0u};
+                    if ((uint32_t)(k0 + k) < n) o[k] = {__shfl_xor_sync(0xFFFFFFFFu, pl[k0 + k].lo, off), __shfl_xor_sync(0xFFFFFFFFu, pl[k0 + k].hi, off)};
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((uint32_t)(k0 + k) <= n) csa(carry, pl[k0 + k], pl[k0 + k], o[k], carry);
+            }
+            ++n;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kVertFoldPlanes; ++k) fold[(size_t)c * kVertFoldPlanes + k] = ((uint64_t)pl[k].hi << 32) | pl[k].lo;
+        }
+    }
+    __syncthreads();
+    // ===== read the bins out: bit b of plane k of a counter's total weighs 2^k =====
+    for (uint32_t i = tid; i < (uint32_t)(C * 64); i += kScanThreads) {
+        const uint32_t c = i >> 6, b = i & 63u;
+        const uint64_t *f = fold + (size_t)c * kVertFoldPlanes;
         uint32_t total = 0;
-        for (uint32_t k = 0; k < 4u + P + 5u; ++k) total += (uint32_t)((f[k] >> b) & 1ull) << k;
+        for (uint32_t k = 0; k < 4u + P + 8u; ++k) total += (uint32_t)((f[k] >> b) & 1ull) << k;
         if (!total) continue;
         if (HIST && c == 0) {
             atomicAdd(&s.hist_cnt[b], total);  // (the tail rows' atomics are in there already; bits above G are never set)
             atomicSub(s_missing, total);
         } else {
-            atomicAdd(&cls_tot[(c - HIST) * 64u + b], total);
+            cls_tot[(c - HIST) * 64u + b] = total;
         }
     }
     __syncthreads();
@@ -1192,8 +1219,10 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
         uint64_t worst_grid = env_u32("PGX_SCAN_GRID") ? env_u32("PGX_SCAN_GRID") : (uint64_t)sm_count;  // fewest CTAs the launch may use
         if (worst_grid > n_tiles) worst_grid = n_tiles;
         const uint64_t blocks = worst_grid ? (n_tiles + worst_grid - 1u) / worst_grid : 0u;  // 16-blocks a thread adds up
+        // 2^P - 1 >= 2 x blocks: with the dynamic tile scheduler a CTA may take up to twice its share before it stops
+        // asking for tiles (scan_producer's max_tiles); the grid's joint capacity then still covers every tile
         uint32_t P = 1;
-        while (P <= 32u && (blocks >> P)) ++P;  // 2^P > blocks
+        while (P <= 32u && ((2u * blocks + 1u) >> P)) ++P;
         if (C >= 1u && P <= (uint32_t)kVertMaxPlanes) {
             vert = true;
             p.flags |= kVertical;
@@ -1202,9 +1231,9 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
             L.off_cls_lo = off;
             off += D * 64u * 4u;
             L.off_carry = off = align_up(off, 16u);
-            off += (uint32_t)kConsumerWarps * C * (uint32_t)kVertFoldPlanes * 8u;
+            off += C * (uint32_t)kVertFoldPlanes * 8u;
             L.off_priv = off = align_up(off, 16u);
-            off += C * P * 2048u;
+            off += C * (P + 4u) * 2048u;  // P ripple planes + 4 slots for the trees' register planes (fold)
             L.vert_planes = P;
             L.vert_counters = C;
             L.vert_end = off;

@@ -860,3 +860,35 @@ def test_transpose_kernels(N, G, monkeypatch):
             pg = a.permuted_growth(orders, [1], None, weighted=False)
             for k in range(len(orders)):
                 assert np.array_equal(pg[k, 0].astype(np.uint64), want[k]), (mode, k)
+
+
+@pytest.mark.parametrize("N,G", [(30_000, 70), (9000, 300)])
+def test_permuted_growth_coverage_sorted_copy(N, G, monkeypatch):
+    """k_gm_quorum on the coverage-sorted group-major copy (counting, general thresholds with cutoffs > 1, >= 4 orders):
+    warps whose 2048 items all stay below a threshold's coverage cutoff skip its rank logic.  Same curves as on the
+    natural copy (PGX_GM_COVSORT=0) and as the oracle, including a cutoff almost no item reaches and one no item does."""
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=N + 7 * G)
+    orders = synth.random_orders(4, G, seed=5)
+    pairs = [(1, 0.0), (2, 0.5), (4, 0.9), (G - 1, 0.3), (G + 1, 0.2), (1, 0.7)]
+    cov, thr = cutoffs(G, pairs)
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        monkeypatch.setenv("PGX_GM_COVSORT", "0")
+        plain = a.permuted_growth(orders, cov, thr, weighted=False)
+        assert "coverage-sorted" not in a.last_launch_info()
+        monkeypatch.delenv("PGX_GM_COVSORT")
+        got = a.permuted_growth(orders, cov, thr, weighted=False)
+        assert "coverage-sorted" in a.last_launch_info(), a.last_launch_info()
+        assert np.array_equal(got, plain)
+        for p in range(orders.shape[0]):
+            exp = oracle_all(pb.pack_bits(bits[:, orders[p]]), G, weights, pairs)
+            for t, (c, q) in enumerate(pairs):
+                assert np.array_equal(got[p, t].astype(np.float64), exp[("node", c, q)]), (p, c, q)
+        # a single order afterwards reuses the copy; the weighted mode keeps its weight-sorted copy
+        one = a.permuted_growth(orders[:1], cov, thr, weighted=False)
+        assert np.array_equal(one[0], got[0])
+        w = a.permuted_growth(orders, cov, thr, weighted=True)
+        assert "coverage-sorted" not in a.last_launch_info()
+        for t, (c, q) in enumerate(pairs):
+            exp = oracle_all(pb.pack_bits(bits[:, orders[1]]), G, weights, pairs)
+            assert np.array_equal(w[1, t].astype(np.float64), exp[("bp", c, q)]), (c, q)
