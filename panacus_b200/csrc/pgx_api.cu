@@ -206,9 +206,9 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
         uint64_t t0 = ~0ull;
         for (int b = 0; b < grid; ++b)
             if (ts[(size_t)b * 8u]) t0 = std::min(t0, ts[(size_t)b * 8u]);
-        static const char *names[6] = {"cta_start", "init_done", "first_tile", "loop_done", "epilogue_start", "reds_issued"};
+        static const char *names[8] = {"cta_start", "init_done", "first_tile", "loop_done", "epilogue_start", "reds_issued", "fold_start", "fold_done"};
         fprintf(stderr, "PGX_SCAN_TS grid=%d (ns after the first CTA's start: min / median / max over CTAs)", grid);
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 8; ++k) {
             std::vector<uint64_t> v;
             for (int b = 0; b < grid; ++b)
                 if (ts[(size_t)b * 8u + k]) v.push_back(ts[(size_t)b * 8u + k] - t0);

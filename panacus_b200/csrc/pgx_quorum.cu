@@ -90,7 +90,10 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : ((T <= 2 && !WEIGHT
         s_off[i] = (unsigned long long)order[i < p.G ? i : p.G - 1u] * p.gm_stride * 8ull;
     for (uint32_t i = tid; i < p.G * T; i += kQThreads) {
         const uint32_t j = i / T, t = i - j * T;
-        rank_mask_row<P>(__ldg(p.thr + (size_t)t * p.G + j), p.G, s_mask + (size_t)i * PP);
+        // ranks are <= j + 1 at position j: any cutoff above that never passes, j + 2 stands for all of them -- which keeps
+        // every cutoff below 2^PE for the plane-skipping blocks further down (jend + 1 < 2^PE)
+        const uint32_t K = __ldg(p.thr + (size_t)t * p.G + j);
+        rank_mask_row<P>(K < j + 2u ? K : j + 2u, p.G, s_mask + (size_t)i * PP);
     }
     for (uint32_t i = tid; i < p.G * (T + NF) * (WEIGHTED ? 2u : 1u); i += kQThreads) s_dlo[i] = 0u;
     __syncthreads();
@@ -172,6 +175,9 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : ((T <= 2 && !WEIGHT
     for (int t = 0; t < T + NF; ++t) park[t] = 0;
     for (uint32_t jb = 0; jb < p.G; jb += 32u) {
       const uint32_t jend = jb + 32u < p.G ? jb + 32u : p.G;
+      // 32 positions with the rank planes that can be non-zero by their end (ranks <= jend, cutoffs <= jend): PE planes
+      auto block = [&](auto pe_tag) {
+      constexpr int PE = decltype(pe_tag)::value;
       for (uint32_t j0 = jb; j0 < jend; j0 += kPrefetch) {
 #pragma unroll
         for (int u = 0; u < kPrefetch; ++u) {
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : ((T <= 2 && !WEIGHT
             const uint64_t rowbits = ring[u];
             ring[u] = load_row(j + kPrefetch);
             const uint32_t blo = (uint32_t)rowbits, bhi = (uint32_t)(rowbits >> 32);
-            if (any_act) R.add(blo, bhi);
+            if (any_act) R.template add_n<PE>(blo, bhi);
             if (n_fast != 0u) {  // warp-uniform: an item starts counting at its first group and never stops (q = 0)
                 const uint32_t olo = slo, ohi = shi;
                 slo |= blo;
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : ((T <= 2 && !WEIGHT
                     m[4 * q + 3] = x.w;
                 }
                 uint32_t glo, ghi;
-                R.ge(m, glo, ghi);
+                R.template ge_n<PE>(m, glo, ghi);
                 const uint32_t nlo = verdict_update(blo, glo, vlo[t]), nhi = verdict_update(bhi, ghi, vhi[t]);
                 if (!WEIGHTED) {
                     const int c = __popc(nlo & elo[t]) + __popc(nhi & ehi[t]);
@@ -252,6 +258,13 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : ((T <= 2 && !WEIGHT
             }
         }
       }
+      };
+      if (P >= 4 && jend + 1u < (1u << (P - 2)))
+          block(std::integral_constant<int, (P >= 4 ? P - 2 : P)>{});
+      else if (P >= 4 && jend + 1u < (1u << (P - 1)))
+          block(std::integral_constant<int, (P >= 4 ? P - 1 : P)>{});
+      else
+          block(std::integral_constant<int, P>{});
       if (jb + lane < jend) {  // lane l holds the warp sums of position jb + l
 #pragma unroll
           for (int t = 0; t < T + NF; ++t) {

@@ -65,11 +65,13 @@ struct RankColumn {
         for (int k = 0; k < P; ++k) lo[k] = hi[k] = 0u;
     }
 
-    // rank += b (one bit per item): ripple-carry increment
-    PGX_HD void add(uint32_t blo, uint32_t bhi) {
+    // rank += b (one bit per item): ripple-carry increment.  PE <= P: only the low PE planes take part -- exact while
+    // every rank stays below 2^PE (at position j ranks are <= j + 1: the planes above bitlen(j + 1) are still zero)
+    template <int PE>
+    PGX_HD void add_n(uint32_t blo, uint32_t bhi) {
         uint32_t clo = blo, chi = bhi;
 #pragma unroll
-        for (int k = 0; k < P; ++k) {
+        for (int k = 0; k < PE; ++k) {
             const uint32_t tlo = lo[k] & clo, thi = hi[k] & chi;
             lo[k] ^= clo;
             hi[k] ^= chi;
@@ -77,17 +79,20 @@ struct RankColumn {
             chi = thi;
         }
     }
+    PGX_HD void add(uint32_t blo, uint32_t bhi) { add_n<P>(blo, bhi); }
 
-    // per item: rank >= K, with K given as its mask row
-    PGX_HD void ge(const uint32_t *mask_row, uint32_t &glo, uint32_t &ghi) const {
+    // per item: rank >= K, with K given as its mask row (PE as above; K < 2^PE as well: K <= j + 1)
+    template <int PE>
+    PGX_HD void ge_n(const uint32_t *mask_row, uint32_t &glo, uint32_t &ghi) const {
         glo = ghi = ~0u;
 #pragma unroll
-        for (int k = 0; k < P; ++k) {
+        for (int k = 0; k < PE; ++k) {
             const uint32_t m = mask_row[k];
             glo = ge_plane(glo, lo[k], m);
             ghi = ge_plane(ghi, hi[k], m);
         }
     }
+    PGX_HD void ge(const uint32_t *mask_row, uint32_t &glo, uint32_t &ghi) const { ge_n<P>(mask_row, glo, ghi); }
 };
 
 // Verdict update of one threshold at one position: items of the group (b) take the fresh test result, all

@@ -1075,6 +1075,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
     // resident CTAs cost 5-9 us, profiles/r2_scan_timeline_v2.txt), shared-memory loads are not: lane l first adds the
     // planes of threads l, l + 32, .. l + 224 (conflict-free LDS.64, ripple-carry full adders), then one butterfly over
     // the warp's 32 lanes finishes the sum; lane 0 keeps it for the read-out.
+    if (tid == 0) ts_mark(p, 6);
     if (warp < (uint32_t)C) {
         const uint32_t c = warp;
         V64 pl[kVertFoldPlanes];
@@ -1082,7 +1083,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
         for (int k = 0; k < kVertFoldPlanes; ++k) pl[k] = {0u, 0u};
         // plane-major: the eight threads' words of a plane are loaded together (independent LDS), then added one after
         // the other, each with its own carry word -- the eight ripple chains run pipelined across the planes instead of
-        // one after the other (this phase is pure latency: one warp per counter)
+        // one after the other.  (This phase is pure latency, one warp per counter: 3.2 us as written here; rolled loops over
+        // the thread groups / butterfly levels were measured at 8.6 us, a butterfly over all eight warps at 5-9 us:
+        // profiles/r2_scan_timeline_v*.txt.)
         const uint32_t src = planes0 + ((c * (P + 4u)) * 256u + lane) * 8u;
         V64 carry[kConsumerWarps];
 #pragma unroll
@@ -1103,7 +1106,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
         uint32_t n = 4u + P + 3u;  // planes that can be non-zero
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            V64 carry = {0u, 0u};
+            V64 carry2 = {0u, 0u};
 #pragma unroll
             for (int k0 = 0; k0 < kVertFoldPlanes; k0 += 8) {  // eight planes' shuffles in flight, then their carry chain
                 if ((uint32_t)k0 > n) break;
@@ -1115,7 +1118,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    if ((uint32_t)(k0 + k) <= n) csa(carry, pl[k0 + k], pl[k0 + k], o[k], carry);
+                    if ((uint32_t)(k0 + k) <= n) csa(carry2, pl[k0 + k], pl[k0 + k], o[k], carry2);
             }
             ++n;
         }
@@ -1124,6 +1127,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
             for (int k = 0; k < kVertFoldPlanes; ++k) fold[(size_t)c * kVertFoldPlanes + k] = ((uint64_t)pl[k].hi << 32) | pl[k].lo;
         }
     }
+    if (tid == 0) ts_mark(p, 7);
     __syncthreads();
     // ===== read the bins out: bit b of plane k of a counter's total weighs 2^k =====
     for (uint32_t i = tid; i < (uint32_t)(C * 64); i += kScanThreads) {
@@ -1223,7 +1227,9 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
         // asking for tiles (scan_producer's max_tiles); the grid's joint capacity then still covers every tile
         uint32_t P = 1;
         while (P <= 32u && ((2u * blocks + 1u) >> P)) ++P;
-        if (C >= 1u && P <= (uint32_t)kVertMaxPlanes) {
+        // (measured: every counter costs ~9 LOP3 per item; from three counters on the loop is ALU-bound and the
+        // lane-private kernel is faster -- profiles/r2_scan_shapes_v5.jsonl: 10M x 44, T = 3: 45 vs 43 us)
+        if (C >= 1u && C <= (env_u32("PGX_SCAN_VERT") == 1u ? 4u : 2u) && P <= (uint32_t)kVertMaxPlanes) {  // (PGX_SCAN_VERT=1: up to 4)
             vert = true;
             p.flags |= kVertical;
             p.n_classes = D;

@@ -806,17 +806,25 @@ def test_vertical_counter_kernel(N, G, monkeypatch):
             assert np.array_equal(hc, exp["hist"]) and np.array_equal(ct, exp["countable"])
             hc, _, _ = a.hist(count=True, weight=False)
             assert np.array_equal(hc, exp["hist"])
-            for pairs in cases:
-                cov = [c for c, _ in pairs]
-                D = len(set(cov))
-                h2, _, cv = a.hist_ordered_growth(cov, None, weighted=False, hist_count=True, hist_weight=False)
-                assert f"k_scan_vert<hist=1,D={D}>" in a.last_launch_info(), a.last_launch_info()
-                assert np.array_equal(h2, exp["hist"])
-                only = a.ordered_growth(cov, None, weighted=False)
-                assert f"k_scan_vert<hist=0,D={D}>" in a.last_launch_info(), a.last_launch_info()
-                for t, (c, q) in enumerate(pairs):
-                    assert np.array_equal(cv[t].astype(np.float64), exp[("node", c, q)]), (grid, pairs, c)
-                    assert np.array_equal(only[t].astype(np.float64), exp[("node", c, q)]), (grid, pairs, c)
+            # the library's own choice: at most two counters (from three on the lane-private kernel is faster);
+            # PGX_SCAN_VERT=1 takes the kernel up to its four counters
+            for force in (False, True):
+                if force:
+                    monkeypatch.setenv("PGX_SCAN_VERT", "1")
+                else:
+                    monkeypatch.delenv("PGX_SCAN_VERT", raising=False)
+                for pairs in cases:
+                    cov = [c for c, _ in pairs]
+                    D = len(set(cov))
+                    h2, _, cv = a.hist_ordered_growth(cov, None, weighted=False, hist_count=True, hist_weight=False)
+                    assert (f"k_scan_vert<hist=1,D={D}>" in a.last_launch_info()) == (force or D <= 1), a.last_launch_info()
+                    assert np.array_equal(h2, exp["hist"])
+                    only = a.ordered_growth(cov, None, weighted=False)
+                    assert (f"k_scan_vert<hist=0,D={D}>" in a.last_launch_info()) == (force or D <= 2), a.last_launch_info()
+                    for t, (c, q) in enumerate(pairs):
+                        assert np.array_equal(cv[t].astype(np.float64), exp[("node", c, q)]), (grid, pairs, c)
+                        assert np.array_equal(only[t].astype(np.float64), exp[("node", c, q)]), (grid, pairs, c)
+            monkeypatch.delenv("PGX_SCAN_VERT", raising=False)
             # the weighted modes and more than 3 cutoffs stay on the other kernels
             _, hw, _ = a.hist(count=False, weight=True)
             assert "k_scan_vert" not in a.last_launch_info() and np.array_equal(hw, exp["hist_bp"])
@@ -892,3 +900,39 @@ def test_permuted_growth_coverage_sorted_copy(N, G, monkeypatch):
         for t, (c, q) in enumerate(pairs):
             exp = oracle_all(pb.pack_bits(bits[:, orders[1]]), G, weights, pairs)
             assert np.array_equal(w[1, t].astype(np.float64), exp[("bp", c, q)]), (c, q)
+
+
+def test_arbitrary_cutoff_tables_agree_across_kernels(monkeypatch):
+    """The ABI takes a u32 cutoff per position.  The documented tables are ceil((j + 1) q), non-decreasing; k_gm_quorum
+    (plane-skipping blocks, cutoffs clamped to j + 2) must also agree with the first-generation k_gm_growth on ANY table
+    (cutoffs above j + 1 -- never reachable at position j --, zeros in the middle, huge values), and both with the
+    node-major k_scan<quorum>, whose per-word shortcuts assume a non-decreasing table, on non-decreasing ones."""
+    N, G = 6000, 300
+    bits, bitmap, weights = synth.numpy_table(N, G, seed=77)
+    rng = np.random.default_rng(5)
+    j = np.arange(G)
+    wild = np.stack([rng.integers(0, G + 4, G), j + rng.integers(0, 4, G), np.full(G, 0xFFFFFFFF),
+                     np.where(j % 7 == 0, 0, j // 2 + 1)]).astype(np.uint32)
+    mono = np.stack([np.cumsum(rng.integers(0, 3, G)), np.ceil((j + 1) * 0.5) + 3, np.full(G, 0xFFFFFFFF),
+                     np.minimum(np.cumsum(rng.integers(0, 2, G)) + 1, 40)]).astype(np.uint32)
+    wild[0, 0] = 0  # (a table of all zeros would be a q = 0 threshold; none of these is)
+    cov = [1, 2, 1, 3]
+    orders = synth.random_orders(4, G, seed=8)
+    orders[0] = np.arange(G)
+    with pb.DeviceAbacus(N, G) as a:
+        a.upload(bitmap, weights)
+        for thr, with_scan in ((wild, False), (mono, True)):
+            for weighted in (False, True):
+                monkeypatch.delenv("PGX_GM_QUORUM", raising=False)
+                new = a.permuted_growth(orders, cov, thr, weighted=weighted)
+                assert "k_gm_quorum" in a.last_launch_info()
+                monkeypatch.setenv("PGX_GM_QUORUM", "old")
+                old = a.permuted_growth(orders, cov, thr, weighted=weighted)
+                monkeypatch.delenv("PGX_GM_QUORUM")
+                assert np.array_equal(new, old), (with_scan, weighted)
+                assert not new[:, 2].any()  # a cutoff nobody reaches
+                if with_scan:
+                    monkeypatch.setenv("PGX_QUORUM_PATH", "scan")
+                    scan = a.ordered_growth(cov, thr, weighted=weighted)
+                    monkeypatch.delenv("PGX_QUORUM_PATH")
+                    assert np.array_equal(new[0], scan), weighted
