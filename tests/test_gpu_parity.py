@@ -936,3 +936,33 @@ def test_arbitrary_cutoff_tables_agree_across_kernels(monkeypatch):
                     scan = a.ordered_growth(cov, thr, weighted=weighted)
                     monkeypatch.delenv("PGX_QUORUM_PATH")
                     assert np.array_equal(new[0], scan), weighted
+
+
+def test_similarity_and_csr_against_independent_witness(monkeypatch):
+    """The CUDA path against tests/golden/similarity_csr_witness.json (intersections, group sizes and the CSR {r, c, v}
+    counted straight from the GFA's S / P lines, independent of the oracle): CUDA-core and tensor-core similarity
+    kernels, bp-weighted similarity, the device CSR."""
+    d = json.load(open(os.path.join(GOLDEN, "similarity_csr_witness.json")))
+    for case in d["cases"]:
+        g, t, op, og, names, bits, weights = fixture_bitmap(case["gfa"], case["count"], groupby_sample=case["grouping"] == "sample",
+                                                            groupby_haplotype=case["grouping"] == "haplotype")
+        assert list(names) == case["groups"]
+        if t.n_items == 0:
+            continue
+        G = len(names)
+        path_group = np.full(len(t.id_prefsum) - 1, -1, dtype=np.int64)
+        path_group[op.astype(np.int64)] = og.astype(np.int64)
+        with pb.DeviceAbacus(t.n_items, G) as a:
+            a.build(t.items, t.id_prefsum, path_group, t.exclude)
+            a.upload(None, weights)
+            for sim in ("csa", "mma"):
+                if sim == "mma" and case["count"] == "bp":
+                    continue  # the tensor-core kernel counts; bp sums stay on the CUDA-core kernel
+                monkeypatch.setenv("PGX_SIM", sim)
+                inter, ln = a.similarity(weighted=(case["count"] == "bp"))
+                assert inter.tolist() == case["inter"] and ln.tolist() == case["len"], (case["gfa"], case["grouping"], case["count"], sim)
+            monkeypatch.delenv("PGX_SIM")
+            if "r" in case:
+                r, c, v = a.csr(t.items, t.id_prefsum, path_group, t.exclude)
+                assert [int(x) for x in r] == case["r"] and [int(x) for x in c] == case["c"] and [int(x) for x in v] == case["v"], \
+                    (case["gfa"], case["grouping"], case["count"])

@@ -269,3 +269,29 @@ def test_ordered_growth_against_independent_witness():
             got = po.calc_growth(r, c, len(names), po.absolute(cov), po.relative(q), count_bp=(case["count"] == "bp"),
                                  node_lens=g.node_lens)
             assert [int(x) for x in got] == want, (case["gfa"], case["grouping"], case["count"], cov, q)
+
+
+def test_similarity_and_csr_against_independent_witness():
+    """Like ordered growth, Similarity::set_table's integer loops and the AbacusByGroup CSR have no golden vector in the
+    reference.  tests/golden/similarity_csr_witness.json counts both straight from the S / P lines of the fixture GFAs
+    (tests/golden/make_similarity_csr_witness.py, nothing imported from oracle/); the oracle's chain GFA parser ->
+    ItemTable -> cursor passes -> similarity loops must agree for every grouping and count type."""
+    import json
+    from oracle import gfa_oracle as go
+    d = json.load(open(os.path.join(GOLDEN, "similarity_csr_witness.json")))
+    for case in d["cases"]:
+        g = go.parse_gfa(os.path.join(GOLDEN, case["gfa"]))
+        mask = go.make_mask(g, groupby_sample=case["grouping"] == "sample", groupby_haplotype=case["grouping"] == "haplotype")
+        t = go.item_tables(g, mask, case["count"])
+        op, og, names = go.path_order_arrays(mask, g)
+        assert list(names) == case["groups"], (case["gfa"], case["grouping"])
+        G = len(names)
+        if t.n_items == 0:
+            assert not any(any(row) for row in case["inter"])
+            continue
+        r, c, v = po.csr_build(t.n_items, t.items, t.id_prefsum, op, og, t.exclude)
+        if "r" in case:
+            assert [int(x) for x in r] == case["r"] and [int(x) for x in c] == case["c"] and [int(x) for x in v] == case["v"], \
+                (case["gfa"], case["grouping"], case["count"])
+        inter, ln, _ = po.similarity(r, c, G, count_bp=(case["count"] == "bp"), node_lens=g.node_lens)
+        assert inter.tolist() == case["inter"] and ln.tolist() == case["len"], (case["gfa"], case["grouping"], case["count"])
