@@ -392,71 +392,7 @@ int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
 }
 
 // ---- similarity: Jaccard + hierarchical clustering order (analyses/similarity.rs:119-254) ---------------------------
-// The reference delegates the clustering to kodama 0.3.0 (not in the tree): this is a restatement of the
-// published Lance-Williams scheme with scipy/fastcluster-style step sorting; tie-breaking is unpinned.
-struct Step2 {
-    size_t c1, c2;
-    float d;
-};
-
-std::vector<size_t> cluster_leaf_order(const std::vector<std::vector<float>> &table, const std::string &method) {
-    const size_t n = table.size();
-    std::vector<size_t> leaves;
-    if (n < 2) {
-        for (size_t i = 0; i < n; ++i) leaves.push_back(i);
-        return leaves;
-    }
-    const bool squared = method == "ward" || method == "centroid" || method == "median";
-    std::vector<std::vector<double>> D(n, std::vector<double>(n, 0.0));
-    for (size_t i = 0; i < n; ++i)
-        for (size_t j = i + 1; j < n; ++j) {
-            float s = 0.f;  // euclidean distance between rows, f32 like similarity.rs:238-244 (`powf(2.0)`, which LLVM
-                            // turns into a multiplication: x * x is the correctly rounded square either way)
-            for (size_t k = 0; k < n; ++k) {
-                const float d = table[i][k] - table[j][k];
-                s += d * d;
-            }
-            const float d = std::sqrt(s);
-            D[i][j] = D[j][i] = squared ? (double)d * d : (double)d;
-        }
-    std::vector<bool> active(n, true);
-    std::vector<size_t> size(n, 1), label(n);
-    for (size_t i = 0; i < n; ++i) label[i] = i;
-    std::vector<Step2> steps;
-    for (size_t it = 0; it + 1 < n; ++it) {
-        size_t bi = 0, bj = 0;
-        double best = INFINITY;
-        for (size_t i = 0; i < n; ++i)
-            if (active[i])
-                for (size_t j = i + 1; j < n; ++j)
-                    if (active[j] && D[i][j] < best) best = D[i][j], bi = i, bj = j;
-        const double ni = (double)size[bi], nj = (double)size[bj];
-        for (size_t k = 0; k < n; ++k) {
-            if (!active[k] || k == bi || k == bj) continue;
-            const double dik = D[bi][k], djk = D[bj][k], nk = (double)size[k];
-            double d;
-            if (method == "single") d = std::min(dik, djk);
-            else if (method == "complete") d = std::max(dik, djk);
-            else if (method == "average") d = (ni * dik + nj * djk) / (ni + nj);
-            else if (method == "weighted") d = 0.5 * (dik + djk);
-            else if (method == "ward") d = ((ni + nk) * dik + (nj + nk) * djk - nk * best) / (ni + nj + nk);
-            else if (method == "median") d = 0.5 * dik + 0.5 * djk - 0.25 * best;
-            else d = (ni * dik + nj * djk) / (ni + nj) - ni * nj * best / ((ni + nj) * (ni + nj));  // centroid
-            D[bj][k] = D[k][bj] = d;
-        }
-        steps.push_back({label[bi], label[bj], (float)(squared ? std::sqrt(std::max(best, 0.0)) : best)});
-        active[bi] = false;
-        size[bj] += size[bi];
-        label[bj] = n + it;
-    }
-    std::stable_sort(steps.begin(), steps.end(), [](const Step2 &x, const Step2 &y) { return x.d < y.d; });
-    for (auto &s : steps) {  // get_order_from_dendrogram, similarity.rs:206-219
-        const size_t a = std::min(s.c1, s.c2), b = std::max(s.c1, s.c2);
-        if (a < n) leaves.push_back(a);
-        if (b < n) leaves.push_back(b);
-    }
-    return leaves;
-}
+// The clustering itself (kodama 0.3.0 in the reference) lives in cluster.cpp.
 
 int cmd_similarity(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
@@ -591,6 +527,21 @@ int cmd_debug_table_tsv(const Args &a, std::ostream &os) {
 // `panacus debug-growth <hist.tsv> -l .. -q ..`: the closed-form growth values of every hist column as C hex floats
 // (%a: every bit of the f64), one line per threshold pair -- a test hook: the TSV prints floor(), which would hide a
 // last-bit difference between the threaded host code and the oracle's statement-by-statement port.
+// `panacus debug-linkage <file> -m method [--f32=1]`: the dendrogram of a condensed distance vector (first line: n, then
+// the n (n - 1) / 2 distances, whitespace separated) as "cluster1 cluster2 height" lines (tests/test_cluster.py)
+int cmd_debug_linkage(const Args &a, std::ostream &os) {
+    std::ifstream in(a.positional.at(0));
+    if (!in) throw Error("cannot open " + a.positional.at(0));
+    size_t n = 0;
+    in >> n;
+    std::vector<double> cond;
+    double x;
+    while (in >> x) cond.push_back(x);
+    if (n < 1 || cond.size() != n * (n - 1) / 2) throw Error("debug-linkage: expected n and n (n - 1) / 2 distances");
+    os << debug_linkage(cond, n, a.get("method", "centroid"), a.has("f32"));
+    return 0;
+}
+
 int cmd_debug_growth(const Args &a, std::ostream &os) {
     const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
     std::vector<std::string> comments;
@@ -957,6 +908,7 @@ int dispatch(int argc, char **argv, std::ostream &os) {
     if (a.sub == "debug-table-tsv") return cmd_debug_table_tsv(a, os);
     if (a.sub == "debug-parse") return cmd_debug_parse(a, os);
     if (a.sub == "debug-growth") return cmd_debug_growth(a, os);
+    if (a.sub == "debug-linkage") return cmd_debug_linkage(a, os);
     if (a.sub == "debug-synth-gfa") return cmd_debug_synth_gfa(a, os);
     if (a.sub == "debug-dump-tables") return cmd_debug_dump_tables(a, os);
     if (a.sub == "debug-tables") return cmd_debug_tables(a, os);

@@ -187,6 +187,10 @@ std::string write_metadata_comments(const std::string &argv_joined, bool with_ve
 std::string abacus_by_group_to_tsv(const GraphStorage &g, CountType count, bool total, const std::vector<std::string> &groups,
                                    const std::vector<uint64_t> &r, const std::vector<uint64_t> &c, const std::vector<uint32_t> &v,
                                    const std::map<uint64_t, uint64_t> &uncovered_bps);
+// hierarchical clustering of the similarity table (cluster.cpp; kodama::linkage in the reference, similarity.rs:165-181):
+// the observations in the order the dendrogram's steps name them (get_order_from_dendrogram, similarity.rs:206-219)
+std::vector<size_t> cluster_leaf_order(const std::vector<std::vector<float>> &table, const std::string &method);
+std::string debug_linkage(const std::vector<double> &condensed, size_t n, const std::string &method, bool f32);
 // hist-only TSV re-ingestion for `growth <file.tsv>` (io.rs:152-290)
 std::vector<Hist> parse_hists(const std::string &path, std::vector<std::string> &comments);
 
