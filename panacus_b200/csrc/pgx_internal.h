@@ -23,6 +23,7 @@ enum ScanFlags : uint32_t {
     kWeighted = 4u,    // growth deltas sum weight[i] instead of 1
     kJoint = 8u,       // small G: one joint (coverage, first group) histogram, marginalised in the epilogue
     kPrivate = 16u,    // lane-private narrow counters (plain LDS / STS; a shared atomic only when one wraps), folded after the last tile
+    kPrivGrowthAtomics = 64u,  // kPrivate, but only the histogram is lane-private: the curves' bins keep their shared atomics
     kVertical = 32u,   // G <= 64, counts: bit-sliced vertical counters (carry-save adders over one-hot words), no atomics in the loop
 };
 

@@ -744,6 +744,17 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
                 if (has_cls && cc) atomicAdd(carry + cbin, cc);
             }
         };
+        // kPrivGrowthAtomics: the curves' first differences keep their shared atomics (as in k_scan)
+        const bool growth_atomics = (p.flags & kPrivGrowthAtomics) != 0u;
+        auto growth_atomic = [&](uint32_t cov, uint32_t first, uint32_t wgt) {
+            for (uint32_t t = 0; t < p.T; ++t)
+                if (cov >= p.cov[t]) {
+                    if (WEIGHTED)
+                        smem_add64(s.delta_lo + t * p.G, s.delta_hi + t * p.G, first, wgt, 0u);
+                    else
+                        atomicAdd(&s.delta_lo[t * p.G + first], 1u);
+                }
+        };
         // items per thread and step: their row loads, popcounts and class look-ups are independent and overlap; only the
         // counter updates run one item after the other (two items of a thread may share a bin)
         constexpr int K = (C_T < 0 || C_T == 1) ? 4 : 2;
@@ -788,6 +799,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) account(valid[k], cov[k], first[k], wgt[k], cb[k]);
+                if (growth_atomics) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (valid[k] && cov[k]) growth_atomic(cov[k], first[k], wgt[k]);
+                }
             }
             if (tid < rows - trows) {  // <= 3 tail rows of the last tile, straight from global memory
                 const uint64_t item = row0 + trows + tid;
@@ -800,6 +816,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
                 }
                 if (p.countable) p.countable[item] = item ? cov : 0xFFFFFFFFu;
                 account(item != 0, cov, first, wgt, has_cls ? s_cbase[cov] : 0xFFFFFFFFu);
+                if (growth_atomics && item != 0 && cov) growth_atomic(cov, first, wgt);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8u * st);
@@ -814,7 +831,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
     priv_fold<CW, WEIGHTED>(p, s, cls_lo, cls_hi, carry, priv_base, tid);
     __syncthreads();
     // classes -> first differences of every threshold's curve: threshold t counts the classes >= cls_rank[t]
-    for (uint32_t i = tid; i < p.T * p.G; i += kScanThreads) {
+    // (kPrivGrowthAtomics: the first differences are in place already)
+    for (uint32_t i = tid; i < ((p.flags & kPrivGrowthAtomics) ? 0u : p.T * p.G); i += kScanThreads) {
         const uint32_t t = i / p.G, f = i - t * p.G;
         uint64_t v = 0;
         for (uint32_t k = p.cls_rank[t] - 1u; k < p.n_classes; ++k)
@@ -1193,7 +1211,7 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     L.priv_bins = L.priv_cw = L.priv_hist_bins = 0;
     p.n_classes = 0;
     bool priv = false, vert = false;
-    uint32_t priv_tile = 0;
+    uint32_t priv_tile = 0, priv_min_stages = 3;
     L.vert_planes = L.vert_counters = L.vert_end = 0;
     // distinct coverage cutoffs, ascending (k_scan_priv: threshold t sums the classes >= its rank; k_scan_vert: counter
     // cls_rank[t] - 1 holds the items of coverage >= cutoff)
@@ -1253,7 +1271,36 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
         if (count_mode || weight_mode) {
             const uint32_t cw = count_mode ? 1u : 2u;
             const uint32_t hist_bins = (count_mode ? (p.flags & kHistCount) : (p.flags & kHistWeight)) ? G1 : 0u;
-            const uint64_t bins = std::max<uint64_t>(1u, (uint64_t)hist_bins + (uint64_t)D * p.G);
+            // Dp: coverage classes that get lane-private bins.  When histogram + classes do not leave room for two CTAs per
+            // SM but the histogram alone does (G ~ 130 .. 300), only the histogram goes private and the curves keep their
+            // shared atomics (kPrivGrowthAtomics): half the ATOMS of the atomics kernel, which are what bounds it there.
+            uint32_t Dp = D;
+            uint32_t min_stages = 3u;
+            auto fixed_bytes = [&](uint32_t dp) {
+                const uint64_t b = std::max<uint64_t>(1u, (uint64_t)hist_bins + (uint64_t)dp * p.G);
+                return (uint64_t)off + (uint64_t)dp * p.G * 4u * (count_mode ? 1u : 2u) + 16u + b * (256u * cw + 4u) + G1 * 4u + 128u;
+            };
+            auto fits_two = [&](uint32_t dp, uint32_t stages) {
+                const uint32_t mt = rowbytes <= 16u ? 1024u : 512u;
+                uint32_t t0;
+                if (rowbytes <= 8u) t0 = 3072u;
+                else if (rowbytes <= 16u) t0 = 2048u;
+                else if (rowbytes <= 32u) t0 = 1024u;
+                else t0 = std::max(512u, 32768u / rowbytes / 512u * 512u);
+                for (uint32_t t = t0; t >= mt; t >>= 1) {
+                    const uint64_t st_bytes = align_up(t * rowbytes, 128u) + (p.weight ? align_up(t * 4u, 128u) : 0u);
+                    if (fixed_bytes(dp) + stages * st_bytes <= 232448u / 2u - 1024u) return true;
+                }
+                return false;
+            };
+            // (not where the joint histogram of the atomics kernel applies, G <~ 100: that is one atomic per item already)
+            const bool joint_fits = (uint64_t)G1 * p.G * 4u * (count_mode ? 1u : 2u) <= 44u * 1024u;
+            if (D > 0u && hist_bins > 0u && !joint_fits && !fits_two(D, 3u) && fits_two(0u, 2u) && env_u32("PGX_SCAN_PRIV") != 1u &&
+                env_u32("PGX_SCAN_HYBRID") != 2u) {
+                Dp = 0u;
+                min_stages = fits_two(0u, 3u) ? 3u : 2u;
+            }
+            const uint64_t bins = std::max<uint64_t>(1u, (uint64_t)hist_bins + (uint64_t)Dp * p.G);
             uint32_t tile;
             if (rowbytes <= 8u) tile = 3072u;
             else if (rowbytes <= 16u) tile = 2048u;
@@ -1264,23 +1311,20 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
             // measured (profiles/r2_scan_shapes_*.txt): the private counters only pay with two CTAs per SM -- with one
             // (8 consumer warps) the dependent shared-memory round trips of the updates are not hidden and the atomics
             // kernel (16 warps, fire-and-forget ATOMS) is faster; so: eligible iff 3 stages of some tile fit in half an SM
-            const uint64_t fixed = (uint64_t)off + (uint64_t)D * p.G * 4u * (count_mode ? 1u : 2u) + 16u + bins * (256u * cw + 4u) + G1 * 4u + 128u;
-            const uint32_t min_tile = rowbytes <= 16u ? 1024u : 512u;
-            bool two_ctas = false;
-            for (uint32_t t = tile; t >= min_tile && !two_ctas; t >>= 1) {
-                const uint64_t st_bytes = align_up(t * rowbytes, 128u) + (p.weight ? align_up(t * 4u, 128u) : 0u);
-                two_ctas = fixed + 3u * st_bytes <= 232448u / 2u - 1024u;
-            }
+            const uint64_t fixed = fixed_bytes(Dp);
+            const bool two_ctas = fits_two(Dp, min_stages);
             (void)stage;
             if ((two_ctas || env_u32("PGX_SCAN_PRIV") == 1u) && fixed + 2ull * stage <= 232448u && rowbytes <= 64u) {
                 priv = true;
                 priv_tile = tile;
+                priv_min_stages = min_stages;
                 p.flags |= kPrivate;
-                p.n_classes = D;
+                if (Dp != D) p.flags |= kPrivGrowthAtomics;
+                p.n_classes = Dp;
                 L.off_cls_lo = off;
-                off += D * p.G * 4u;
+                off += Dp * p.G * 4u;
                 L.off_cls_hi = off;
-                off += count_mode ? 0u : D * p.G * 4u;
+                off += count_mode ? 0u : Dp * p.G * 4u;
                 L.off_carry = off;
                 off += (uint32_t)bins * 4u;
                 off = align_up(off, 16u);
@@ -1332,10 +1376,10 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
         const uint32_t min_tile = rowbytes <= 16u ? 1024u : 512u;  // a thread takes 4 (narrow rows) or 2 items per step
         for (uint32_t t = priv_tile; t >= min_tile; t >>= 1) {
             const uint32_t stage = align_up(t * rowbytes, 128u) + (p.weight ? align_up(t * 4u, 128u) : 0u);
-            if (off + 3u * stage <= 232448u / 2u - 1024u) {
+            if (off + priv_min_stages * stage <= 232448u / 2u - 1024u) {
                 tile = t;
                 want_ctas = 2;
-                want_stages = 3;
+                want_stages = priv_min_stages;
                 break;
             }
         }
