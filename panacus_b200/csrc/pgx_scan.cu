@@ -1295,8 +1295,13 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
             };
             // (not where the joint histogram of the atomics kernel applies, G <~ 100: that is one atomic per item already)
             const bool joint_fits = (uint64_t)G1 * p.G * 4u * (count_mode ? 1u : 2u) <= 44u * 1024u;
+            // Measured (profiles/r2_scan_shapes_v6_hybrid.jsonl): pays for bp sums only (10M x 100 / 128, hist + one curve:
+            // 86.1 -> 77.9 / 82.4 -> 78.4 us -- a weighted atomic is a lo / carry pair); when counting, the private update is
+            // slower than the ATOMS it replaces (10M x 256: 86.8 -> 105 us, c2: 18.8 -> 21.3 us), so counting needs
+            // PGX_SCAN_HYBRID=1 to get it.
+            const uint32_t hyb = env_u32("PGX_SCAN_HYBRID");
             if (D > 0u && hist_bins > 0u && !joint_fits && !fits_two(D, 3u) && fits_two(0u, 2u) && env_u32("PGX_SCAN_PRIV") != 1u &&
-                env_u32("PGX_SCAN_HYBRID") != 2u) {
+                hyb != 2u && (!count_mode || hyb == 1u)) {
                 Dp = 0u;
                 min_stages = fits_two(0u, 3u) ? 3u : 2u;
             }

@@ -244,6 +244,20 @@ def test_lane_private_counter_kernel(N, G, monkeypatch):
                 assert np.array_equal(one[0].astype(np.float64), exp[("node", 2, 0.0)])
                 if mode == "force" and G <= 256:
                     assert "k_scan_priv<u8>" in a.last_launch_info(), a.last_launch_info()
+                if mode == "auto":
+                    # hist-only private counters + shared atomics for the curves (default for bp sums where histogram +
+                    # classes leave no room for two CTAs; PGX_SCAN_HYBRID=1 also when counting)
+                    monkeypatch.setenv("PGX_SCAN_HYBRID", "1")
+                    h4, _, cv4 = a.hist_ordered_growth(cov[:2], None, weighted=False, hist_count=True, hist_weight=False)
+                    info = a.last_launch_info()
+                    _, w4, cvw4 = a.hist_ordered_growth(cov[:2], None, weighted=True, hist_count=False, hist_weight=True)
+                    monkeypatch.delenv("PGX_SCAN_HYBRID")
+                    if G in (130, 256):
+                        assert "hist-only" in info, info
+                    assert np.array_equal(h4, exp["hist"]) and np.array_equal(w4, exp["hist_bp"])
+                    for t, (c, q) in enumerate(pairs[:2]):
+                        assert np.array_equal(cv4[t].astype(np.float64), exp[("node", c, q)]), (grid, c)
+                        assert np.array_equal(cvw4[t].astype(np.float64), exp[("bp", c, q)]), (grid, c)
 
 
 def test_dense_and_sparse_variants():
