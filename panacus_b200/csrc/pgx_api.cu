@@ -223,8 +223,8 @@ int scan_launch(pgx_abacus *a, bool quorum, uint32_t flags, const std::vector<ui
     a->launches++;
     char buf[320];
     if (p.flags & kVertical)
-        snprintf(buf, sizeof buf, "k_scan_vert<hist=%u,D=%u> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u planes=%u",
-                 (p.flags & kHistCount) ? 1u : 0u, p.n_classes, grid, kScanThreads, p.L.total, p.tile_items, p.stages, p.n_tiles, p.T, p.L.vert_planes);
+        snprintf(buf, sizeof buf, "k_scan_vert<hist=%u,D=%u> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u planes=%u row_words=%u",
+                 (p.flags & kHistCount) ? 1u : 0u, p.n_classes, grid, kScanThreads, p.L.total, p.tile_items, p.stages, p.n_tiles, p.T, p.L.vert_planes, p.Wp);
     else if (p.flags & kPrivate)
         snprintf(buf, sizeof buf, "k_scan_priv<u%u%s> grid=%d block=%d smem=%u tile_items=%u stages=%u tiles=%u T=%u classes=%u bins=%u",
                  p.L.priv_cw * 8u, (p.flags & kPrivGrowthAtomics) ? ",hist-only" : "", grid, kScanThreads, p.L.total, p.tile_items, p.stages,

@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_priv(const __grid_cons
     scan_epilogue(p, s, tid);
 }
 
-// ---- bit-sliced vertical counters (kVertical): G <= 64, counting nodes / edges ---------------------------------------
+// ---- bit-sliced vertical counters (kVertical): G <= 128, counting nodes / edges --------------------------------------
 // An item's row is one 64-bit word x.  Its two facts are turned into ONE-HOT words -- 1 << popc(x) (coverage) and x & -x
 // (first group) -- so a histogram is the column sum of a 64-column bit matrix.  Column sums of words are what carry-save
 // adders do: a thread adds 16 one-hot words with 15 full adders (xor3 / majority = 2 LOP3 per 32-bit half) into the four
@@ -882,21 +882,24 @@ constexpr int kVertK = 16;          // items per thread and step = inputs of one
 constexpr int kVertMaxPlanes = 12;  // shared-memory planes per counter (sixteens .. ): 16 * 2^12 items per thread
 constexpr int kVertFoldPlanes = 4 + kVertMaxPlanes + 8;  // a CTA's total: 256 threads = 8 more bits
 
-// four more words of the running 16-block (quarter Q = 0..3 of it); the last quarter returns the sixteens word in s16
-template <int Q>
-__device__ __forceinline__ void vert_feed4(VertTree &t, const V64 v0, const V64 v1, const V64 v2, const V64 v3, V64 &s16) {
+// four more words of the running block (quarter Q of NQ): a block is 16 words (NQ = 4; its last quarter returns the
+// "sixteens" word) or 8 words (NQ = 2, two-word rows: the last quarter returns the "eights" word and p8 stays unused)
+template <int Q, int NQ>
+__device__ __forceinline__ void vert_feed4(VertTree &t, const V64 v0, const V64 v1, const V64 v2, const V64 v3, V64 &out) {
     V64 a2, b2, f4, e8;
     csa(a2, t.p1, t.p1, v0, v1);
     csa(b2, t.p1, t.p1, v2, v3);
     csa(f4, t.p2, t.p2, a2, b2);
-    if (Q == 0 || Q == 2) {
+    if (Q % 2 == 0) {
         t.q4 = f4;
     } else {
         csa(e8, t.p4, t.p4, t.q4, f4);
-        if (Q == 1)
+        if (NQ == 2)
+            out = e8;
+        else if (Q == 1)
             t.q8 = e8;
         else
-            csa(s16, t.p8, t.p8, t.q8, e8);
+            csa(out, t.p8, t.p8, t.q8, e8);
     }
 }
 // ripple the sixteens word into the thread's shared-memory planes (plane stride: 256 threads x 8 bytes)
@@ -910,71 +913,89 @@ __device__ __forceinline__ void vert_ripple(uint32_t addr, uint32_t n_planes, V6
     }
 }
 
-// One step of a consumer thread: 16 rows of the stage at `base` (rows li0 + k * 256) into the trees; s16[c] = the
-// sixteens word of counter c.  SLOW: per-slot validity (item 0, rows past the end of a short tile) and the per-item
-// coverage output; every other tile takes the branch-free path (immediate-offset loads, no predicates).
-template <int HIST, int D, bool C1, bool SLOW>
-__device__ __forceinline__ void vert_step(const ScanParams &p, VertTree (&tree)[HIST + D], V64 (&s16)[HIST + D], uint32_t base,
-                                          uint32_t li0, uint32_t trows, uint32_t tile, uint64_t row0, const uint32_t *cthr,
-                                          uint32_t mask_lo, uint32_t mask_hi) {
-    uint64_t x[kVertK];
+// One step of a consumer thread: K = 16 / NW rows of NW 64-bit words of the stage at `base` (rows li0 + k * 256) into the
+// trees; out[c * NW + w] = the word that falls out of the tree of counter c, row word w.  SLOW: per-slot validity (item 0,
+// rows past the end of a short tile) and the per-item coverage output; every other tile takes the branch-free path.
+template <int NW, int HIST, int D, bool C1, bool SLOW>
+__device__ __forceinline__ void vert_step(const ScanParams &p, VertTree (&tree)[(HIST + D) * NW], V64 (&out)[(HIST + D) * NW],
+                                          uint32_t base, uint32_t li0, uint32_t trows, uint32_t tile, uint64_t row0,
+                                          const uint32_t *cthr) {
+    constexpr int K = kVertK / NW, NQ = K / 4;
+    uint64_t x[K][NW];
 #pragma unroll
-    for (int k = 0; k < kVertK; ++k) {
+    for (int k = 0; k < K; ++k) {
         const uint32_t lk = li0 + (uint32_t)k * kConsumerThreads;
-        x[k] = lds_u64(base + ((SLOW && lk >= trows) ? li0 : lk) * 8u);
+        const uint32_t addr = base + ((SLOW && lk >= trows) ? li0 : lk) * (8u * NW);
+        if (NW == 1)
+            x[k][0] = lds_u64(addr);
+        else
+            lds_v2_u64(addr, x[k][0], x[k][NW - 1]);
     }
     auto quarter = [&](auto qtag) {
         constexpr int Q = decltype(qtag)::value;
-        V64 oh[4], fw[D > 0 ? D : 1][4];
+        V64 oh[NW][4], fw[D > 0 ? D : 1][NW][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = Q * 4 + j;
             const uint32_t lk = li0 + (uint32_t)k * kConsumerThreads;
-            uint32_t lo = (uint32_t)x[k] & mask_lo, hi = (uint32_t)(x[k] >> 32) & mask_hi;
+            uint64_t xm[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) xm[w] = x[k][w];
+            xm[NW - 1] &= (NW == 1) ? p.last_mask0 : p.last_mask1;  // bits >= G of the last word are ignored
             bool valid = true;
             if (SLOW) {
                 valid = lk < trows && (tile | lk) != 0u;  // item 0: the reference's dummy item, never counted
-                lo = valid ? lo : 0u;
-                hi = valid ? hi : 0u;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) xm[w] = valid ? xm[w] : 0ull;
             }
-            const uint32_t cov = __popc(lo) + __popc(hi);
+            uint32_t cov = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) cov += __popc((uint32_t)xm[w]) + __popc((uint32_t)(xm[w] >> 32));
             if (SLOW && p.countable && lk < trows) p.countable[row0 + lk] = valid ? cov : 0xFFFFFFFFu;
             if (HIST) {
+                // 1 << cov in 32-bit pieces (shl.b32 clamps: shifts >= 32, also "negative" ones, give 0); the top coverage
+                // 64 NW has no bit and is recovered in the read-out
                 const uint32_t one = SLOW ? (valid ? 1u : 0u) : 1u;
-                uint32_t olo, ohi;  // 1 << cov in two halves (shl.b32 clamps: shifts >= 32 give 0; coverage 64: see the read-out)
-                asm("shl.b32 %0, %1, %2;" : "=r"(olo) : "r"(one), "r"(cov));
-                asm("shl.b32 %0, %1, %2;" : "=r"(ohi) : "r"(one), "r"(cov - 32u));
-                oh[j] = {olo, ohi};
+                uint32_t h[2 * NW];
+#pragma unroll
+                for (int i = 0; i < 2 * NW; ++i) asm("shl.b32 %0, %1, %2;" : "=r"(h[i]) : "r"(one), "r"(cov - 32u * (uint32_t)i));
+#pragma unroll
+                for (int w = 0; w < NW; ++w) oh[w][j] = {h[2 * w], h[2 * w + 1]};
             }
             if (D > 0) {
-                const uint64_t xm = ((uint64_t)hi << 32) | lo;
-                const uint64_t first = xm & (0ull - xm);
-                const uint32_t flo = (uint32_t)first, fhi = (uint32_t)(first >> 32);
+                uint64_t f[NW];
+                f[0] = xm[0] & (0ull - xm[0]);
+                if (NW == 2) f[NW - 1] = xm[0] ? 0ull : (xm[NW - 1] & (0ull - xm[NW - 1]));
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    if (C1 && d == 0) {
-                        fw[d][j] = {flo, fhi};
-                    } else {
-                        const uint32_t m = cov >= cthr[d] ? 0xFFFFFFFFu : 0u;
-                        fw[d][j] = {flo & m, fhi & m};
-                    }
+                    const uint32_t m = (C1 && d == 0) ? 0xFFFFFFFFu : (cov >= cthr[d] ? 0xFFFFFFFFu : 0u);
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) fw[d][w][j] = {(uint32_t)f[w] & m, (uint32_t)(f[w] >> 32) & m};
                 }
             }
         }
-        if (HIST) vert_feed4<Q>(tree[0], oh[0], oh[1], oh[2], oh[3], s16[0]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) vert_feed4<Q>(tree[HIST + d], fw[d][0], fw[d][1], fw[d][2], fw[d][3], s16[HIST + d]);
+        for (int w = 0; w < NW; ++w) {
+            if (HIST) vert_feed4<Q, NQ>(tree[w], oh[w][0], oh[w][1], oh[w][2], oh[w][3], out[w]);
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                vert_feed4<Q, NQ>(tree[(HIST + d) * NW + w], fw[d][w][0], fw[d][w][1], fw[d][w][2], fw[d][w][3], out[(HIST + d) * NW + w]);
+        }
     };
     quarter(std::integral_constant<int, 0>{});
     quarter(std::integral_constant<int, 1>{});
-    quarter(std::integral_constant<int, 2>{});
-    quarter(std::integral_constant<int, 3>{});
+    if (NQ == 4) {
+        quarter(std::integral_constant<int, NQ == 4 ? 2 : 0>{});
+        quarter(std::integral_constant<int, NQ == 4 ? 3 : 1>{});
+    }
 }
 
-template <int HIST, int D, bool C1>
+template <int NW, int HIST, int D, bool C1>
 __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_constant__ ScanParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int C = HIST + D;
+    constexpr int C = HIST + D, CW = C * NW;      // counters, counter words (one 64-bin word per row word)
+    constexpr int K = kVertK / NW;                // rows per thread and step
+    constexpr uint32_t TREE = NW == 1 ? 4u : 3u;  // register planes of a tree: 1, 2, 4 (, 8); the shared-memory planes follow
     const uint32_t tid = threadIdx.x;
     if (tid == 0) ts_mark(p, 0);
     const uint32_t warp = tid >> 5, lane = tid & 31u;
@@ -992,9 +1013,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
     s.delta_hi = nullptr;
     s.thr = nullptr;
     s.joint_cnt = s.joint_wlo = s.joint_whi = nullptr;
-    uint32_t *cls_tot = reinterpret_cast<uint32_t *>(smem + p.L.off_cls_lo);  // [D][64]
-    uint64_t *fold = reinterpret_cast<uint64_t *>(smem + p.L.off_carry);      // [C][kVertFoldPlanes]: the CTA's totals
-    const uint32_t planes0 = smem_u32(smem + p.L.off_priv);                   // [C][P][256] u64
+    uint32_t *cls_tot = reinterpret_cast<uint32_t *>(smem + p.L.off_cls_lo);  // [D][64 NW]
+    uint64_t *fold = reinterpret_cast<uint64_t *>(smem + p.L.off_carry);      // [CW][kVertFoldPlanes]: the CTA's totals
+    const uint32_t planes0 = smem_u32(smem + p.L.off_priv);                   // [CW][TREE + P][256] u64
     __shared__ uint32_t s_missing_word;
     uint32_t *s_missing = &s_missing_word;
 
@@ -1026,11 +1047,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
             if (p.zero_epoch) direct_wait_zeroed(p);
         }
     } else {
-        // ===== consumers: 16 items per thread and step =====
-        VertTree tree[C];
-        uint32_t seen = 0;  // (thread 0) items fed to the trees: the histogram's bins must add up to it (coverage 64, see below)
+        // ===== consumers: K rows per thread and step =====
+        VertTree tree[CW];
+        uint32_t seen = 0;  // (thread 0) items fed to the trees: the histogram's bins must add up to it (top coverage, see below)
         const uint32_t my_planes = planes0 + tid * 8u;
-        const uint32_t mask_lo = (uint32_t)p.last_mask0, mask_hi = (uint32_t)(p.last_mask0 >> 32);
         uint32_t cthr[D > 0 ? D : 1];
 #pragma unroll
         for (int d = 0; d < D; ++d) cthr[d] = p.cls_thr[d];
@@ -1045,26 +1065,30 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
             const uint32_t trows = rows & ~3u;
             const uint32_t base = stage0 + st * p.L.stage_stride;
             const bool slow = tile == 0u || trows != p.tile_items || p.countable != nullptr;  // item 0 / a short tile / coverage output
-            for (uint32_t li0 = tid; li0 < trows; li0 += kVertK * kConsumerThreads) {
-                V64 s16[C];
+            for (uint32_t li0 = tid; li0 < trows; li0 += (uint32_t)K * kConsumerThreads) {
+                V64 out[CW];
                 if (slow)
-                    vert_step<HIST, D, C1, true>(p, tree, s16, base, li0, trows, tile, row0, cthr, mask_lo, mask_hi);
+                    vert_step<NW, HIST, D, C1, true>(p, tree, out, base, li0, trows, tile, row0, cthr);
                 else
-                    vert_step<HIST, D, C1, false>(p, tree, s16, base, li0, trows, tile, row0, cthr, mask_lo, mask_hi);
+                    vert_step<NW, HIST, D, C1, false>(p, tree, out, base, li0, trows, tile, row0, cthr);
 #pragma unroll
-                for (int c = 0; c < C; ++c) vert_ripple(my_planes + ((uint32_t)c * (P + 4u) + 4u) * 2048u, P, s16[c]);
+                for (int cw = 0; cw < CW; ++cw) vert_ripple(my_planes + ((uint32_t)cw * (P + TREE) + TREE) * 2048u, P, out[cw]);
             }
             if (tid == 0) seen += trows - (tile == 0u && trows ? 1u : 0u);  // items this CTA fed to the trees
             if (tid < rows - trows) {  // <= 3 tail rows of the last tile, straight from global memory, plain shared atomics
                 const uint64_t item = row0 + trows + tid;
-                const uint64_t xm = __ldg(p.bitmap + item) & p.last_mask0;
-                const uint32_t cov = __popcll(xm);
+                uint32_t cov = 0, first = 0xFFFFFFFFu;
+                for (uint32_t w = 0; w < p.W; ++w) {
+                    const uint64_t xw = __ldg(p.bitmap + item * p.Wp + w) & word_mask(p, w);
+                    cov += __popcll(xw);
+                    if (xw && first == 0xFFFFFFFFu) first = w * 64u + first_bit(xw);
+                }
                 if (p.countable) p.countable[item] = item ? cov : 0xFFFFFFFFu;
                 if (item) {
                     if (HIST) atomicAdd(&s.hist_cnt[cov], 1u);
                     if (cov)
                         for (uint32_t t = 0; t < p.T; ++t)
-                            if (cov >= p.cov[t]) atomicAdd(&s.delta_lo[t * p.G + first_bit(xm)], 1u);
+                            if (cov >= p.cov[t]) atomicAdd(&s.delta_lo[t * p.G + first], 1u);
                 }
             }
             __syncwarp();
@@ -1076,26 +1100,26 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
         }
         if (tid == 0) ts_mark(p, 3);
         if (HIST && tid == 0) *s_missing = seen;
-        // the trees' register planes join the thread's shared-memory planes (slots 0..3 of each counter) ...
+        // the trees' register planes join the thread's shared-memory planes (slots 0 .. TREE - 1 of each counter word) ...
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const uint32_t a = my_planes + (uint32_t)c * (P + 4u) * 2048u;
-            const VertTree &t = tree[c];
+        for (int cw = 0; cw < CW; ++cw) {
+            const uint32_t a = my_planes + (uint32_t)cw * (P + TREE) * 2048u;
+            const VertTree &t = tree[cw];
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(t.p1.lo), "r"(t.p1.hi) : "memory");
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 2048u), "r"(t.p2.lo), "r"(t.p2.hi) : "memory");
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 4096u), "r"(t.p4.lo), "r"(t.p4.hi) : "memory");
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 6144u), "r"(t.p8.lo), "r"(t.p8.hi) : "memory");
+            if (TREE == 4u) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 6144u), "r"(t.p8.lo), "r"(t.p8.hi) : "memory");
         }
     }
     __syncthreads();
-    // ===== fold: warp c adds up counter c =====
+    // ===== fold: warp cw adds up counter word cw =====
     // Shuffles are the scarce resource here (~0.25 warp-SHFL per clock and SM: a butterfly over all 8 warps of both
     // resident CTAs cost 5-9 us, profiles/r2_scan_timeline_v2.txt), shared-memory loads are not: lane l first adds the
     // planes of threads l, l + 32, .. l + 224 (conflict-free LDS.64, ripple-carry full adders), then one butterfly over
     // the warp's 32 lanes finishes the sum; lane 0 keeps it for the read-out.
     if (tid == 0) ts_mark(p, 6);
-    if (warp < (uint32_t)C) {
-        const uint32_t c = warp;
+    if (warp < (uint32_t)CW) {
+        const uint32_t c = warp;  // counter word
         V64 pl[kVertFoldPlanes];
 #pragma unroll
         for (int k = 0; k < kVertFoldPlanes; ++k) pl[k] = {0u, 0u};
@@ -1104,24 +1128,24 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
         // one after the other.  (This phase is pure latency, one warp per counter: 3.2 us as written here; rolled loops over
         // the thread groups / butterfly levels were measured at 8.6 us, a butterfly over all eight warps at 5-9 us:
         // profiles/r2_scan_timeline_v*.txt.)
-        const uint32_t src = planes0 + ((c * (P + 4u)) * 256u + lane) * 8u;
+        const uint32_t src = planes0 + ((c * (P + TREE)) * 256u + lane) * 8u;
         V64 carry[kConsumerWarps];
 #pragma unroll
         for (int j = 0; j < kConsumerWarps; ++j) carry[j] = {0u, 0u};
 #pragma unroll
         for (int k = 0; k < kVertFoldPlanes; ++k) {
-            if ((uint32_t)k >= P + 4u + 3u) break;  // 8 numbers of P + 4 planes: P + 7 planes
+            if ((uint32_t)k >= P + TREE + 3u) break;  // 8 numbers of P + TREE planes: 3 planes more
             V64 o[kConsumerWarps];
 #pragma unroll
             for (int j = 0; j < kConsumerWarps; ++j) {
                 o[j] = {0u, 0u};
-                if ((uint32_t)k < P + 4u)
+                if ((uint32_t)k < P + TREE)
                     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(o[j].lo), "=r"(o[j].hi) : "r"(src + (uint32_t)k * 2048u + (uint32_t)j * 256u));
             }
 #pragma unroll
             for (int j = 0; j < kConsumerWarps; ++j) csa(carry[j], pl[k], pl[k], o[j], carry[j]);
         }
-        uint32_t n = 4u + P + 3u;  // planes that can be non-zero
+        uint32_t n = TREE + P + 3u;  // planes that can be non-zero
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             V64 carry2 = {0u, 0u};
@@ -1147,26 +1171,26 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_scan_vert(const __grid_cons
     }
     if (tid == 0) ts_mark(p, 7);
     __syncthreads();
-    // ===== read the bins out: bit b of plane k of a counter's total weighs 2^k =====
-    for (uint32_t i = tid; i < (uint32_t)(C * 64); i += kScanThreads) {
-        const uint32_t c = i >> 6, b = i & 63u;
-        const uint64_t *f = fold + (size_t)c * kVertFoldPlanes;
+    // ===== read the bins out: bit b of plane k of a counter word's total weighs 2^k =====
+    for (uint32_t i = tid; i < (uint32_t)(CW * 64); i += kScanThreads) {
+        const uint32_t cw = i >> 6, c = cw / (uint32_t)NW, bin = (cw % (uint32_t)NW) * 64u + (i & 63u);
+        const uint64_t *f = fold + (size_t)cw * kVertFoldPlanes;
         uint32_t total = 0;
-        for (uint32_t k = 0; k < 4u + P + 8u; ++k) total += (uint32_t)((f[k] >> b) & 1ull) << k;
+        for (uint32_t k = 0; k < TREE + P + 8u; ++k) total += (uint32_t)((f[k] >> (i & 63u)) & 1ull) << k;
         if (!total) continue;
         if (HIST && c == 0) {
-            atomicAdd(&s.hist_cnt[b], total);  // (the tail rows' atomics are in there already; bits above G are never set)
+            atomicAdd(&s.hist_cnt[bin], total);  // (the tail rows' atomics are in there already; bits above G are never set)
             atomicSub(s_missing, total);
         } else {
-            cls_tot[(c - HIST) * 64u + b] = total;
+            cls_tot[(c - HIST) * (64u * NW) + bin] = total;
         }
     }
     __syncthreads();
-    // coverage 64 (G = 64) has no bit in the one-hot word: those items are the ones the 64 bins did not account for
-    if (HIST && tid == 0 && p.G == 64u && *s_missing) s.hist_cnt[64] += *s_missing;
+    // the top coverage 64 NW (G = 64 NW) has no bit in the one-hot words: those items are the ones the bins did not account for
+    if (HIST && tid == 0 && p.G == 64u * NW && *s_missing) s.hist_cnt[p.G] += *s_missing;
     for (uint32_t i = tid; i < p.T * p.G; i += kScanThreads) {
         const uint32_t t = i / p.G, f = i - t * p.G;
-        s.delta_lo[i] += cls_tot[(p.cls_rank[t] - 1u) * 64u + f];
+        s.delta_lo[i] += cls_tot[(p.cls_rank[t] - 1u) * (64u * NW) + f];
     }
     __syncthreads();
     scan_epilogue(p, s, tid);
@@ -1232,32 +1256,35 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
             for (uint32_t d = 0; d < D; ++d)
                 if (p.cls_thr[d] == p.cov[t]) p.cls_rank[t] = d + 1u;
     }
-    // bit-sliced vertical counters: one-word rows (G <= 64), counting (no weights), at most 3 distinct cutoffs
+    // bit-sliced vertical counters: rows of one or two words (G <= 128), counting (no weights), few distinct cutoffs
     // (PGX_SCAN_VERT=2 switches it off; PGX_SCAN_PRIV=1 / 2 ask for the lane-private / the shared-atomics kernel explicitly)
-    if (!quorum && p.Wp == 1u && !(p.flags & (kWeighted | kHistWeight)) && D <= 3u && env_u32("PGX_SCAN_VERT") != 2u &&
+    if (!quorum && p.Wp <= 2u && !(p.flags & (kWeighted | kHistWeight)) && D <= 3u && env_u32("PGX_SCAN_VERT") != 2u &&
         env_u32("PGX_SCAN_PRIV") == 0u) {
+        const uint32_t NW = p.Wp, tree_slots = NW == 1u ? 4u : 3u;
         const uint32_t C = ((p.flags & kHistCount) ? 1u : 0u) + D;
-        const uint64_t n_tiles = (p.n_rows + 4095u) / 4096u;
+        const uint32_t tile_rows = (uint32_t)kVertK / NW * (uint32_t)kConsumerThreads;  // one block per thread and tile
+        const uint64_t n_tiles = (p.n_rows + tile_rows - 1u) / tile_rows;
         uint64_t worst_grid = env_u32("PGX_SCAN_GRID") ? env_u32("PGX_SCAN_GRID") : (uint64_t)sm_count;  // fewest CTAs the launch may use
         if (worst_grid > n_tiles) worst_grid = n_tiles;
-        const uint64_t blocks = worst_grid ? (n_tiles + worst_grid - 1u) / worst_grid : 0u;  // 16-blocks a thread adds up
+        const uint64_t blocks = worst_grid ? (n_tiles + worst_grid - 1u) / worst_grid : 0u;  // blocks a thread adds up
         // 2^P - 1 >= 2 x blocks: with the dynamic tile scheduler a CTA may take up to twice its share before it stops
         // asking for tiles (scan_producer's max_tiles); the grid's joint capacity then still covers every tile
         uint32_t P = 1;
         while (P <= 32u && ((2u * blocks + 1u) >> P)) ++P;
-        // (measured: every counter costs ~9 LOP3 per item; from three counters on the loop is ALU-bound and the
-        // lane-private kernel is faster -- profiles/r2_scan_shapes_v5.jsonl: 10M x 44, T = 3: 45 vs 43 us)
-        if (C >= 1u && C <= (env_u32("PGX_SCAN_VERT") == 1u ? 4u : 2u) && P <= (uint32_t)kVertMaxPlanes) {  // (PGX_SCAN_VERT=1: up to 4)
+        // (measured: every counter costs ~9 LOP3 per item and row word; from three counters on the loop is ALU-bound and
+        // the lane-private kernel is faster -- profiles/r2_scan_shapes_v5.jsonl: 10M x 44, T = 3: 45 vs 43 us)
+        const uint32_t max_c = (NW == 1u && env_u32("PGX_SCAN_VERT") == 1u) ? 4u : 2u;  // (PGX_SCAN_VERT=1: up to 4 for one-word rows)
+        if (C >= 1u && C <= max_c && P <= (uint32_t)kVertMaxPlanes) {
             vert = true;
             p.flags |= kVertical;
             p.n_classes = D;
             off = align_up(off, 16u);
             L.off_cls_lo = off;
-            off += D * 64u * 4u;
+            off += D * 64u * NW * 4u;
             L.off_carry = off = align_up(off, 16u);
-            off += C * (uint32_t)kVertFoldPlanes * 8u;
+            off += C * NW * (uint32_t)kVertFoldPlanes * 8u;
             L.off_priv = off = align_up(off, 16u);
-            off += C * (P + 4u) * 2048u;  // P ripple planes + 4 slots for the trees' register planes (fold)
+            off += C * NW * (P + tree_slots) * 2048u;  // per counter word: the trees' register planes (fold) + P ripple planes
             L.vert_planes = P;
             L.vert_counters = C;
             L.vert_end = off;
@@ -1370,7 +1397,7 @@ int plan_scan(ScanParams &p, bool quorum, int sm_count, int *grid_out) {
     uint32_t tile, want_ctas, want_stages;
     const bool heavy = quorum || (p.flags & (kHistWeight | kWeighted)) != 0;  // more atomics per item
     if (vert) {
-        tile = (uint32_t)kVertK * (uint32_t)kConsumerThreads;  // one 16-block per thread and tile
+        tile = (uint32_t)kVertK / p.Wp * (uint32_t)kConsumerThreads;  // one block (16 / NW rows) per thread and tile
         want_ctas = 2, want_stages = 3;
     } else if (priv) {
         // two CTAs per SM (16 consumer warps hide the shared-memory latencies of the counter updates) whenever three
@@ -1473,30 +1500,40 @@ int launch_priv(const ScanParams &p, int grid, cudaStream_t stream) {
     }
 }
 
-template <int HIST, int D, bool C1>
+template <int NW, int HIST, int D, bool C1>
 int launch_vert_one(const ScanParams &p, int grid, cudaStream_t stream) {
-    auto kern = k_scan_vert<HIST, D, C1>;
+    auto kern = k_scan_vert<NW, HIST, D, C1>;
     PGX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.L.total));
     kern<<<grid, kScanThreads, p.L.total, stream>>>(p);
     PGX_CUDA(cudaGetLastError());
     return PGX_OK;
 }
 
-template <int HIST>
+template <int NW, int HIST>
 int launch_vert(const ScanParams &p, int grid, cudaStream_t stream) {
     const bool c1 = p.n_classes && p.cls_thr[0] <= 1u;
     switch (p.n_classes) {
         case 0:
-            if constexpr (HIST != 0) return launch_vert_one<1, 0, false>(p, grid, stream);
+            if constexpr (HIST != 0) return launch_vert_one<NW, 1, 0, false>(p, grid, stream);
             return fail(PGX_ERR_INVALID, "k_scan_vert without a counter");
-        case 1: return c1 ? launch_vert_one<HIST, 1, true>(p, grid, stream) : launch_vert_one<HIST, 1, false>(p, grid, stream);
-        case 2: return c1 ? launch_vert_one<HIST, 2, true>(p, grid, stream) : launch_vert_one<HIST, 2, false>(p, grid, stream);
-        default: return c1 ? launch_vert_one<HIST, 3, true>(p, grid, stream) : launch_vert_one<HIST, 3, false>(p, grid, stream);
+        case 1: return c1 ? launch_vert_one<NW, HIST, 1, true>(p, grid, stream) : launch_vert_one<NW, HIST, 1, false>(p, grid, stream);
+        case 2:
+            if constexpr (NW == 1 || HIST == 0)
+                return c1 ? launch_vert_one<NW, HIST, 2, true>(p, grid, stream) : launch_vert_one<NW, HIST, 2, false>(p, grid, stream);
+            break;
+        default:
+            if constexpr (NW == 1)
+                return c1 ? launch_vert_one<NW, HIST, 3, true>(p, grid, stream) : launch_vert_one<NW, HIST, 3, false>(p, grid, stream);
+            break;
     }
+    return fail(PGX_ERR_INVALID, "k_scan_vert: too many counters for two-word rows");
 }
 
 int launch_scan(const ScanParams &p, bool quorum, int grid, cudaStream_t stream) {
-    if (p.flags & kVertical) return (p.flags & kHistCount) ? launch_vert<1>(p, grid, stream) : launch_vert<0>(p, grid, stream);
+    if (p.flags & kVertical) {
+        if (p.Wp == 1u) return (p.flags & kHistCount) ? launch_vert<1, 1>(p, grid, stream) : launch_vert<1, 0>(p, grid, stream);
+        return (p.flags & kHistCount) ? launch_vert<2, 1>(p, grid, stream) : launch_vert<2, 0>(p, grid, stream);
+    }
     if (p.flags & kPrivate) return p.L.priv_cw == 1u ? launch_priv<1, false>(p, grid, stream) : launch_priv<2, true>(p, grid, stream);
     if (quorum) return launch_one<true, 0, true>(p, grid, stream);
     if (p.Wp == 1u) return launch_one<false, -1, true>(p, grid, stream);
