@@ -394,7 +394,12 @@ int ensure_planes(pgx_abacus *a) {
     if (!a->d_uniform_w) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_uniform_w), a->gm_stride * 8u));
     if (!a->d_plane_mask) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_plane_mask), a->gm_stride * 4u));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a->d_planes), std::max<size_t>((size_t)np, 1) * a->gm_stride * 8u));
-    int rc = sort_items_by_weight(a->d_weight, a->n_rows, a->d_perm, a->d_sorted_w, a->stream);
+    // among equal weights the items are ordered by coverage when that is known: half the nodes of a pangenome are 1 bp
+    // long, and inside such a run k_gm_quorum's warps then hold items of one coverage class (see ensure_gm_cov)
+    const char *cs = getenv("PGX_GM_COVSORT");
+    a->planes_cov_order = a->countable_valid && a->d_countable != nullptr && !(cs && !strcmp(cs, "0"));
+    int rc = sort_items_by_weight(a->d_weight, a->n_rows, a->d_perm, a->d_sorted_w, a->stream,
+                                  a->planes_cov_order ? a->d_countable : nullptr);
     if (rc) return rc;
     if ((rc = launch_transpose(a->d_bitmap, a->n_rows, a->G, a->Wp, a->d_gm_w, a->gm_stride, a->d_perm, a->stream))) return rc;
     if ((rc = launch_weight_planes(a->d_sorted_w, a->n_rows, a->d_planes, a->gm_stride, np, a->d_uniform_w, a->d_plane_mask, 0,
@@ -503,7 +508,16 @@ int gm_growth_launch(pgx_abacus *a, uint32_t n_orders, const uint32_t *d_orders,
         return gm_growth_launch_legacy(a, n_orders, d_orders, ts, cov, thr, weighted, d_out_base, out_order_stride);
     int rc;
     const bool sorted = w && a->d_weight != nullptr;  // weight-sorted item order: uniform-weight columns are the rule
-    if (sorted && (rc = ensure_planes(a))) return rc;
+    if (sorted) {
+        // bp sums with coverage cutoffs over several orders: rebuild the weight-sorted copy once with the coverage as the tie
+        // order (it may have been derived before the coverages were known, e.g. by a weighted similarity call)
+        bool any_cut = false;
+        for (uint32_t t : gen) any_cut |= cov[t] > 1u;
+        const char *cs = getenv("PGX_GM_COVSORT");
+        if (a->planes_valid && !a->planes_cov_order && any_cut && a->countable_valid && n_orders >= 4u && !(cs && !strcmp(cs, "0")))
+            a->planes_valid = false;
+        if ((rc = ensure_planes(a))) return rc;
+    }
     // counting, general thresholds with coverage cutoffs > 1, several orders: run on the coverage-sorted copy, where whole
     // warps hold only items below a cutoff and skip that threshold's rank comparison (or the ranks altogether).  One sort +
     // one permuted transpose per graph, so only when the work is repeated (PGX_GM_COVSORT=0 / 1: never / always).

@@ -921,27 +921,52 @@ int launch_weight_planes(const uint32_t *weight, uint64_t n_rows, uint64_t *plan
     return PGX_OK;
 }
 
-// perm[i] = item at sorted position i (weights descending), sorted_w[i] = its weight
-int sort_items_by_weight(const uint32_t *weight, uint64_t n_rows, uint32_t *perm, uint32_t *sorted_w, cudaStream_t stream) {
-    uint32_t *keys = nullptr, *vals = nullptr;
+__global__ void __launch_bounds__(256) k_gather_keys(const uint32_t *__restrict__ weight, const uint32_t *__restrict__ order,
+                                                     uint64_t n_rows, uint32_t *__restrict__ keys) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    if (i < n_rows) {
+        const uint32_t item = order[i];
+        keys[i] = item ? __ldg(weight + item) : 0u;  // the dummy item sorts with the zero weights
+    }
+}
+
+// perm[i] = item at sorted position i (weights descending), sorted_w[i] = its weight.  secondary != nullptr: items of
+// equal weight are ordered by that key (descending) -- two passes of the stable radix sort, the secondary key first.
+int sort_items_by_weight(const uint32_t *weight, uint64_t n_rows, uint32_t *perm, uint32_t *sorted_w, cudaStream_t stream,
+                         const uint32_t *secondary) {
+    uint32_t *keys = nullptr, *vals = nullptr, *vals2 = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
     const int64_t n = (int64_t)n_rows;  // CUB takes a 64-bit count: n_rows may exceed 2^31
     auto cleanup = [&]() {
         cudaFree(keys);
         cudaFree(vals);
+        cudaFree(vals2);
         cudaFree(tmp);
     };
     cudaError_t e;
     if ((e = cudaMalloc(reinterpret_cast<void **>(&keys), n_rows * 4u)) != cudaSuccess ||
-        (e = cudaMalloc(reinterpret_cast<void **>(&vals), n_rows * 4u)) != cudaSuccess) {
+        (e = cudaMalloc(reinterpret_cast<void **>(&vals), n_rows * 4u)) != cudaSuccess ||
+        (secondary && (e = cudaMalloc(reinterpret_cast<void **>(&vals2), n_rows * 4u)) != cudaSuccess)) {
         cleanup();
         return fail(PGX_ERR_NOMEM, cudaGetErrorString(e));
     }
-    k_sort_keys<<<(unsigned)((n_rows + 255u) / 256u), 256, 0, stream>>>(weight, n_rows, keys, vals);
+    const unsigned blocks = (unsigned)((n_rows + 255u) / 256u);
     e = cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, keys, sorted_w, vals, perm, n, 0, 32, stream);
     if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
-    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, keys, sorted_w, vals, perm, n, 0, 32, stream);
+    if (e == cudaSuccess && secondary) {
+        // pass 1: by the secondary key (sorted_w doubles as the scratch output for the sorted keys)
+        k_sort_keys<<<blocks, 256, 0, stream>>>(secondary, n_rows, keys, vals);
+        e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, keys, sorted_w, vals, vals2, n, 0, 32, stream);
+        // pass 2: by weight, stable: the order of pass 1 survives among equal weights
+        if (e == cudaSuccess) {
+            k_gather_keys<<<blocks, 256, 0, stream>>>(weight, vals2, n_rows, keys);
+            e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, keys, sorted_w, vals2, perm, n, 0, 32, stream);
+        }
+    } else if (e == cudaSuccess) {
+        k_sort_keys<<<blocks, 256, 0, stream>>>(weight, n_rows, keys, vals);
+        e = cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, keys, sorted_w, vals, perm, n, 0, 32, stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cleanup();
     if (e != cudaSuccess) {

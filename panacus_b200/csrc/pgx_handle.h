@@ -38,6 +38,7 @@ struct pgx_abacus {
     uint32_t *d_plane_mask = nullptr;
     uint32_t n_planes = 0;
     bool planes_valid = false;
+    bool planes_cov_order = false;  // items of equal weight are ordered by coverage (k_gm_quorum's warp-uniform skips)
 
     // general-quorum growth under many orders (counting): a third group-major copy with the items sorted by coverage,
     // so that whole warps of k_gm_quorum hold only items below a threshold's coverage cutoff and skip its rank logic

@@ -116,7 +116,8 @@ int launch_scan(const ScanParams &p, bool quorum, int grid, cudaStream_t stream)
 uint64_t gm_stride_words(uint64_t n_rows);
 int launch_transpose(const uint64_t *bitmap, uint64_t n_rows, uint32_t G, uint32_t Wp, uint64_t *gm,
                      uint64_t gm_stride, const uint32_t *perm /*nullptr = natural item order*/, cudaStream_t stream);
-int sort_items_by_weight(const uint32_t *weight, uint64_t n_rows, uint32_t *perm, uint32_t *sorted_w, cudaStream_t stream);
+int sort_items_by_weight(const uint32_t *weight, uint64_t n_rows, uint32_t *perm, uint32_t *sorted_w, cudaStream_t stream,
+                         const uint32_t *secondary = nullptr);  // secondary: tie order among equal weights (descending)
 
 struct GmGrowthParams {
     const uint64_t *gm;      // G x gm_stride
