@@ -259,10 +259,15 @@ __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : ((T <= 2 && !WEIGHT
         }
       }
       };
-      if (P >= 4 && jend + 1u < (1u << (P - 2)))
-          block(std::integral_constant<int, (P >= 4 ? P - 2 : P)>{});
-      else if (P >= 4 && jend + 1u < (1u << (P - 1)))
-          block(std::integral_constant<int, (P >= 4 ? P - 1 : P)>{});
+      // Three instantiations of the block triple the loop's code.  Counting with T <= 2 gains from it (19.4 -> 18.6 ms at
+      // c3); the larger weighted body then no longer fits the instruction cache -- ncu: "no_instruction" became the top
+      // stall and the kernel went from 8.0 to 10.1 ms per 20 orders (profiles/r2b_quorum_ncu_summary.txt) -- so only the
+      // small bodies skip planes.
+      constexpr bool kSkipPlanes = !WEIGHTED && T <= 2 && P >= 4;
+      if (kSkipPlanes && jend + 1u < (1u << (P - 2)))
+          block(std::integral_constant<int, (kSkipPlanes ? P - 2 : P)>{});
+      else if (kSkipPlanes && jend + 1u < (1u << (P - 1)))
+          block(std::integral_constant<int, (kSkipPlanes ? P - 1 : P)>{});
       else
           block(std::integral_constant<int, P>{});
       if (jb + lane < jend) {  // lane l holds the warp sums of position jb + l
