@@ -28,6 +28,12 @@
 #include "pgx_internal.h"
 #include "pgx_rank.cuh"
 
+// rows in flight per thread for counting with T <= 2 (tools/gpu_run38.sh compiles the variant on the GPU box): 4 -> 18.39 ms,
+// 8 -> 19.78 ms at c3 (80 registers, 32 bytes of spills)
+#ifndef PGX_QUORUM_PREFETCH
+#define PGX_QUORUM_PREFETCH 4
+#endif
+
 namespace pgx {
 
 namespace {
@@ -72,7 +78,8 @@ template <int P, int T, int NF, bool WEIGHTED>
 __global__ void __launch_bounds__(kQThreads, (P >= 16) ? 1 : ((T <= 2 && !WEIGHTED && P <= 10) ? 3 : 2)) k_gm_quorum(const __grid_constant__ GmGrowthParams p) {
     static_assert(T >= 1 && T <= (int)kGmQuorumMaxT && NF == 1, "1..4 general thresholds and at most one q = 0 rider");
     constexpr int PP = RankMaskWords<P>::value;
-    constexpr int kPrefetch = 4;  // rows in flight per thread (divides 32); a single order streams from DRAM, many orders from L2
+    // rows in flight per thread (divides 32, at most 8: the padding of s_off); a single order streams from DRAM, many orders from L2
+    constexpr int kPrefetch = (!WEIGHTED && T <= 2) ? PGX_QUORUM_PREFETCH : 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *s_mask = reinterpret_cast<uint32_t *>(smem_raw);  // [G][T][PP]
     // byte offset of the row added at position j (+ 8 entries repeating the last row: the prefetch needs no bounds check)
