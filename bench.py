@@ -294,6 +294,31 @@ class Ctx:
     pass
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """N > 1: run this rank (and allocate its page-locked tables) on the NUMA node its GPU hangs off, so that eight ranks'
+    uploads do not cross the inter-socket link.  Best effort: returns the node, or None when it cannot be determined / the
+    node's CPUs are not in this process' affinity mask / PGX_BENCH_NUMA=0."""
+    if os.environ.get("PGX_BENCH_NUMA") == "0":
+        return None
+    try:
+        prop = torch.cuda.get_device_properties(local)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def setup_gpu(args):
     import torch
     import torch.distributed as dist
@@ -306,6 +331,7 @@ def setup_gpu(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(c.local)
     c.dev = torch.device("cuda", c.local)
+    c.numa_node = bind_to_gpu_numa_node(torch, c.local) if c.world > 1 else None
     if c.world > 1:
         dist.init_process_group("nccl", device_id=c.dev)
     # one explicit (non-default) stream carries the kernels, the events that time them and the exchange
@@ -540,6 +566,7 @@ def run_ordered(args):
             hc3, _, cv3 = b.hist_ordered_growth(cov, None, weighted=False)  # (collective with the fused exchange: every rank)
             e2e = {"value": cells_per_step * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(items.nbytes + prefsum.nbytes + path_group.nbytes),
                    "d2h_bytes_per_step": int((2 * (G + 1) + G) * 8), "steps": n_e2e, "seam": "ItemTable (same as the reference arm)",
+                   "numa_node_of_rank0": c.numa_node,
                    "item_table_steps": int(items.size), "ids": "u32, page-locked host memory",
                    "build_steps_per_s": float(items.size) / dt_build, "build": build_info,
                    "api": "pgx_abacus_clear + pgx_abacus_build_u32 (chunked H2D overlapped with k_build) + pgx_hist_ordered_growth"}
