@@ -3,13 +3,19 @@
 // (reference src/graph_broker/abacus.rs:719-787) and AbacusByGroup::calc_growth (abacus.rs:989-1032).
 //
 // Structure (one persistent CTA per SM slot, 8 scanning warps + 1 TMA producer warp):
-//   producer lane : 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) of `tile_items` bitmap rows
-//                   (+ their u32 weights) into a ring of shared-memory stages, completion on mbarriers
-//   consumers     : one thread per item; 128-bit shared loads in a per-lane rotated chunk order
-//                   (bank-conflict free for any row width), popcount -> coverage, first set bit ->
-//                   growth column, 32-bit shared atomics into per-CTA accumulators
-//   epilogue      : per-CTA accumulators -> global u64 accumulators (RED.64); the last CTA snapshots
-//                   them into `out` and re-zeroes accumulators + ticket (self-cleaning, one launch)
+//   producer lane : tiles from a global counter (a CTA's first one is blockIdx.x); 1-D TMA bulk copies
+//                   (cp.async.bulk, SASS UBLKCP) of `tile_items` bitmap rows (+ their u32 weights)
+//                   into a ring of shared-memory stages, completion on mbarriers (scan_producer)
+//   consumers     : k_scan       one thread per item; 128-bit shared loads in a per-lane rotated chunk
+//                                order (bank-conflict free for any row width), popcount -> coverage,
+//                                first set bit -> growth column, 32-bit shared atomics
+//                   k_scan_priv  G <~ 300: lane-private narrow counters instead of the atomics
+//                   k_scan_vert  G <= 128, counting: bit-sliced vertical counters (carry-save adders
+//                                over one-hot words), no atomics in the loop
+//   epilogue      : single GPU: CTA 0 zeroes the result vector and publishes an epoch, every CTA adds
+//                   its sums straight into it (RED.64) -- the end of the kernel is the end of the pass;
+//                   multi-GPU exchange: global accumulators, completion ticket, the last CTA pushes the
+//                   vector to its peers over NVLink and sums their slots (scan_epilogue)
 //
 // Integer-only, HBM-bandwidth-bound: algorithmic bytes per item = W*8 (+4 weighted).
 #include <algorithm>
