@@ -35,8 +35,12 @@ void DeviceAbacus::build(const ItemTables &t, const std::vector<std::pair<uint64
         if (group_names.empty() || group_names.back() != po.second) group_names.push_back(po.second);
         path_group[po.first] = (int64_t)group_names.size() - 1;
     }
-    check(pgx_abacus_build(H(h_), t.items.data(), t.items.size(), t.id_prefsum.data(), path_group.size(), path_group.data(), ex),
-          "pgx_abacus_build");
+    if (t.items32)  // lean parse: u32 ids, half the bytes on the wire and no narrowing pass
+        check(pgx_abacus_build_u32(H(h_), t.items32, t.n_steps, t.id_prefsum.data(), path_group.size(), path_group.data(), ex),
+              "pgx_abacus_build_u32");
+    else
+        check(pgx_abacus_build(H(h_), t.items.data(), t.items.size(), t.id_prefsum.data(), path_group.size(), path_group.data(), ex),
+              "pgx_abacus_build");
 }
 
 void DeviceAbacus::csr(const ItemTables &t, const std::vector<std::pair<uint64_t, std::string>> &path_order,

@@ -1,9 +1,16 @@
 // gfa.cpp -- GFA front end, PanSN path names, grouping / ordering, subset / exclude bookkeeping.
 // Semantics follow the reference (marschall-lab/panacus @ 395ba41); every function cites what it mirrors.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <regex>
@@ -21,36 +28,55 @@ namespace {
 
 constexpr uint64_t kUsizeMax = ~0ull;
 
-// whole file into memory (transparently gunzips, like io.rs:23-33)
-std::string slurp(const std::string &path) {
-    {  // plain (not gzip) files: one read into the buffer instead of zlib's pass-through copies
-        std::ifstream in(path, std::ios::binary);
-        if (!in) throw Error("cannot open " + path);
-        unsigned char magic[2] = {0, 0};
-        in.read(reinterpret_cast<char *>(magic), 2);
-        if (!(in.gcount() == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
-            in.clear();
-            in.seekg(0, std::ios::end);
-            const std::streamoff size = in.tellg();
-            if (size >= 0) {
-                std::string data((size_t)size, '\0');
-                in.seekg(0);
-                in.read(data.data(), size);
-                if (in.gcount() != size) throw Error("read error in " + path);
-                return data;
-            }
+// The whole file as one read-only byte range.  Plain files are mapped (no copy: the page cache is the buffer; reading
+// 1.25 GB into a zero-filled std::string was 0.5-1.2 s of the chr22-sized parse); gzip files are inflated into memory
+// (transparently, like io.rs:23-33).
+struct FileData {
+    const char *ptr = nullptr;
+    size_t len = 0;
+    std::string owned;
+    void *map = nullptr;
+    FileData() = default;
+    FileData(const FileData &) = delete;
+    FileData &operator=(const FileData &) = delete;
+    ~FileData() {
+        if (map) munmap(map, len);
+    }
+};
+
+void load_file(const std::string &path, FileData &f) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw Error("cannot open " + path);
+    unsigned char magic[2] = {0, 0};
+    const ssize_t got = pread(fd, magic, 2, 0);
+    struct stat st;
+    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (!gz && fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+        if (st.st_size == 0) {
+            close(fd);
+            return;
+        }
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, (size_t)st.st_size, MADV_WILLNEED);
+            close(fd);
+            f.map = m;
+            f.ptr = static_cast<const char *>(m);
+            f.len = (size_t)st.st_size;
+            return;
         }
     }
-    gzFile f = gzopen(path.c_str(), "rb");
-    if (!f) throw Error("cannot open " + path);
-    std::string data;
+    close(fd);
+    gzFile z = gzopen(path.c_str(), "rb");  // (also reads plain data: pipes, files that could not be mapped)
+    if (!z) throw Error("cannot open " + path);
     std::vector<char> buf(1 << 20);
     int n;
-    while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)n);
+    while ((n = gzread(z, buf.data(), (unsigned)buf.size())) > 0) f.owned.append(buf.data(), (size_t)n);
     const bool bad = n < 0;
-    gzclose(f);
+    gzclose(z);
     if (bad) throw Error("read error in " + path);
-    return data;
+    f.ptr = f.owned.data();
+    f.len = f.owned.size();
 }
 
 std::vector<std::string> split(const std::string &s, char sep) {
@@ -322,6 +348,45 @@ uint64_t GraphStorage::edge_key(uint32_t u, bool fu, uint32_t v, bool fv) {
 
 namespace {
 
+int g_host_threads = 0;  // 0 = hardware concurrency
+
+// fn(k) for k in [0, n) on `nthreads` threads, work handed out through an atomic counter (the units differ a lot in
+// size); the first exception stops the hand-out and is rethrown on the caller's thread
+template <typename F>
+void parallel_for(size_t n, unsigned nthreads, F fn) {
+    nthreads = std::max(1u, std::min<unsigned>({nthreads, 32u, (unsigned)std::max<size_t>(n, 1)}));
+    if (nthreads == 1) {
+        for (size_t k = 0; k < n; ++k) fn(k);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::mutex err_mu;
+    std::string err;
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= n) return;
+                try {
+                    fn(k);
+                } catch (const std::exception &e) {
+                    std::lock_guard<std::mutex> lock(err_mu);
+                    if (err.empty()) err = e.what();
+                    next.store(n);
+                    return;
+                }
+            }
+        });
+    for (auto &th : pool) th.join();
+    if (!err.empty()) throw Error(err);
+}
+
+// -t N is taken literally; the default is one thread per core for inputs worth the thread start-up
+unsigned host_threads(bool big_input) {
+    return g_host_threads > 0 ? (unsigned)g_host_threads : (big_input ? std::max(1u, std::thread::hardware_concurrency()) : 1u);
+}
+
 // Segment name -> item id (1-based, S-line order).  Real pangenome GFAs (pggb, minigraph-cactus) name their segments
 // with decimal integers: then the lookup is a direct table indexed by the value, filled and read without hashing
 // (one hash probe per path step is what dominated the parse: ~260 ns per step in a 1M-entry map).  Any other naming
@@ -345,29 +410,49 @@ struct NodeIndex {
         return true;
     }
 
-    void build(const std::vector<std::string_view> &names) {
-        uint64_t mx = 0;
-        numeric = !names.empty();
-        for (auto &nm : names) {
-            uint64_t v;
-            if (!parse_canonical(nm.data(), nm.data() + nm.size(), v)) {
-                numeric = false;
-                break;
+    void build(const std::vector<std::string_view> &names, unsigned nthreads) {
+        const size_t n = names.size();
+        numeric = n != 0;
+        // every name parsed once, in slices on the worker threads: value (or "not a canonical decimal") and the maximum
+        std::vector<uint64_t> vals(n);
+        const size_t n_slices = std::max<size_t>(1, std::min<size_t>((size_t)nthreads * 4u, n / 65536u + 1u));
+        const size_t per = (n + n_slices - 1) / std::max<size_t>(n_slices, 1);
+        std::vector<uint64_t> slice_max(n_slices, 0);
+        std::vector<uint8_t> slice_ok(n_slices, 1);
+        parallel_for(n_slices, nthreads, [&](size_t c) {
+            uint64_t mx = 0;
+            for (size_t i = c * per; i < std::min(n, (c + 1) * per); ++i) {
+                uint64_t v;
+                if (!parse_canonical(names[i].data(), names[i].data() + names[i].size(), v)) {
+                    slice_ok[c] = 0;
+                    return;
+                }
+                vals[i] = v;
+                mx = std::max(mx, v);
             }
-            mx = std::max(mx, v);
+            slice_max[c] = mx;
+        });
+        uint64_t mx = 0;
+        for (size_t c = 0; c < n_slices; ++c) {
+            numeric = numeric && slice_ok[c];
+            mx = std::max(mx, slice_max[c]);
         }
-        if (numeric && mx > 8ull * names.size() + (1ull << 20)) numeric = false;  // sparse numbering: the table would be mostly holes
+        if (numeric && mx > 8ull * n + (1ull << 20)) numeric = false;  // sparse numbering: the table would be mostly holes
         if (numeric) {
             num2id.assign(mx + 1, 0u);
-            for (size_t i = 0; i < names.size(); ++i) {
-                uint64_t v = 0;
-                parse_canonical(names[i].data(), names[i].data() + names[i].size(), v);
-                if (num2id[v]) throw Error("Segment with ID " + std::string(names[i]) + " occurs multiple times in GFA");
-                num2id[v] = (uint32_t)i + 1u;
-            }
+            // distinct values hit distinct slots, so the slices can fill the table concurrently; a duplicate name is two
+            // writers of one slot, one of which loses: the verification pass finds the loser
+            parallel_for(n_slices, nthreads, [&](size_t c) {
+                for (size_t i = c * per; i < std::min(n, (c + 1) * per); ++i) num2id[vals[i]] = (uint32_t)i + 1u;
+            });
+            parallel_for(n_slices, nthreads, [&](size_t c) {
+                for (size_t i = c * per; i < std::min(n, (c + 1) * per); ++i)
+                    if (num2id[vals[i]] != (uint32_t)i + 1u)
+                        throw Error("Segment with ID " + std::string(names[i]) + " occurs multiple times in GFA");
+            });
         } else {
-            name2id.reserve(names.size() * 2);
-            for (size_t i = 0; i < names.size(); ++i)
+            name2id.reserve(n * 2);
+            for (size_t i = 0; i < n; ++i)
                 if (!name2id.emplace(names[i], (uint32_t)i + 1u).second)
                     throw Error("Segment with ID " + std::string(names[i]) + " occurs multiple times in GFA");
         }
@@ -425,43 +510,63 @@ void parse_walk_steps(const NodeIndex &idx, const char *b, const char *e, std::v
     }
 }
 
-int g_host_threads = 0;  // 0 = hardware concurrency
-
-// fn(k) for k in [0, n) on `nthreads` threads, work handed out through an atomic counter (the units differ a lot in
-// size); the first exception stops the hand-out and is rethrown on the caller's thread
-template <typename F>
-void parallel_for(size_t n, unsigned nthreads, F fn) {
-    nthreads = std::max(1u, std::min<unsigned>({nthreads, 32u, (unsigned)std::max<size_t>(n, 1)}));
-    if (nthreads == 1) {
-        for (size_t k = 0; k < n; ++k) fn(k);
-        return;
+// ---- lean variants: node ids only (same tokenisation as the two functions above) -------------------------------------
+uint64_t count_path_steps(const char *b, const char *e) {  // non-empty comma separated tokens
+    uint64_t n = 0;
+    bool in_token = false;
+    for (const char *s = b; s < e; ++s) {
+        const bool sep = *s == ',';
+        n += (!sep && !in_token) ? 1u : 0u;
+        in_token = !sep;
     }
-    std::atomic<size_t> next{0};
-    std::mutex err_mu;
-    std::string err;
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < nthreads; ++t)
-        pool.emplace_back([&] {
-            for (;;) {
-                const size_t k = next.fetch_add(1);
-                if (k >= n) return;
-                try {
-                    fn(k);
-                } catch (const std::exception &e) {
-                    std::lock_guard<std::mutex> lock(err_mu);
-                    if (err.empty()) err = e.what();
-                    next.store(n);
-                    return;
-                }
-            }
-        });
-    for (auto &th : pool) th.join();
-    if (!err.empty()) throw Error(err);
+    return n;
 }
 
-// -t N is taken literally; the default is one thread per core for inputs worth the thread start-up
-unsigned host_threads(bool big_input) {
-    return g_host_threads > 0 ? (unsigned)g_host_threads : (big_input ? std::max(1u, std::thread::hardware_concurrency()) : 1u);
+uint64_t count_walk_steps(const char *b, const char *e) {  // '>' / '<' followed by a non-empty name
+    uint64_t n = 0;
+    for (const char *s = b; s < e;) {
+        const char *q = s + 1;
+        while (q < e && *q != '>' && *q != '<') ++q;
+        if (q > s + 1) ++n;
+        s = q;
+    }
+    return n;
+}
+
+uint64_t parse_path_nodes(const NodeIndex &idx, const char *b, const char *e, uint32_t *out) {
+    uint64_t n = 0;
+    const char *s = b;
+    while (s < e) {
+        if (idx.numeric) {
+            uint64_t v = 0;
+            const char *q = s;
+            while (q < e && (unsigned)(*q - '0') <= 9u && q - s < 18) v = v * 10u + (unsigned)(*q++ - '0');
+            if (q > s && q < e && (*q == '+' || *q == '-') && !(q - s > 1 && *s == '0') && (q + 1 == e || q[1] == ',')) {
+                const uint32_t id = v < idx.num2id.size() ? idx.num2id[v] : 0u;
+                if (!id) throw Error("unknown node " + std::string(s, (size_t)(q - s)));
+                out[n++] = id;
+                s = q + 2;
+                continue;
+            }
+        }
+        const void *t = memchr(s, ',', (size_t)(e - s));
+        const char *te = t ? (const char *)t : e;
+        if (te > s) out[n++] = idx.get(s, te - 1);
+        s = te + 1;
+    }
+    return n;
+}
+
+uint64_t parse_walk_nodes(const NodeIndex &idx, const char *b, const char *e, uint32_t *out) {
+    uint64_t n = 0;
+    const char *s = b;
+    while (s < e) {
+        const char *q = s + 1;
+        while (q < e && *q != '>' && *q != '<') ++q;
+        if (q > s + 1) out[n++] = idx.get(s + 1, q);
+        s = q;
+    }
+    return n;
 }
 
 }  // namespace
@@ -469,19 +574,53 @@ unsigned host_threads(bool big_input) {
 void set_host_threads(int n) { g_host_threads = n > 0 ? n : 0; }
 unsigned host_thread_budget() { return host_threads(true); }
 
-GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bool with_names) {
+GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bool with_names, bool lean) {
     GraphStorage g;
     g.node_lens.push_back(0);
     g.has_edges = with_edges;
-    const std::string data = slurp(path);
-    const char *base = data.data();
-    std::vector<std::pair<size_t, size_t>> lines;  // [begin, end) without the newline
-    for (size_t i = 0; i < data.size();) {
-        const void *nl = memchr(base + i, '\n', data.size() - i);
-        const size_t j = nl ? (size_t)((const char *)nl - base) : data.size();
-        if (j > i) lines.emplace_back(i, j);
-        i = j + 1;
+    const bool tm = getenv("PGX_PARSE_TIMING") != nullptr;  // stage times on stderr (measurement aid)
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!tm) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "from_gfa %s: %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    FileData file;
+    load_file(path, file);
+    const char *base = file.ptr;
+    const size_t size = file.len;
+    const unsigned nt = host_threads(size >= (8u << 20));
+    lap("open / map file");
+    // line index: every thread collects the newlines of its slice of the file; the [begin, end) pairs (without the
+    // newline, empty lines dropped) are then strung together in file order
+    std::vector<std::pair<size_t, size_t>> lines;
+    {
+        const size_t n_slices = std::max<size_t>(1, std::min<size_t>((size_t)nt * 4u, size / (1u << 20) + 1u));
+        const size_t slice = (size + n_slices - 1) / n_slices;
+        std::vector<std::vector<size_t>> nls(n_slices);
+        parallel_for(n_slices, nt, [&](size_t c) {
+            const size_t lo = c * slice, hi = std::min(size, lo + slice);
+            for (size_t i = lo; i < hi;) {
+                const void *nl = memchr(base + i, '\n', hi - i);
+                if (!nl) break;
+                const size_t j = (size_t)((const char *)nl - base);
+                nls[c].push_back(j);
+                i = j + 1;
+            }
+        });
+        size_t total = 0;
+        for (auto &v : nls) total += v.size();
+        lines.reserve(total + 1);
+        size_t prev = 0;
+        for (auto &v : nls)
+            for (size_t j : v) {
+                if (j > prev) lines.emplace_back(prev, j);
+                prev = j + 1;
+            }
+        if (prev < size) lines.emplace_back(prev, size);
     }
+    lap("line index");
     auto field = [&](size_t b, size_t e, int k, size_t &fb, size_t &fe) -> bool {  // k-th TAB separated field
         size_t s = b;
         for (int c = 0; c < k; ++c) {
@@ -492,46 +631,76 @@ GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bo
         const void *t = memchr(base + s, '\t', e - s);
         fb = s;
         fe = t ? (size_t)((const char *)t - base) : e;
-        while (fe > fb && data[fe - 1] == '\r') --fe;
+        while (fe > fb && base[fe - 1] == '\r') --fe;
         return true;
     };
-    // pass 1: segments and path names (graph.rs:308-375); ids follow the S-line order
+    // pass 1: segments and path names (graph.rs:308-375); ids follow the S-line order.  Blocks of lines are scanned on
+    // the worker threads and their finds concatenated in file order.
     std::vector<std::string_view> names;
     std::vector<size_t> path_lines;  // indices into `lines` of the P / W lines, file order
-    for (size_t li = 0; li < lines.size(); ++li) {
-        const auto &ln = lines[li];
-        const char tag = data[ln.first];
-        size_t fb, fe;
-        if (tag == 'S') {
-            if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed S line");
-            names.emplace_back(base + fb, fe - fb);
-            size_t sb, se;
-            uint32_t len = 0;
-            if (field(ln.first, ln.second, 2, sb, se)) len = (uint32_t)(se - sb);
-            g.node_lens.push_back(len);
-        } else if (tag == 'P') {
-            if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed P line");
-            g.path_segments.push_back(PathSegment::from_str(data.substr(fb, fe - fb)));
-            path_lines.push_back(li);
-        } else if (tag == 'W') {
-            std::string f[6];
-            for (int k = 1; k <= 5; ++k) {
-                if (!field(ln.first, ln.second, k, fb, fe)) throw Error("malformed W line");
-                f[k] = data.substr(fb, fe - fb);
+    {
+        struct Found {
+            std::vector<std::string_view> names;
+            std::vector<uint32_t> lens;
+            std::vector<size_t> path_lines;
+            std::vector<PathSegment> segs;
+        };
+        const size_t n_blocks = std::max<size_t>(1, std::min<size_t>((size_t)nt * 8u, lines.size() / 4096u + 1u));
+        const size_t per = (lines.size() + n_blocks - 1) / n_blocks;
+        std::vector<Found> found(n_blocks);
+        parallel_for(n_blocks, nt, [&](size_t blk) {
+            Found &f = found[blk];
+            const size_t lo = blk * per, hi = std::min(lines.size(), lo + per);
+            for (size_t li = lo; li < hi; ++li) {
+                const auto &ln = lines[li];
+                const char tag = base[ln.first];
+                size_t fb, fe;
+                if (tag == 'S') {
+                    if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed S line");
+                    f.names.emplace_back(base + fb, fe - fb);
+                    size_t sb, se;
+                    uint32_t len = 0;
+                    if (field(ln.first, ln.second, 2, sb, se)) len = (uint32_t)(se - sb);
+                    f.lens.push_back(len);
+                } else if (tag == 'P') {
+                    if (!field(ln.first, ln.second, 1, fb, fe)) throw Error("malformed P line");
+                    f.segs.push_back(PathSegment::from_str(std::string(base + fb, fe - fb)));
+                    f.path_lines.push_back(li);
+                } else if (tag == 'W') {
+                    std::string w[6];
+                    for (int k = 1; k <= 5; ++k) {
+                        if (!field(ln.first, ln.second, k, fb, fe)) throw Error("malformed W line");
+                        w[k] = std::string(base + fb, fe - fb);
+                    }
+                    PathSegment ps;  // util.rs:368-398
+                    ps.sample = w[1];
+                    ps.haplotype = w[2];
+                    ps.seqid = w[3];
+                    if (w[4] != "*") ps.start = std::stoull(w[4]);
+                    if (w[5] != "*") ps.end = std::stoull(w[5]);
+                    f.segs.push_back(ps);
+                    f.path_lines.push_back(li);
+                }
             }
-            PathSegment p;  // util.rs:368-398
-            p.sample = f[1];
-            p.haplotype = f[2];
-            p.seqid = f[3];
-            if (f[4] != "*") p.start = std::stoull(f[4]);
-            if (f[5] != "*") p.end = std::stoull(f[5]);
-            g.path_segments.push_back(p);
-            path_lines.push_back(li);
+        });
+        size_t n_seg = 0, n_path = 0;
+        for (auto &f : found) n_seg += f.names.size(), n_path += f.path_lines.size();
+        names.reserve(n_seg);
+        g.node_lens.reserve(n_seg + 1);
+        path_lines.reserve(n_path);
+        g.path_segments.reserve(n_path);
+        for (auto &f : found) {
+            names.insert(names.end(), f.names.begin(), f.names.end());
+            g.node_lens.insert(g.node_lens.end(), f.lens.begin(), f.lens.end());
+            path_lines.insert(path_lines.end(), f.path_lines.begin(), f.path_lines.end());
+            for (auto &x : f.segs) g.path_segments.push_back(std::move(x));
         }
     }
+    lap("pass 1 (S / P / W lines)");
     if (names.size() >= (1u << 31)) throw Error("more than 2^31 segments are not supported");
     NodeIndex idx;
-    idx.build(names);
+    idx.build(names, nt);
+    lap("segment index");
     if (with_names) {
         g.node_names.reserve(names.size() + 1);
         g.node_names.emplace_back();
@@ -540,30 +709,59 @@ GraphStorage GraphStorage::from_gfa(const std::string &path, bool with_edges, bo
     // pass 1b: links (graph.rs:276-306)
     if (with_edges) {
         for (auto &ln : lines) {
-            if (data[ln.first] != 'L') continue;
+            if (base[ln.first] != 'L') continue;
             size_t b1, e1, b2, e2, b3, e3, b4, e4;
             if (!field(ln.first, ln.second, 1, b1, e1) || !field(ln.first, ln.second, 2, b2, e2) ||
                 !field(ln.first, ln.second, 3, b3, e3) || !field(ln.first, ln.second, 4, b4, e4))
                 throw Error("malformed L line");
-            const uint64_t e = canonical_edge(idx.get(base + b1, base + e1), data[b2] == '+', idx.get(base + b3, base + e3), data[b4] == '+');
+            const uint64_t e = canonical_edge(idx.get(base + b1, base + e1), base[b2] == '+', idx.get(base + b3, base + e3), base[b4] == '+');
             g.edge2id.emplace(e, (uint32_t)g.edge2id.size() + 1);  // no-op if the edge is already known
         }
+        lap("links");
     }
-    // pass 2: steps.  Every P / W line is independent and the index is read-only: the lines are handed out to a few
-    // threads through an atomic counter (the lines of a pangenome differ a lot in length).
+    // pass 2: steps.  Every P / W line is independent and the index is read-only: the lines are handed out to the
+    // worker threads through an atomic counter (the lines of a pangenome differ a lot in length).
+    auto steps_field = [&](size_t k, size_t &fb, size_t &fe) -> bool {  // the step list of path line k; true: P line
+        const auto &ln = lines[path_lines[k]];
+        const bool is_p = base[ln.first] == 'P';
+        if (!field(ln.first, ln.second, is_p ? 2 : 6, fb, fe)) throw Error(is_p ? "malformed P line" : "malformed W line");
+        return is_p;
+    };
+    if (lean) {
+        // Counting nodes / bp without subset or exclude lists only needs WHICH nodes a path visits: the ids go straight
+        // into one flat u32 array (the wire format of pgx_abacus_build_u32) -- no per-path vectors of (node, orientation),
+        // no u64 ItemTable copy, no narrowing pass: 4 bytes written per step instead of 8 + 8 + 4.
+        g.lean = true;
+        const size_t P = path_lines.size();
+        g.flat_prefsum.assign(P + 1, 0);
+        parallel_for(P, nt, [&](size_t k) {
+            size_t fb, fe;
+            const bool is_p = steps_field(k, fb, fe);
+            g.flat_prefsum[k + 1] = is_p ? count_path_steps(base + fb, base + fe) : count_walk_steps(base + fb, base + fe);
+        });
+        for (size_t k = 0; k < P; ++k) g.flat_prefsum[k + 1] += g.flat_prefsum[k];
+        g.flat_nodes.reset(new uint32_t[std::max<uint64_t>(1, g.flat_prefsum[P])]);  // (uninitialised: every word is written below)
+        parallel_for(P, nt, [&](size_t k) {
+            size_t fb, fe;
+            const bool is_p = steps_field(k, fb, fe);
+            uint32_t *out = g.flat_nodes.get() + g.flat_prefsum[k];
+            const uint64_t n = g.flat_prefsum[k + 1] - g.flat_prefsum[k];
+            const uint64_t got = is_p ? parse_path_nodes(idx, base + fb, base + fe, out) : parse_walk_nodes(idx, base + fb, base + fe, out);
+            if (got != n) throw Error("internal error: step count mismatch while parsing a path");
+        });
+        lap("pass 2 (path steps -> flat u32 ids)");
+        return g;
+    }
     g.path_steps.resize(path_lines.size());
     auto parse_line = [&](size_t k) {
-        const auto &ln = lines[path_lines[k]];
         size_t fb, fe;
-        if (data[ln.first] == 'P') {
-            if (!field(ln.first, ln.second, 2, fb, fe)) throw Error("malformed P line");
+        if (steps_field(k, fb, fe))
             parse_path_steps(idx, base + fb, base + fe, g.path_steps[k]);
-        } else {
-            if (!field(ln.first, ln.second, 6, fb, fe)) throw Error("malformed W line");
+        else
             parse_walk_steps(idx, base + fb, base + fe, g.path_steps[k]);
-        }
     };
-    parallel_for(path_lines.size(), host_threads(data.size() >= (8u << 20)), parse_line);
+    parallel_for(path_lines.size(), nt, parse_line);
+    lap("pass 2 (path steps)");
     return g;
 }
 
@@ -824,10 +1022,25 @@ void update_tables_edgecount(const GraphStorage &g, const std::vector<Step> &ste
 
 }  // namespace
 
+uint64_t GraphStorage::step_count() const {
+    if (lean) return flat_prefsum.empty() ? 0 : flat_prefsum.back();
+    uint64_t n = 0;
+    for (auto &v : path_steps) n += v.size();
+    return n;
+}
+
 ItemTables build_item_tables(const GraphStorage &g, const GraphMask &mask, CountType count) {
     ItemTables t;
     const bool edge = count == CountType::Edge;
     t.n_items = edge ? g.edge_count() : g.node_count();
+    if (g.lean) {  // the parser already wrote the table (from_gfa): every step of every path counts its node
+        if (edge || mask.include_coords || mask.exclude_coords)
+            throw Error("internal error: lean parse used with edge counting or subset / exclude lists");
+        t.items32 = g.flat_nodes.get();
+        t.id_prefsum = g.flat_prefsum;
+        t.n_steps = g.flat_prefsum.empty() ? 0 : g.flat_prefsum.back();
+        return t;
+    }
     std::optional<IntervalContainer> subset_covered;
     if (count == CountType::Bp && mask.include_coords) subset_covered.emplace();
     std::optional<ActiveTable> exclude_table;
@@ -866,6 +1079,7 @@ ItemTables build_item_tables(const GraphStorage &g, const GraphMask &mask, Count
                 for (size_t k = 0; k < steps.size(); ++k) dst[k] = steps[k].node;
             }
         });
+        t.n_steps = t.items.size();
         return t;
     }
     t.items.reserve(total_steps);
@@ -921,6 +1135,7 @@ ItemTables build_item_tables(const GraphStorage &g, const GraphMask &mask, Count
         }
     }
     if (exclude_table) t.exclude = exclude_table->items;
+    t.n_steps = t.items.size();
     return t;
 }
 

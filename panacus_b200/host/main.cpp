@@ -36,7 +36,7 @@ const std::map<char, std::string> kShort = {{'s', "subset"},  {'e', "exclude"}, 
                                              {'S', "groupby-sample"}, {'c', "count"}, {'l', "coverage"}, {'q', "quorum"},
                                              {'a', "hist"},    {'O', "order"},    {'m', "method"},  {'t', "threads"},
                                              {'v', "verbose"}};
-const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json", "names", "no-cluster", "timing"};
+const std::set<std::string> kFlags = {"groupby-haplotype", "groupby-sample", "hist", "verbose", "total", "dry-run", "json", "names", "no-cluster", "timing", "lean"};
 
 Args parse_args(int argc, char **argv) {
     Args a;
@@ -132,12 +132,15 @@ struct Run {
     std::vector<std::pair<uint64_t, std::string>> path_order;
 };
 
-Run load(const Args &a, const std::vector<CountType> &counts, bool with_order, bool with_names = false) {
+// lean_ok: the caller only feeds the ItemTable to the device build (hist / growth / ordered growth / similarity); then,
+// without edge counting and subset / exclude lists, the parser writes the u32 table directly (GraphStorage::lean)
+Run load(const Args &a, const std::vector<CountType> &counts, bool with_order, bool with_names = false, bool lean_ok = false) {
     bool edges = false;
     for (auto c : counts) edges = edges || c == CountType::Edge;
     Run r;
     g_phase.lap("other");
-    r.graph = GraphStorage::from_gfa(a.positional.at(0), edges, with_names);
+    const bool lean = lean_ok && !edges && a.get("subset").empty() && a.get("exclude").empty() && !getenv("PGX_NO_LEAN_PARSE");
+    r.graph = GraphStorage::from_gfa(a.positional.at(0), edges, with_names, lean);
     g_phase.lap("gfa_parse");
     GraphMaskParameters p;
     p.groupby = a.get("groupby");
@@ -214,7 +217,7 @@ bool ends_with(const std::string &s, const std::string &suf) {
     return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
 }
 
-Source open_source(const Args &a, const std::vector<CountType> &counts, bool with_order, bool with_names = false) {
+Source open_source(const Args &a, const std::vector<CountType> &counts, bool with_order, bool with_names = false, bool lean_ok = false) {
     Source src;
     src.path = a.positional.at(0);
     src.cached = ends_with(src.path, ".pabm");
@@ -223,7 +226,7 @@ Source open_source(const Args &a, const std::vector<CountType> &counts, bool wit
             if (a.has(k)) throw Error(std::string("--") + k + " cannot be combined with a packed-abacus (.pabm) input: grouping, "
                                       "subset and order are fixed when the cache is written");
     } else {
-        src.run = load(a, counts, with_order, with_names);
+        src.run = load(a, counts, with_order, with_names, lean_ok);
     }
     return src;
 }
@@ -303,7 +306,7 @@ std::vector<double> as_f64(const std::vector<uint64_t> &v) { return std::vector<
 int cmd_hist(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     const auto counts = expand(count);
-    const Source src = open_source(a, counts, false);
+    const Source src = open_source(a, counts, false, false, true);
     std::vector<std::vector<std::string>> headers = {{"panacus", "count", "", ""}};
     std::vector<std::vector<double>> cols;
     for (auto c : counts) {
@@ -351,7 +354,7 @@ int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth, std::
     // `growth <gfa>` has no --count: node (graph_broker.rs:158-160); histgrowth takes -c
     const CountType count = histgrowth ? count_type_from_str(a.get("count", "node")) : CountType::Node;
     const auto counts = expand(count);
-    const Source src = open_source(a, counts, false);
+    const Source src = open_source(a, counts, false, false, true);
     std::vector<Hist> hists;
     for (auto c : counts) hists.push_back(device_hist(src, c, a));
     os << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
@@ -362,7 +365,7 @@ int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     if (count == CountType::All) throw Error("ordered-histgrowth does not accept count type 'all'");
     const ThresholdContainer aux = ThresholdContainer::parse_params(a.get("quorum", "0"), a.get("coverage", "1"));
-    const Source src = open_source(a, {count}, true);
+    const Source src = open_source(a, {count}, true, false, true);
     Counted k = get_counted(src, count, a);
     const std::vector<std::string> &groups = k.groups;
     if (count == CountType::Bp) {  // weights = node_lens - uncovered_bps (abacus.rs:1016-1023)
@@ -399,7 +402,7 @@ int cmd_similarity(const Args &a, const std::string &cmdline, std::ostream &os) 
     if (count == CountType::All) throw Error("similarity does not accept count type 'all'");
     std::string method = a.get("method", "centroid");
     std::transform(method.begin(), method.end(), method.begin(), [](unsigned char c) { return (char)std::tolower(c); });
-    const Source src = open_source(a, {count}, false);
+    const Source src = open_source(a, {count}, false, false, true);
     Counted k = get_counted(src, count, a);
     const std::vector<std::string> &groups = k.groups;
     if (count == CountType::Bp) k.ab->set_weights(k.weights);  // no uncovered_bps correction here (similarity.rs:130-150)
@@ -478,7 +481,8 @@ int cmd_debug_parse(const Args &a, std::ostream &os) {
     auto ms = [](auto t0, auto t1) { return std::chrono::duration<double, std::milli>(t1 - t0).count(); };
     const auto t0 = now();
     Args b = a;
-    GraphStorage g = GraphStorage::from_gfa(a.positional.at(0), count == CountType::Edge, a.has("names"));
+    const bool lean = a.has("lean") && count != CountType::Edge && a.get("subset").empty() && a.get("exclude").empty();
+    GraphStorage g = GraphStorage::from_gfa(a.positional.at(0), count == CountType::Edge, a.has("names"), lean);
     const auto t1 = now();
     GraphMaskParameters p;
     p.groupby = a.get("groupby");
@@ -492,10 +496,9 @@ int cmd_debug_parse(const Args &a, std::ostream &os) {
     const auto t2 = now();
     const ItemTables t = build_item_tables(g, mask, count);
     const auto t3 = now();
-    uint64_t steps = 0;
-    for (auto &v : g.path_steps) steps += v.size();
+    const uint64_t steps = g.step_count();
     os << "nodes\t" << g.node_count() << "\nedges\t" << g.edge_count() << "\npaths\t" << g.path_segments.size() << "\nsteps\t" << steps
-       << "\ngroups\t" << count_groups(order) << "\nitems\t" << t.items.size() << "\nparse_ms\t" << ms(t0, t1) << "\nmask_ms\t"
+       << "\ngroups\t" << count_groups(order) << "\nitems\t" << t.n_steps << "\nparse_ms\t" << ms(t0, t1) << "\nmask_ms\t"
        << ms(t1, t2) << "\nitem_table_ms\t" << ms(t2, t3) << "\n";
     return 0;
 }
@@ -623,7 +626,7 @@ int cmd_debug_dump_tables(const Args &a, std::ostream &os) {
 int cmd_coverage_line(const Args &a, const std::string &cmdline, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     const auto counts = expand(count);
-    const Source src = open_source(a, counts, false);
+    const Source src = open_source(a, counts, false, false, true);
     std::vector<std::vector<std::string>> headers = {{"panacus", "count", "", ""}};
     std::vector<std::vector<double>> cols;
     for (auto c : counts) {  // the reference iterates a HashMap here: column order across count types is unspecified
@@ -641,7 +644,7 @@ int cmd_coverage_line(const Args &a, const std::string &cmdline, std::ostream &o
 int cmd_debug_tables(const Args &a, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     if (count == CountType::All) throw Error("debug-tables takes one count type");
-    const Run r = load(a, {count}, true);
+    const Run r = load(a, {count}, true, false, a.has("lean"));  // --lean: the parser's direct u32 table where it applies
     const ItemTables t = build_item_tables(r.graph, r.mask, count);
     std::vector<std::string> groups;
     os << "path_order";
@@ -654,7 +657,10 @@ int cmd_debug_tables(const Args &a, std::ostream &os) {
     os << "\nn_items\t" << t.n_items << "\nid_prefsum";
     for (auto v : t.id_prefsum) os << "\t" << v;
     os << "\nitems";
-    for (auto v : t.items) os << "\t" << v;
+    if (t.items32)
+        for (uint64_t k = 0; k < t.n_steps; ++k) os << "\t" << t.items32[k];
+    else
+        for (auto v : t.items) os << "\t" << v;
     os << "\nexclude";
     for (size_t i = 0; i < t.exclude.size(); ++i)
         if (t.exclude[i]) os << "\t" << i;

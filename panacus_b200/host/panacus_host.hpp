@@ -125,7 +125,13 @@ class EdgeMap {
 struct GraphStorage {  // graph.rs:150-375
     std::vector<uint32_t> node_lens;  // [0] = 0; node ids are 1..=node_count() in S-line order (graph.rs:323-340)
     std::vector<PathSegment> path_segments;
-    std::vector<std::vector<Step>> path_steps;  // steps of every P / W line, file order
+    std::vector<std::vector<Step>> path_steps;  // steps of every P / W line, file order (empty when `lean`)
+    // lean parse (counting nodes / bp without subset or exclude lists): the node ids of all paths in one flat u32 array,
+    // path k = flat_nodes[flat_prefsum[k] .. flat_prefsum[k + 1]) -- the wire format of pgx_abacus_build_u32
+    bool lean = false;
+    std::unique_ptr<uint32_t[]> flat_nodes;
+    std::vector<uint64_t> flat_prefsum;
+    uint64_t step_count() const;  // total path steps, either representation
     // canonical edge (graph.rs:142-148) packed as ((u << 1 | fwd_u) << 32) | (v << 1 | fwd_v) -> id (1-based)
     EdgeMap edge2id;
     bool has_edges = false;
@@ -135,7 +141,7 @@ struct GraphStorage {  // graph.rs:150-375
     uint64_t node_count() const { return node_lens.size() - 1; }
     uint64_t edge_count() const { return edge2id.size(); }
     static uint64_t edge_key(uint32_t u, bool fu, uint32_t v, bool fv);
-    static GraphStorage from_gfa(const std::string &path, bool with_edges, bool with_names = false);
+    static GraphStorage from_gfa(const std::string &path, bool with_edges, bool with_names = false, bool lean = false);
 };
 
 // ---- src/graph_broker/abacus.rs: GraphMask ---------------------------------------------------------------
@@ -160,6 +166,8 @@ std::vector<PathSegment> parse_bed_to_path_segments(const std::string &path, boo
 // ---- ItemTable + subset / exclude bookkeeping (src/util.rs:80-310, graph_broker/util.rs:208-790) -------------
 struct ItemTables {
     std::vector<uint64_t> items;       // ItemTable.items
+    const uint32_t *items32 = nullptr;  // lean parse: the same ids as u32, owned by the GraphStorage (then `items` is empty)
+    uint64_t n_steps = 0;               // number of ids in items / items32
     std::vector<uint64_t> id_prefsum;  // ItemTable.id_prefsum (P + 1)
     std::vector<uint8_t> exclude;      // ActiveTable.items (N + 1) or empty
     std::map<uint64_t, uint64_t> uncovered_bps;  // abacus.rs:1187-1229

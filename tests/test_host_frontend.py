@@ -25,6 +25,14 @@ def debug_tables(gfa, count, flags):
 
 
 def check(gfa, count, flags, kw):
+    _check(gfa, count, flags, kw)
+    if count != "edge" and "subset" not in kw and "exclude" not in kw:
+        # the lean parse (node ids straight into one flat u32 table: what hist / growth / similarity runs use) must hand
+        # over exactly the same tables
+        _check(gfa, count, list(flags) + ["--lean"], kw)
+
+
+def _check(gfa, count, flags, kw):
     got = debug_tables(gfa, count, flags)
     g = go.parse_gfa(gfa)
     mask = go.make_mask(g, **kw)
@@ -216,3 +224,37 @@ def test_threaded_front_end_matches_oracle(count):
     check(B("chrM_test.gfa"), count, ["-t", "4"], {})
     check(B("chrM_test.gfa"), count, ["-t", "4", "-S"], {"groupby_sample": True})
     check(B("chrM_test.gfa"), count, ["-t", "4", "-e", B("exclusion.bed3")], {"exclude": B("exclusion.bed3")})
+
+
+def test_lean_parse_on_awkward_files(tmp_path):
+    """CRLF line ends, no trailing newline, empty lines, empty step tokens, tags after the sequence, walks, many threads
+    on a file that is cut into several slices: default and lean parse agree with each other and with the oracle."""
+    rng = np.random.default_rng(9)
+    n = 5000
+    names = [str(i) for i in range(1, n + 1)]
+    lines = ["H\tVN:Z:1.1", ""]
+    for i, nm in enumerate(names):
+        lines.append(f"S\t{nm}\t{'ACGT'[i % 4] * (1 + i % 7)}" + ("\tLN:i:9\tSN:Z:x" if i % 11 == 0 else ""))
+    for p in range(40):
+        k = int(rng.integers(1, 3000))
+        st = [f"{int(j)}{'+-'[int(o)]}" for j, o in zip(rng.integers(1, n + 1, k), rng.integers(0, 2, k))]
+        lines.append(f"P\ts{p // 4}#{p % 2 + 1}#c{p}\t" + ",".join(st) + ("," if p % 5 == 0 else "") + "\t*")
+    lines.append("W\tw0\t1\tchrW\t0\t10\t" + "".join(f">{int(j)}" if j % 2 else f"<{int(j)}" for j in rng.integers(1, n + 1, 500)))
+    for name, text in (("lf.gfa", "\n".join(lines) + "\n"), ("crlf.gfa", "\r\n".join(lines) + "\r\n"), ("noeol.gfa", "\n".join(lines))):
+        gfa = str(tmp_path / name)
+        with open(gfa, "w", newline="") as f:
+            f.write(text)
+        for threads in ("1", "5"):
+            a = debug_tables(gfa, "bp", ["-S", "-t", threads])
+            b = debug_tables(gfa, "bp", ["-S", "-t", threads, "--lean"])
+            assert a == b, (name, threads)
+        if name == "lf.gfa":
+            check(gfa, "node", ["-t", "5"], {})
+    # errors surface from the lean parse as well
+    bad = str(tmp_path / "bad.gfa")
+    _write_gfa(bad, ["1", "2", "3"], [("a#1#x", [("1", "+"), ("9", "-")])])
+    r = subprocess.run([BIN, "debug-tables", bad, "--lean"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unknown node 9" in r.stderr
+    _write_gfa(bad, ["1", "2", "2"], [("a#1#x", [("1", "+")])])
+    r = subprocess.run([BIN, "debug-tables", bad, "--lean", "-t", "3"], capture_output=True, text=True)
+    assert r.returncode != 0 and "occurs multiple times" in r.stderr
