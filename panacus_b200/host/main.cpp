@@ -599,8 +599,11 @@ int cmd_debug_synth_gfa(const Args &a, std::ostream &os) {
 int cmd_debug_dump_tables(const Args &a, std::ostream &os) {
     const CountType count = count_type_from_str(a.get("count", "node"));
     if (count == CountType::All) throw Error("debug-dump-tables takes one count type");
-    const Run r = load(a, {count}, true);
+    const auto t_start = std::chrono::steady_clock::now();
+    const Run r = load(a, {count}, true, false, a.has("lean"));  // --lean: the direct u32 table (what the GPU commands use)
     const ItemTables t = build_item_tables(r.graph, r.mask, count);
+    // front end = everything up to the ItemTable, without writing the dump (the CPU baseline of bench.py --workload c5)
+    const double front_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     std::vector<std::string> groups;
     std::vector<int64_t> path_group(t.id_prefsum.size() - 1, -1);
     for (auto &po : r.path_order) {
@@ -612,11 +615,15 @@ int cmd_debug_dump_tables(const Args &a, std::ostream &os) {
         if (!o) throw Error("cannot write " + a.get("out") + suffix);
         o.write(static_cast<const char *>(p), (std::streamsize)bytes);
     };
-    dump(".items.u64", t.items.data(), t.items.size() * 8);
+    if (t.items32)
+        dump(".items.u32", t.items32, t.n_steps * 4);
+    else
+        dump(".items.u64", t.items.data(), t.items.size() * 8);
     dump(".prefsum.u64", t.id_prefsum.data(), t.id_prefsum.size() * 8);
     dump(".path_group.i64", path_group.data(), path_group.size() * 8);
     dump(".node_lens.u32", r.graph.node_lens.data(), r.graph.node_lens.size() * 4);
-    os << "n_items\t" << t.n_items << "\nsteps\t" << t.items.size() << "\ngroups";
+    os << "n_items\t" << t.n_items << "\nsteps\t" << t.n_steps << "\nfront_ms\t" << front_ms << "\nitems_dtype\t" << (t.items32 ? "u32" : "u64")
+       << "\ngroups";
     for (auto &g : groups) os << "\t" << g;
     os << "\n";
     return 0;

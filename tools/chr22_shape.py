@@ -65,19 +65,20 @@ def cpu_port(gfa: str, threads: int, workdir: str):
     """front end (shared C++) + the oracle's coverage / bp histogram / closed-form growth on the dumped ItemTable"""
     from oracle import oracle as po
     prefix = os.path.join(workdir, "c5_tables")
-    t0 = time.perf_counter()
-    r = subprocess.run([BIN, "debug-dump-tables", gfa, "--out", prefix, "-c", "bp", "-S", "-t", str(threads)], capture_output=True, text=True)
-    front_s = time.perf_counter() - t0
+    r = subprocess.run([BIN, "debug-dump-tables", gfa, "--out", prefix, "-c", "bp", "-S", "-t", str(threads), "--lean"], capture_output=True, text=True)
     if r.returncode != 0:
         raise SystemExit("debug-dump-tables failed: " + r.stderr[-2000:])
     info = dict(line.split("\t", 1) for line in r.stdout.strip().split("\n"))
+    # the front end's own clock (GFA -> ItemTable, the lean parse the GPU commands use), NOT the time to write the dump
+    front_s = float(info["front_ms"]) * 1e-3
     groups = info["groups"].split("\t")
     G, n_items = len(groups), int(info["n_items"])
-    items = np.fromfile(prefix + ".items.u64", dtype=np.uint64)
+    suffix = ".items." + info.get("items_dtype", "u64")
+    items = np.fromfile(prefix + suffix, dtype=np.uint32 if suffix.endswith("u32") else np.uint64).astype(np.uint64)
     prefsum = np.fromfile(prefix + ".prefsum.u64", dtype=np.uint64)
     path_group = np.fromfile(prefix + ".path_group.i64", dtype=np.int64)
     node_lens = np.fromfile(prefix + ".node_lens.u32", dtype=np.uint32)
-    for suf in (".items.u64", ".prefsum.u64", ".path_group.i64", ".node_lens.u32"):
+    for suf in (suffix, ".prefsum.u64", ".path_group.i64", ".node_lens.u32"):
         os.unlink(prefix + suf)
     # counting order: the paths of a group are contiguous (abacus.rs:310-347); path_group is already the group id
     order_path = np.array([p for p in np.argsort(path_group, kind="stable") if path_group[p] >= 0], dtype=np.uint64)
