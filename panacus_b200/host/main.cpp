@@ -126,19 +126,6 @@ struct PhaseTimer {
 };
 PhaseTimer g_phase;
 
-// One-shot runs (everything but `batch` and the sections of a `report`): once the table is on the stream the process
-// leaves from here, without unwinding the command -- no cudaFree / context teardown, no munmap of the GFA, no frees
-// of GB-sized tables (a quarter of a second at chr22 scale, all of it after the result was complete).
-bool g_exit_when_done = false;
-int done(std::ostream &os, int rc = 0) {
-    if (!g_exit_when_done) return rc;
-    os.flush();
-    g_phase.lap("other");
-    g_phase.report();
-    std::cerr.flush();
-    std::_Exit(rc);
-}
-
 struct Run {
     GraphStorage graph;
     GraphMask mask;
@@ -286,6 +273,9 @@ Counted get_counted(const Source &src, CountType c, const Args &a) {
 
 // Hist::from_abacus (graph_broker/hist.rs:39-49): coverage histogram of one count type
 Hist device_hist(const Source &src, CountType c, const Args &a) {
+    struct Teardown {
+        ~Teardown() { g_phase.lap("device_teardown"); }
+    } teardown;  // (declared first: laps after `k` released its handle -- cudaFree x 25, page-locked staging buffers)
     Counted k = get_counted(src, c, a);
     struct Lap {
         ~Lap() { g_phase.lap("kernels"); }
@@ -328,7 +318,7 @@ int cmd_hist(const Args &a, const std::string &cmdline, std::ostream &os) {
         headers.push_back({"hist", to_string(c), "", ""});
     }
     os << write_metadata_comments(cmdline, true) << write_table(headers, cols) << "\n";
-    return done(os);
+    return 0;
 }
 
 std::string growth_table(const std::vector<Hist> &hists, const ThresholdContainer &aux, bool add_hist) {
@@ -362,7 +352,7 @@ int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth, std::
         const std::vector<Hist> hists = parse_hists(file, comments);
         for (auto &c : comments) os << c << "\n";
         os << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
-        return done(os);
+        return 0;
     }
     // `growth <gfa>` has no --count: node (graph_broker.rs:158-160); histgrowth takes -c
     const CountType count = histgrowth ? count_type_from_str(a.get("count", "node")) : CountType::Node;
@@ -371,7 +361,7 @@ int cmd_growth(const Args &a, const std::string &cmdline, bool histgrowth, std::
     std::vector<Hist> hists;
     for (auto c : counts) hists.push_back(device_hist(src, c, a));
     os << "# " << cmdline << "\n" << growth_table(hists, aux, a.has("hist")) << "\n";
-    return done(os);
+    return 0;
 }
 
 int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
@@ -404,7 +394,7 @@ int cmd_ordered(const Args &a, const std::string &cmdline, std::ostream &os) {
     for (size_t k = 0; k < aux.coverage.size(); ++k)
         headers.push_back({"ordered-growth", to_string(count), aux.coverage[k].get_string(), aux.quorum[k].get_string()});
     os << write_metadata_comments(cmdline, true) << write_ordered_table(headers, cols, groups) << "\n";
-    return done(os);
+    return 0;
 }
 
 // ---- similarity: Jaccard + hierarchical clustering order (analyses/similarity.rs:119-254) ---------------------------
@@ -456,7 +446,7 @@ int cmd_similarity(const Args &a, const std::string &cmdline, std::ostream &os) 
         out += "\n";
     }
     os << out << "\n";
-    return done(os);
+    return 0;
 }
 
 // `table` (src/commands/table.rs, analyses/table.rs:14-35 -> AbacusByGroup::to_tsv, abacus.rs:1056-1178): one row per
@@ -482,7 +472,7 @@ int cmd_table(const Args &a, const std::string &cmdline, bool with_order, std::o
     ab.csr(t, run.path_order, r, c, v, !total);
     os << write_metadata_comments(cmdline, true)
        << abacus_by_group_to_tsv(run.graph, count, total, groups, r, c, v, t.uncovered_bps) << "\n";
-    return done(os);
+    return 0;
 }
 
 // `panacus debug-parse <gfa> [-c count] [grouping / subset / exclude flags]`: wall time of the host front-end stages
@@ -655,7 +645,7 @@ int cmd_coverage_line(const Args &a, const std::string &cmdline, std::ostream &o
         headers.push_back({"hist", to_string(c), "", ""});
     }
     os << write_metadata_comments(cmdline, true) << write_table(headers, cols, 1) << "\n";
-    return done(os);
+    return 0;
 }
 
 // `panacus debug-tables <gfa> [-c count] [grouping / subset / exclude / order flags]`: dumps what the host front
@@ -813,8 +803,6 @@ std::string lower(std::string s) {
 int cmd_report(const Args &a0, std::ostream &os) {
     const std::vector<RunSpec> runs = parse_report_yaml(a0.positional.at(0));
     const bool dry = a0.has("dry-run");
-    const bool exit_when_done = g_exit_when_done;
-    g_exit_when_done = false;  // the sections return here
     int rc = 0;
     for (size_t ri = 0; ri < runs.size(); ++ri) {
         const RunSpec &run = runs[ri];
@@ -892,8 +880,7 @@ int cmd_report(const Args &a0, std::ostream &os) {
             }
         }
     }
-    g_exit_when_done = exit_when_done;
-    return done(os, rc);
+    return rc;
 }
 
 void usage() {
@@ -982,7 +969,6 @@ int main(int argc, char **argv) {
     int rc;
     try {
         if (argc == 3 && std::string(argv[1]) == "batch") return run_batch(argv[0], argv[2]);
-        g_exit_when_done = true;
         rc = dispatch(argc, argv, std::cout);
     } catch (const std::exception &e) {
         std::cerr << "error: " << e.what() << "\n";

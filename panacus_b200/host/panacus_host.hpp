@@ -234,7 +234,6 @@ class DeviceAbacus {
     ~DeviceAbacus();
     DeviceAbacus(const DeviceAbacus &) = delete;
     DeviceAbacus &operator=(const DeviceAbacus &) = delete;
-
     // a5/a6 replacement: one scatter per path in counting order
     void build(const ItemTables &t, const std::vector<std::pair<uint64_t, std::string>> &path_order,
                std::vector<std::string> &group_names);
