@@ -258,3 +258,81 @@ def test_lean_parse_on_awkward_files(tmp_path):
     _write_gfa(bad, ["1", "2", "2"], [("a#1#x", [("1", "+")])])
     r = subprocess.run([BIN, "debug-tables", bad, "--lean", "-t", "3"], capture_output=True, text=True)
     assert r.returncode != 0 and "occurs multiple times" in r.stderr
+
+
+# ---- seeded fuzz: random graphs, naming schemes, line orders, P / W mixes, grouping flags, subset / exclude lists --------
+
+def _fuzz_case(seed, d):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 400))
+    scheme = int(rng.integers(0, 4))
+    if scheme == 0:
+        names = [str(i) for i in rng.permutation(np.arange(1, n + 1))]
+    elif scheme == 1:
+        names = [str(int(v)) for v in rng.choice(10 ** 9, n, replace=False) + 1]
+    elif scheme == 2:
+        names = [f"{i:04d}" for i in range(1, n + 1)]
+    else:
+        names = [f"n{i}x" for i in range(n)]
+    seg = [f"S\t{nm}\t{'ACGT'[i % 4] * int(rng.integers(1, 9))}" + ("\tRC:i:3" if rng.random() < .2 else "") for i, nm in enumerate(names)]
+    pw, used, pnames = [], [], []
+    for p in range(int(rng.integers(1, 12))):
+        k = int(rng.integers(1, 300))
+        idx, ori = rng.integers(0, n, k), rng.integers(0, 2, k)
+        used += [(int(idx[i]), int(ori[i]), int(idx[i + 1]), int(ori[i + 1])) for i in range(k - 1)]
+        if rng.random() < .7:
+            nm = [f"s{p // 3}#{p % 2 + 1}#c{p}", f"s{p // 3}#{p % 2 + 1}#c{p}:{10 * p}-{10 * p + k}", f"plain{p}", f"s{p // 2}#{p % 2}"][int(rng.integers(0, 4))]
+            pw.append(f"P\t{nm}\t" + ",".join(f"{names[int(j)]}{'-+'[int(o)]}" for j, o in zip(idx, ori)) + "\t*")
+            pnames.append(nm)
+        else:
+            pw.append(f"W\tw{p // 2}\t{p % 2 + 1}\tchr{p}\t{5 * p}\t{5 * p + k}\t" + "".join(("<>"[int(o)]) + names[int(j)] for j, o in zip(idx, ori)))
+            pnames.append(f"w{p // 2}#{p % 2 + 1}#chr{p}:{5 * p}-{5 * p + k}")
+    for _ in range(int(rng.integers(0, 50))):
+        u, v = rng.integers(0, n, 2)
+        used.append((int(u), int(rng.integers(0, 2)), int(v), int(rng.integers(0, 2))))
+    links = []
+    for u, ou, v, ov in used:  # every edge a path walks has its L line (the reference panics otherwise), some twice
+        links.append(f"L\t{names[u]}\t{'-+'[ou]}\t{names[v]}\t{'-+'[ov]}\t0M")
+        if rng.random() < .3:
+            links.append(links[-1])
+    body = seg + pw + links
+    if rng.random() < .5:  # the record types may come in any order
+        body = [body[i] for i in rng.permutation(len(body))]
+    gfa = os.path.join(d, f"f{seed}.gfa")
+    with open(gfa, "w") as f:
+        f.write("\n".join(["H\tVN:Z:1.0"] + body) + ("\n" if rng.random() < .8 else ""))
+    count = ["node", "bp", "edge"][int(rng.integers(0, 3))]
+    flags, kw = [([], {}), (["-S"], {"groupby_sample": True}), (["-H"], {"groupby_haplotype": True})][int(rng.integers(0, 3))]
+    flags, kw = flags + ["-t", str(int(rng.integers(1, 6)))], dict(kw)
+    for kind in ("subset", "exclude"):  # 1-column lists (names with / without coordinates) or BED3 intervals
+        r = rng.random()
+        if r < .35:
+            continue
+        rows = []
+        for nm in pnames:
+            if rng.random() < .5:
+                continue
+            base, _, coords = nm.partition(":")
+            if r < .65:
+                rows.append(nm if rng.random() < .5 else base)
+            else:
+                off = int(coords.split("-")[0]) if "-" in coords else 0
+                a = off + int(rng.integers(0, 40))
+                rows.append(f"{base}\t{a}\t{a + int(rng.integers(0, 200))}")
+        if not rows and kind == "subset":
+            rows.append(pnames[0])
+        if rows:
+            lp = os.path.join(d, f"f{seed}.{kind}")
+            with open(lp, "w") as f:
+                f.write("\n".join(rows) + "\n")
+            flags += ["-s" if kind == "subset" else "-e", lp]
+            kw[kind] = lp
+    return gfa, count, flags, kw
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_front_end_fuzz(block, tmp_path):
+    """Whatever the file looks like, the C++ front end (default and lean parse) hands over the oracle's tables."""
+    for seed in range(block * 15, block * 15 + 15):
+        gfa, count, flags, kw = _fuzz_case(seed, str(tmp_path))
+        check(gfa, count, flags, kw)
