@@ -16,6 +16,7 @@
 #include <regex>
 #include <set>
 #include <sstream>
+#include <memory>
 #include <mutex>
 #include <string_view>
 #include <thread>
@@ -30,11 +31,12 @@ constexpr uint64_t kUsizeMax = ~0ull;
 
 // The whole file as one read-only byte range.  Plain files are mapped (no copy: the page cache is the buffer; reading
 // 1.25 GB into a zero-filled std::string was 0.5-1.2 s of the chr22-sized parse); gzip files are inflated into memory
-// (transparently, like io.rs:23-33).
+// (transparently, like io.rs:23-33) -- bgzip-written ones block by block on the worker threads, see load_file.
 struct FileData {
     const char *ptr = nullptr;
     size_t len = 0;
     std::string owned;
+    std::unique_ptr<char[]> heap;  // inflated BGZF blocks (not zero-filled first)
     void *map = nullptr;
     FileData() = default;
     FileData(const FileData &) = delete;
@@ -43,41 +45,6 @@ struct FileData {
         if (map) munmap(map, len);
     }
 };
-
-void load_file(const std::string &path, FileData &f) {
-    const int fd = open(path.c_str(), O_RDONLY);
-    if (fd < 0) throw Error("cannot open " + path);
-    unsigned char magic[2] = {0, 0};
-    const ssize_t got = pread(fd, magic, 2, 0);
-    struct stat st;
-    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
-    if (!gz && fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
-        if (st.st_size == 0) {
-            close(fd);
-            return;
-        }
-        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (m != MAP_FAILED) {
-            madvise(m, (size_t)st.st_size, MADV_WILLNEED);
-            close(fd);
-            f.map = m;
-            f.ptr = static_cast<const char *>(m);
-            f.len = (size_t)st.st_size;
-            return;
-        }
-    }
-    close(fd);
-    gzFile z = gzopen(path.c_str(), "rb");  // (also reads plain data: pipes, files that could not be mapped)
-    if (!z) throw Error("cannot open " + path);
-    std::vector<char> buf(1 << 20);
-    int n;
-    while ((n = gzread(z, buf.data(), (unsigned)buf.size())) > 0) f.owned.append(buf.data(), (size_t)n);
-    const bool bad = n < 0;
-    gzclose(z);
-    if (bad) throw Error("read error in " + path);
-    f.ptr = f.owned.data();
-    f.len = f.owned.size();
-}
 
 std::vector<std::string> split(const std::string &s, char sep) {
     std::vector<std::string> out;
@@ -385,6 +352,132 @@ void parallel_for(size_t n, unsigned nthreads, F fn) {
 // -t N is taken literally; the default is one thread per core for inputs worth the thread start-up
 unsigned host_threads(bool big_input) {
     return g_host_threads > 0 ? (unsigned)g_host_threads : (big_input ? std::max(1u, std::thread::hardware_concurrency()) : 1u);
+}
+
+// ---- input: mapped as it is, or inflated into memory ---------------------------------------------------------------------
+// A gzip file written by bgzip (BGZF: independent members of <= 64 KiB, each carrying its compressed size in a "BC" extra
+// field and its inflated size in the trailer) is inflated block by block on the worker threads: the headers are walked
+// first (no inflation), which gives every block its place in the output.  Any other gzip stream is one serial inflate.
+
+struct BgzfBlock {
+    size_t in_off, in_len;  // raw deflate data
+    size_t out_off;
+    uint32_t out_len, crc;
+};
+
+// block list of a BGZF file, or false if the data is not (entirely) BGZF
+bool bgzf_index(const unsigned char *z, size_t n, std::vector<BgzfBlock> &blocks, size_t &total) {
+    size_t o = 0;
+    total = 0;
+    while (o < n) {
+        if (n - o < 18 + 8 || z[o] != 0x1f || z[o + 1] != 0x8b || z[o + 2] != 8 || !(z[o + 3] & 4)) return false;
+        const size_t xlen = (size_t)z[o + 10] | ((size_t)z[o + 11] << 8);
+        if (z[o + 3] & ~4u) return false;  // (bgzip sets FEXTRA only: no name / comment / header crc to skip)
+        if (o + 12 + xlen > n) return false;
+        size_t bsize = 0;
+        for (size_t x = o + 12; x + 4 <= o + 12 + xlen;) {
+            const size_t slen = (size_t)z[x + 2] | ((size_t)z[x + 3] << 8);
+            if (z[x] == 'B' && z[x + 1] == 'C' && slen == 2 && x + 6 <= o + 12 + xlen) bsize = ((size_t)z[x + 4] | ((size_t)z[x + 5] << 8)) + 1;
+            x += 4 + slen;
+        }
+        if (bsize < 12 + xlen + 8 || o + bsize > n) return false;
+        const unsigned char *t = z + o + bsize - 8;
+        BgzfBlock b;
+        b.in_off = o + 12 + xlen;
+        b.in_len = bsize - (12 + xlen) - 8;
+        b.crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        b.out_len = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+        b.out_off = total;
+        total += b.out_len;
+        if (b.out_len) blocks.push_back(b);  // (the end-of-file marker is an empty block)
+        o += bsize;
+    }
+    return !blocks.empty() || n > 0;
+}
+
+void inflate_bgzf(const std::string &path, const unsigned char *z, const std::vector<BgzfBlock> &blocks, size_t total, FileData &f) {
+    f.heap.reset(new char[total ? total : 1]);
+    char *out = f.heap.get();
+    // a few blocks per hand-out: a block is ~64 KiB of output, ~50 us of work
+    const size_t kBatch = 16, n_batches = (blocks.size() + kBatch - 1) / kBatch;
+    parallel_for(n_batches, host_threads(total >= (8u << 20)), [&](size_t bi) {
+        z_stream zs;
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) throw Error("zlib: inflateInit2 failed");
+        for (size_t k = bi * kBatch; k < std::min(blocks.size(), (bi + 1) * kBatch); ++k) {
+            const BgzfBlock &b = blocks[k];
+            zs.next_in = const_cast<unsigned char *>(z + b.in_off);
+            zs.avail_in = (uInt)b.in_len;
+            zs.next_out = reinterpret_cast<unsigned char *>(out + b.out_off);
+            zs.avail_out = b.out_len;
+            const int rc = inflate(&zs, Z_FINISH);
+            const bool ok = rc == Z_STREAM_END && zs.avail_out == 0 &&
+                            (uint32_t)crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const unsigned char *>(out + b.out_off), b.out_len) == b.crc;
+            if (!ok) {
+                inflateEnd(&zs);
+                throw Error("corrupt BGZF block in " + path);
+            }
+            inflateReset(&zs);
+        }
+        inflateEnd(&zs);
+    });
+    f.ptr = out;
+    f.len = total;
+}
+
+void load_file(const std::string &path, FileData &f) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw Error("cannot open " + path);
+    unsigned char magic[2] = {0, 0};
+    const ssize_t got = pread(fd, magic, 2, 0);
+    struct stat st;
+    std::memset(&st, 0, sizeof(st));
+    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+        if (st.st_size == 0) {
+            close(fd);
+            return;
+        }
+        void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, (size_t)st.st_size, MADV_WILLNEED);
+            if (!gz) {
+                close(fd);
+                f.map = m;
+                f.ptr = static_cast<const char *>(m);
+                f.len = (size_t)st.st_size;
+                return;
+            }
+            std::vector<BgzfBlock> blocks;
+            size_t total = 0;
+            const bool bgzf = bgzf_index(static_cast<const unsigned char *>(m), (size_t)st.st_size, blocks, total);
+            try {
+                if (bgzf) inflate_bgzf(path, static_cast<const unsigned char *>(m), blocks, total, f);
+            } catch (...) {
+                munmap(m, (size_t)st.st_size);
+                close(fd);
+                throw;
+            }
+            munmap(m, (size_t)st.st_size);
+            if (bgzf) {
+                close(fd);
+                return;
+            }
+        }
+    }
+    close(fd);
+    gzFile z = gzopen(path.c_str(), "rb");  // (also reads plain data: pipes, files that could not be mapped)
+    if (!z) throw Error("cannot open " + path);
+    gzbuffer(z, 1u << 20);
+    if (gz && S_ISREG(st.st_mode)) f.owned.reserve((size_t)st.st_size * 4u);  // GFA text deflates ~3-4x: one or no regrowth
+    std::vector<char> buf(4u << 20);
+    int n;
+    while ((n = gzread(z, buf.data(), (unsigned)buf.size())) > 0) f.owned.append(buf.data(), (size_t)n);
+    const bool bad = n < 0;
+    gzclose(z);
+    if (bad) throw Error("read error in " + path);
+    f.ptr = f.owned.data();
+    f.len = f.owned.size();
 }
 
 // Segment name -> item id (1-based, S-line order).  Real pangenome GFAs (pggb, minigraph-cactus) name their segments

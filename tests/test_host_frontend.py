@@ -336,3 +336,65 @@ def test_front_end_fuzz(block, tmp_path):
     for seed in range(block * 15, block * 15 + 15):
         gfa, count, flags, kw = _fuzz_case(seed, str(tmp_path))
         check(gfa, count, flags, kw)
+
+
+# ---- bgzip-compressed input: blocks inflated on the worker threads --------------------------------------------------------
+
+def _bgzf(data, block=65280, eof=True):
+    """BGZF as bgzip writes it: gzip members of <= 64 KiB with a 'BC' extra field holding the member size - 1"""
+    import struct
+    import zlib
+    out = bytearray()
+
+    def member(chunk):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        d = c.compress(chunk) + c.flush()
+        out.extend(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, 12 + 6 + len(d) + 8 - 1))
+        out.extend(d + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    for i in range(0, len(data), block):
+        member(data[i:i + block])
+    if eof:
+        member(b"")
+    return bytes(out)
+
+
+def test_bgzf_input(tmp_path):
+    import gzip
+    rng = np.random.default_rng(21)
+    n = 3000
+    names = [str(i) for i in range(1, n + 1)]
+    paths = [(f"s{p // 2}#{p % 2 + 1}#c{p}", [(names[int(j)], "+-"[int(o)]) for j, o in zip(rng.integers(0, n, 4000), rng.integers(0, 2, 4000))])
+             for p in range(12)]
+    plain = str(tmp_path / "g.gfa")
+    _write_gfa(plain, names, paths)
+    data = open(plain, "rb").read()
+    want = debug_tables(plain, "bp", ["-S"])
+    variants = {
+        "blocks.gfa.gz": _bgzf(data, block=4096),                        # ~60 blocks, lines straddle them
+        "noeof.gfa.gz": _bgzf(data, eof=False),
+        "one.gfa.gz": _bgzf(data, block=1 << 30) if len(data) < 60000 else _bgzf(data, block=60000),
+        "mixed.gfa.gz": _bgzf(data[:50000], eof=False) + gzip.compress(data[50000:]),  # not BGZF throughout: serial inflate
+        "plain.gfa.gz": gzip.compress(data),
+    }
+    for name, blob in variants.items():
+        f = str(tmp_path / name)
+        with open(f, "wb") as fo:
+            fo.write(blob)
+        for threads in ("1", "4"):
+            assert debug_tables(f, "bp", ["-S", "-t", threads]) == want, (name, threads)
+            assert debug_tables(f, "bp", ["-S", "-t", threads, "--lean"]) == want, (name, threads)
+    check(str(tmp_path / "blocks.gfa.gz"), "node", ["-t", "3"], {})      # and against the oracle's parser
+    # a damaged block is an error, not silently different text
+    blob = bytearray(variants["blocks.gfa.gz"])
+    blob[len(blob) // 2] ^= 0x5A
+    bad = str(tmp_path / "bad.gfa.gz")
+    with open(bad, "wb") as fo:
+        fo.write(bytes(blob))
+    r = subprocess.run([BIN, "debug-tables", bad, "-t", "4"], capture_output=True, text=True)
+    assert r.returncode != 0 and r.stderr.strip()
+    # only the end-of-file marker: an empty graph, like an empty file
+    empty = str(tmp_path / "empty.gfa.gz")
+    with open(empty, "wb") as fo:
+        fo.write(_bgzf(b""))
+    r = subprocess.run([BIN, "debug-parse", empty], capture_output=True, text=True)
+    assert r.returncode == 0 and "nodes\t0" in r.stdout
