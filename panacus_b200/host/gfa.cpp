@@ -1122,13 +1122,44 @@ uint64_t GraphStorage::step_count() const {
     return n;
 }
 
+bool GraphStorage::lean_apply_subset(const GraphMask &mask) {
+    if (!lean || !mask.include_coords) return true;
+    const std::map<std::string, Intervals> include_map = build_subpath_map(*mask.include_coords);
+    const Intervals none = {};
+    const size_t P = path_segments.size();
+    std::vector<uint8_t> keep(P, 0);
+    for (size_t pi = 0; pi < P; ++pi) {  // the same three cases as build_item_tables below
+        const PathSegment &seg = path_segments[pi];
+        auto it = include_map.find(seg.id());
+        const Intervals &inc = it == include_map.end() ? none : it->second;
+        const auto c = seg.coords();
+        const std::pair<uint64_t, uint64_t> whole = {c ? c->first : 0, c ? c->second : kUsizeMax};
+        if (!intersects(inc, whole)) continue;
+        if (!is_contained(inc, whole)) return false;
+        keep[pi] = 1;
+    }
+    uint64_t w = 0;
+    std::vector<uint64_t> prefsum(P + 1, 0);
+    for (size_t pi = 0; pi < P; ++pi) {
+        const uint64_t b = flat_prefsum[pi], n = flat_prefsum[pi + 1] - b;
+        if (keep[pi]) {
+            if (w != b) std::memmove(flat_nodes.get() + w, flat_nodes.get() + b, n * sizeof(uint32_t));
+            w += n;
+        }
+        prefsum[pi + 1] = w;
+    }
+    flat_prefsum.swap(prefsum);
+    lean_subset_applied = true;
+    return true;
+}
+
 ItemTables build_item_tables(const GraphStorage &g, const GraphMask &mask, CountType count) {
     ItemTables t;
     const bool edge = count == CountType::Edge;
     t.n_items = edge ? g.edge_count() : g.node_count();
-    if (g.lean) {  // the parser already wrote the table (from_gfa): every step of every path counts its node
-        if (edge || mask.include_coords || mask.exclude_coords)
-            throw Error("internal error: lean parse used with edge counting or subset / exclude lists");
+    if (g.lean) {  // the parser already wrote the table (from_gfa): every step of every (subset) path counts its node
+        if (edge || mask.exclude_coords || (mask.include_coords && !g.lean_subset_applied))
+            throw Error("internal error: lean parse used with edge counting, an exclude list or an unapplied subset list");
         t.items32 = g.flat_nodes.get();
         t.id_prefsum = g.flat_prefsum;
         t.n_steps = g.flat_prefsum.empty() ? 0 : g.flat_prefsum.back();

@@ -139,7 +139,7 @@ Run load(const Args &a, const std::vector<CountType> &counts, bool with_order, b
     for (auto c : counts) edges = edges || c == CountType::Edge;
     Run r;
     g_phase.lap("other");
-    const bool lean = lean_ok && !edges && a.get("subset").empty() && a.get("exclude").empty() && !getenv("PGX_NO_LEAN_PARSE");
+    const bool lean = lean_ok && !edges && a.get("exclude").empty() && !getenv("PGX_NO_LEAN_PARSE");
     r.graph = GraphStorage::from_gfa(a.positional.at(0), edges, with_names, lean);
     g_phase.lap("gfa_parse");
     GraphMaskParameters p;
@@ -153,6 +153,10 @@ Run load(const Args &a, const std::vector<CountType> &counts, bool with_order, b
     r.mask = GraphMask::from_graph(r.graph, p);
     r.path_order = r.mask.get_path_order(r.graph.path_segments);
     g_phase.lap("grouping_order");
+    if (lean && !r.graph.lean_apply_subset(r.mask)) {  // a path only partly inside the subset (BED intervals): the general parse
+        r.graph = GraphStorage::from_gfa(a.positional.at(0), edges, with_names, false);
+        g_phase.lap("gfa_parse");
+    }
     return r;
 }
 
@@ -484,7 +488,7 @@ int cmd_debug_parse(const Args &a, std::ostream &os) {
     auto ms = [](auto t0, auto t1) { return std::chrono::duration<double, std::milli>(t1 - t0).count(); };
     const auto t0 = now();
     Args b = a;
-    const bool lean = a.has("lean") && count != CountType::Edge && a.get("subset").empty() && a.get("exclude").empty();
+    const bool lean = a.has("lean") && count != CountType::Edge && a.get("exclude").empty();
     GraphStorage g = GraphStorage::from_gfa(a.positional.at(0), count == CountType::Edge, a.has("names"), lean);
     const auto t1 = now();
     GraphMaskParameters p;
@@ -496,6 +500,7 @@ int cmd_debug_parse(const Args &a, std::ostream &os) {
     p.negative_list = a.get("exclude");
     const GraphMask mask = GraphMask::from_graph(g, p);
     const auto order = mask.get_path_order(g.path_segments);
+    if (lean && !g.lean_apply_subset(mask)) g = GraphStorage::from_gfa(a.positional.at(0), false, a.has("names"), false);
     const auto t2 = now();
     const ItemTables t = build_item_tables(g, mask, count);
     const auto t3 = now();

@@ -132,6 +132,11 @@ struct GraphStorage {  // graph.rs:150-375
     std::unique_ptr<uint32_t[]> flat_nodes;
     std::vector<uint64_t> flat_prefsum;
     uint64_t step_count() const;  // total path steps, either representation
+    // lean parse + a subset list that takes every path entirely or not at all (the usual list of path names, or a regex):
+    // paths outside the subset lose their steps -- an empty id range, as the general table build leaves them
+    // (util.rs:276-291).  False (nothing changed) if some path is only partly inside: parse again, the general way.
+    bool lean_apply_subset(const struct GraphMask &mask);
+    bool lean_subset_applied = false;
     // canonical edge (graph.rs:142-148) packed as ((u << 1 | fwd_u) << 32) | (v << 1 | fwd_v) -> id (1-based)
     EdgeMap edge2id;
     bool has_edges = false;

@@ -26,9 +26,10 @@ def debug_tables(gfa, count, flags):
 
 def check(gfa, count, flags, kw):
     _check(gfa, count, flags, kw)
-    if count != "edge" and "subset" not in kw and "exclude" not in kw:
+    if count != "edge":
         # the lean parse (node ids straight into one flat u32 table: what hist / growth / similarity runs use) must hand
-        # over exactly the same tables
+        # over exactly the same tables -- also with a subset list (whole paths in or out: applied to the flat table; BED
+        # intervals that cut a path: the front end falls back to the general parse) and with an exclude list (general parse)
         _check(gfa, count, list(flags) + ["--lean"], kw)
 
 
